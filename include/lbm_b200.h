@@ -1,0 +1,153 @@
+/*
+ * lbm_b200.h -- C ABI of liblbm_b200.so: the B200 (sm_100a) banded mul!/materialize
+ * hot path behind LazyBandedMatrices.jl's API.
+ *
+ * What this boundary replaces.  In the reference the path ends in the only FFI it
+ * has: BandedMatrices.jl `gbmv!` -> `ccall((@blasfunc(dgbmv_), libblastrampoline), ...)`
+ * with the Fortran signature (trans,m,n,kl,ku,alpha,A,lda,x,incx,beta,y,incy)
+ * (un-vendored dependency, /root/reference/Project.toml:7; reached from the layout
+ * traits the reference declares at src/tridiag.jl:685-688, src/bidiag.jl:438-440,
+ * src/LazyBandedMatrices.jl:14-21).  Every entry point below is what a Julia host
+ * shim binds with `ccall` in place of that BLAS call (see INTEGRATION.md and
+ * lazybandedmatrices.jl_b200/julia/LBMB200.jl); argument meaning follows BLAS/LAPACK.
+ *
+ * Conventions
+ *  - Plain C: pointers + int64 sizes, no C++/torch types.  All matrix/vector pointers
+ *    are DEVICE pointers on the handle's GPU unless the function name ends in `_host`.
+ *  - Band storage = BandedMatrices `(kl+ku+1) x n` column-major "AB" format:
+ *        A[i,j] = data[(ku + i - j) + lda*j]   (0-based), -ku <= i-j <= kl.
+ *    Out-of-matrix slots are never read (masked by INDEX, never by value).
+ *  - Return value (LAPACK `info` style): 0 ok; -k = k-th argument invalid (the host
+ *    shim maps it to DimensionMismatch/ArgumentError, mirroring
+ *    /root/reference/src/bidiag.jl:363-377 and test/test_tridiag.jl:272-279);
+ *    >0 = CUDA error (cudaError_t), text via lbm_last_error_string().
+ *  - Calls ENQUEUE on the handle's stream and return; lbm_sync() waits.  `_host`
+ *    variants copy in, compute, copy out and synchronise before returning.
+ *  - beta == 0 means y/C is not read (BLAS convention; NaNs do not propagate).
+ *  - A handle is bound to one device and is not thread-safe.
+ *  - There is NO CPU fallback: without a CUDA device lbm_create() fails.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lbm_handle_s *lbm_handle_t;
+
+/* ---- handle ---------------------------------------------------------------------- */
+int lbm_version(void);                                   /* 10000*major + 100*minor + patch */
+int lbm_create(lbm_handle_t *out, int device);           /* owns a non-blocking stream */
+int lbm_destroy(lbm_handle_t h);
+int lbm_set_stream(lbm_handle_t h, void *cuda_stream);   /* borrow caller's cudaStream_t (NULL = own) */
+int lbm_sync(lbm_handle_t h);
+const char *lbm_last_error_string(lbm_handle_t h);       /* h may be NULL: last create error */
+int64_t lbm_launch_count(lbm_handle_t h);                /* kernels launched through h so far */
+int lbm_set_tuning(lbm_handle_t h, const char *key, int64_t value); /* kernel selection knobs */
+int64_t lbm_get_tuning(lbm_handle_t h, const char *key);
+
+/* ---- memory helpers (for hosts without their own CUDA allocator, e.g. the Julia shim) - */
+int lbm_malloc(lbm_handle_t h, void **dptr, size_t bytes);
+int lbm_free(lbm_handle_t h, void *dptr);
+int lbm_host_alloc(lbm_handle_t h, void **hptr, size_t bytes);   /* pinned */
+int lbm_host_free(lbm_handle_t h, void *hptr);
+int lbm_memcpy_h2d(lbm_handle_t h, void *dst, const void *src, size_t bytes);  /* async on stream */
+int lbm_memcpy_d2h(lbm_handle_t h, void *dst, const void *src, size_t bytes);
+int lbm_memset0(lbm_handle_t h, void *dst, size_t bytes);
+
+/* ---- synthetic data: counter-based U[0,1) (same stream as oracle/) ---- */
+int lbm_dfill_uniform(lbm_handle_t h, uint64_t seed, int64_t offset, int64_t count, double *dst);
+int lbm_sfill_uniform(lbm_handle_t h, uint64_t seed, int64_t offset, int64_t count, float *dst);
+
+/* ---- banded matrix * vector:  y <- alpha*op(A)*x + beta*y  --------------------------- */
+/* Replaces BandedMatrices.gbmv! -> BLAS ?gbmv_; trans in {'N','T','C'}. */
+int lbm_dgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+              double alpha, const double *A, int64_t lda, const double *x, double beta, double *y);
+int lbm_sgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+              float alpha, const float *A, int64_t lda, const float *x, float beta, float *y);
+/* same, HOST pointers (pageable or pinned): H2D(A,x[,y]) + kernel + D2H(y) + sync. */
+int lbm_dgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+                   double alpha, const double *A, int64_t lda, const double *x, double beta, double *y);
+int lbm_sgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
+                   float alpha, const float *A, int64_t lda, const float *x, float beta, float *y);
+
+/* ---- Tridiagonal / SymTridiagonal / Bidiagonal:  Y <- alpha*A*X + beta*Y ------------- */
+/* A = Tridiagonal(dl,d,du), n x n (reference src/tridiag.jl:327-341, elements :471-484).
+ * SymTridiagonal(dv,ev) passes dl == du == ev (src/tridiag.jl:6-16, :301-314; only
+ * ev[0..n-2] is read).  Bidiagonal(dv,ev,'U') passes dl == NULL, 'L' passes du == NULL
+ * (src/bidiag.jl:111-124).  X, Y are n x nrhs column-major with leading dims ldx, ldy. */
+int lbm_dtridiag_mv(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du,
+                    double alpha, const double *X, int64_t ldx, int64_t nrhs,
+                    double beta, double *Y, int64_t ldy);
+int lbm_stridiag_mv(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du,
+                    float alpha, const float *X, int64_t ldx, int64_t nrhs,
+                    float beta, float *Y, int64_t ldy);
+int lbm_dbidiag_mv(lbm_handle_t h, char uplo, int64_t n, const double *dv, const double *ev,
+                   double alpha, const double *X, int64_t ldx, int64_t nrhs,
+                   double beta, double *Y, int64_t ldy);
+int lbm_sbidiag_mv(lbm_handle_t h, char uplo, int64_t n, const float *dv, const float *ev,
+                   float alpha, const float *X, int64_t ldx, int64_t nrhs,
+                   float beta, float *Y, int64_t ldy);
+
+/* ---- banded * banded -> banded:  C <- alpha*A*B + beta*C ------------------------------ */
+/* Materialises ApplyMatrix(*, A, B) (reference README.md:8-26; [up] BandedMatrices gbmm!).
+ * A m x k (kla,kua), B k x n (klb,kub), C m x n stored with band (klc,kuc) which must
+ * cover the product band clipped to the matrix: klc >= min(kla+klb, m-1),
+ * kuc >= min(kua+kub, n-1).  Out-of-matrix slots of C are written 0 when beta == 0. */
+int lbm_dgbmm(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double alpha,
+              int64_t kla, int64_t kua, const double *A, int64_t lda,
+              int64_t klb, int64_t kub, const double *B, int64_t ldb, double beta,
+              int64_t klc, int64_t kuc, double *C, int64_t ldc);
+int lbm_sgbmm(lbm_handle_t h, int64_t m, int64_t n, int64_t k, float alpha,
+              int64_t kla, int64_t kua, const float *A, int64_t lda,
+              int64_t klb, int64_t kub, const float *B, int64_t ldb, float beta,
+              int64_t klc, int64_t kuc, float *C, int64_t ldc);
+
+/* ---- batched lazy chain  D_b = (A_b*B_b)*C_b,  b = 0..batch-1 -------------------------- */
+/* Square n x n factors with tight leading dimension kl[i]+ku[i]+1; item b of factor F
+ * starts at F + b*strideF (elements).  D has band (sum kl, sum ku), tight ld.  The
+ * intermediate band never touches HBM. */
+int lbm_sgbmm_chain3_batched(lbm_handle_t h, int64_t batch, int64_t n,
+                             const int64_t *kl, const int64_t *ku,
+                             const float *A, int64_t strideA, const float *B, int64_t strideB,
+                             const float *C, int64_t strideC, float *D, int64_t strideD);
+int lbm_dgbmm_chain3_batched(lbm_handle_t h, int64_t batch, int64_t n,
+                             const int64_t *kl, const int64_t *ku,
+                             const double *A, int64_t strideA, const double *B, int64_t strideB,
+                             const double *C, int64_t strideC, double *D, int64_t strideD);
+
+/* ---- block-Kronecker operators applied without forming them -------------------------- */
+/* y <- alpha*(kron(A,I_n2) + kron(I_n1,B))*x + beta*y = alpha*vec(X*A^T + B*X) + beta*y,
+ * x = vec(X), X n2 x n1 column-major; A n1 x n1 (kla,kua), B n2 x n2 (klb,kub) banded.
+ * This is BlockKron(A,I)+BlockKron(I,B) -- the 2-D Laplacian of
+ * /root/reference/test/test_blockkron.jl:296-306 -- via the identity the reference uses at
+ * src/blockkron.jl:272-278,:440. */
+int lbm_dkronsum2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
+                      int64_t kla, int64_t kua, const double *A, int64_t lda,
+                      int64_t klb, int64_t kub, const double *B, int64_t ldb,
+                      double alpha, const double *x, double beta, double *y);
+int lbm_skronsum2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
+                      int64_t kla, int64_t kua, const float *A, int64_t lda,
+                      int64_t klb, int64_t kub, const float *B, int64_t ldb,
+                      float alpha, const float *x, float beta, float *y);
+/* y <- alpha*kron(A,B)*x + beta*y = alpha*vec(B*X*A^T) + beta*y  (BlockKron(A,B)*x;
+ * work = n1*n2 elements of scratch owned by the handle). */
+int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
+                   int64_t kla, int64_t kua, const double *A, int64_t lda,
+                   int64_t klb, int64_t kub, const double *B, int64_t ldb,
+                   double alpha, const double *x, double beta, double *y);
+
+/* ---- structure helpers (pure integer, host side, no GPU needed) ------------------------ */
+/* bandwidths(ApplyMatrix(*, F1..Fnf)) = min.(size-1, (sum kl, sum ku))  ([up] LazyArrays;
+ * reference README.md:13-26 shows (1,1)*(1,1) -> (2,2)). */
+int lbm_prod_bandwidths(int64_t m, int64_t n, int nf, const int64_t *kl, const int64_t *ku,
+                        int64_t *out_kl, int64_t *out_ku);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

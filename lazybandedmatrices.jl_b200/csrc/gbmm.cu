@@ -1,0 +1,314 @@
+// gbmm.cu -- banded x banded -> banded:  C <- alpha*A*B + beta*C, all three in diagonal-major
+// storage.  Materialises ApplyMatrix(*, A, B) (reference README.md:8-26); upstream
+// BandedMatrices gbmm! does this as n tiny gbmv ccalls.
+//
+//   C[i,j] = sum_p A[i,p] B[p,j],  p in [max(i-kla, j-kub, 0), min(i+kua, j+klb, k-1)]
+//
+//  * gbmm_diag_kernel: "diagonal-wise": a CTA owns a tile of output columns; the slab of A it
+//    needs (columns [j0-kub, j1+klb), one contiguous range) and the tile of B are staged in
+//    shared memory; consecutive threads own consecutive band rows of one output column, so
+//    A is read at consecutive smem addresses, B as a broadcast, and C is written contiguously.
+//  * gbmm_chain3_kernel: D = (A*B)*C for a batch of small-band factors with the intermediate
+//    band A*B living only in shared memory.
+//  * wide bands (FP64 DMMA tiles) live in gbmm_dmma.cu.
+#include "lbm_common.cuh"
+
+int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double alpha, int64_t kla, int64_t kua,
+                      const double *A, int64_t lda, int64_t klb, int64_t kub, const double *B, int64_t ldb,
+                      double beta, int64_t klc, int64_t kuc, double *C, int64_t ldc, bool *handled);
+
+namespace {
+
+using namespace lbm;
+
+template <typename T>
+struct GbmmArgs {
+    int64_t m, n, k;
+    int64_t kla, kua, lda, klb, kub, ldb, klc, kuc, ldc;
+    T alpha, beta;
+    const T *A;
+    const T *B;
+    T *C;
+    int tile;  // output columns per CTA
+    int64_t sA_elems;
+};
+
+template <typename T, bool USE_SMEM>
+__global__ void __launch_bounds__(256) gbmm_diag_kernel(const GbmmArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sA = reinterpret_cast<T *>(smem_raw);
+    T *sB = sA + a.sA_elems;
+    const int tid = threadIdx.x;
+    const int64_t j0 = (int64_t)blockIdx.x * a.tile;
+    const int64_t j1 = j0 + a.tile < a.n ? j0 + a.tile : a.n;
+    int64_t p0 = j0 - a.kub > 0 ? j0 - a.kub : 0;       // A columns needed: [p0, p1)
+    int64_t p1 = j1 + a.klb < a.k ? j1 + a.klb : a.k;
+    if (p1 < p0) p1 = p0;
+    const T *Ag = a.A + p0 * a.lda;
+    const T *Bg = a.B + j0 * a.ldb;
+    if (USE_SMEM) {
+        const int64_t cntA = (p1 - p0) * a.lda;
+        const int64_t cntB = (j1 - j0) * a.ldb;
+        for (int64_t e = tid; e < cntA; e += 256) sA[e] = Ag[e];
+        for (int64_t e = tid; e < cntB; e += 256) sB[e] = Bg[e];
+        __syncthreads();
+    }
+    const T *Ar = USE_SMEM ? sA : Ag;
+    const T *Br = USE_SMEM ? sB : Bg;
+    const int nbc = (int)(a.klc + a.kuc + 1);
+    const int64_t total = (j1 - j0) * nbc;
+    for (int64_t e = tid; e < total; e += 256) {
+        const int jj = (int)(e / nbc);
+        const int r = (int)(e - (int64_t)jj * nbc);
+        const int64_t j = j0 + jj;
+        const int64_t i = j + r - a.kuc;
+        T *c = a.C + r + a.ldc * j;
+        if (i < 0 || i >= a.m) {
+            if (a.beta == (T)0) *c = (T)0;
+            continue;
+        }
+        int64_t plo = i - a.kla > j - a.kub ? i - a.kla : j - a.kub;
+        int64_t phi = i + a.kua < j + a.klb ? i + a.kua : j + a.klb;
+        if (plo < 0) plo = 0;
+        if (phi > a.k - 1) phi = a.k - 1;
+        T acc = 0;
+        // A index: (kua + i - p) + lda*(p - p0);  B index: (kub + p - j) + ldb*jj
+        int64_t ia = (a.kua + i - plo) + a.lda * (plo - p0);
+        int64_t ib = (a.kub + plo - j) + a.ldb * jj;
+        for (int64_t p = plo; p <= phi; ++p) {
+            acc = fma(Ar[ia], Br[ib], acc);
+            ia += a.lda - 1;
+            ib += 1;
+        }
+        *c = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *c, a.alpha * acc);
+    }
+}
+
+template <typename T>
+int gbmm_impl(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64_t kla, int64_t kua, const T *A,
+              int64_t lda, int64_t klb, int64_t kub, const T *B, int64_t ldb, T beta, int64_t klc, int64_t kuc, T *C,
+              int64_t ldc) {
+    if (!h) return -1;
+    if (m < 0) return lbm_fail_arg(h, 2, "m < 0");
+    if (n < 0) return lbm_fail_arg(h, 3, "n < 0");
+    if (k < 0) return lbm_fail_arg(h, 4, "k < 0");
+    if (kla < 0) return lbm_fail_arg(h, 6, "kla < 0");
+    if (kua < 0) return lbm_fail_arg(h, 7, "kua < 0");
+    if (lda < kla + kua + 1) return lbm_fail_arg(h, 9, "lda < kla+kua+1");
+    if (klb < 0) return lbm_fail_arg(h, 10, "klb < 0");
+    if (kub < 0) return lbm_fail_arg(h, 11, "kub < 0");
+    if (ldb < klb + kub + 1) return lbm_fail_arg(h, 13, "ldb < klb+kub+1");
+    if (klc < 0) return lbm_fail_arg(h, 15, "klc < 0");
+    if (kuc < 0) return lbm_fail_arg(h, 16, "kuc < 0");
+    if (ldc < klc + kuc + 1) return lbm_fail_arg(h, 18, "ldc < klc+kuc+1");
+    // C's band must hold every structurally non-zero entry of the product
+    const int64_t need_l = kla + klb < m - 1 ? kla + klb : m - 1;
+    const int64_t need_u = kua + kub < n - 1 ? kua + kub : n - 1;
+    if (k > 0 && klc < need_l) return lbm_fail_arg(h, 15, "klc < min(kla+klb, m-1)");
+    if (k > 0 && kuc < need_u) return lbm_fail_arg(h, 16, "kuc < min(kua+kub, n-1)");
+    if (n == 0) return 0;
+    if (!C) return lbm_fail_arg(h, 17, "C == NULL");
+    if (k > 0 && !A) return lbm_fail_arg(h, 8, "A == NULL");
+    if (k > 0 && !B) return lbm_fail_arg(h, 12, "B == NULL");
+    lbm_device_guard g(h->device);
+
+    GbmmArgs<T> a;
+    a.m = m; a.n = n; a.k = k; a.kla = kla; a.kua = kua; a.lda = lda; a.klb = klb; a.kub = kub; a.ldb = ldb;
+    a.klc = klc; a.kuc = kuc; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.A = A; a.B = B; a.C = C;
+    int64_t tile = h->tune.gbmm_tile > 0 ? h->tune.gbmm_tile : 128;
+    // keep >= 2 CTAs per SM worth of tiles when the matrix is small
+    while (tile > 16 && (n + tile - 1) / tile < 2 * h->sm_count) tile /= 2;
+    const int64_t smem_cap = 96 * 1024;
+    auto smem_need = [&](int64_t tl) { return ((tl + klb + kub) * lda + tl * ldb) * (int64_t)sizeof(T); };
+    while (tile > 8 && smem_need(tile) > smem_cap) tile /= 2;
+    a.tile = (int)tile;
+    a.sA_elems = (tile + klb + kub) * lda;
+    const int64_t grid = (n + tile - 1) / tile;
+    if (smem_need(tile) <= smem_cap) {
+        static int configured_dev_mask = 0;
+        auto kern = gbmm_diag_kernel<T, true>;
+        if (!(configured_dev_mask & (1 << h->device))) {
+            LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+            configured_dev_mask |= (1 << h->device);
+        }
+        kern<<<(unsigned)grid, 256, (size_t)smem_need(tile), h->stream>>>(a);
+    } else {
+        gbmm_diag_kernel<T, false><<<(unsigned)grid, 256, 0, h->stream>>>(a);
+    }
+    LBM_LAUNCH_CHECK(h, "gbmm_diag_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched fused chain  D_b = (A_b*B_b)*C_b
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct ChainArgs {
+    int64_t batch, n;
+    int kla, kua, klb, kub, klc, kuc;
+    const T *A;
+    const T *B;
+    const T *C;
+    T *D;
+    int64_t sA, sB, sC, sD;  // batch strides (elements)
+    int tile;
+    int offB, offC, offAB;   // smem offsets (elements)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) gbmm_chain3_kernel(const ChainArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sA = reinterpret_cast<T *>(smem_raw);
+    T *sB = sA + a.offB;
+    T *sC = sA + a.offC;
+    T *sAB = sA + a.offAB;
+    const int tid = threadIdx.x;
+    const int64_t n = a.n;
+    const int64_t b = blockIdx.y;
+    const int lda = a.kla + a.kua + 1, ldb = a.klb + a.kub + 1, ldc = a.klc + a.kuc + 1;
+    const int l01 = a.kla + a.klb, u01 = a.kua + a.kub, ld01 = l01 + u01 + 1;
+    const int ld3 = l01 + a.klc, ud3 = u01 + a.kuc, ldd = ld3 + ud3 + 1;
+    const int64_t j0 = (int64_t)blockIdx.x * a.tile;
+    const int64_t j1 = j0 + a.tile < n ? j0 + a.tile : n;
+    const int64_t q0 = j0 - a.kuc > 0 ? j0 - a.kuc : 0;   // columns of A*B (and of B) needed
+    const int64_t q1 = j1 + a.klc < n ? j1 + a.klc : n;
+    const int64_t p0 = q0 - a.kub > 0 ? q0 - a.kub : 0;   // columns of A needed
+    const int64_t p1 = q1 + a.klb < n ? q1 + a.klb : n;
+    const T *Ag = a.A + b * a.sA + p0 * lda;
+    const T *Bg = a.B + b * a.sB + q0 * ldb;
+    const T *Cg = a.C + b * a.sC + j0 * ldc;
+    for (int64_t e = tid; e < (p1 - p0) * lda; e += 256) sA[e] = Ag[e];
+    for (int64_t e = tid; e < (q1 - q0) * ldb; e += 256) sB[e] = Bg[e];
+    for (int64_t e = tid; e < (j1 - j0) * ldc; e += 256) sC[e] = Cg[e];
+    __syncthreads();
+    // phase 1: AB[:, q0..q1) into shared memory (band (l01,u01))
+    const int tot1 = (int)(q1 - q0) * ld01;
+    for (int e = tid; e < tot1; e += 256) {
+        const int qq = e / ld01;
+        const int r = e - qq * ld01;
+        const int64_t q = q0 + qq;
+        const int64_t i = q + r - u01;
+        T acc = 0;
+        if (i >= 0 && i < n) {
+            int64_t plo = i - a.kla > q - a.kub ? i - a.kla : q - a.kub;
+            int64_t phi = i + a.kua < q + a.klb ? i + a.kua : q + a.klb;
+            if (plo < 0) plo = 0;
+            if (phi > n - 1) phi = n - 1;
+            int ia = (int)((a.kua + i - plo) + lda * (plo - p0));
+            int ib = (int)((a.kub + plo - q) + ldb * qq);
+            for (int64_t p = plo; p <= phi; ++p) {
+                acc = fma(sA[ia], sB[ib], acc);
+                ia += lda - 1;
+                ib += 1;
+            }
+        }
+        sAB[e] = acc;
+    }
+    __syncthreads();
+    // phase 2: D[:, j0..j1) = AB * C
+    T *Dg = a.D + b * a.sD;
+    const int tot2 = (int)(j1 - j0) * ldd;
+    for (int e = tid; e < tot2; e += 256) {
+        const int jj = e / ldd;
+        const int r = e - jj * ldd;
+        const int64_t j = j0 + jj;
+        const int64_t i = j + r - ud3;
+        T acc = 0;
+        if (i >= 0 && i < n) {
+            int64_t qlo = i - l01 > j - a.kuc ? i - l01 : j - a.kuc;
+            int64_t qhi = i + u01 < j + a.klc ? i + u01 : j + a.klc;
+            if (qlo < 0) qlo = 0;
+            if (qhi > n - 1) qhi = n - 1;
+            int ia = (int)((u01 + i - qlo) + ld01 * (qlo - q0));
+            int ic = (int)((a.kuc + qlo - j) + ldc * jj);
+            for (int64_t q = qlo; q <= qhi; ++q) {
+                acc = fma(sAB[ia], sC[ic], acc);
+                ia += ld01 - 1;
+                ic += 1;
+            }
+        }
+        Dg[r + (int64_t)ldd * j] = acc;
+    }
+}
+
+template <typename T>
+int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, const int64_t *ku, const T *A, int64_t sA,
+                const T *B, int64_t sB, const T *C, int64_t sC, T *D, int64_t sD) {
+    if (!h) return -1;
+    if (batch < 0) return lbm_fail_arg(h, 2, "batch < 0");
+    if (n < 0) return lbm_fail_arg(h, 3, "n < 0");
+    if (!kl) return lbm_fail_arg(h, 4, "kl == NULL");
+    if (!ku) return lbm_fail_arg(h, 5, "ku == NULL");
+    for (int f = 0; f < 3; ++f) {
+        if (kl[f] < 0) return lbm_fail_arg(h, 4, "kl[i] < 0");
+        if (ku[f] < 0) return lbm_fail_arg(h, 5, "ku[i] < 0");
+    }
+    if (batch == 0 || n == 0) return 0;
+    if (!A) return lbm_fail_arg(h, 6, "A == NULL");
+    if (!B) return lbm_fail_arg(h, 8, "B == NULL");
+    if (!C) return lbm_fail_arg(h, 10, "C == NULL");
+    if (!D) return lbm_fail_arg(h, 12, "D == NULL");
+    if (batch > 65535) return lbm_fail_arg(h, 2, "batch > 65535 (split the call)");
+    lbm_device_guard g(h->device);
+    ChainArgs<T> a;
+    a.batch = batch; a.n = n;
+    a.kla = (int)kl[0]; a.kua = (int)ku[0]; a.klb = (int)kl[1]; a.kub = (int)ku[1]; a.klc = (int)kl[2]; a.kuc = (int)ku[2];
+    a.A = A; a.B = B; a.C = C; a.D = D; a.sA = sA; a.sB = sB; a.sC = sC; a.sD = sD;
+    const int64_t lda = kl[0] + ku[0] + 1, ldb = kl[1] + ku[1] + 1, ldc = kl[2] + ku[2] + 1;
+    const int64_t ld01 = kl[0] + kl[1] + ku[0] + ku[1] + 1;
+    int64_t tile = h->tune.chain_tile > 0 ? h->tune.chain_tile : 128;
+    auto layout = [&](int64_t tl, int64_t &oB, int64_t &oC, int64_t &oAB) {
+        const int64_t qc = tl + kl[2] + ku[2];
+        const int64_t pc = qc + kl[1] + ku[1];
+        oB = pc * lda;
+        oC = oB + qc * ldb;
+        oAB = oC + tl * ldc;
+        return (oAB + qc * ld01) * (int64_t)sizeof(T);
+    };
+    int64_t oB, oC, oAB;
+    const int64_t smem_cap = 160 * 1024;
+    while (tile > 8 && layout(tile, oB, oC, oAB) > smem_cap) tile /= 2;
+    const int64_t smem = layout(tile, oB, oC, oAB);
+    if (smem > smem_cap) return lbm_fail_arg(h, 4, "bands too wide for the fused chain kernel (use lbm_?gbmm twice)");
+    a.tile = (int)tile; a.offB = (int)oB; a.offC = (int)oC; a.offAB = (int)oAB;
+    static int configured_dev_mask = 0;
+    auto kern = gbmm_chain3_kernel<T>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        configured_dev_mask |= (1 << h->device);
+    }
+    dim3 grid((unsigned)((n + tile - 1) / tile), (unsigned)batch);
+    kern<<<grid, 256, (size_t)smem, h->stream>>>(a);
+    LBM_LAUNCH_CHECK(h, "gbmm_chain3_kernel");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+int lbm_dgbmm(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double alpha, int64_t kla, int64_t kua, const double *A,
+              int64_t lda, int64_t klb, int64_t kub, const double *B, int64_t ldb, double beta, int64_t klc,
+              int64_t kuc, double *C, int64_t ldc) {
+    if (h && h->tune.gbmm_force != 1) {
+        bool handled = false;
+        int rc = lbm_gbmm_dmma_f64(h, m, n, k, alpha, kla, kua, A, lda, klb, kub, B, ldb, beta, klc, kuc, C, ldc, &handled);
+        if (handled) return rc;
+    }
+    return gbmm_impl<double>(h, m, n, k, alpha, kla, kua, A, lda, klb, kub, B, ldb, beta, klc, kuc, C, ldc);
+}
+int lbm_sgbmm(lbm_handle_t h, int64_t m, int64_t n, int64_t k, float alpha, int64_t kla, int64_t kua, const float *A,
+              int64_t lda, int64_t klb, int64_t kub, const float *B, int64_t ldb, float beta, int64_t klc, int64_t kuc,
+              float *C, int64_t ldc) {
+    return gbmm_impl<float>(h, m, n, k, alpha, kla, kua, A, lda, klb, kub, B, ldb, beta, klc, kuc, C, ldc);
+}
+int lbm_sgbmm_chain3_batched(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, const int64_t *ku,
+                             const float *A, int64_t strideA, const float *B, int64_t strideB, const float *C,
+                             int64_t strideC, float *D, int64_t strideD) {
+    return chain3_impl<float>(h, batch, n, kl, ku, A, strideA, B, strideB, C, strideC, D, strideD);
+}
+int lbm_dgbmm_chain3_batched(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, const int64_t *ku,
+                             const double *A, int64_t strideA, const double *B, int64_t strideB, const double *C,
+                             int64_t strideC, double *D, int64_t strideD) {
+    return chain3_impl<double>(h, batch, n, kl, ku, A, strideA, B, strideB, C, strideC, D, strideD);
+}
+}

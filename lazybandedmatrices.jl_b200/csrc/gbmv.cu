@@ -1,0 +1,551 @@
+// gbmv.cu -- y <- alpha*op(A)*x + beta*y for a banded A in BandedMatrices' diagonal-major
+// (kl+ku+1) x n storage.  Replaces BandedMatrices.gbmv! -> BLAS ?gbmv_,
+// the leaf of every `mul!` in the reference's hot path.
+//
+// HBM-bound (0.25 flop/B): every kernel here is organised around moving the band data
+// exactly once at full bandwidth.
+//
+//  * gbmv_tile_kernel   (narrow bands, kl+ku+1 <= ~33): persistent CTAs walk output tiles.
+//    The tile's slab of A -- columns [o0-kl, o1+ku), ONE contiguous byte range of the
+//    diagonal-major array -- and its x window are fetched by 1-D bulk TMA (UBLKCP) into a
+//    multi-stage shared-memory ring guarded by mbarriers; threads then read one data element
+//    per FMA from smem (stride lda between lanes: conflict-free for odd lda) and write y
+//    coalesced.  No thread ever issues a global load for A.
+//  * gbmv_wide_n_kernel (wide bands, op = N): a CTA owns a contiguous run of rows and streams
+//    the columns it needs through the smem ring in chunks of C columns; row i lives in thread
+//    (i - R0) mod NT with its accumulator in a register for the ~(kl+ku+C)/C chunks that
+//    touch it, so each element of A is read from smem by exactly one thread, lanes read
+//    consecutive addresses, and completed rows retire as coalesced stores.
+//  * gbmv_wide_t_kernel (wide bands, op = T): one warp per output; the column of A is a
+//    contiguous vector, read coalesced, reduced with warp shuffles.
+//  * gbmv_direct_kernel: any alignment / any lda fallback, thread per output, L1/L2 served.
+#include "lbm_common.cuh"
+
+namespace {
+
+using namespace lbm;
+
+constexpr int GBMV_NT = 256;
+constexpr int GBMV_MAX_STAGES = 8;
+
+template <typename T>
+struct GbmvArgs {
+    int64_t m, n, kl, ku, lda;
+    int64_t nout;  // outputs: m (N) or n (T)
+    T alpha, beta;
+    const T *A;
+    const T *x;
+    T *y;
+    int64_t tile;    // outputs per tile (multiple of GBMV_NT)
+    int64_t ntiles;
+    int stages;
+    int64_t sA_elems, sx_elems;  // per-stage smem capacity in elements (multiples of 16B)
+};
+
+// ------------------------------------------------------------------------------------------
+// narrow bands: streamed tiles
+// ------------------------------------------------------------------------------------------
+template <typename T, int NB, bool TRANS>
+__global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int S = a.stages;
+    const int nb = NB > 0 ? NB : (int)(a.kl + a.ku + 1);
+    const int64_t stage_elems = a.sA_elems + a.sx_elems;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // tiles of this CTA: t = blockIdx.x + k*gridDim.x
+    const int64_t first = blockIdx.x;
+    const int64_t step = gridDim.x;
+    const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
+
+    auto ranges = [&](int64_t t, int64_t &o0, int64_t &o1, int64_t &c0, int64_t &c1, int64_t &x0, int64_t &x1) {
+        o0 = t * a.tile;
+        o1 = o0 + a.tile < a.nout ? o0 + a.tile : a.nout;
+        if (!TRANS) {
+            c0 = o0 - a.kl > 0 ? o0 - a.kl : 0;
+            c1 = o1 + a.ku < a.n ? o1 + a.ku : a.n;
+            if (c0 > a.n) c0 = a.n;
+            if (c1 < c0) c1 = c0;
+            x0 = c0;
+            x1 = c1;
+        } else {
+            c0 = o0;
+            c1 = o1;
+            x0 = o0 - a.ku > 0 ? o0 - a.ku : 0;
+            x1 = o1 + a.kl < a.m ? o1 + a.kl : a.m;
+            if (x0 > a.m) x0 = a.m;
+            if (x1 < x0) x1 = x0;
+        }
+    };
+
+    auto issue = [&](int64_t t, int s) {  // thread 0 only
+        int64_t o0, o1, c0, c1, x0, x1;
+        ranges(t, o0, o1, c0, c1, x0, x1);
+        const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        const int64_t cntA = c1 * a.lda - e0a;
+        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        const int64_t cntx = x1 - x0a;
+        T *sA = sbase + (int64_t)s * stage_elems;
+        T *sx = sA + a.sA_elems;
+        mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + stage_bytes_bulk<T>(cntx));
+        stage_issue<T>(sA, a.A + e0a, cntA, &bars[s]);
+        stage_issue<T>(sx, a.x + x0a, cntx, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+
+    if (tid == 0) {
+        const int64_t pro = mine < S ? mine : S;
+        for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
+    }
+
+    const int lda = (int)a.lda;
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = (int)(k % S);
+        const uint32_t parity = (uint32_t)((k / S) & 1);
+        const int64_t t = first + k * step;
+        int64_t o0, o1, c0, c1, x0, x1;
+        ranges(t, o0, o1, c0, c1, x0, x1);
+        const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        const T *sA = sbase + (int64_t)s * stage_elems;
+        const T *sx = sA + a.sA_elems;
+
+        mbar_wait(&bars[s], parity);
+
+        // interior tiles need no index masks
+        const bool interior = TRANS ? (o0 - a.ku >= 0 && o1 - 1 + a.kl < a.m)
+                                    : (o0 - a.kl >= 0 && o1 - 1 + a.ku < a.n);
+        for (int64_t o = o0 + tid; o < o1; o += GBMV_NT) {
+            T acc = 0;
+            if (!TRANS) {
+                // terms j = o-kl .. o+ku (ascending), band row r = ku + o - j
+                const int jb = (int)(o - a.kl - x0a);                         // sx index of j = o-kl
+                const int ab = (int)((a.kl + a.ku) + (o - a.kl) * a.lda - e0a);  // sA index of (r=kl+ku, j=o-kl)
+                if (interior) {
+#pragma unroll
+                    for (int q = 0; q < nb; ++q) acc = fma(sA[ab + q * (lda - 1)], sx[jb + q], acc);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < nb; ++q) {
+                        const int64_t j = o - a.kl + q;
+                        if (j >= 0 && j < a.n) acc = fma(sA[ab + q * (lda - 1)], sx[jb + q], acc);
+                    }
+                }
+            } else {
+                // terms i = o-ku .. o+kl (ascending), band row r = ku + i - o
+                const int ib = (int)(o - a.ku - x0a);
+                const int ab = (int)(o * a.lda - e0a);
+                if (interior) {
+#pragma unroll
+                    for (int q = 0; q < nb; ++q) acc = fma(sA[ab + q], sx[ib + q], acc);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < nb; ++q) {
+                        const int64_t i = o - a.ku + q;
+                        if (i >= 0 && i < a.m) acc = fma(sA[ab + q], sx[ib + q], acc);
+                    }
+                }
+            }
+            a.y[o] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[o], a.alpha * acc);
+        }
+        __syncthreads();  // every thread is done reading stage s
+        if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// wide bands, op = N: column-streaming with register-resident row accumulators
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct GbmvWideArgs {
+    int64_t m, n, kl, ku, lda;
+    T alpha, beta;
+    const T *A;
+    const T *x;
+    T *y;
+    int64_t run;    // rows per CTA
+    int chunk;      // columns per chunk (multiple of 16B worth of elements)
+    int stages;
+    int64_t sA_elems, sx_elems;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024) gbmv_wide_n_kernel(const GbmvWideArgs<T> a) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int NT = blockDim.x;
+    const int S = a.stages;
+    const int64_t stage_elems = a.sA_elems + a.sx_elems;
+    const int C = a.chunk;
+
+    const int64_t R0 = (int64_t)blockIdx.x * a.run;
+    const int64_t R1 = R0 + a.run < a.m ? R0 + a.run : a.m;
+    if (R0 >= R1) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int64_t cs = R0 - a.kl > 0 ? R0 - a.kl : 0;
+    cs &= ~(int64_t)(EPV - 1);
+    int64_t ce = R1 + a.ku < a.n ? R1 + a.ku : a.n;  // exclusive
+    if (cs > ce) cs = ce & ~(int64_t)(EPV - 1);
+    const int64_t nchunks = (ce - cs + C - 1) / C;
+
+    auto issue = [&](int64_t q, int s) {  // thread 0 only
+        const int64_t cb = cs + q * C;
+        const int64_t cq = cb + C < ce ? C : ce - cb;
+        T *sA = sbase + (int64_t)s * stage_elems;
+        T *sx = sA + a.sA_elems;
+        const int64_t cntA = cq * a.lda;
+        mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + stage_bytes_bulk<T>(cq));
+        stage_issue<T>(sA, a.A + cb * a.lda, cntA, &bars[s]);
+        stage_issue<T>(sx, a.x + cb, cq, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+
+    if (tid == 0) {
+        const int64_t pro = nchunks < S ? nchunks : S;
+        for (int64_t q = 0; q < pro; ++q) issue(q, (int)q);
+    }
+
+    int64_t i = R0 + tid;  // the row this thread currently accumulates
+    T acc = 0;
+    const int lda = (int)a.lda;
+
+    for (int64_t q = 0; q < nchunks; ++q) {
+        const int s = (int)(q % S);
+        const uint32_t parity = (uint32_t)((q / S) & 1);
+        const int64_t cb = cs + q * C;
+        const int cq = (int)(cb + C < ce ? C : ce - cb);
+        const T *sA = sbase + (int64_t)s * stage_elems;
+        const T *sx = sA + a.sA_elems;
+
+        mbar_wait(&bars[s], parity);
+
+        if (i < R1) {
+            // columns of this chunk that touch row i: j in [i-kl, i+ku]
+            int jlo = (int)(i - a.kl - cb);
+            int jhi = (int)(i + a.ku - cb);
+            if (jlo < 0) jlo = 0;
+            if (jhi > cq - 1) jhi = cq - 1;
+            // sA index of (row i, column cb+jj): (ku + i - cb - jj) + lda*jj = base + jj*(lda-1)
+            const int base = (int)(a.ku + i - cb);
+#pragma unroll 4
+            for (int jj = jlo; jj <= jhi; ++jj) acc = fma(sA[base + jj * (lda - 1)], sx[jj], acc);
+            if (i + a.ku < cb + cq || q == nchunks - 1) {  // all columns of row i seen
+                a.y[i] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[i], a.alpha * acc);
+                i += NT;
+                acc = 0;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && q + S < nchunks) issue(q + S, s);
+    }
+    // rows with an empty column range (m > n + kl) or an empty sweep
+    for (; i < R1; i += NT) a.y[i] = (a.beta == (T)0) ? (T)0 : a.beta * a.y[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// wide bands, op = T: warp per output, coalesced column read + shuffle reduction
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gbmv_wide_t_kernel(int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha,
+                                                         const T *__restrict__ A, int64_t lda,
+                                                         const T *__restrict__ x, T beta, T *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nb = (int)(kl + ku + 1);
+    for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+        const T *col = A + j * lda;
+        T acc = 0;
+        for (int r = lane; r < nb; r += 32) {
+            const int64_t i = j + r - ku;
+            if (i >= 0 && i < m) acc = fma(col[r], x[i], acc);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) y[j] = (beta == (T)0) ? alpha * acc : fma(beta, y[j], alpha * acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fallback: thread per output, direct global loads
+// ------------------------------------------------------------------------------------------
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(256) gbmv_direct_kernel(int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha,
+                                                         const T *__restrict__ A, int64_t lda,
+                                                         const T *__restrict__ x, T beta, T *__restrict__ y) {
+    const int64_t nout = TRANS ? n : m;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nout; o += stride) {
+        T acc = 0;
+        if (!TRANS) {
+            int64_t jlo = o - kl > 0 ? o - kl : 0;
+            int64_t jhi = o + ku < n - 1 ? o + ku : n - 1;
+            for (int64_t j = jlo; j <= jhi; ++j) acc = fma(A[(ku + o - j) + lda * j], x[j], acc);
+        } else {
+            int64_t ilo = o - ku > 0 ? o - ku : 0;
+            int64_t ihi = o + kl < m - 1 ? o + kl : m - 1;
+            for (int64_t i = ilo; i <= ihi; ++i) acc = fma(A[(ku + i - o) + lda * o], x[i], acc);
+        }
+        y[o] = (beta == (T)0) ? alpha * acc : fma(beta, y[o], alpha * acc);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(int64_t n, T beta, T *__restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += stride)
+        y[o] = (beta == (T)0) ? (T)0 : beta * y[o];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+template <typename T, int NB, bool TRANS>
+int launch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem) {
+    static int configured_dev_mask = 0;
+    auto kern = gbmv_tile_kernel<T, NB, TRANS>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        configured_dev_mask |= (1 << h->device);
+    }
+    kern<<<grid, GBMV_NT, smem, h->stream>>>(a);
+    LBM_LAUNCH_CHECK(h, "gbmv_tile_kernel");
+    return 0;
+}
+
+template <typename T, bool TRANS>
+int dispatch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem) {
+    switch ((int)(a.kl + a.ku + 1)) {
+        case 1: return launch_tile<T, 1, TRANS>(h, a, grid, smem);
+        case 2: return launch_tile<T, 2, TRANS>(h, a, grid, smem);
+        case 3: return launch_tile<T, 3, TRANS>(h, a, grid, smem);
+        case 5: return launch_tile<T, 5, TRANS>(h, a, grid, smem);
+        case 7: return launch_tile<T, 7, TRANS>(h, a, grid, smem);
+        case 9: return launch_tile<T, 9, TRANS>(h, a, grid, smem);
+        case 17: return launch_tile<T, 17, TRANS>(h, a, grid, smem);
+        case 33: return launch_tile<T, 33, TRANS>(h, a, grid, smem);
+        default: return launch_tile<T, 0, TRANS>(h, a, grid, smem);
+    }
+}
+
+template <typename T>
+int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha, const T *A,
+              int64_t lda, const T *x, T beta, T *y) {
+    if (!h) return -1;
+    const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
+    if (!tr && !(trans == 'N' || trans == 'n')) return lbm_fail_arg(h, 2, "trans must be N, T or C");
+    if (m < 0) return lbm_fail_arg(h, 3, "m < 0");
+    if (n < 0) return lbm_fail_arg(h, 4, "n < 0");
+    if (kl < 0) return lbm_fail_arg(h, 5, "kl < 0");
+    if (ku < 0) return lbm_fail_arg(h, 6, "ku < 0");
+    if (lda < kl + ku + 1) return lbm_fail_arg(h, 9, "lda < kl+ku+1");
+    const int64_t nout = tr ? n : m;
+    const int64_t nin = tr ? m : n;
+    if (nout == 0) return 0;
+    if (!y) return lbm_fail_arg(h, 12, "y == NULL");
+    lbm_device_guard g(h->device);
+    constexpr int EPV = 16 / (int)sizeof(T);
+
+    if (nin == 0 || alpha == (T)0) {  // y <- beta*y
+        int64_t blocks = (nout + 255) / 256;
+        if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
+        scale_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(nout, beta, y);
+        LBM_LAUNCH_CHECK(h, "scale_kernel");
+        return 0;
+    }
+    if (!A) return lbm_fail_arg(h, 8, "A == NULL");
+    if (!x) return lbm_fail_arg(h, 10, "x == NULL");
+
+    const int64_t nb = kl + ku + 1;
+    const bool aligned = lbm_aligned16(A) && lbm_aligned16(x);
+    const int64_t smem_cap = h->max_smem_optin - 1024;
+    const int64_t force = h->tune.gbmv_force;
+
+    // ---- narrow streamed-tile path ------------------------------------------------------
+    // feasible when a 256-output tile (+halo columns) of the slab fits one ~100 KB stage
+    const int64_t min_stage_bytes = ((GBMV_NT + nb) * (lda + 1) + 2 * EPV) * (int64_t)sizeof(T);
+    bool narrow_ok = aligned && min_stage_bytes <= 100 * 1024 && lda <= 4 * nb + 8;
+    bool wide_ok = aligned && !tr && (nb + 32) <= 1024 && (32 * lda + 64) * (int64_t)sizeof(T) <= smem_cap;
+    int path;  // 1 direct, 2 narrow, 3 wide-n, 4 wide-t
+    if (force == 1) path = 1;
+    else if (force == 2 && narrow_ok) path = 2;
+    else if (force == 3 && wide_ok) path = 3;
+    else if (narrow_ok) path = 2;
+    else if (wide_ok) path = 3;
+    else if (tr && nb >= 32) path = 4;
+    else path = 1;
+
+    if (path == 2) {
+        GbmvArgs<T> a;
+        a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda; a.nout = nout;
+        a.alpha = alpha; a.beta = beta; a.A = A; a.x = x; a.y = y;
+        // tile: aim for ~32 KB of slab per stage, at least one row per thread
+        int64_t tile = h->tune.gbmv_tile;
+        if (tile <= 0) {
+            tile = (32 * 1024) / (lda * (int64_t)sizeof(T));
+            tile = tile / GBMV_NT * GBMV_NT;
+            if (tile < GBMV_NT) tile = GBMV_NT;
+            if (tile > 2048) tile = 2048;
+        }
+        tile = round_up(tile, GBMV_NT);
+        auto stage_elems = [&](int64_t tl, int64_t &sa, int64_t &sx) {
+            sa = round_up((tl + kl + ku) * lda + EPV, EPV);
+            sx = round_up(tl + kl + ku + EPV, EPV);
+        };
+        int64_t sa, sx;
+        stage_elems(tile, sa, sx);
+        while (tile > GBMV_NT && (sa + sx) * (int64_t)sizeof(T) + 128 > smem_cap) {
+            tile -= GBMV_NT;
+            stage_elems(tile, sa, sx);
+        }
+        a.tile = tile;
+        a.ntiles = (nout + tile - 1) / tile;
+        a.sA_elems = sa;
+        a.sx_elems = sx;
+        const int64_t stage_bytes = (sa + sx) * (int64_t)sizeof(T);
+        int64_t ctas = h->tune.gbmv_ctas_per_sm > 0 ? h->tune.gbmv_ctas_per_sm : 2;
+        int64_t stages = h->tune.gbmv_stages > 0 ? h->tune.gbmv_stages : 3;
+        if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+        // fit ctas * (128 + stages*stage_bytes) into the SM's shared memory
+        const int64_t sm_smem = 227 * 1024;
+        while (stages > 1 && ctas * (stages * stage_bytes + 128 + 1024) > sm_smem) --stages;
+        while (ctas > 1 && ctas * (stages * stage_bytes + 128 + 1024) > sm_smem) --ctas;
+        a.stages = (int)stages;
+        int64_t grid = (int64_t)h->sm_count * ctas;
+        if (grid > a.ntiles) grid = a.ntiles;
+        const size_t smem = (size_t)(128 + stages * stage_bytes);
+        return tr ? dispatch_tile<T, true>(h, a, (int)grid, smem) : dispatch_tile<T, false>(h, a, (int)grid, smem);
+    }
+
+    if (path == 3) {
+        GbmvWideArgs<T> a;
+        a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda;
+        a.alpha = alpha; a.beta = beta; a.A = A; a.x = x; a.y = y;
+        int64_t chunk = h->tune.gbmvw_chunk;
+        if (chunk <= 0) {
+            chunk = (64 * 1024) / (lda * (int64_t)sizeof(T));
+            chunk = chunk / 32 * 32;
+            if (chunk < 32) chunk = 32;
+        }
+        chunk = round_up(chunk, 32);
+        while (chunk > 32 && (chunk + kl + ku > 1024 || (chunk * (lda + 1) + 2 * EPV) * (int64_t)sizeof(T) + 128 > smem_cap))
+            chunk -= 32;
+        const int64_t nt = round_up(chunk + kl + ku, 32);
+        a.chunk = (int)chunk;
+        a.sA_elems = round_up(chunk * lda + EPV, EPV);
+        a.sx_elems = round_up(chunk + EPV, EPV);
+        const int64_t stage_bytes = (a.sA_elems + a.sx_elems) * (int64_t)sizeof(T);
+        int64_t stages = h->tune.gbmvw_stages > 0 ? h->tune.gbmvw_stages : 3;
+        if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+        while (stages > 1 && stages * stage_bytes + 128 > smem_cap) --stages;
+        a.stages = (int)stages;
+        const int64_t smem_cta = stages * stage_bytes + 128;
+        int64_t ctas = h->tune.gbmvw_ctas_per_sm > 0 ? h->tune.gbmvw_ctas_per_sm : (227 * 1024) / (smem_cta + 1024);
+        if (ctas < 1) ctas = 1;
+        if (ctas * nt > 2048) ctas = 2048 / nt;
+        if (ctas < 1) ctas = 1;
+        int64_t grid = (int64_t)h->sm_count * ctas;
+        int64_t run = (m + grid - 1) / grid;
+        const int64_t min_run = 4 * (kl + ku) > 1024 ? 4 * (kl + ku) : 1024;  // keep halo re-reads <= 25 %
+        if (run < min_run) run = min_run;
+        run = round_up(run, EPV);
+        grid = (m + run - 1) / run;
+        a.run = run;
+        static int configured_dev_mask = 0;
+        auto kern = gbmv_wide_n_kernel<T>;
+        if (!(configured_dev_mask & (1 << h->device))) {
+            LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+            configured_dev_mask |= (1 << h->device);
+        }
+        kern<<<(unsigned)grid, (unsigned)nt, (size_t)smem_cta, h->stream>>>(a);
+        LBM_LAUNCH_CHECK(h, "gbmv_wide_n_kernel");
+        return 0;
+    }
+
+    if (path == 4) {
+        int64_t blocks = (n + 7) / 8;  // 8 warps per block, one output per warp
+        if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
+        gbmv_wide_t_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(m, n, kl, ku, alpha, A, lda, x, beta, y);
+        LBM_LAUNCH_CHECK(h, "gbmv_wide_t_kernel");
+        return 0;
+    }
+
+    {
+        int64_t blocks = (nout + 255) / 256;
+        if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
+        if (tr)
+            gbmv_direct_kernel<T, true><<<(unsigned)blocks, 256, 0, h->stream>>>(m, n, kl, ku, alpha, A, lda, x, beta, y);
+        else
+            gbmv_direct_kernel<T, false><<<(unsigned)blocks, 256, 0, h->stream>>>(m, n, kl, ku, alpha, A, lda, x, beta, y);
+        LBM_LAUNCH_CHECK(h, "gbmv_direct_kernel");
+        return 0;
+    }
+}
+
+template <typename T>
+int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha, const T *A,
+                   int64_t lda, const T *x, T beta, T *y) {
+    if (!h) return -1;
+    const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
+    if (m < 0) return lbm_fail_arg(h, 3, "m < 0");
+    if (n < 0) return lbm_fail_arg(h, 4, "n < 0");
+    if (kl < 0) return lbm_fail_arg(h, 5, "kl < 0");
+    if (ku < 0) return lbm_fail_arg(h, 6, "ku < 0");
+    if (lda < kl + ku + 1) return lbm_fail_arg(h, 9, "lda < kl+ku+1");
+    const int64_t nout = tr ? n : m, nin = tr ? m : n;
+    if (nout == 0) return 0;
+    lbm_device_guard g(h->device);
+    void *dA, *dx, *dy;
+    int rc;
+    if ((rc = lbm_stage(h, 0, (size_t)(lda * n) * sizeof(T) + 16, &dA))) return rc;
+    if ((rc = lbm_stage(h, 1, (size_t)nin * sizeof(T) + 16, &dx))) return rc;
+    if ((rc = lbm_stage(h, 2, (size_t)nout * sizeof(T) + 16, &dy))) return rc;
+    if (lda * n > 0) LBM_CUDA(h, cudaMemcpyAsync(dA, A, (size_t)(lda * n) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    if (nin) LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    rc = gbmv_impl<T>(h, trans, m, n, kl, ku, alpha, (const T *)dA, lda, (const T *)dx, beta, (T *)dy);
+    if (rc) return rc;
+    LBM_CUDA(h, cudaMemcpyAsync(y, dy, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    LBM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+int lbm_dgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
+              const double *A, int64_t lda, const double *x, double beta, double *y) {
+    return gbmv_impl<double>(h, trans, m, n, kl, ku, alpha, A, lda, x, beta, y);
+}
+int lbm_sgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha, const float *A,
+              int64_t lda, const float *x, float beta, float *y) {
+    return gbmv_impl<float>(h, trans, m, n, kl, ku, alpha, A, lda, x, beta, y);
+}
+int lbm_dgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
+                   const double *A, int64_t lda, const double *x, double beta, double *y) {
+    return gbmv_host_impl<double>(h, trans, m, n, kl, ku, alpha, A, lda, x, beta, y);
+}
+int lbm_sgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha,
+                   const float *A, int64_t lda, const float *x, float beta, float *y) {
+    return gbmv_host_impl<float>(h, trans, m, n, kl, ku, alpha, A, lda, x, beta, y);
+}
+}

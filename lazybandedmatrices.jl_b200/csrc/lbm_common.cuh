@@ -1,0 +1,177 @@
+// lbm_common.cuh -- shared plumbing of liblbm_b200.so (sm_100a only).
+//
+// Handle state, LAPACK-style status handling, and the Blackwell async-copy primitives
+// (mbarrier + 1-D bulk TMA `cp.async.bulk`, SASS UBLKCP) every streaming kernel uses.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lbm_b200.h"
+
+#define LBM_VERSION 10100
+
+struct lbm_tuning {
+    // gbmv narrow (streamed tile) kernel
+    int64_t gbmv_tile;        // outputs per tile (0 = auto)
+    int64_t gbmv_stages;      // smem ring depth (0 = auto)
+    int64_t gbmv_ctas_per_sm; // persistent grid = SMs * this (0 = auto)
+    int64_t gbmv_force;       // 0 auto, 1 direct, 2 narrow-stream, 3 wide-stream
+    // gbmv wide (column-streaming) kernel
+    int64_t gbmvw_chunk;      // columns per chunk (0 = auto)
+    int64_t gbmvw_stages;
+    int64_t gbmvw_ctas_per_sm;
+    // tridiagonal kernel
+    int64_t tri_ctas_per_sm;  // 0 = auto
+    int64_t tri_force_scalar;
+    // kron
+    int64_t kron_tr, kron_tc;
+    // gbmm
+    int64_t gbmm_force;       // 0 auto, 1 generic, 2 dmma
+    int64_t gbmm_tile;
+    int64_t chain_tile;
+};
+
+struct lbm_handle_s {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    int64_t launches;
+    char err[512];
+    lbm_tuning tune;
+    void *scratch;
+    size_t scratch_bytes;
+    void *stage[4];           // device staging for *_host entry points
+    size_t stage_bytes[4];
+};
+
+int lbm_fail_cuda(lbm_handle_t h, cudaError_t e, const char *what);
+int lbm_fail_arg(lbm_handle_t h, int argno, const char *what);
+int lbm_scratch(lbm_handle_t h, size_t bytes, void **out);
+int lbm_stage(lbm_handle_t h, int slot, size_t bytes, void **out);
+
+#define LBM_CUDA(h, call)                                          \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return lbm_fail_cuda(h, e__, #call); \
+    } while (0)
+
+#define LBM_LAUNCH_CHECK(h, name)                                  \
+    do {                                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) return lbm_fail_cuda(h, e__, name); \
+        (h)->launches++;                                           \
+    } while (0)
+
+struct lbm_device_guard {
+    int prev;
+    bool changed;
+    explicit lbm_device_guard(int dev) : prev(-1), changed(false) {
+        cudaGetDevice(&prev);
+        if (prev != dev) { cudaSetDevice(dev); changed = true; }
+    }
+    ~lbm_device_guard() { if (changed) cudaSetDevice(prev); }
+};
+
+static inline bool lbm_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#ifdef __CUDACC__
+namespace lbm {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// expect_tx WITHOUT arriving: lets the producer arm the byte count, issue the copies, write
+// any sub-16-byte tails with plain stores, and only then arrive (release) -- so waiters see
+// both the async-proxy bytes and the generic-proxy tail.
+__device__ __forceinline__ void mbar_add_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D bulk TMA global -> shared, completion signalled on `bar` (complete_tx::bytes).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Streaming (read-once) global loads / stores that do not pollute L1.
+template <typename T> struct vec16;  // 16-byte vector of T
+template <> struct vec16<double> { using type = double2; static constexpr int N = 2; };
+template <> struct vec16<float> { using type = float4; static constexpr int N = 4; };
+
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(double2 *p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// Issue the copy of `count` elements src[0..count) into smem `dst` on behalf of the CTA:
+// the 16-byte-aligned body goes through ONE bulk TMA copy (issued by the calling thread,
+// which must be the thread that armed `bar` with the returned byte count), and the < 16-byte
+// tail is written with plain stores by the same thread.  `src` must be 16-byte aligned.
+// Returns the number of bytes the bulk copy will signal on the barrier.
+template <typename T>
+__device__ __forceinline__ uint32_t stage_bytes_bulk(int64_t count) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    return (uint32_t)((count / EPV) * EPV * (int64_t)sizeof(T));
+}
+template <typename T>
+__device__ __forceinline__ void stage_issue(T *dst, const T *src, int64_t count, uint64_t *bar) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int64_t body = (count / EPV) * EPV;
+    if (body > 0) bulk_g2s(dst, src, (uint32_t)(body * (int64_t)sizeof(T)), bar);
+    for (int64_t e = body; e < count; ++e) dst[e] = src[e];
+}
+
+}  // namespace lbm
+#endif  // __CUDACC__

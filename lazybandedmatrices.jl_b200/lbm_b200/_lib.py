@@ -1,0 +1,180 @@
+"""ctypes binding of liblbm_b200.so -- a 1:1 mirror of the `ccall`s in julia/LBMB200.jl.
+
+The product has NO CPU fallback: if the shared library is missing, or no CUDA device is
+present when a compute entry point is reached, this module raises -- it never routes
+anywhere else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import threading
+
+from .errors import LbmArgumentError, LbmCudaError, LbmLibraryMissing
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liblbm_b200.so")
+HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "lbm_b200.h"))
+
+_lib = None
+_lock = threading.Lock()
+
+i64 = C.c_int64
+u64 = C.c_uint64
+vp = C.c_void_p
+f64 = C.c_double
+f32 = C.c_float
+ch = C.c_char
+sz = C.c_size_t
+
+
+def _sigs():
+    H = vp
+    s = {
+        "lbm_version": (C.c_int, []),
+        "lbm_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "lbm_destroy": (C.c_int, [H]),
+        "lbm_set_stream": (C.c_int, [H, vp]),
+        "lbm_sync": (C.c_int, [H]),
+        "lbm_last_error_string": (C.c_char_p, [H]),
+        "lbm_launch_count": (i64, [H]),
+        "lbm_set_tuning": (C.c_int, [H, C.c_char_p, i64]),
+        "lbm_get_tuning": (i64, [H, C.c_char_p]),
+        "lbm_malloc": (C.c_int, [H, C.POINTER(vp), sz]),
+        "lbm_free": (C.c_int, [H, vp]),
+        "lbm_host_alloc": (C.c_int, [H, C.POINTER(vp), sz]),
+        "lbm_host_free": (C.c_int, [H, vp]),
+        "lbm_memcpy_h2d": (C.c_int, [H, vp, vp, sz]),
+        "lbm_memcpy_d2h": (C.c_int, [H, vp, vp, sz]),
+        "lbm_memset0": (C.c_int, [H, vp, sz]),
+        "lbm_dfill_uniform": (C.c_int, [H, u64, i64, i64, vp]),
+        "lbm_sfill_uniform": (C.c_int, [H, u64, i64, i64, vp]),
+        "lbm_prod_bandwidths": (C.c_int, [i64, i64, C.c_int, C.POINTER(i64), C.POINTER(i64),
+                                          C.POINTER(i64), C.POINTER(i64)]),
+    }
+    for p, ft in (("d", f64), ("s", f32)):
+        s[f"lbm_{p}gbmv"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
+        s[f"lbm_{p}gbmv_host"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
+        s[f"lbm_{p}tridiag_mv"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, i64, i64, ft, vp, i64])
+        s[f"lbm_{p}bidiag_mv"] = (C.c_int, [H, ch, i64, vp, vp, ft, vp, i64, i64, ft, vp, i64])
+        s[f"lbm_{p}gbmm"] = (C.c_int, [H, i64, i64, i64, ft, i64, i64, vp, i64, i64, i64, vp, i64, ft,
+                                       i64, i64, vp, i64])
+        s[f"lbm_{p}gbmm_chain3_batched"] = (C.c_int, [H, i64, i64, C.POINTER(i64), C.POINTER(i64),
+                                                      vp, i64, vp, i64, vp, i64, vp, i64])
+        s[f"lbm_{p}kronsum2d_mv"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, ft,
+                                               vp, ft, vp])
+    s["lbm_dkron2d_mv"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, f64, vp, f64, vp])
+    return s
+
+
+SIGNATURES = _sigs()
+
+
+def header_symbols(path: str = HEADER_PATH):
+    """Every function name include/lbm_b200.h declares (used by the ABI test)."""
+    with open(path, encoding="utf-8") as fh:
+        src = fh.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (no GPU needed just to load it)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(SO_PATH):
+                raise LbmLibraryMissing(
+                    f"{SO_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback)")
+            L = C.CDLL(SO_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+class Handle:
+    """One per device per host thread (`lbm_create`).  Kernels enqueue on `stream`
+    (defaults to torch's current stream at call time when torch drives the device)."""
+
+    def __init__(self, device: int = 0):
+        self._h = vp()
+        L = lib()
+        rc = L.lbm_create(C.byref(self._h), int(device))
+        if rc != 0:
+            msg = L.lbm_last_error_string(None).decode()
+            raise LbmCudaError(rc, f"lbm_create(device={device}) failed: {msg} "
+                                   "(liblbm_b200 has no CPU fallback)")
+        self.device = int(device)
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def check(self, rc: int, what: str = ""):
+        if rc == 0:
+            return
+        msg = lib().lbm_last_error_string(self._h).decode()
+        if rc < 0:
+            # LAPACK-info style (-k = k-th argument).  Shape errors never get this far: the host
+            # layer throws DimensionMismatch BEFORE the call, as the reference does
+            # (src/bidiag.jl:363-377, test/test_tridiag.jl:272-279).
+            raise LbmArgumentError(f"{what}: {msg}")
+        raise LbmCudaError(rc, f"{what}: {msg}")
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(lib().lbm_set_stream(self._h, vp(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self.check(lib().lbm_sync(self._h), "lbm_sync")
+
+    def launch_count(self) -> int:
+        return int(lib().lbm_launch_count(self._h))
+
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            self.check(lib().lbm_set_tuning(self._h, k.encode(), int(v)), f"lbm_set_tuning({k})")
+
+    def get_tuning(self, key: str) -> int:
+        return int(lib().lbm_get_tuning(self._h, key.encode()))
+
+    def close(self):
+        if self._h:
+            lib().lbm_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def handle_for(device: int) -> Handle:
+    """Process-wide handle cache keyed by (thread, device)."""
+    key = (threading.get_ident(), int(device))
+    h = _handles.get(key)
+    if h is None:
+        h = Handle(device)
+        _handles[key] = h
+    return h
+
+
+def handle_of(t) -> Handle:
+    """Handle for the device a torch tensor lives on, bound to torch's current stream."""
+    if not t.is_cuda:
+        raise LbmCudaError(0, "operands must be CUDA-resident tensors: liblbm_b200 has no CPU path")
+    h = handle_for(t.device.index if t.device.index is not None else 0)
+    h.use_torch_stream()
+    return h

@@ -1,0 +1,110 @@
+"""`ApplyMatrix(*, A, B, ...)`: lazy banded products, their `bandwidths`, `materialize` and `mul!`.
+
+Host-side mirror of the LazyArrays surface the reference imports
+(/root/reference/src/LazyBandedMatrices.jl:18-20; shown in README.md:8-26):
+
+  * `bandwidths(M) = min.(size(M) .- 1, (sum l_i, sum u_i))`                       
+  * `BandedMatrix(M)` / `materialize(M)`: pairwise left-to-right banded products   (item 3)
+  * `mul!(y, M, x)`: flattened right-to-left `A*(B*(...x))` with k-1 temporaries  (item 4; the
+    same rule the reference relies on at src/blockkron.jl:208-214, test/test_blockkron.jl:345-348)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .banded import BandedMatrix, _pfx, _ptr, gbmm
+from .errors import DimensionMismatch, LbmArgumentError
+
+
+class ApplyMatrix:
+    def __init__(self, f, *args):
+        if f not in ("*", "mul"):
+            raise LbmArgumentError("only ApplyMatrix(*, ...) is on the B200 path")
+        if len(args) < 1:
+            raise LbmArgumentError("ApplyMatrix(*) needs factors")
+        for a, b in zip(args[:-1], args[1:]):
+            if a.shape[1] != b.shape[0]:
+                raise DimensionMismatch(
+                    f"second entry of size(A)={tuple(a.shape)} and first entry of size(B) = {tuple(b.shape)} must match.")
+        self.f = "*"
+        self.args = tuple(args)
+
+    @property
+    def shape(self):
+        return (self.args[0].shape[0], self.args[-1].shape[1])
+
+    @property
+    def dtype(self):
+        return self.args[0].dtype
+
+    @property
+    def device(self):
+        return self.args[0].device
+
+    def bandwidths(self):
+        m, n = self.shape
+        kl = (C.c_int64 * len(self.args))(*[a.bandwidths()[0] for a in self.args])
+        ku = (C.c_int64 * len(self.args))(*[a.bandwidths()[1] for a in self.args])
+        ol, ou = C.c_int64(), C.c_int64()
+        rc = _lib.lib().lbm_prod_bandwidths(m, n, len(self.args), kl, ku, C.byref(ol), C.byref(ou))
+        if rc:
+            raise LbmArgumentError(f"lbm_prod_bandwidths: argument {-rc} invalid")
+        return (int(ol.value), int(ou.value))
+
+    def materialize(self) -> BandedMatrix:
+        """`BandedMatrix(ApplyMatrix(*, ...))`: pairwise, left to right."""
+        out = self.args[0]
+        for nxt in self.args[1:]:
+            out = gbmm(_as_banded(out), _as_banded(nxt))
+        return out
+
+    def mul_(self, y, x, alpha=1.0, beta=0.0):
+        from .linalg import mul_ as _mul
+        if x.shape[0] != self.shape[1]:
+            raise DimensionMismatch(
+                f"second entry of size(A)={self.shape} and first entry of size(B) = {tuple(x.shape)} must match.")
+        if y.shape[0] != self.shape[0]:
+            raise DimensionMismatch(f"sizes size(A)={self.shape} and size(C) = {tuple(y.shape)} must match at first entry.")
+        v = x
+        for a in reversed(self.args[1:]):
+            t = torch.empty((a.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            _mul(t, a, v)
+            v = t
+        return _mul(y, self.args[0], v, alpha, beta)
+
+    def __matmul__(self, x):
+        y = torch.empty((self.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        return self.mul_(y, x)
+
+
+def _as_banded(a) -> BandedMatrix:
+    if isinstance(a, BandedMatrix):
+        return a
+    if hasattr(a, "as_banded"):
+        return a.as_banded()
+    raise LbmArgumentError(f"cannot materialise a factor of type {type(a).__name__} as BandedMatrix")
+
+
+def chain3_batched(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, kl, ku) -> torch.Tensor:
+    """Batched `A_b*B_b*C_b` materialisation, fused (the intermediate band stays on chip).
+    Factor tensors are (batch, n, kl_i+ku_i+1): per item the column-major band array."""
+    batch, n = A.shape[0], A.shape[1]
+    for t, l, u in zip((A, B, Cm), kl, ku):
+        if t.shape[0] != batch or t.shape[1] != n or t.shape[2] != l + u + 1 or not t.is_contiguous():
+            raise DimensionMismatch("factor tensors must be contiguous (batch, n, kl+ku+1)")
+    ldd = sum(kl) + sum(ku) + 1
+    D = torch.empty((batch, n, ldd), dtype=A.dtype, device=A.device)
+    h = _lib.handle_of(A)
+    fn = getattr(_lib.lib(), f"lbm_{_pfx(A.dtype)}gbmm_chain3_batched")
+    klc = (C.c_int64 * 3)(*kl)
+    kuc = (C.c_int64 * 3)(*ku)
+    done = 0
+    while done < batch:  # the kernel's grid.y covers <= 65535 items per call
+        nb = min(batch - done, 65535)
+        h.check(fn(h.ptr, nb, n, klc, kuc, _ptr(A[done]), A[0].numel(), _ptr(B[done]), B[0].numel(),
+                   _ptr(Cm[done]), Cm[0].numel(), _ptr(D[done]), D[0].numel()), "lbm_gbmm_chain3_batched")
+        done += nb
+    return D
