@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- banded mul! HBM GB/s & % roofline (BASELINE.json metric).
+
+One "step" = one pass of the hot path over the metric's single-GPU-sized workload:
+    mul!(y, A, x) for A = brand(n,n,l,u) Float64, n = 2^27, (l,u) in {(1,1), (8,8)}
+row-sharded over the N ranks (one process per GPU; ghost-cell halo exchange of x over NCCL
+inside the timed region).  `value` = algorithmic bytes of both applies / step time, aggregated
+over all ranks (GB/s).  The (128,128) point of the metric does not fit one GPU at n = 2^27
+(A = 276 GB); it is reported in `breakdown` at the largest n that fits.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun ... bench.py --gpus N ...          (N > 1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "lazybandedmatrices.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+BANDS = [(1, 1), (8, 8)]
+LOG2N = 27
+METRIC = "banded mul! aggregate HBM throughput (algorithmic bytes / time), n=2^27, l=u in {1,8}"
+
+
+def alg_bytes(n, l, u, w=8):
+    """gbmv (beta=0) moves w*[(l+u+1)*n + n + n] algorithmic bytes."""
+    return w * n * (l + u + 1 + 2)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: OpenBLAS ?gbmv -- the BLAS routine the reference's gbmv! ccalls
+# --------------------------------------------------------------------------------------------
+def cpu_gbmv_sample(log2n_sample, repeats):
+    """Times scipy.linalg.blas.dgbmv (OpenBLAS, all host threads) and the repo's OpenMP oracle on
+    a bounded sample of the workload; returns GB/s of the faster with the sample description."""
+    import numpy as np
+    from scipy.linalg import blas
+    from oracle import oracle as O
+    n = 1 << log2n_sample
+    tot_bytes, t_blas, t_orc = 0, 0.0, 0.0
+    for (l, u) in BANDS:
+        A = O.brand(n, n, l, u, seed=1)
+        x = O.fill_uniform(9, n)
+        y = np.zeros(n)
+        blas.dgbmv(n, n, l, u, 1.0, A, x, beta=0.0, y=y, overwrite_y=1)   # warm
+        best_b = best_o = 1e30
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            blas.dgbmv(n, n, l, u, 1.0, A, x, beta=0.0, y=y, overwrite_y=1)
+            best_b = min(best_b, time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            O.gbmv("N", n, n, l, u, 1.0, A, x)
+            best_o = min(best_o, time.perf_counter() - t0)
+        tot_bytes += alg_bytes(n, l, u)
+        t_blas += best_b
+        t_orc += best_o
+        del A
+    cores = os.cpu_count() or 1
+    return {
+        "openblas_gbs": tot_bytes / t_blas / 1e9, "oracle_omp_gbs": tot_bytes / t_orc / 1e9,
+        "seconds_blas": t_blas, "seconds_oracle": t_orc, "cores": cores,
+        "sample": f"dgbmv f64 n=2^{log2n_sample}, l=u in {{1,8}} (same workload at reduced n; best of {repeats})",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    log2n = 24
+    # warm-up + K timed steps, each step = one pass over the bounded sample
+    cpu_gbmv_sample(log2n, 1)
+    vals, secs, omp = [], [], []
+    for _ in range(max(1, args.steps)):
+        r = cpu_gbmv_sample(log2n, 1)
+        vals.append(r["openblas_gbs"])
+        omp.append(r["oracle_omp_gbs"])
+        secs.append(r["seconds_blas"])
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"gbmv f64 l=u in {{1,8}}, bounded sample n=2^{log2n} of the n=2^27 workload",
+                   "note": "reference is pure Julia (not runnable here); timed = OpenBLAS dgbmv (scipy.linalg.blas, "
+                           "all host threads): the BLAS routine BandedMatrices.gbmv! ccalls, i.e. what the reference "
+                           "executes for this path (BASELINE.md section 4). The repo's own OpenMP oracle port is "
+                           "timed beside it as cpu_baseline.oracle_omp_gbs."},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                         "which": "openblas_dgbmv", "oracle_omp_gbs": sum(omp) / len(omp)},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import lbm_b200 as L
+    from lbm_b200.shard import ShardedBanded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = L.handle_for(local)
+    n = 1 << (args.log2n or LOG2N)
+    K, W = args.steps, max(3, args.warmup)
+
+    # ---- resident operands (generated on device from the counter-based stream) -------------
+    shards, xbufs, ys = [], [], []
+    for (l, u) in BANDS:
+        sh = ShardedBanded.brand(n, l, u, rank, world, dtype=torch.float64, device=dev, seed=0x1)
+        xb = sh.plan.new_vector(torch.float64, dev)
+        own = sh.plan.owned(xb)
+        tmp = torch.empty(sh.plan.m_loc, dtype=torch.float64, device=dev)
+        L.fill_uniform(tmp, 0x9, offset=sh.plan.r0)
+        own.copy_(tmp)
+        del tmp
+        shards.append(sh)
+        xbufs.append(xb)
+        ys.append(torch.empty(sh.plan.m_loc, dtype=torch.float64, device=dev))
+    torch.cuda.synchronize()
+
+    def step():
+        for sh, xb, y in zip(shards, xbufs, ys):
+            sh.mul_(y, xb)          # halo exchange (N>1) + lbm_dgbmv on the slab
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream -------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stream = torch.cuda.current_stream()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(BANDS) + 1)] for _ in range(K)]
+    launches0 = h.launch_count()
+    barrier()
+    for k in range(K):
+        ev[k][0].record(stream)
+        for b, (sh, xb, y) in enumerate(zip(shards, xbufs, ys)):
+            sh.mul_(y, xb)
+            ev[k][b + 1].record(stream)
+    barrier()
+    launches = h.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0][0].elapsed_time(ev[K - 1][len(BANDS)])
+    per_band_ms = [sum(ev[k][b].elapsed_time(ev[k][b + 1]) for k in range(K)) / K for b in range(len(BANDS))]
+    t = torch.tensor([total_ms] + per_band_ms + [float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, per_band_ms = float(tmax[0]), [float(v) for v in tmax[1:1 + len(BANDS)]]
+        launches = int(tsum[-1])
+    step_bytes = sum(alg_bytes(n, l, u) for (l, u) in BANDS)
+    ms_per_step = total_ms / K
+    value = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (l=u=8 slab apply) ----------------------------------
+    peak, peak_src = peaks()
+    dom = max(range(len(BANDS)), key=lambda b: per_band_ms[b])
+    l, u = BANDS[dom]
+    kern_bytes = alg_bytes(n, l, u) / world          # per launch (one launch per rank per apply)
+    achieved = kern_bytes / (per_band_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(f"gbmv_l{l}_n2^{args.log2n or LOG2N}_gpus{world}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": f"gbmv_tile_kernel<double,{l + u + 1}> (l=u={l})",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": kern_bytes,
+                "includes_halo_exchange": world > 1}
+    breakdown = {f"l{l}u{u}": {"ms": per_band_ms[b], "gbs": alg_bytes(n, l, u) / (per_band_ms[b] * 1e-3) / 1e9,
+                                "frac_of_peak": alg_bytes(n, l, u) / (per_band_ms[b] * 1e-3) / 1e9 / (peak * world)}
+                 for b, (l, u) in enumerate(BANDS)}
+
+    # ---- the l=u=128 metric point at the largest n that fits (not part of `value`) ------------
+    del shards, xbufs, ys
+    torch.cuda.empty_cache()
+    if not args.no_wide:
+        try:
+            free = torch.cuda.mem_get_info()[0]
+            log2w = min(LOG2N, (int(free * 0.8) * world // (257 * 8)).bit_length() - 1)
+            nw = 1 << log2w
+            sh = ShardedBanded.brand(nw, 128, 128, rank, world, dtype=torch.float64, device=dev, seed=0x1)
+            xb = sh.plan.new_vector(torch.float64, dev)
+            L.fill_uniform(xb, 0x9, offset=sh.plan.c0)
+            yw = torch.empty(sh.plan.m_loc, dtype=torch.float64, device=dev)
+            for _ in range(2):
+                sh.mul_(yw, xb)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record(stream)
+            for _ in range(reps):
+                sh.mul_(yw, xb)
+            e1.record(stream)
+            barrier()
+            msw = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(msw, op=dist.ReduceOp.MAX)
+            gbs = alg_bytes(nw, 128, 128) / (float(msw[0]) * 1e-3) / 1e9
+            breakdown["l128u128"] = {"n": f"2^{log2w}", "ms": float(msw[0]), "gbs": gbs,
+                                     "frac_of_peak": gbs / (peak * world)}
+            del sh, xb, yw
+            torch.cuda.empty_cache()
+        except Exception as e:  # never lose the headline line to the optional point
+            breakdown["l128u128"] = {"error": str(e)[:200]}
+
+    # ---- e2e: the same metric through the C-ABI host-buffer call (H2D + kernel + D2H timed) ---
+    e2e = None if args.no_e2e else run_e2e(args, L, h, n, rank, world, dev, barrier)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_gbmv_sample(24, 2)
+        cpu = {"value": r["openblas_gbs"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "which": "openblas_dgbmv (the routine the reference's gbmv! ccalls)",
+               "oracle_omp_gbs": r["oracle_omp_gbs"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"mul!(y,A,x), A=brand(n,n,l,u) f64, n=2^{args.log2n or LOG2N}, l=u in {{1,8}}, "
+                                   f"row-sharded over {world} GPU(s), NCCL ghost exchange in the timed region",
+                       "l2": "inputs (3.2 GB and 18.3 GB slabs) far larger than the 126 MB L2; no flush needed",
+                       "algorithmic_bytes_per_step": step_bytes},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "breakdown": breakdown, "frac_of_aggregate_peak": value / (peak * world),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, L, h, n, rank, world, dev, barrier):
+    """Host buffers (pinned) -> lbm_dgbmv_host -> host result, every step: H2D of A and x, the
+    kernel, D2H of y.  Each rank pushes its own slab (no halo needed: the host x is global)."""
+    import ctypes as C
+
+    import psutil
+    import torch
+    import torch.distributed as dist
+    from lbm_b200.shard import RowShard
+
+    try:
+        bands = list(BANDS)
+        need = sum((l + u + 1 + 2) * 8 * (n // world + l + u) for (l, u) in bands)
+        avail = psutil.virtual_memory().available // max(1, world if world > 1 else 1)
+        if need * 1.3 > avail:
+            bands = [(1, 1)]
+        host = []
+        for (l, u) in bands:
+            p = RowShard.plan(n, l, u, rank, world)
+            lda = l + u + 1
+            d = torch.empty((p.n_loc, lda), dtype=torch.float64, device=dev)
+            L.fill_uniform(d, 0x1, offset=lda * p.c0)
+            xa = torch.empty(p.n_loc, dtype=torch.float64, device=dev)
+            L.fill_uniform(xa, 0x9, offset=p.c0)
+            hA = torch.empty((p.n_loc, lda), dtype=torch.float64, pin_memory=True)
+            hx = torch.empty(p.n_loc, dtype=torch.float64, pin_memory=True)
+            hy = torch.empty(p.m_loc, dtype=torch.float64, pin_memory=True)
+            hA.copy_(d)
+            hx.copy_(xa)
+            del d, xa
+            host.append((p, hA, hx, hy))
+        torch.cuda.empty_cache()
+        fn = L.lib().lbm_dgbmv_host
+
+        def step():
+            for (p, hA, hx, hy) in host:
+                rc = fn(h.ptr, b"N", p.m_loc, p.n_loc, p.kl_loc, p.ku_loc, 1.0, C.c_void_p(hA.data_ptr()),
+                        p.l + p.u + 1, C.c_void_p(hx.data_ptr()), 0.0, C.c_void_p(hy.data_ptr()))
+                h.check(rc, "lbm_dgbmv_host")
+
+        step()  # warm (allocates the device staging)
+        barrier()
+        steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()     # synchronous: returns when y is on the host
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        bytes_alg = sum(alg_bytes(n, l, u) for (l, u) in bands)
+        h2d = sum(hA.numel() * 8 + hx.numel() * 8 for (_, hA, hx, _) in host)
+        d2h = sum(hy.numel() * 8 for (_, _, _, hy) in host)
+        if world > 1:   # whole-job bytes
+            tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+            h2d, d2h = int(tb[0]), int(tb[1])
+        checksum = float(sum(hy[:: max(1, hy.numel() // 1024)].sum() for (_, _, _, hy) in host))
+        return {"value": bytes_alg / (float(dt[0]) / steps) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": steps, "bands": bands, "result_checksum": checksum,
+                "note": "lbm_dgbmv_host with pinned host buffers: H2D(A,x) + kernel + D2H(y) inside the timed region"}
+    except Exception as e:
+        return {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(e)[:300]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=0, help="override n = 2^k (testing only; metric is 2^27)")
+    ap.add_argument("--no-wide", action="store_true", help="skip the l=u=128 breakdown point")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,7 +43,8 @@ typedef struct lbm_handle_s *lbm_handle_t;
 int lbm_version(void);                                   /* 10000*major + 100*minor + patch */
 int lbm_create(lbm_handle_t *out, int device);           /* owns a non-blocking stream */
 int lbm_destroy(lbm_handle_t h);
-int lbm_set_stream(lbm_handle_t h, void *cuda_stream);   /* borrow caller's cudaStream_t (NULL = own) */
+int lbm_set_stream(lbm_handle_t h, void *cuda_stream);   /* borrow caller's cudaStream_t; NULL = CUDA's legacy default stream */
+int lbm_use_own_stream(lbm_handle_t h);                  /* back to the handle's private non-blocking stream */
 int lbm_sync(lbm_handle_t h);
 const char *lbm_last_error_string(lbm_handle_t h);       /* h may be NULL: last create error */
 int64_t lbm_launch_count(lbm_handle_t h);                /* kernels launched through h so far */

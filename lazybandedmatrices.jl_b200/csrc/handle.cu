@@ -93,7 +93,13 @@ int lbm_destroy(lbm_handle_t h) {
 
 int lbm_set_stream(lbm_handle_t h, void *cuda_stream) {
     if (!h) return -1;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cudaStream_t)cuda_stream;  // NULL is a valid stream: the legacy default stream
+    return 0;
+}
+
+int lbm_use_own_stream(lbm_handle_t h) {
+    if (!h) return -1;
+    h->stream = h->own_stream;
     return 0;
 }
 

@@ -109,7 +109,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
     const uint32_t a = smem_u32(bar);
+    uint32_t spins = 0;
     while (!done) {
+        // a lost transaction must surface as a CUDA error, never as a hung GPU
+        if (++spins > (1u << 24)) __trap();
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -36,6 +36,7 @@ def _sigs():
         "lbm_create": (C.c_int, [C.POINTER(vp), C.c_int]),
         "lbm_destroy": (C.c_int, [H]),
         "lbm_set_stream": (C.c_int, [H, vp]),
+        "lbm_use_own_stream": (C.c_int, [H]),
         "lbm_sync": (C.c_int, [H]),
         "lbm_last_error_string": (C.c_char_p, [H]),
         "lbm_launch_count": (i64, [H]),
@@ -127,7 +128,12 @@ class Handle:
         raise LbmCudaError(rc, f"{what}: {msg}")
 
     def set_stream(self, cuda_stream_ptr):
-        self.check(lib().lbm_set_stream(self._h, vp(cuda_stream_ptr) if cuda_stream_ptr else None))
+        """`cuda_stream_ptr` is a cudaStream_t as an integer; 0 = CUDA's legacy default stream
+        (which is what torch's default stream is)."""
+        self.check(lib().lbm_set_stream(self._h, vp(int(cuda_stream_ptr) or None)))
+
+    def use_own_stream(self):
+        self.check(lib().lbm_use_own_stream(self._h))
 
     def use_torch_stream(self):
         import torch

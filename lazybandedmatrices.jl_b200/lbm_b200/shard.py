@@ -1,0 +1,165 @@
+"""Row-sharding of banded `mul!` across the GPUs of one box: one process per GPU
+(`torch.distributed`, NCCL over NVLink 5 / NVSwitch; gloo on CPU for the host-logic tests).
+
+Output rows are independent given an x window: rank r owns rows [r0, r1) and needs
+x[r0-l, r1+u).  In diagonal-major storage the rows [r0,r1) of A live in the COLUMN slice
+[c0,c1) = [max(0,r0-l), min(n,r1+u)) of the global `data` array, and that slice, taken as is
+(same lda, same band-row index u+i-j), is a (r1-r0) x (c1-c0) banded matrix with bandwidths
+(l - left, u + left), left = r0 - c0.  So a shard is an ordinary rectangular lbm_?gbmv on a
+ghost-cell vector [left ghosts | owned | right ghosts]; the only communication is the
+nearest-neighbour exchange that fills the max(l,u)-wide ghosts.  There is no
+all-reduce / all-gather on the path, and no replicated compute.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from .errors import LbmArgumentError
+
+
+def split_rows(n: int, world: int, rank: int, align: int = 4):
+    """Contiguous near-equal row blocks whose starts are multiples of `align` (keeps every
+    shard's slab and vectors 16-byte aligned for the bulk-TMA path)."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    r0 = min(n, rank * per)
+    r1 = min(n, r0 + per)
+    return r0, r1
+
+
+@dataclass
+class RowShard:
+    n: int          # global size (square n x n operator)
+    l: int
+    u: int
+    rank: int
+    world: int
+    r0: int
+    r1: int
+    c0: int
+    c1: int
+
+    @classmethod
+    def plan(cls, n: int, l: int, u: int, rank: int, world: int) -> "RowShard":
+        r0, r1 = split_rows(n, world, rank)
+        if world > 1 and (r1 - r0) < max(l, u, 1):
+            raise LbmArgumentError(
+                f"shard of {r1 - r0} rows is narrower than the halo max(l,u)={max(l, u)}: use fewer ranks")
+        return cls(n, l, u, rank, world, r0, r1, max(0, r0 - l), min(n, r1 + u))
+
+    # geometry ------------------------------------------------------------------------
+    @property
+    def m_loc(self):
+        return self.r1 - self.r0
+
+    @property
+    def n_loc(self):
+        return self.c1 - self.c0
+
+    @property
+    def left(self):     # ghost entries before the owned block
+        return self.r0 - self.c0
+
+    @property
+    def right(self):    # ghost entries after it
+        return self.c1 - self.r1
+
+    @property
+    def kl_loc(self):
+        return self.l - self.left
+
+    @property
+    def ku_loc(self):
+        return self.u + self.left
+
+    def owned(self, xbuf: torch.Tensor) -> torch.Tensor:
+        """View of the owned block inside a ghost-cell vector."""
+        return xbuf[self.left: self.left + self.m_loc]
+
+    def new_vector(self, dtype, device) -> torch.Tensor:
+        return torch.zeros(self.n_loc, dtype=dtype, device=device)
+
+    # communication ------------------------------------------------------------------
+    def exchange_ops(self, xbuf: torch.Tensor, group=None):
+        """P2P ops that fill this rank's ghosts and serve the neighbours' ghosts."""
+        ops = []
+        own = self.owned(xbuf)
+        if self.rank > 0:
+            # previous rank's right ghost = my first u owned entries (clipped at n by construction)
+            cnt = min(self.u, self.m_loc)
+            if cnt:
+                ops.append(dist.P2POp(dist.isend, own[:cnt], self.rank - 1, group))
+            if self.left:
+                ops.append(dist.P2POp(dist.irecv, xbuf[: self.left], self.rank - 1, group))
+        if self.rank < self.world - 1:
+            cnt = min(self.l, self.m_loc)
+            if cnt:
+                ops.append(dist.P2POp(dist.isend, own[self.m_loc - cnt:], self.rank + 1, group))
+            if self.right:
+                ops.append(dist.P2POp(dist.irecv, xbuf[self.left + self.m_loc:], self.rank + 1, group))
+        return ops
+
+    def exchange(self, xbuf: torch.Tensor, group=None):
+        ops = self.exchange_ops(xbuf, group)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class ShardedBanded:
+    """This rank's slab of a global n x n BandedMatrix (bandwidths (l,u)), plus the plan."""
+
+    def __init__(self, plan: RowShard, data_loc: torch.Tensor):
+        lda = plan.l + plan.u + 1
+        if tuple(data_loc.shape) != (plan.n_loc, lda):
+            raise LbmArgumentError(f"local slab must be ({plan.n_loc}, {lda}), got {tuple(data_loc.shape)}")
+        self.plan = plan
+        self.data = data_loc.contiguous()
+
+    @classmethod
+    def brand(cls, n, l, u, rank, world, dtype=torch.float64, device="cuda", seed=1):
+        """The rank's slice of `brand(n,n,l,u)` generated in place from the counter-based
+        stream (bit-identical to slicing the global matrix; no transfer)."""
+        from .banded import fill_uniform
+        p = RowShard.plan(n, l, u, rank, world)
+        lda = l + u + 1
+        data = torch.empty((p.n_loc, lda), dtype=dtype, device=device)
+        if data.numel():
+            fill_uniform(data, seed, offset=lda * p.c0)
+        return cls(p, data)
+
+    def local_matrix(self):
+        from .banded import BandedMatrix
+        p = self.plan
+        return BandedMatrix(self.data, p.m_loc, p.kl_loc, p.ku_loc)
+
+    def mul_(self, y_own: torch.Tensor, xbuf: torch.Tensor, alpha=1.0, beta=0.0, group=None,
+             local_gbmv: Optional[Callable] = None, exchange: bool = True):
+        """y_own <- alpha * A[r0:r1, :] x + beta * y_own; `xbuf` is the ghost-cell vector whose
+        owned block holds x[r0:r1].  `local_gbmv` exists so the host logic can be exercised on
+        CPU (gloo) with the oracle in tests; the product path is the CUDA kernel."""
+        p = self.plan
+        if exchange and p.world > 1:
+            p.exchange(xbuf, group)
+        if local_gbmv is None:
+            from .banded import gbmv_
+            return gbmv_(y_own, self.local_matrix(), xbuf, alpha, beta, "N")
+        return local_gbmv(y_own, self, xbuf, alpha, beta)
+
+
+def sharded_chain_mul_(y_own, factors, xbuf, tmp_bufs, group=None, local_gbmv=None):
+    """`mul!(y, ApplyMatrix(*, F1, ..., Fk), x)` row-sharded: right-to-left; stage output i is
+    written into the owned block of a ghost-cell vector laid out for the factor that consumes
+    it, whose `mul_` then exchanges that intermediate's halo (width max(l,u) of the consumer)."""
+    order = list(reversed(factors))          # F_k ... F_1
+    v = xbuf                                 # ghost layout of F_k
+    for idx, f in enumerate(order[:-1]):
+        consumer = order[idx + 1]
+        t = tmp_bufs[idx]                    # consumer.plan.new_vector(...)
+        f.mul_(consumer.plan.owned(t), v, group=group, local_gbmv=local_gbmv)
+        v = t
+    return order[-1].mul_(y_own, v, group=group, local_gbmv=local_gbmv)

@@ -1,0 +1,168 @@
+"""GPU parity: banded x banded materialize, lazy chains (ApplyMatrix), batched fused chains and
+the never-materialised block-Kronecker applies, vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import tol_rows
+
+pytestmark = pytest.mark.gpu
+NP = {torch.float64: np.float64, torch.float32: np.float32}
+
+
+def _band(L, oracle, m, n, l, u, seed, dt):
+    A_np = oracle.brand(m, n, l, u, seed=seed, dtype=NP[dt])
+    return A_np, L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(A_np.T)).cuda(), m, l, u)
+
+
+def _cmp_band(oracle, got_bm, want_np, m, l, u, tol):
+    got = np.asfortranarray(got_bm.data.cpu().numpy().T)
+    dg = oracle.band_to_dense(got, m, l, u)
+    dw = oracle.band_to_dense(want_np, m, l, u)
+    err = np.max(np.abs(dg - dw)) if dg.size else 0.0
+    assert err <= tol, (err, tol)
+    # out-of-matrix slots are written as zeros (beta == 0)
+    n = got.shape[1]
+    for j in list(range(min(n, u + 1))) + list(range(max(0, n - l - 1), n)):
+        for r in range(l + u + 1):
+            i = j + r - u
+            if i < 0 or i >= m:
+                assert got[r, j] == 0.0
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_gbmm_shapes(L, oracle, dt):
+    cases = [(6, 6, 6, 1, 1, 1, 1), (10, 8, 9, 2, 0, 1, 3), (5, 5, 5, 4, 4, 4, 4), (12, 12, 12, 0, 0, 2, 1),
+             (1, 1, 1, 0, 0, 0, 0), (200, 170, 230, 3, 2, 1, 4), (10000, 10000, 10000, 1, 1, 1, 1),
+             (3000, 3000, 3000, 8, 8, 8, 8), (2000, 2100, 1900, 16, 3, 5, 20), (1500, 1500, 1500, 40, 40, 40, 40)]
+    for s, (m, n, k, kla, kua, klb, kub) in enumerate(cases):
+        A_np, A = _band(L, oracle, m, k, kla, kua, 11 + s, dt)
+        B_np, B = _band(L, oracle, k, n, klb, kub, 12 + s, dt)
+        want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
+        C = A @ B
+        assert C.bandwidths() == (kla + klb, kua + kub) and C.shape == (m, n)
+        tol = tol_rows(NP[dt], min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
+        _cmp_band(oracle, C, want, m, kla + klb, kua + kub, tol)
+
+
+def test_gbmm_alpha_beta_and_wider_output_band(L, oracle):
+    m = n = k = 500
+    A_np, A = _band(L, oracle, m, k, 2, 1, 1, torch.float64)
+    B_np, B = _band(L, oracle, k, n, 1, 3, 2, torch.float64)
+    C0_np, C0 = _band(L, oracle, m, n, 5, 6, 3, torch.float64)      # band wider than (3,4)
+    want = oracle.gbmm(m, n, k, A_np, 2, 1, B_np, 1, 3, klc=5, kuc=6, alpha=2.0, beta=0.5, Cin=C0_np)
+    L.gbmm(A, B, alpha=2.0, out=C0, beta=0.5)
+    got = np.asfortranarray(C0.data.cpu().numpy().T)
+    dg, dw = oracle.band_to_dense(got, m, 5, 6), oracle.band_to_dense(want, m, 5, 6)
+    assert np.max(np.abs(dg - dw)) <= tol_rows(np.float64, 4, 1.0, 1.0, 2.0, 0.5, 1.0)
+    with pytest.raises(L.LbmArgumentError):                            # output band too narrow
+        L.gbmm(A, B, out=L.brand(m, n, 1, 1))
+    with pytest.raises(L.DimensionMismatch):
+        A @ L.brand(k + 1, n, 1, 1)
+
+
+def test_applymatrix_config1(L, oracle):
+    """BASELINE config 1: ApplyMatrix(*, A, A), A = brand(10_000,10_000,1,1): bandwidths,
+    materialize and mul! (README.md:8-26)."""
+    n = 10_000
+    A_np, A = _band(L, oracle, n, n, 1, 1, 0x1, torch.float64)
+    M = L.ApplyMatrix("*", A, A)
+    assert M.bandwidths() == (2, 2)
+    C = M.materialize()
+    want = oracle.gbmm(n, n, n, A_np, 1, 1, A_np, 1, 1)
+    _cmp_band(oracle, C, want, n, 2, 2, tol_rows(np.float64, 3, 1.0, 1.0))
+    x_np = oracle.fill_uniform(0x9, n)
+    y = M @ torch.from_numpy(x_np).cuda()
+    t = oracle.gbmv("N", n, n, 1, 1, 1.0, A_np, x_np)
+    want_y = oracle.gbmv("N", n, n, 1, 1, 1.0, A_np, t)
+    # two stages: stage bounds add (SURVEY.md 8d tolerance row); ||A x|| <= 3
+    assert np.max(np.abs(y.cpu().numpy() - want_y)) <= 2 * tol_rows(np.float64, 3, 1.0, 3.0)
+    # materialised product applied to x agrees with the lazy apply
+    y2 = C @ torch.from_numpy(x_np).cuda()
+    assert np.max(np.abs(y2.cpu().numpy() - want_y)) <= 2 * tol_rows(np.float64, 5, 3.0, 1.0)
+    # three-factor chain, mixed kinds
+    T = L.SymTridiagonal(torch.from_numpy(oracle.fill_uniform(3, n)).cuda(), torch.from_numpy(oracle.fill_uniform(4, n - 1)).cuda())
+    M3 = L.ApplyMatrix("*", A, T, A.T)
+    y3 = M3 @ torch.from_numpy(x_np).cuda()
+    dense_y = A.to_dense() @ (T.to_dense() @ (A.to_dense().t() @ torch.from_numpy(x_np).cuda()))
+    assert torch.max(torch.abs(y3 - dense_y)).item() <= 1e-12
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_chain3_batched(L, oracle, dt):
+    npdt = NP[dt]
+    for (batch, n, kl, ku) in [(5, 300, [4, 4, 4], [4, 4, 4]), (3, 1000, [1, 2, 0], [0, 1, 3]), (2, 70, [0, 0, 0], [0, 0, 0]),
+                               (7, 4096, [4, 4, 4], [4, 4, 4])]:
+        fs = [oracle.fill_uniform(1 + i, batch * n * (kl[i] + ku[i] + 1), npdt).reshape(batch, n, kl[i] + ku[i] + 1)
+              for i in range(3)]
+        want = oracle.gbmm_chain3_batched(n, kl, ku, *fs)
+        got = L.chain3_batched(*[torch.from_numpy(f).cuda() for f in fs], kl, ku).cpu().numpy()
+        nb = [kl[i] + ku[i] + 1 for i in range(3)]
+        # per-stage bounds: stage 1 terms <= nb0 (entries <= 1), stage 2 terms <= nb2 with |AB| <= nb0
+        tol = tol_rows(npdt, nb[0], 1.0, 1.0) * nb[2] + tol_rows(npdt, nb[2], float(nb[0]), 1.0)
+        assert got.shape == want.shape
+        ld = want.shape[2]
+        l3, u3 = sum(kl), sum(ku)
+        for b in range(batch):   # compare in-matrix entries
+            dg = oracle.band_to_dense(np.asfortranarray(got[b].T), n, l3, u3)
+            dw = oracle.band_to_dense(np.asfortranarray(want[b].T), n, l3, u3)
+            assert np.max(np.abs(dg - dw)) <= tol, (batch, n, kl, ku)
+        assert ld == l3 + u3 + 1
+
+
+def _lap(L, n, dtype=torch.float64):
+    h = 1.0 / n
+    return L.banded_from_diagonals(n, {0: -2.0 / h**2, 1: 1.0 / h**2, -1: 1.0 / h**2}, dtype=dtype)
+
+
+def test_kronsum_laplacian(L, oracle):
+    """2-D Laplacian BlockKron(D2,I)+BlockKron(I,D2) (test/test_blockkron.jl:296-306)."""
+    for n in (4, 33, 257, 1000):
+        D = _lap(L, n)
+        Dxx = L.BlockKron(D, L.Eye(n))
+        Dyy = L.BlockKron(L.Eye(n), D)
+        Lap = L.KronSum.from_broadcast(Dxx, Dyy)
+        assert Lap.blockbandwidths() == (1, 1) and Lap.subblockbandwidths() == (1, 1)
+        x_np = oracle.fill_uniform(5, n * n)
+        D_np = np.asfortranarray(D.data.cpu().numpy().T)
+        want = oracle.kronsum2d_mv(n, n, D_np, 1, 1, D_np, 1, 1, x_np)
+        got = (Lap @ torch.from_numpy(x_np).cuda()).cpu().numpy()
+        scale = 2.0 * n * n                      # ||D2||_max = 2/h^2
+        assert np.max(np.abs(got - want)) <= tol_rows(np.float64, 6, scale, 1.0)
+        if n <= 33:                              # and against the literally formed Kronecker matrices
+            Dd = oracle.band_to_dense(D_np, n, 1, 1)
+            dense = (np.kron(Dd, np.eye(n)) + np.kron(np.eye(n), Dd)) @ x_np
+            assert np.max(np.abs(got - dense)) <= tol_rows(np.float64, 6, scale, 1.0)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_kronsum_general_bands_rectangular_grid(L, oracle, dt):
+    npdt = NP[dt]
+    for (n1, n2, la, ua, lb, ub) in [(7, 5, 1, 1, 1, 1), (300, 200, 2, 1, 0, 3), (64, 1000, 3, 3, 2, 2), (1, 50, 0, 0, 1, 1),
+                                     (50, 1, 1, 1, 0, 0), (513, 511, 1, 1, 1, 1)]:
+        A_np, A = _band(L, oracle, n1, n1, la, ua, 3, dt)
+        B_np, B = _band(L, oracle, n2, n2, lb, ub, 4, dt)
+        x_np = oracle.fill_uniform(5, n1 * n2, npdt)
+        y0 = oracle.fill_uniform(6, n1 * n2, npdt)
+        want = oracle.kronsum2d_mv(n1, n2, A_np, la, ua, B_np, lb, ub, x_np, 1.5, 0.5, y0)
+        y = torch.from_numpy(y0.copy()).cuda()
+        L.KronSum(A, B).mul_(y, torch.from_numpy(x_np).cuda(), 1.5, 0.5)
+        tol = tol_rows(npdt, la + ua + lb + ub + 2, 1.0, 1.0, 1.5, 0.5, 1.0)
+        assert np.max(np.abs(y.cpu().numpy() - want)) <= tol
+
+
+def test_blockkron_apply(L, oracle):
+    """BlockKron(A,B)*x = vec(B X A') without forming kron(A,B) (src/blockkron.jl:440 identity)."""
+    for (n1, n2, la, ua, lb, ub) in [(4, 4, 1, 1, 0, 0), (40, 30, 1, 1, 2, 1), (257, 300, 2, 2, 1, 1)]:
+        A_np, A = _band(L, oracle, n1, n1, la, ua, 3, torch.float64)
+        B_np, B = _band(L, oracle, n2, n2, lb, ub, 4, torch.float64)
+        K = L.BlockKron(A, B)
+        assert K.blockbandwidths() == (la, ua) and K.subblockbandwidths() == (lb, ub)
+        x_np = oracle.fill_uniform(5, n1 * n2)
+        want = oracle.kron2d_mv(n1, n2, A_np, la, ua, B_np, lb, ub, x_np)
+        got = (K @ torch.from_numpy(x_np).cuda()).cpu().numpy()
+        tol = tol_rows(np.float64, (la + ua + 1) * (lb + ub + 1), 1.0, 1.0)
+        assert np.max(np.abs(got - want)) <= tol
+        if n1 * n2 <= 2000:
+            dense = np.kron(oracle.band_to_dense(A_np, n1, la, ua), oracle.band_to_dense(B_np, n2, lb, ub)) @ x_np
+            assert np.max(np.abs(got - dense)) <= tol

@@ -1,0 +1,130 @@
+"""GPU parity: Tridiagonal / SymTridiagonal / Bidiagonal mul! (mat-vec and mat-mat) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import tol_rows
+
+pytestmark = pytest.mark.gpu
+NP = {torch.float64: np.float64, torch.float32: np.float32}
+SIZES = [1, 2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1000, 4097, 100003, 1 << 20]
+
+
+def _mk(oracle, n, dt, seed):
+    npdt = NP[dt]
+    d = oracle.fill_uniform(seed, n, npdt)
+    dl = oracle.fill_uniform(seed + 1, max(n - 1, 0), npdt)
+    du = oracle.fill_uniform(seed + 2, max(n - 1, 0), npdt)
+    return dl, d, du
+
+
+def _t(a):
+    return torch.from_numpy(a).cuda()
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("kind", ["tri", "sym", "symlong", "biU", "biL"])
+def test_structured_matvec(L, oracle, dt, kind):
+    npdt = NP[dt]
+    for n in SIZES:
+        dl, d, du = _mk(oracle, n, dt, 40 + n % 7)
+        if kind == "tri":
+            A = L.Tridiagonal(_t(dl), _t(d), _t(du))
+            o = (dl, d, du)
+        elif kind == "sym":
+            A = L.SymTridiagonal(_t(d), _t(du))
+            o = (du, d, du)
+        elif kind == "symlong":  # len(ev) == n is allowed; only ev[:n-1] is used (src/tridiag.jl:11)
+            ev = oracle.fill_uniform(3, n, npdt)
+            A = L.SymTridiagonal(_t(d), _t(ev))
+            o = (ev[: n - 1], d, ev[: n - 1])
+        elif kind == "biU":
+            A = L.Bidiagonal(_t(d), _t(du), "U")
+            o = (None, d, du)
+        else:
+            A = L.Bidiagonal(_t(d), _t(dl), "L")
+            o = (dl, d, None)
+        odl, od, odu = o
+        if n == 1:
+            odl = odu = None
+        for alpha, beta in [(1.0, 0.0), (2.0, 1.0)]:
+            x = oracle.fill_uniform(50, n, npdt)
+            y0 = oracle.fill_uniform(51, n, npdt)
+            want = oracle.tridiag_mv(n, odl, od, odu, x, alpha, beta, y0)
+            y = _t(y0.copy())
+            L.mul_(y, A, _t(x), alpha, beta)
+            err = np.max(np.abs(y.cpu().numpy() - want))
+            assert err <= tol_rows(npdt, 3, 1.0, 1.0, alpha, beta, 1.0), (kind, n, alpha, beta, err)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_structured_matmat_and_transposes(L, oracle, dt):
+    npdt = NP[dt]
+    for n in (2, 64, 1000, 4100):
+        dl, d, du = _mk(oracle, n, dt, 7)
+        X = np.asfortranarray(oracle.fill_uniform(8, n * 3, npdt).reshape(n, 3, order="F"))
+        A = L.Tridiagonal(_t(dl), _t(d), _t(du))
+        for At, (a, b) in ((A, (dl, du)), (A.T, (du, dl))):          # transpose = swap dl,du
+            want = oracle.tridiag_mv(n, a, d, b, X)
+            Xg = torch.from_numpy(X).cuda()                            # column-major view (stride (1,n))
+            got = (At @ Xg).cpu().numpy()
+            assert np.max(np.abs(got - want)) <= tol_rows(npdt, 3, 1.0, 1.0)
+            Xr = torch.from_numpy(np.ascontiguousarray(X)).cuda()      # row-major input also accepted
+            got = (At @ Xr).cpu().numpy()
+            assert np.max(np.abs(got - want)) <= tol_rows(npdt, 3, 1.0, 1.0)
+        B = L.Bidiagonal(_t(d), _t(du), "U")
+        want = oracle.tridiag_mv(n, du, d, None, X)                    # B' is lower with the same ev
+        assert np.max(np.abs((B.T @ torch.from_numpy(X).cuda()).cpu().numpy() - want)) <= tol_rows(npdt, 2, 1.0, 1.0)
+
+
+def test_structured_kats(L, kats):
+    """The reference's own KATs for the structured types, run on the GPU."""
+    k = next(k for k in kats if k["kind"] == "symtridiag_mv")           # test/test_tridiag.jl:339-341
+    T = L.SymTridiagonal(torch.tensor(k["dv"], dtype=torch.float64).cuda(), torch.tensor(k["ev"], dtype=torch.float64).cuda())
+    assert (T @ torch.tensor(k["x"], dtype=torch.float64).cuda()).cpu().tolist() == k["expect"]
+    k = next(k for k in kats if k["kind"] == "symtridiag_empty")        # test/test_tridiag.jl:342
+    T = L.SymTridiagonal(torch.ones(0, dtype=torch.float64).cuda(), torch.ones(0, dtype=torch.float64).cuda())
+    out = T @ torch.ones((0, 2), dtype=torch.float64).cuda()
+    assert tuple(out.shape) == (0, 2)
+    for kind, mk in (("dense_tridiagonal", lambda k: L.Tridiagonal(*(torch.tensor(k[s], dtype=torch.float64).cuda() for s in ("dl", "d", "du")))),
+                     ("dense_symtridiagonal", lambda k: L.SymTridiagonal(*(torch.tensor(k[s], dtype=torch.float64).cuda() for s in ("dv", "ev")))),
+                     ("dense_bidiagonal", lambda k: L.Bidiagonal(*(torch.tensor(k[s], dtype=torch.float64).cuda() for s in ("dv", "ev")), k["uplo"]))):
+        k = next(k for k in kats if k["kind"] == kind)
+        A = mk(k)
+        n = len(k["expect"])
+        dense = A @ torch.eye(n, dtype=torch.float64).cuda()
+        assert dense.cpu().tolist() == k["expect"], k["src"]
+        assert A.to_dense().cpu().tolist() == k["expect"]
+
+
+def test_structured_mul_errors(L):
+    """test/test_tridiag.jl:272-279: DimensionMismatch on mis-shaped mul!."""
+    n = 6
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64, device="cuda")
+    A = L.Tridiagonal(z(n - 1), z(n), z(n - 1))
+    B = L.SymTridiagonal(z(n), z(n - 1))
+    Cnn, Cnm, Cmn = z(n, n), z(n, n + 1), z(n + 1, n)
+    for args in [(Cnn, A, Cnm), (Cnn, A, Cmn), (Cnn, B, Cmn), (Cmn, B, Cnn), (Cnm, B, Cnn)]:
+        with pytest.raises(L.DimensionMismatch):
+            L.mul_(*args)
+
+
+def test_structured_scalar_fallback_matches(L, oracle):
+    n = 50001
+    dl, d, du = _mk(oracle, n, torch.float64, 3)
+    x = oracle.fill_uniform(9, n)
+    want = oracle.tridiag_mv(n, dl, d, du, x)
+    A = L.Tridiagonal(_t(dl), _t(d), _t(du))
+    h = L.handle_for(0)
+    h.set_tuning(tri_force_scalar=1)
+    try:
+        got = (A @ _t(x)).cpu().numpy()
+    finally:
+        h.set_tuning(tri_force_scalar=0)
+    assert np.max(np.abs(got - want)) <= tol_rows(np.float64, 3, 1.0, 1.0)
+    # unaligned views
+    buf = _t(oracle.fill_uniform(1, n + 1))
+    xv = buf[1:]
+    got = (A @ xv).cpu().numpy()
+    want = oracle.tridiag_mv(n, dl, d, du, xv.cpu().numpy())
+    assert np.max(np.abs(got - want)) <= tol_rows(np.float64, 3, 1.0, 1.0)

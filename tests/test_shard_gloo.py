@@ -1,0 +1,130 @@
+"""N>1 host logic on CPU: world_size-2 (and 3) gloo process groups run the row-sharding plan and
+the ghost-cell halo exchange of lbm_b200.shard, with the oracle standing in for the local CUDA
+kernel (tests may use the oracle; the product path cannot).  Checks the sharded result equals
+the single-process oracle BIT-EXACTLY (same per-row summation order)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_local_gbmv(y_own, shard, xbuf, alpha, beta):
+    from oracle import oracle as O
+    p = shard.plan
+    A = np.asfortranarray(shard.data.numpy().T)
+    out = O.gbmv("N", p.m_loc, p.n_loc, p.kl_loc, p.ku_loc, alpha, A, xbuf.numpy(), beta, y_own.numpy())
+    y_own.copy_(torch.from_numpy(out))
+    return y_own
+
+
+def _worker(rank, world, port, n, bands, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "lazybandedmatrices.jl_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from lbm_b200.shard import RowShard, ShardedBanded, sharded_chain_mul_
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = {}
+        x_full = O.fill_uniform(0x9, n)
+        factors = []
+        for fi, (l, u) in enumerate(bands):
+            lda = l + u + 1
+            p = RowShard.plan(n, l, u, rank, world)
+            # the rank's column slice of the global brand(n,n,l,u), regenerated from the stream
+            slab = O.fill_uniform(0x1 + fi, lda * p.n_loc, offset=lda * p.c0).reshape(p.n_loc, lda)
+            factors.append(ShardedBanded(p, torch.from_numpy(slab)))
+        # single mul!: y = F_last x
+        f = factors[-1]
+        xbuf = f.plan.new_vector(torch.float64, "cpu")
+        f.plan.owned(xbuf).copy_(torch.from_numpy(x_full[f.plan.r0:f.plan.r1]))
+        y = torch.zeros(f.plan.m_loc, dtype=torch.float64)
+        f.mul_(y, xbuf, local_gbmv=_oracle_local_gbmv)
+        out["single"] = (f.plan.r0, y.numpy().copy())
+        # ghosts really were filled from the neighbours
+        assert np.array_equal(xbuf.numpy(), x_full[f.plan.c0:f.plan.c1])
+        # lazy chain: y = F1 (F2 (... x))
+        tmp = [factors[len(factors) - 2 - i].plan.new_vector(torch.float64, "cpu") for i in range(len(factors) - 1)]
+        y2 = torch.zeros(factors[0].plan.m_loc, dtype=torch.float64)
+        sharded_chain_mul_(y2, factors, xbuf, tmp, local_gbmv=_oracle_local_gbmv)
+        out["chain"] = (factors[0].plan.r0, y2.numpy().copy())
+        q.put((rank, out))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,bands", [
+    (2, 1000, [(1, 1), (1, 1)]),
+    (2, 4099, [(8, 8), (2, 5), (1, 1)]),
+    (3, 2000, [(128, 128), (3, 0)]),
+    (2, 64, [(0, 1), (1, 0)]),
+])
+def test_row_sharded_mul_matches_single_process(world, n, bands, oracle):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, bands, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        rank, out = q.get(timeout=120)
+        res[rank] = out
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process oracle on the full operator
+    x = oracle.fill_uniform(0x9, n)
+    mats = [np.asfortranarray(oracle.fill_uniform(0x1 + i, (l + u + 1) * n).reshape((l + u + 1, n), order="F"))
+            for i, (l, u) in enumerate(bands)]
+    l, u = bands[-1]
+    want_single = oracle.gbmv("N", n, n, l, u, 1.0, mats[-1], x)
+    v = x
+    for (l, u), M in zip(reversed(bands), reversed(mats)):
+        v = oracle.gbmv("N", n, n, l, u, 1.0, M, v)
+    for key, want in (("single", want_single), ("chain", v)):
+        got = np.zeros(n)
+        covered = np.zeros(n, dtype=bool)
+        for r in range(world):
+            r0, yy = res[r][key]
+            got[r0:r0 + len(yy)] = yy
+            covered[r0:r0 + len(yy)] = True
+        assert covered.all()
+        assert np.array_equal(got, want), key
+
+
+def test_plan_geometry():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "lazybandedmatrices.jl_b200"))
+    from lbm_b200.shard import RowShard, split_rows
+    n, l, u, W = 1 << 27, 8, 8, 8
+    plans = [RowShard.plan(n, l, u, r, W) for r in range(W)]
+    assert plans[0].r0 == 0 and plans[-1].r1 == n
+    for a, b in zip(plans[:-1], plans[1:]):
+        assert a.r1 == b.r0
+    assert plans[0].left == 0 and plans[0].kl_loc == l and plans[0].ku_loc == u
+    assert plans[3].left == l and plans[3].kl_loc == 0 and plans[3].ku_loc == l + u
+    assert plans[-1].right == 0
+    assert all(p.r0 % 4 == 0 for p in plans)
+    # uneven split, world that does not divide n
+    rr = [split_rows(1003, 3, r) for r in range(3)]
+    assert rr[0][0] == 0 and rr[-1][1] == 1003 and all(a[1] == b[0] for a, b in zip(rr[:-1], rr[1:]))
+    from lbm_b200.errors import LbmArgumentError
+    with pytest.raises(LbmArgumentError):
+        RowShard.plan(64, 128, 128, 0, 4)
