@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""All BASELINE.json configs on ONE GPU: time, algorithmic GB/s (or TFLOP/s), fraction of the
+measured roofline.  JSON lines on stdout.
+    python benchmarks/configs.py [--only C2,C3] [--small]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "lazybandedmatrices.jl_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+import lbm_b200 as L  # noqa: E402
+
+PEAK = 6551.7
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def emit(name, ms, byts=None, flops=None, **kw):
+    r = {"config": name, "ms": ms}
+    if byts is not None:
+        r["alg_GB"] = byts / 1e9
+        r["GBs"] = byts / ms / 1e6
+        r["frac_hbm_measured"] = r["GBs"] / PEAK
+    if flops is not None:
+        r["TFLOPs"] = flops / ms / 1e9
+    r.update(kw)
+    print(json.dumps(r), flush=True)
+
+
+def vec(n, seed, dt=torch.float64):
+    t = torch.empty(n, dtype=dt, device="cuda")
+    L.fill_uniform(t, seed)
+    return t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="M,C1,C2,C3,C4,C5")
+    ap.add_argument("--small", action="store_true")
+    a = ap.parse_args()
+    only = a.only.split(",")
+    sh = 3 if a.small else 0
+    h = L.handle_for(0)
+
+    if "M" in only:
+        n = 1 << (27 - sh)
+        for (l, u) in ((1, 1), (8, 8)):
+            A = L.brand(n, n, l, u)
+            x, y = vec(n, 9), torch.empty(n, dtype=torch.float64, device="cuda")
+            emit(f"M gbmv f64 n=2^{27 - sh} l=u={l}", timeit(lambda: L.mul_(y, A, x)), 8 * n * (l + u + 3))
+            emit(f"M gbmv^T f64 n=2^{27 - sh} l=u={l}", timeit(lambda: L.mul_(y, A.T, x)), 8 * n * (l + u + 3))
+            del A, x, y
+            torch.cuda.empty_cache()
+        n = 1 << (25 - sh)
+        A = L.brand(n, n, 128, 128)
+        x, y = vec(n, 9), torch.empty(n, dtype=torch.float64, device="cuda")
+        emit(f"M gbmv f64 n=2^{25 - sh} l=u=128 (n=2^27 needs >= 2 GPUs)", timeit(lambda: L.mul_(y, A, x), 5, 2), 8 * n * 259)
+        emit(f"M gbmv^T f64 n=2^{25 - sh} l=u=128", timeit(lambda: L.mul_(y, A.T, x), 5, 2), 8 * n * 259)
+        del A, x, y
+        torch.cuda.empty_cache()
+
+    if "C1" in only:
+        n = 10_000
+        A = L.brand(n, n, 1, 1)
+        M = L.ApplyMatrix("*", A, A)
+        x, y = vec(n, 9), torch.empty(n, dtype=torch.float64, device="cuda")
+        Cm = M.materialize()
+        emit("C1 materialize A*A n=10^4 (1,1)->(2,2)", timeit(lambda: L.gbmm(A, A, out=Cm), 50, 5), 8 * n * 11, note="launch-latency bound: report us")
+        emit("C1 mul!(y, ApplyMatrix(*,A,A), x) n=10^4", timeit(lambda: M.mul_(y, x), 50, 5), 8 * n * 10, note="two gbmv launches + a temporary")
+
+    if "C2" in only:
+        n = 1 << (28 - sh)
+        d, e, x = vec(n, 1), vec(n - 1, 2), vec(n, 4)
+        y = torch.empty(n, dtype=torch.float64, device="cuda")
+        for nm, A, arr in (("SymTridiagonal", L.SymTridiagonal(d, e), 4), ("Bidiagonal U", L.Bidiagonal(d, e, "U"), 4),
+                           ("Bidiagonal L", L.Bidiagonal(d, e, "L"), 4)):
+            emit(f"C2 {nm} mul! f64 n=2^{28 - sh}", timeit(lambda: L.mul_(y, A, x)), arr * 8 * n)
+        e2 = vec(n - 1, 3)
+        T = L.Tridiagonal(e, d, e2)
+        emit(f"C2 Tridiagonal mul! f64 n=2^{28 - sh}", timeit(lambda: L.mul_(y, T, x)), 5 * 8 * n)
+        h.set_tuning(tri_force_shuffle=1)
+        emit(f"C2 SymTridiagonal (shuffle kernel) n=2^{28 - sh}", timeit(lambda: L.mul_(y, L.SymTridiagonal(d, e), x)), 4 * 8 * n)
+        h.set_tuning(tri_force_shuffle=0)
+        del d, e, e2, x, y
+        torch.cuda.empty_cache()
+
+    if "C3" in only:
+        g = 8192 >> sh
+        hh = 1.0 / g
+        D = L.banded_from_diagonals(g, {0: -2.0 / hh**2, 1: 1.0 / hh**2, -1: 1.0 / hh**2})
+        Lap = L.KronSum(D, D)
+        x = vec(g * g, 5)
+        y = torch.empty_like(x)
+        best = None
+        for tr, tc in ((256, 16), (256, 32), (512, 16), (128, 32), (1024, 8), (256, 8), (512, 32)):
+            h.set_tuning(kron_tr=tr, kron_tc=tc)
+            ms = timeit(lambda: Lap.mul_(y, x))
+            emit(f"C3 2-D Laplacian kronsum {g}x{g} tile {tr}x{tc}", ms, 16 * g * g)
+            if best is None or ms < best[0]:
+                best = (ms, tr, tc)
+        h.set_tuning(kron_tr=0, kron_tc=0)
+        emit(f"C3 2-D Laplacian kronsum {g}x{g} default", timeit(lambda: Lap.mul_(y, x)), 16 * g * g, best_tile=best[1:])
+        del x, y
+        torch.cuda.empty_cache()
+
+    if "C5" in only:
+        batch, n = 4096 >> sh, 4096
+        fs = [torch.empty((batch, n, 9), dtype=torch.float32, device="cuda") for _ in range(3)]
+        for i, f in enumerate(fs):
+            L.fill_uniform(f, 1 + i)
+        byts = batch * 4 * n * (9 + 9 + 9 + 25)
+        flops = batch * 2 * n * (9 * 9 + 17 * 9)
+        for tile in (64, 128, 256, 512):
+            h.set_tuning(chain_tile=tile)
+            emit(f"C5 fused chain A*B*C f32 batch={batch} n=4096 (4,4)^3 tile={tile}",
+                 timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2), byts, flops)
+        h.set_tuning(chain_tile=0)
+        del fs
+        torch.cuda.empty_cache()
+
+    if "C4" in only:
+        n = 1 << (20 - sh)
+        A = L.brand(n, n, 128, 128, seed=1)
+        B = L.brand(n, n, 128, 128, seed=2)
+        Cm = L.BandedMatrix(torch.empty((n, 513), dtype=torch.float64, device="cuda"), n, 256, 256)
+        flops = 2 * n * 257 * 257
+        byts = 8 * n * (257 + 257 + 513)
+        for force in (1, 0):
+            h.set_tuning(gbmm_force=force)
+            ms = timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1)
+            emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 gbmm_force={force}", ms, byts, flops)
+        h.set_tuning(gbmm_force=0)
+
+
+if __name__ == "__main__":
+    main()

@@ -231,6 +231,211 @@ __global__ void __launch_bounds__(256) gbmm_chain3_kernel(const ChainArgs<T> a) 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// register-blocked fused chain for compile-time bands (the (4,4)^3 Float32 config C5)
+// ------------------------------------------------------------------------------------------
+// Thread-per-4-columns: a thread keeps the 4 output columns of a product (band rows in
+// registers) and streams the 12 operand columns it needs from shared memory, so each smem
+// value feeds up to 4 FMAs (~0.33 LDS per MAC instead of 2).  Operand tiles are stored with a
+// mod-4 SPLIT column order -- column c lives in slot (c % 4) * H + c / 4 with an odd column
+// pitch -- which makes "thread t reads column 4t + w" a stride-(odd) access: bank-conflict-free.
+// Out-of-matrix columns are zero-filled, coefficient loads are masked BY INDEX, and garbage in
+// out-of-matrix band slots can only reach out-of-matrix outputs, which are stored as 0.
+constexpr int CH_NT = 128;           // phase-2 threads (4 columns each) -> 512 columns per CTA
+constexpr int CH_TCOL = 4 * CH_NT;
+
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
+struct ChainGeom {
+    static constexpr int LDA = KLA + KUA + 1, LDB = KLB + KUB + 1, LDC = KLC + KUC + 1;
+    static constexpr int L01 = KLA + KLB, U01 = KUA + KUB, LD01 = L01 + U01 + 1;
+    static constexpr int L3 = L01 + KLC, U3 = U01 + KUC, LDD = L3 + U3 + 1;
+    // halo columns, rounded to multiples of 4 so every tile start stays 4-aligned
+    static constexpr int HQ = ((KLC > KUC ? KLC : KUC) + 3) / 4 * 4;           // AB/B halo each side
+    static constexpr int HP = HQ + ((KLB > KUB ? KLB : KUB) + 3) / 4 * 4;      // A halo each side
+    static constexpr int NQ = CH_TCOL + 2 * HQ;    // AB / B columns per tile
+    static constexpr int NP = CH_TCOL + 2 * HP;    // A columns per tile
+    static constexpr int PA = LDA | 1, PB = LDB | 1, PC = LDC | 1, P01 = LD01 | 1, PD = LDD | 1;  // odd pitches
+    static constexpr int HA4 = NP / 4, HB4 = NQ / 4, HC4 = CH_TCOL / 4;
+    static constexpr int OFF_B = NP * PA, OFF_C = OFF_B + NQ * PB, OFF_AB = OFF_C + CH_TCOL * PC;
+    // D staging starts at 0 and may overlap every operand tile: all are dead by then
+    static constexpr int SMEM_ELEMS = (OFF_AB + NQ * P01) > (CH_TCOL * PD) ? (OFF_AB + NQ * P01) : (CH_TCOL * PD);
+};
+
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
+__global__ void __launch_bounds__(CH_NT + 32) gbmm_chain3_reg_kernel(int64_t n, const T *__restrict__ A, int64_t sA_,
+                                                                    const T *__restrict__ B, int64_t sB_,
+                                                                    const T *__restrict__ C, int64_t sC_,
+                                                                    T *__restrict__ D, int64_t sD_) {
+    using G = ChainGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    T *sA = sm, *sB = sm + G::OFF_B, *sC = sm + G::OFF_C, *sAB = sm + G::OFF_AB;
+    T *sD = sm;  // D staging; only written after every operand tile is dead
+    const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
+    const int64_t b = blockIdx.y;
+    const int64_t j0 = (int64_t)blockIdx.x * CH_TCOL;
+    const int64_t q0 = j0 - G::HQ;  // first AB / B column of the tile (may be < 0)
+    const int64_t p0 = j0 - G::HP;  // first A column of the tile
+    const T *Ag = A + b * sA_;
+    const T *Bg = B + b * sB_;
+    const T *Cg = C + b * sC_;
+    T *Dg = D + b * sD_;
+
+    // ---- stage operand tiles (coalesced global reads -> split-column smem), zero outside [0,n)
+    for (int e = tid; e < G::NP * G::LDA; e += nthr) {
+        const int lc = e / G::LDA, f = e - lc * G::LDA;
+        const int64_t c = p0 + lc;
+        sA[((lc & 3) * G::HA4 + (lc >> 2)) * G::PA + f] = (c >= 0 && c < n) ? Ag[c * G::LDA + f] : (T)0;
+    }
+    for (int e = tid; e < G::NQ * G::LDB; e += nthr) {
+        const int lc = e / G::LDB, f = e - lc * G::LDB;
+        const int64_t c = q0 + lc;
+        sB[((lc & 3) * G::HB4 + (lc >> 2)) * G::PB + f] = (c >= 0 && c < n) ? Bg[c * G::LDB + f] : (T)0;
+    }
+    for (int e = tid; e < CH_TCOL * G::LDC; e += nthr) {
+        const int lc = e / G::LDC, f = e - lc * G::LDC;
+        const int64_t c = j0 + lc;
+        sC[((lc & 3) * G::HC4 + (lc >> 2)) * G::PC + f] = (c < n) ? Cg[c * G::LDC + f] : (T)0;
+    }
+    __syncthreads();
+
+    // ---- phase 1: AB[:, q0 + 4u + w], w = 0..3, for u = tid < NQ/4 --------------------------
+    if (tid < G::NQ / 4) {
+        const int u = tid;
+        T acc[4][G::LD01];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int r = 0; r < G::LD01; ++r) acc[w][r] = (T)0;
+        // B coefficients of the 4 columns: bco[w][e'] = B[q+e, q], e = e' - KUB, masked by index
+        T bco[4][G::LDB];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int64_t q = q0 + 4 * u + w;
+#pragma unroll
+            for (int ep = 0; ep < G::LDB; ++ep) {
+                const int64_t p = q + ep - KUB;
+                bco[w][ep] = (q >= 0 && q < n && p >= 0 && p < n) ? sB[(w * G::HB4 + u) * G::PB + ep] : (T)0;
+            }
+        }
+        // A columns needed: p = q + e for the 4 q's: local A index = (q0 - p0) + 4u + w + e, i.e.
+        // la = 4u + v with v = (HP - HQ) - KUB .. (HP - HQ) + 3 + KLB
+        constexpr int V0 = (G::HP - G::HQ) - KUB;
+        constexpr int NV = 4 + KLB + KUB;
+#pragma unroll
+        for (int vv = 0; vv < NV; ++vv) {
+            const int v = V0 + vv;                     // column offset relative to 4u (may be negative)
+            const int vq = (v % 4 + 4) % 4;            // (4u + v) % 4
+            const int vd = (v - vq) / 4;               // (4u + v) / 4 - u
+            const T *col = sA + (vq * G::HA4 + u + vd) * G::PA;
+            T av[G::LDA];
+#pragma unroll
+            for (int f = 0; f < G::LDA; ++f) av[f] = col[f];
+            // this A column (p) pairs with output column w when e = p - q = vv - KUB ... :
+            //   p = q0' + 4u + v, q = q0' + 4u + (HP-HQ) + w  =>  e = v - (HP-HQ) - w = vv - KUB - w
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int e = vv - KUB - w;
+                if (e >= -KUB && e <= KLB) {
+                    const T bc = bco[w][e + KUB];
+                    // A[i,p], band row f  ->  AB band row r = U01 + i - q = U01 + (f - KUA) + e
+#pragma unroll
+                    for (int f = 0; f < G::LDA; ++f) acc[w][G::U01 - KUA + e + f] = fma(av[f], bc, acc[w][G::U01 - KUA + e + f]);
+                }
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int64_t q = q0 + 4 * u + w;
+            const bool qok = q >= 0 && q < n;
+#pragma unroll
+            for (int r = 0; r < G::LD01; ++r) sAB[(w * G::HB4 + u) * G::P01 + r] = qok ? acc[w][r] : (T)0;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: D[:, j0 + 4t + w] = sum_e AB[:, j+e] * C[j+e, j] ---------------------------
+    T dacc[4][G::LDD];
+    if (tid < CH_NT) {
+        const int t = tid;
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int r = 0; r < G::LDD; ++r) dacc[w][r] = (T)0;
+        T cco[4][G::LDC];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int64_t j = j0 + 4 * t + w;
+#pragma unroll
+            for (int ep = 0; ep < G::LDC; ++ep) {
+                const int64_t q = j + ep - KUC;
+                cco[w][ep] = (j < n && q >= 0 && q < n) ? sC[(w * G::HC4 + t) * G::PC + ep] : (T)0;
+            }
+        }
+        constexpr int V0 = G::HQ - KUC;
+        constexpr int NV = 4 + KLC + KUC;
+#pragma unroll
+        for (int vv = 0; vv < NV; ++vv) {
+            const int v = V0 + vv;
+            const int vq = (v % 4 + 4) % 4;
+            const int vd = (v - vq) / 4;
+            const T *col = sAB + (vq * G::HB4 + t + vd) * G::P01;
+            T av[G::LD01];
+#pragma unroll
+            for (int f = 0; f < G::LD01; ++f) av[f] = col[f];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int e = vv - KUC - w;
+                if (e >= -KUC && e <= KLC) {
+                    const T cc = cco[w][e + KUC];
+                    // AB[i,q] band row f -> D band row r = U3 + i - j = U3 + (f - U01) + e
+#pragma unroll
+                    for (int f = 0; f < G::LD01; ++f) dacc[w][G::U3 - G::U01 + e + f] = fma(av[f], cc, dacc[w][G::U3 - G::U01 + e + f]);
+                }
+            }
+        }
+    }
+    __syncthreads();  // everyone is done reading sC / sAB before D staging overwrites the A/B/C region
+    if (tid < CH_NT) {
+        const int t = tid;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int64_t j = j0 + 4 * t + w;
+#pragma unroll
+            for (int r = 0; r < G::LDD; ++r) {
+                const int64_t i = j + r - G::U3;
+                sD[(w * G::HC4 + t) * G::PD + r] = (i >= 0 && i < n) ? dacc[w][r] : (T)0;
+            }
+        }
+    }
+    __syncthreads();
+    // coalesced copy-out of the contiguous D tile
+    const int64_t ncol = j0 + CH_TCOL <= n ? CH_TCOL : n - j0;
+    T *Dt = Dg + j0 * G::LDD;
+    for (int e = tid; e < (int)ncol * G::LDD; e += nthr) {
+        const int lc = e / G::LDD, r = e - lc * G::LDD;
+        Dt[e] = sD[((lc & 3) * G::HC4 + (lc >> 2)) * G::PD + r];
+    }
+}
+
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
+int chain3_reg_launch(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int64_t sA, const T *B, int64_t sB,
+                      const T *C, int64_t sC, T *D, int64_t sD) {
+    using G = ChainGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    constexpr size_t smem = (size_t)G::SMEM_ELEMS * sizeof(T);
+    static int configured_dev_mask = 0;
+    auto kern = gbmm_chain3_reg_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_dev_mask |= (1 << h->device);
+    }
+    dim3 grid((unsigned)((n + CH_TCOL - 1) / CH_TCOL), (unsigned)batch);
+    kern<<<grid, CH_NT + 32, smem, h->stream>>>(n, A, sA, B, sB, C, sC, D, sD);
+    LBM_LAUNCH_CHECK(h, "gbmm_chain3_reg_kernel");
+    return 0;
+}
+
 template <typename T>
 int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, const int64_t *ku, const T *A, int64_t sA,
                 const T *B, int64_t sB, const T *C, int64_t sC, T *D, int64_t sD) {
@@ -250,6 +455,14 @@ int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, con
     if (!D) return lbm_fail_arg(h, 12, "D == NULL");
     if (batch > 65535) return lbm_fail_arg(h, 2, "batch > 65535 (split the call)");
     lbm_device_guard g(h->device);
+    if (!h->tune.chain_force_generic) {
+        auto all = [&](int64_t l, int64_t u) {
+            return kl[0] == l && kl[1] == l && kl[2] == l && ku[0] == u && ku[1] == u && ku[2] == u;
+        };
+        if (all(4, 4)) return chain3_reg_launch<T, 4, 4, 4, 4, 4, 4>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+        if (all(1, 1)) return chain3_reg_launch<T, 1, 1, 1, 1, 1, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+        if (all(2, 2)) return chain3_reg_launch<T, 2, 2, 2, 2, 2, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+    }
     ChainArgs<T> a;
     a.batch = batch; a.n = n;
     a.kla = (int)kl[0]; a.kua = (int)ku[0]; a.klb = (int)kl[1]; a.kub = (int)ku[1]; a.klc = (int)kl[2]; a.kuc = (int)ku[2];

@@ -398,20 +398,22 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         GbmvArgs<T> a;
         a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda; a.nout = nout;
         a.alpha = alpha; a.beta = beta; a.A = A; a.x = x; a.y = y;
-        // tile: aim for ~32 KB of slab per stage, at least one row per thread
-        int64_t tile = h->tune.gbmv_tile;
-        if (tile <= 0) {
-            tile = (32 * 1024) / (lda * (int64_t)sizeof(T));
-            tile = tile / GBMV_NT * GBMV_NT;
-            if (tile < GBMV_NT) tile = GBMV_NT;
-            if (tile > 2048) tile = 2048;
-        }
-        tile = round_up(tile, GBMV_NT);
+        // Tuned on B200 (profiles/sweep_r01.jsonl): ~33-39 KB stages, 2-deep ring, and as many
+        // CTAs per SM as keep ~200 KB of bulk copies in flight per SM.
         auto stage_elems = [&](int64_t tl, int64_t &sa, int64_t &sx) {
             sa = round_up((tl + kl + ku) * lda + EPV, EPV);
             sx = round_up(tl + kl + ku + EPV, EPV);
         };
         int64_t sa, sx;
+        int64_t tile = h->tune.gbmv_tile;
+        if (tile <= 0) {
+            tile = GBMV_NT;
+            for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {
+                stage_elems(tl, sa, sx);
+                if ((sa + sx) * (int64_t)sizeof(T) <= 36 * 1024) tile = tl;
+            }
+        }
+        tile = round_up(tile, GBMV_NT);
         stage_elems(tile, sa, sx);
         while (tile > GBMV_NT && (sa + sx) * (int64_t)sizeof(T) + 128 > smem_cap) {
             tile -= GBMV_NT;
@@ -422,9 +424,12 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         a.sA_elems = sa;
         a.sx_elems = sx;
         const int64_t stage_bytes = (sa + sx) * (int64_t)sizeof(T);
-        int64_t ctas = h->tune.gbmv_ctas_per_sm > 0 ? h->tune.gbmv_ctas_per_sm : 2;
-        int64_t stages = h->tune.gbmv_stages > 0 ? h->tune.gbmv_stages : 3;
+        int64_t stages = h->tune.gbmv_stages > 0 ? h->tune.gbmv_stages : 2;
         if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+        int64_t ctas = h->tune.gbmv_ctas_per_sm > 0 ? h->tune.gbmv_ctas_per_sm
+                                                    : (200 * 1024) / (stages * stage_bytes + 256);
+        if (ctas < 1) ctas = 1;
+        if (ctas > 8) ctas = 8;
         // fit ctas * (128 + stages*stage_bytes) into the SM's shared memory
         const int64_t sm_smem = 227 * 1024;
         while (stages > 1 && ctas * (stages * stage_bytes + 128 + 1024) > sm_smem) --stages;
@@ -454,7 +459,7 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         a.sA_elems = round_up(chunk * lda + EPV, EPV);
         a.sx_elems = round_up(chunk + EPV, EPV);
         const int64_t stage_bytes = (a.sA_elems + a.sx_elems) * (int64_t)sizeof(T);
-        int64_t stages = h->tune.gbmvw_stages > 0 ? h->tune.gbmvw_stages : 3;
+        int64_t stages = h->tune.gbmvw_stages > 0 ? h->tune.gbmvw_stages : 3;  // 2..6 within noise on B200
         if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
         while (stages > 1 && stages * stage_bytes + 128 > smem_cap) --stages;
         a.stages = (int)stages;

@@ -8,10 +8,14 @@
 // a 9-values-per-column BandedBlockBandedMatrix (4.8 GB at 8192^2); here the only HBM traffic
 // is X in, Y out, plus the two tiny band arrays.
 //
-// One fused kernel: a CTA owns a TR x TC tile of Y, stages the (TR+klb+kub) x (TC+kla+kua)
-// halo'd tile of X in shared memory (zero outside the grid), stages the tile's coefficient
-// rows of A (per column) and B (per row) with out-of-matrix slots masked to zero BY INDEX, then
-// each thread walks its rows across the tile's columns.
+//  * kron_ring_kernel (narrow bands, aligned grid -- the 2-D Laplacian case): a CTA owns one strip
+//    of TR rows and walks column chunks of G columns; each chunk's halo'd X tile arrives as one
+//    1-D bulk TMA copy per grid column into a multi-stage smem ring (mbarrier-guarded).  B's
+//    coefficients for the thread's rows stay in registers for the whole sweep, A's per-column
+//    coefficients are warp-uniform loads, Y is written coalesced.  Edge tiles predicate by INDEX.
+//  * kron_tile_kernel (any bands / any alignment): a CTA owns a TR x TC tile of Y, stages the
+//    (TR+klb+kub) x (TC+kla+kua) halo'd tile of X in shared memory (zero outside the grid) and
+//    the tile's coefficient rows of A and B with out-of-matrix slots masked to zero BY INDEX.
 #include "lbm_common.cuh"
 
 namespace {
@@ -97,6 +101,222 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// TMA-ring kernel for narrow bands
+// ------------------------------------------------------------------------------------------
+using namespace lbm;
+
+template <typename T>
+struct KronRingArgs {
+    int64_t n1, n2;
+    int kla, kua, klb, kub;
+    int64_t lda, ldb;
+    const T *A;
+    const T *B;
+    T alpha, beta;
+    const T *x;
+    T *y;
+    int tr;        // rows per strip (256 * RPT)
+    int g;         // output columns per chunk
+    int hp;        // row halo padded to a 16-byte multiple
+    int seg;       // smem elements per staged grid column = tr + 2*hp
+    int stages;
+    int64_t nchunks;
+};
+
+template <typename T, int NBA, int NBB, int RPT>
+__global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int S = a.stages;
+    const int scols = a.g + a.kla + a.kua;
+    const int64_t stage_elems = (int64_t)scols * a.seg;
+    const int64_t r0 = (int64_t)blockIdx.x * a.tr;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t first = blockIdx.y, step = gridDim.y;
+    const int64_t mine = first < a.nchunks ? (a.nchunks - first + step - 1) / step : 0;
+    // rows staged per grid column: [rs, re) (both 16-byte aligned: n2 % EPV == 0)
+    const int64_t rs = r0 - a.hp > 0 ? r0 - a.hp : 0;
+    const int64_t re = r0 + a.tr + a.hp < a.n2 ? r0 + a.tr + a.hp : a.n2;
+    const uint32_t col_bytes = (uint32_t)((re - rs) * (int64_t)sizeof(T));
+    const int roff = (int)(rs - (r0 - a.hp));  // smem row offset of rs
+
+    auto issue = [&](int64_t q, int s) {  // thread 0 only
+        const int64_t c0 = q * a.g;
+        int64_t ca = c0 - a.kla > 0 ? c0 - a.kla : 0;
+        int64_t cb = c0 + a.g + a.kua < a.n1 ? c0 + a.g + a.kua : a.n1;
+        T *st = sbase + (int64_t)s * stage_elems;
+        mbar_add_tx(&bars[s], (uint32_t)(cb - ca) * col_bytes);
+        for (int64_t c = ca; c < cb; ++c)
+            bulk_g2s(st + (c - (c0 - a.kla)) * a.seg + roff, a.x + c * a.n2 + rs, col_bytes, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+    if (tid == 0) {
+        const int64_t pro = mine < S ? mine : S;
+        for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
+    }
+
+    // A coefficients of a chunk's columns, ca[cc][t] = A[c, c-kla+t] (zero outside the matrix):
+    // one element per thread, prefetched into a register one chunk ahead and parked in a
+    // double-buffered smem table, so the column loop never waits on a global load.
+    T *sCA = sbase + (int64_t)S * stage_elems;  // [2][g*NBA]
+    const int ncoef = a.g * NBA;
+    auto load_coef = [&](int64_t q) -> T {
+        if (tid >= ncoef) return (T)0;
+        const int cc = tid / NBA, t = tid - cc * NBA;
+        const int64_t c = q * a.g + cc;
+        const int64_t qq = c - a.kla + t;
+        return (c < a.n1 && qq >= 0 && qq < a.n1) ? a.A[(a.kua + a.kla - t) + a.lda * qq] : (T)0;
+    };
+    if (mine > 0 && tid < ncoef) sCA[tid] = load_coef(first);
+
+    // B coefficients of this thread's rows: cb[k][t] = B[r, r-klb+t], zero outside the matrix
+    T cbv[RPT][NBB];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int64_t r = r0 + tid + 256 * k;
+#pragma unroll
+        for (int t = 0; t < NBB; ++t) {
+            const int64_t p = r - a.klb + t;
+            cbv[k][t] = (r < a.n2 && p >= 0 && p < a.n2) ? a.B[(a.kub + a.klb - t) + a.ldb * p] : (T)0;
+        }
+    }
+    const bool row_edge = (r0 - a.klb < 0) || (r0 + a.tr + a.kub > a.n2);
+    __syncthreads();  // sCA[0] visible
+
+    for (int64_t kk = 0; kk < mine; ++kk) {
+        const int s = (int)(kk % S);
+        const uint32_t parity = (uint32_t)((kk / S) & 1);
+        const int64_t q = first + kk * step;
+        const int64_t c0 = q * a.g;
+        const int gq = (int)(c0 + a.g < a.n1 ? a.g : a.n1 - c0);
+        const T *st = sbase + (int64_t)s * stage_elems;
+        const T *ca = sCA + (kk & 1) * ncoef;
+        const bool edge = row_edge || (c0 - a.kla < 0) || (c0 + gq + a.kua > a.n1);
+        T cnext = (T)0;
+        if (kk + 1 < mine) cnext = load_coef(q + step);  // in flight during this chunk's compute
+        mbar_wait(&bars[s], parity);
+#pragma unroll 2
+        for (int cc = 0; cc < gq; ++cc) {
+            const int64_t c = c0 + cc;
+            T cav[NBA];
+#pragma unroll
+            for (int t = 0; t < NBA; ++t) cav[t] = ca[cc * NBA + t];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int rr = tid + 256 * k;
+                const int64_t r = r0 + rr;
+                if (r >= a.n2) continue;
+                const T *xa = st + (int64_t)cc * a.seg + rr + a.hp;              // X[r, c-kla+t] at xa[t*seg]
+                const T *xb = st + (int64_t)(cc + a.kla) * a.seg + rr + a.hp - a.klb;  // X[r-klb+t, c] at xb[t]
+                T acc = 0;
+                if (!edge) {
+#pragma unroll
+                    for (int t = 0; t < NBA; ++t) acc = fma(cav[t], xa[(int64_t)t * a.seg], acc);
+#pragma unroll
+                    for (int t = 0; t < NBB; ++t) acc = fma(cbv[k][t], xb[t], acc);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < NBA; ++t) {
+                        const int64_t qq = c - a.kla + t;
+                        if (qq >= 0 && qq < a.n1) acc = fma(cav[t], xa[(int64_t)t * a.seg], acc);
+                    }
+#pragma unroll
+                    for (int t = 0; t < NBB; ++t) {
+                        const int64_t p = r - a.klb + t;
+                        if (p >= 0 && p < a.n2) acc = fma(cbv[k][t], xb[t], acc);
+                    }
+                }
+                const int64_t o = r + a.n2 * c;
+                a.y[o] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[o], a.alpha * acc);
+            }
+        }
+        if (kk + 1 < mine && tid < ncoef) sCA[((kk + 1) & 1) * ncoef + tid] = cnext;
+        __syncthreads();
+        if (tid == 0 && kk + S < mine) issue(first + (kk + S) * step, s);
+    }
+}
+
+template <typename T, int NBA, int NBB, int RPT>
+int kron_ring_launch3(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem) {
+    static int configured_dev_mask = 0;
+    auto kern = kron_ring_kernel<T, NBA, NBB, RPT>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        configured_dev_mask |= (1 << h->device);
+    }
+    kern<<<grid, 256, smem, h->stream>>>(a);
+    LBM_LAUNCH_CHECK(h, "kron_ring_kernel");
+    return 0;
+}
+
+template <typename T, int NBA, int NBB>
+int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem) {
+    switch (a.tr / 256) {
+        case 1: return kron_ring_launch3<T, NBA, NBB, 1>(h, a, grid, smem);
+        case 2: return kron_ring_launch3<T, NBA, NBB, 2>(h, a, grid, smem);
+        default: return kron_ring_launch3<T, NBA, NBB, 4>(h, a, grid, smem);
+    }
+}
+
+// returns true (and the launch status in *rc) when the ring kernel took the call
+template <typename T>
+bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda,
+                   int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int64_t nba = kla + kua + 1, nbb = klb + kub + 1;
+    const bool shape_ok = (nba == 3 || nba == 1 || nba == 5) && (nbb == 3 || nbb == 1 || nbb == 5) &&
+                          !(nba == 5 && nbb == 1) && !(nba == 1 && nbb == 5) && !(nba == 1 && nbb == 1);
+    if (!shape_ok || n2 % EPV != 0 || !lbm_aligned16(x) || n2 < 512 || n1 < 8 || h->tune.kron_force_tile) return false;
+    KronRingArgs<T> a;
+    a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
+    a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
+    int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
+    tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
+    int64_t g = h->tune.kron_tc > 0 ? h->tune.kron_tc : 16;
+    if (g > n1) g = n1;
+    if (g * nba > 256) g = 256 / nba;  // one A coefficient per thread per chunk
+    const int64_t hmax = klb > kub ? klb : kub;
+    a.hp = (int)((hmax + EPV - 1) / EPV * EPV);
+    a.tr = (int)tr;
+    a.seg = (int)(tr + 2 * a.hp);
+    int64_t stages = h->tune.kron_stages > 0 ? h->tune.kron_stages : 2;
+    const int64_t sm_smem = 227 * 1024;
+    auto stage_bytes = [&](int64_t gg) { return (gg + kla + kua) * (int64_t)a.seg * (int64_t)sizeof(T); };
+    while (g > 2 && stages * stage_bytes(g) + 4096 > sm_smem) g /= 2;
+    a.g = (int)g;
+    a.nchunks = (n1 + g - 1) / g;
+    int64_t cps = h->tune.kron_ctas_per_sm > 0 ? h->tune.kron_ctas_per_sm : (200 * 1024) / (stages * stage_bytes(g) + 256);
+    if (cps < 1) cps = 1;
+    if (cps > 8) cps = 8;
+    while (stages > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --stages;
+    while (cps > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --cps;
+    a.stages = (int)stages;
+    const int64_t nstrips = (n2 + tr - 1) / tr;
+    int64_t phases = ((int64_t)h->sm_count * cps + nstrips - 1) / nstrips;
+    if (phases > a.nchunks) phases = a.nchunks;
+    if (phases > 65535) phases = 65535;
+    if (phases < 1) phases = 1;
+    dim3 grid((unsigned)nstrips, (unsigned)phases);
+    const size_t smem = (size_t)(128 + stages * stage_bytes(g) + 2 * g * nba * (int64_t)sizeof(T));
+    if (nba == 3 && nbb == 3) *rc = kron_ring_launch2<T, 3, 3>(h, a, grid, smem);
+    else if (nba == 1 && nbb == 3) *rc = kron_ring_launch2<T, 1, 3>(h, a, grid, smem);
+    else if (nba == 3 && nbb == 1) *rc = kron_ring_launch2<T, 3, 1>(h, a, grid, smem);
+    else if (nba == 5 && nbb == 5) *rc = kron_ring_launch2<T, 5, 5>(h, a, grid, smem);
+    else if (nba == 3 && nbb == 5) *rc = kron_ring_launch2<T, 3, 5>(h, a, grid, smem);
+    else *rc = kron_ring_launch2<T, 5, 3>(h, a, grid, smem);
+    return true;
+}
+
 template <typename T>
 int kron_launch(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda, int64_t klb,
                 int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int useA, int useB) {
@@ -164,6 +384,7 @@ int kronsum_impl(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t ku
     int rc = kron_check<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, x, y);
     if (rc || n1 == 0 || n2 == 0) return rc;
     lbm_device_guard g(h->device);
+    if (kron_ring_try<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y, &rc)) return rc;
     return kron_launch<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y, 1, 1);
 }
 

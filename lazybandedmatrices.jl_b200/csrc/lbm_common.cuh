@@ -26,12 +26,16 @@ struct lbm_tuning {
     // tridiagonal kernel
     int64_t tri_ctas_per_sm;  // 0 = auto
     int64_t tri_force_scalar;
+    int64_t tri_force_shuffle; // 1 = use the warp-shuffle kernel for mat-vec too
+    int64_t tri_tile, tri_stages;
     // kron
     int64_t kron_tr, kron_tc;
+    int64_t kron_stages, kron_ctas_per_sm, kron_force_tile;
     // gbmm
     int64_t gbmm_force;       // 0 auto, 1 generic, 2 dmma
     int64_t gbmm_tile;
     int64_t chain_tile;
+    int64_t chain_force_generic;
 };
 
 struct lbm_handle_s {

@@ -5,10 +5,13 @@
 //   Bidiagonal(dv,ev,uplo) src/bidiag.jl:4-15, elements :111-124    (dl or du absent)
 //     y[i] = dl[i-1] x[i-1] + d[i] x[i] + du[i] x[i+1]
 //
-// Pure streaming (4-5 arrays, each element touched once): every array is read with 128-bit
-// coalesced loads; the +-1 shifted operands (x[i-1], x[i+1], dl[i-1]) come from the
-// neighbouring lane through warp shuffles, with one scalar load at each warp edge.  A
-// SymTridiagonal reads ev once and reuses it for both off-diagonals.
+// Pure streaming (4-5 arrays, each element touched once).
+//  * tridiag_ring_kernel (mat-vec, the benchmarked case): persistent CTAs walk row tiles; the
+//    tile's windows of d, dl, du and x are fetched by 1-D bulk TMA into a multi-stage smem ring
+//    (mbarrier-guarded), so the +-1 shifted operands are plain smem reads and no thread issues a
+//    global load.  A SymTridiagonal stages ev once and uses it for both off-diagonals.
+//  * tridiag_mv_kernel (mat-mat): 128-bit coalesced loads with the shifted operands taken from
+//    the neighbouring lane by warp shuffle; the diagonals stay in registers across the columns.
 #include "lbm_common.cuh"
 
 namespace {
@@ -126,6 +129,111 @@ __global__ void __launch_bounds__(256) tridiag_mv_kernel(int64_t n, const T *__r
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// mat-vec: TMA ring
+// ------------------------------------------------------------------------------------------
+constexpr int TRI_NT = 256;
+
+template <typename T>
+struct TriRingArgs {
+    int64_t n;
+    const T *dl;
+    const T *d;
+    const T *du;
+    const T *x;
+    T *y;
+    T alpha, beta;
+    int64_t tile, ntiles;
+    int stages;
+    int64_t seg;  // smem elements per staged array (tile + 2*EPV, multiple of EPV)
+};
+
+// smem stage layout: [ d | x | lo | hi ], each `seg` elements, all windows starting at the
+// 16-byte aligned element w0 = max(0, i0 - EPV) so that index (i - w0) works for i0-1 .. i1.
+template <typename T, bool HAS_DL, bool HAS_DU, bool SYM>
+__global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<T> a) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    constexpr int NARR = 2 + ((HAS_DL || HAS_DU) ? 1 : 0) + ((HAS_DL && HAS_DU && !SYM) ? 1 : 0);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int S = a.stages;
+    const int64_t stage_elems = a.seg * NARR;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
+    const int64_t noff = a.n - 1;  // length of the off-diagonals actually read
+
+    auto issue = [&](int64_t t, int s) {  // thread 0 only
+        const int64_t i0 = t * a.tile;
+        const int64_t i1 = i0 + a.tile < a.n ? i0 + a.tile : a.n;
+        const int64_t w0 = i0 >= EPV ? i0 - EPV : 0;
+        T *sd = sbase + (int64_t)s * stage_elems;
+        T *sx = sd + a.seg;
+        T *so0 = sx + a.seg;      // dl (or the only off-diagonal / ev)
+        T *so1 = so0 + a.seg;     // du when both are distinct
+        const int64_t x1 = i1 + 1 < a.n ? i1 + 1 : a.n;       // x window [w0, x1)
+        const int64_t o1 = i1 < noff ? i1 : noff;              // off-diagonal window [w0, o1)
+        const int64_t cd = i1 - w0, cx = x1 - w0, co = o1 > w0 ? o1 - w0 : 0;
+        uint32_t bytes = stage_bytes_bulk<T>(cd) + stage_bytes_bulk<T>(cx);
+        if (NARR >= 3) bytes += stage_bytes_bulk<T>(co);
+        if (NARR >= 4) bytes += stage_bytes_bulk<T>(co);
+        mbar_add_tx(&bars[s], bytes);
+        stage_issue<T>(sd, a.d + w0, cd, &bars[s]);
+        stage_issue<T>(sx, a.x + w0, cx, &bars[s]);
+        if (NARR >= 3) stage_issue<T>(so0, (HAS_DL ? a.dl : a.du) + w0, co, &bars[s]);
+        if (NARR >= 4) stage_issue<T>(so1, a.du + w0, co, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+
+    if (tid == 0) {
+        const int64_t pro = mine < S ? mine : S;
+        for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
+    }
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = (int)(k % S);
+        const uint32_t parity = (uint32_t)((k / S) & 1);
+        const int64_t t = first + k * step;
+        const int64_t i0 = t * a.tile;
+        const int64_t i1 = i0 + a.tile < a.n ? i0 + a.tile : a.n;
+        const int64_t w0 = i0 >= EPV ? i0 - EPV : 0;
+        const T *sd = sbase + (int64_t)s * stage_elems;
+        const T *sx = sd + a.seg;
+        const T *slo = sx + a.seg;                                  // dl window (HAS_DL)
+        const T *shi = (HAS_DL && HAS_DU && !SYM) ? slo + a.seg : slo;  // du window
+        mbar_wait(&bars[s], parity);
+        for (int64_t i = i0 + tid; i < i1; i += TRI_NT) {
+            const int r = (int)(i - w0);
+            T acc = 0;
+            if (HAS_DL && i > 0) acc = slo[r - 1] * sx[r - 1];
+            acc = fma(sd[r], sx[r], acc);
+            if (HAS_DU && i < a.n - 1) acc = fma(shi[r], sx[r + 1], acc);
+            a.y[i] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[i], a.alpha * acc);
+        }
+        __syncthreads();
+        if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
+    }
+}
+
+template <typename T, bool HL, bool HU, bool SY>
+int launch_tri_ring(lbm_handle_t h, const TriRingArgs<T> &a, int grid, size_t smem) {
+    static int configured_dev_mask = 0;
+    auto kern = tridiag_ring_kernel<T, HL, HU, SY>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        configured_dev_mask |= (1 << h->device);
+    }
+    kern<<<grid, TRI_NT, smem, h->stream>>>(a);
+    LBM_LAUNCH_CHECK(h, "tridiag_ring_kernel");
+    return 0;
+}
+
 // any-alignment fallback
 template <typename T>
 __global__ void __launch_bounds__(256) tridiag_mv_scalar_kernel(int64_t n, const T *__restrict__ dl,
@@ -165,13 +273,42 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
     constexpr int VN = 16 / (int)sizeof(T);
     const bool aligned = lbm_aligned16(d) && lbm_aligned16(X) && lbm_aligned16(Y) && (!dl || lbm_aligned16(dl)) &&
                          (!du || lbm_aligned16(du)) && (nrhs == 1 || (ldx % VN == 0 && ldy % VN == 0));
-    const int64_t ctas = h->tune.tri_ctas_per_sm > 0 ? h->tune.tri_ctas_per_sm : 8;
+    const int64_t ctas = h->tune.tri_ctas_per_sm > 0 ? h->tune.tri_ctas_per_sm : 16;
     if (!aligned || h->tune.tri_force_scalar) {
         int64_t blocks = (n + 255) / 256;
         if (blocks > (int64_t)h->sm_count * ctas) blocks = (int64_t)h->sm_count * ctas;
         tridiag_mv_scalar_kernel<T><<<(unsigned)blocks, 256, 0, h->stream>>>(n, dl, d, du, alpha, X, ldx, nrhs, beta, Y, ldy);
         LBM_LAUNCH_CHECK(h, "tridiag_mv_scalar_kernel");
         return 0;
+    }
+    if (nrhs == 1 && !h->tune.tri_force_shuffle) {
+        constexpr int EPV = VN;
+        TriRingArgs<T> a;
+        a.n = n; a.dl = dl; a.d = d; a.du = du; a.x = X; a.y = Y; a.alpha = alpha; a.beta = beta;
+        const bool sym = dl && du && dl == du;
+        const int narr = 2 + ((dl || du) ? 1 : 0) + ((dl && du && !sym) ? 1 : 0);
+        int64_t tile = h->tune.tri_tile > 0 ? h->tune.tri_tile : 1024;
+        tile = (tile + TRI_NT - 1) / TRI_NT * TRI_NT;
+        a.tile = tile;
+        a.ntiles = (n + tile - 1) / tile;
+        a.seg = tile + 2 * EPV;
+        const int64_t stage_bytes = a.seg * narr * (int64_t)sizeof(T);
+        int64_t stages = h->tune.tri_stages > 0 ? h->tune.tri_stages : 2;
+        if (stages > 8) stages = 8;
+        int64_t cps = h->tune.tri_ctas_per_sm > 0 ? h->tune.tri_ctas_per_sm : (200 * 1024) / (stages * stage_bytes + 256);
+        if (cps < 1) cps = 1;
+        if (cps > 8) cps = 8;
+        while (stages > 1 && cps * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --stages;
+        while (cps > 1 && cps * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --cps;
+        a.stages = (int)stages;
+        int64_t grid = (int64_t)h->sm_count * cps;
+        if (grid > a.ntiles) grid = a.ntiles;
+        const size_t smem = (size_t)(128 + stages * stage_bytes);
+        if (sym) return launch_tri_ring<T, true, true, true>(h, a, (int)grid, smem);
+        if (dl && du) return launch_tri_ring<T, true, true, false>(h, a, (int)grid, smem);
+        if (dl) return launch_tri_ring<T, true, false, false>(h, a, (int)grid, smem);
+        if (du) return launch_tri_ring<T, false, true, false>(h, a, (int)grid, smem);
+        return launch_tri_ring<T, false, false, false>(h, a, (int)grid, smem);
     }
     const int64_t ngroups = (n + VN - 1) / VN;
     int64_t blocks = (ngroups + 255) / 256;

@@ -137,18 +137,64 @@ class ShardedBanded:
         p = self.plan
         return BandedMatrix(self.data, p.m_loc, p.kl_loc, p.ku_loc)
 
-    def mul_(self, y_own: torch.Tensor, xbuf: torch.Tensor, alpha=1.0, beta=0.0, group=None,
-             local_gbmv: Optional[Callable] = None, exchange: bool = True):
-        """y_own <- alpha * A[r0:r1, :] x + beta * y_own; `xbuf` is the ghost-cell vector whose
-        owned block holds x[r0:r1].  `local_gbmv` exists so the host logic can be exercised on
-        CPU (gloo) with the oracle in tests; the product path is the CUDA kernel."""
+    # ---- row sub-ranges of the slab are again rectangular banded matrices -----------------
+    def _sub(self, a: int, b: int):
+        """Rows [a,b) of the local matrix as (data_view, m, n, kl, ku, col0): the column slice
+        [col0, col1) of the slab with bandwidths shifted by the rows skipped."""
         p = self.plan
-        if exchange and p.world > 1:
-            p.exchange(xbuf, group)
+        c0 = max(0, a - p.kl_loc)
+        c1 = min(p.n_loc, b + p.ku_loc)
+        shift = a - c0
+        return self.data[c0:c1], b - a, c1 - c0, p.kl_loc - shift, p.ku_loc + shift, c0
+
+    def _apply_rows(self, y_own, xbuf, a, b, alpha, beta, local_gbmv):
+        if b <= a:
+            return
+        data, m, n, kl, ku, c0 = self._sub(a, b)
         if local_gbmv is None:
-            from .banded import gbmv_
-            return gbmv_(y_own, self.local_matrix(), xbuf, alpha, beta, "N")
-        return local_gbmv(y_own, self, xbuf, alpha, beta)
+            from .banded import BandedMatrix, gbmv_
+            gbmv_(y_own[a:b], BandedMatrix(data, m, kl, ku), xbuf[c0:c0 + n], alpha, beta, "N")
+        else:
+            local_gbmv(y_own[a:b], data, m, n, kl, ku, xbuf[c0:c0 + n], alpha, beta)
+
+    def interior_rows(self, align: int = 4):
+        """Local rows whose x window lies entirely in the owned block (no ghost needed); the
+        start is rounded up to `align` so the interior sub-slab keeps the 16-byte alignment the
+        bulk-TMA kernel wants."""
+        p = self.plan
+        a = 0 if p.left == 0 else -(-p.l // align) * align
+        b = p.m_loc if p.right == 0 else p.m_loc - p.u
+        a = min(a, p.m_loc)
+        b = max(a, b)
+        return a, b
+
+    def mul_(self, y_own: torch.Tensor, xbuf: torch.Tensor, alpha=1.0, beta=0.0, group=None,
+             local_gbmv: Optional[Callable] = None, exchange: bool = True, overlap: bool = True):
+        """y_own <- alpha * A[r0:r1, :] x + beta * y_own; `xbuf` is the ghost-cell vector whose
+        owned block holds x[r0:r1].
+
+        With `overlap` the ghost exchange (NCCL send/recv on the communicator's stream) runs
+        while the interior rows -- all but the first ~l and last u -- are computed; the few
+        boundary rows follow once the ghosts have landed.  `local_gbmv` exists so this host logic
+        can be exercised on CPU (gloo) with the oracle in tests; the product path is the CUDA
+        kernel."""
+        p = self.plan
+        if not (exchange and p.world > 1):
+            self._apply_rows(y_own, xbuf, 0, p.m_loc, alpha, beta, local_gbmv)
+            return y_own
+        if not overlap:
+            p.exchange(xbuf, group)
+            self._apply_rows(y_own, xbuf, 0, p.m_loc, alpha, beta, local_gbmv)
+            return y_own
+        ops = p.exchange_ops(xbuf, group)
+        works = dist.batch_isend_irecv(ops) if ops else []
+        a, b = self.interior_rows()
+        self._apply_rows(y_own, xbuf, a, b, alpha, beta, local_gbmv)       # overlaps the exchange
+        for w in works:
+            w.wait()
+        self._apply_rows(y_own, xbuf, 0, a, alpha, beta, local_gbmv)       # needs the left ghosts
+        self._apply_rows(y_own, xbuf, b, p.m_loc, alpha, beta, local_gbmv)  # needs the right ghosts
+        return y_own
 
 
 def sharded_chain_mul_(y_own, factors, xbuf, tmp_bufs, group=None, local_gbmv=None):

@@ -45,6 +45,42 @@ def test_gbmm_shapes(L, oracle, dt):
         _cmp_band(oracle, C, want, m, kla + klb, kua + kub, tol)
 
 
+def test_gbmm_dmma_tensor_path(L, oracle):
+    """Wide bands go to the FP64 DMMA tile kernel; gbmm_force=2 forces it on narrow ones too.
+    Same inputs through the diagonal-wise kernel (gbmm_force=1) must agree with the oracle as well."""
+    h = L.handle_for(0)
+    cases = [  # (m, n, k, kla, kua, klb, kub, force)
+        (1000, 1000, 1000, 128, 128, 128, 128, 0), (700, 650, 720, 40, 35, 33, 50, 0), (300, 280, 310, 3, 2, 1, 4, 2),
+        (64, 64, 64, 1, 1, 1, 1, 2), (129, 67, 200, 16, 0, 0, 16, 2), (500, 500, 500, 64, 10, 10, 64, 2), (5, 5, 5, 4, 4, 4, 4, 2),
+    ]
+    for s, (m, n, k, kla, kua, klb, kub, force) in enumerate(cases):
+        A_np, A = _band(L, oracle, m, k, kla, kua, 31 + s, torch.float64)
+        B_np, B = _band(L, oracle, k, n, klb, kub, 32 + s, torch.float64)
+        want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
+        tol = tol_rows(np.float64, min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
+        for f in (force, 1):
+            h.set_tuning(gbmm_force=f)
+            try:
+                before = h.launch_count()
+                C = A @ B
+                torch.cuda.synchronize()
+                nl = h.launch_count() - before
+            finally:
+                h.set_tuning(gbmm_force=0)
+            assert nl == (2 if f != 1 else 1)      # zero-corners + DMMA tile kernel vs the single diag kernel
+            _cmp_band(oracle, C, want, m, kla + klb, kua + kub, tol)
+    # alpha/beta and an output band wider than the product band, tensor path
+    m = n = k = 400
+    A_np, A = _band(L, oracle, m, k, 40, 33, 1, torch.float64)
+    B_np, B = _band(L, oracle, k, n, 35, 36, 2, torch.float64)
+    C0_np, C0 = _band(L, oracle, m, n, 80, 75, 3, torch.float64)
+    want = oracle.gbmm(m, n, k, A_np, 40, 33, B_np, 35, 36, klc=80, kuc=75, alpha=-1.5, beta=0.25, Cin=C0_np)
+    L.gbmm(A, B, alpha=-1.5, out=C0, beta=0.25)
+    got = np.asfortranarray(C0.data.cpu().numpy().T)
+    dg, dw = oracle.band_to_dense(got, m, 80, 75), oracle.band_to_dense(want, m, 80, 75)
+    assert np.max(np.abs(dg - dw)) <= tol_rows(np.float64, 70, 1.0, 1.0, 1.5, 0.25, 1.0)
+
+
 def test_gbmm_alpha_beta_and_wider_output_band(L, oracle):
     m = n = k = 500
     A_np, A = _band(L, oracle, m, k, 2, 1, 1, torch.float64)
@@ -92,7 +128,8 @@ def test_applymatrix_config1(L, oracle):
 def test_chain3_batched(L, oracle, dt):
     npdt = NP[dt]
     for (batch, n, kl, ku) in [(5, 300, [4, 4, 4], [4, 4, 4]), (3, 1000, [1, 2, 0], [0, 1, 3]), (2, 70, [0, 0, 0], [0, 0, 0]),
-                               (7, 4096, [4, 4, 4], [4, 4, 4])]:
+                               (7, 4096, [4, 4, 4], [4, 4, 4]), (3, 1000, [1, 1, 1], [1, 1, 1]), (2, 513, [2, 2, 2], [2, 2, 2]),
+                               (4, 37, [4, 4, 4], [4, 4, 4]), (2, 1027, [4, 4, 4], [4, 4, 4]), (1, 3, [4, 4, 4], [4, 4, 4])]:
         fs = [oracle.fill_uniform(1 + i, batch * n * (kl[i] + ku[i] + 1), npdt).reshape(batch, n, kl[i] + ku[i] + 1)
               for i in range(3)]
         want = oracle.gbmm_chain3_batched(n, kl, ku, *fs)
@@ -110,6 +147,36 @@ def test_chain3_batched(L, oracle, dt):
         assert ld == l3 + u3 + 1
 
 
+def test_chain3_register_kernel_vs_generic_and_nan_corners(L, oracle):
+    """The register-blocked fused chain == the generic fused chain == oracle, and NaNs parked in
+    out-of-matrix storage slots never reach an in-matrix entry."""
+    h = L.handle_for(0)
+    batch, n, kl, ku = 3, 1500, [4, 4, 4], [4, 4, 4]
+    fs = [oracle.fill_uniform(1 + i, batch * n * 9, np.float32).reshape(batch, n, 9).copy() for i in range(3)]
+    want = oracle.gbmm_chain3_batched(n, kl, ku, *fs)
+    for f in fs:                                       # poison every out-of-matrix slot
+        for j in list(range(4)) + list(range(n - 4, n)):
+            for r in range(9):
+                i = j + r - 4
+                if i < 0 or i >= n:
+                    f[:, j, r] = np.nan
+    gs = [torch.from_numpy(f).cuda() for f in fs]
+    tol = tol_rows(np.float32, 9, 1.0, 1.0) * 9 + tol_rows(np.float32, 9, 9.0, 1.0)
+    outs = []
+    for force in (0, 1):
+        h.set_tuning(chain_force_generic=force)
+        try:
+            outs.append(L.chain3_batched(*gs, kl, ku).cpu().numpy())
+        finally:
+            h.set_tuning(chain_force_generic=0)
+    for got in outs:
+        for b in range(batch):
+            dg = oracle.band_to_dense(np.asfortranarray(got[b].T), n, 12, 12)
+            dw = oracle.band_to_dense(np.asfortranarray(want[b].T), n, 12, 12)
+            assert not np.isnan(dg).any()
+            assert np.max(np.abs(dg - dw)) <= tol
+
+
 def _lap(L, n, dtype=torch.float64):
     h = 1.0 / n
     return L.banded_from_diagonals(n, {0: -2.0 / h**2, 1: 1.0 / h**2, -1: 1.0 / h**2}, dtype=dtype)
@@ -117,7 +184,7 @@ def _lap(L, n, dtype=torch.float64):
 
 def test_kronsum_laplacian(L, oracle):
     """2-D Laplacian BlockKron(D2,I)+BlockKron(I,D2) (test/test_blockkron.jl:296-306)."""
-    for n in (4, 33, 257, 1000):
+    for n in (4, 33, 257, 1000, 1024, 2048):
         D = _lap(L, n)
         Dxx = L.BlockKron(D, L.Eye(n))
         Dyy = L.BlockKron(L.Eye(n), D)
@@ -139,7 +206,12 @@ def test_kronsum_laplacian(L, oracle):
 def test_kronsum_general_bands_rectangular_grid(L, oracle, dt):
     npdt = NP[dt]
     for (n1, n2, la, ua, lb, ub) in [(7, 5, 1, 1, 1, 1), (300, 200, 2, 1, 0, 3), (64, 1000, 3, 3, 2, 2), (1, 50, 0, 0, 1, 1),
-                                     (50, 1, 1, 1, 0, 0), (513, 511, 1, 1, 1, 1)]:
+                                     (50, 1, 1, 1, 0, 0), (513, 511, 1, 1, 1, 1),
+                                     # TMA-ring kernel shapes (n2 % 4 == 0, n2 >= 512): tri x tri, diag x tri,
+                                     # tri x diag, penta x penta, mixed, strips/chunks that do not divide the grid
+                                     (100, 1024, 1, 1, 1, 1), (37, 516, 0, 0, 1, 1), (300, 512, 1, 1, 0, 0),
+                                     (129, 2052, 2, 2, 2, 2), (77, 1000, 1, 1, 2, 2), (9, 768, 2, 2, 1, 1),
+                                     (1030, 520, 0, 2, 2, 0), (16, 4096, 1, 1, 1, 1)]:
         A_np, A = _band(L, oracle, n1, n1, la, ua, 3, dt)
         B_np, B = _band(L, oracle, n2, n2, lb, ub, 4, dt)
         x_np = oracle.fill_uniform(5, n1 * n2, npdt)
@@ -149,6 +221,29 @@ def test_kronsum_general_bands_rectangular_grid(L, oracle, dt):
         L.KronSum(A, B).mul_(y, torch.from_numpy(x_np).cuda(), 1.5, 0.5)
         tol = tol_rows(npdt, la + ua + lb + ub + 2, 1.0, 1.0, 1.5, 0.5, 1.0)
         assert np.max(np.abs(y.cpu().numpy() - want)) <= tol
+
+
+def test_kronsum_ring_tunings_match_tile_kernel(L, oracle):
+    """TMA-ring Kronecker kernel under several launch shapes == generic tile kernel == oracle."""
+    h = L.handle_for(0)
+    n1, n2 = 203, 2048
+    A_np, A = _band(L, oracle, n1, n1, 1, 1, 3, torch.float64)
+    B_np, B = _band(L, oracle, n2, n2, 1, 1, 4, torch.float64)
+    x_np = oracle.fill_uniform(5, n1 * n2)
+    want = oracle.kronsum2d_mv(n1, n2, A_np, 1, 1, B_np, 1, 1, x_np)
+    x = torch.from_numpy(x_np).cuda()
+    tol = tol_rows(np.float64, 6, 1.0, 1.0)
+    for tune in ({"kron_force_tile": 1}, {"kron_tr": 256, "kron_tc": 4, "kron_stages": 1, "kron_ctas_per_sm": 1},
+                 {"kron_tr": 512, "kron_tc": 16, "kron_stages": 3}, {"kron_tr": 1024, "kron_tc": 8, "kron_stages": 2},
+                 {"kron_tr": 256, "kron_tc": 64, "kron_stages": 2, "kron_ctas_per_sm": 2}):
+        h.set_tuning(**tune)
+        try:
+            y = torch.full((n1 * n2,), float("nan"), dtype=torch.float64, device="cuda")
+            L.KronSum(A, B).mul_(y, x)
+            got = y.cpu().numpy()
+        finally:
+            h.set_tuning(**{k: 0 for k in tune})
+        assert np.max(np.abs(got - want)) <= tol, tune
 
 
 def test_blockkron_apply(L, oracle):

@@ -109,6 +109,35 @@ def test_structured_mul_errors(L):
             L.mul_(*args)
 
 
+def test_structured_shuffle_kernel_matvec(L, oracle):
+    """The warp-shuffle kernel (mat-mat path) forced onto mat-vec inputs == the TMA-ring kernel."""
+    h = L.handle_for(0)
+    for n in (1, 2, 65, 4097, 300001):
+        dl, d, du = _mk(oracle, n, torch.float64, 3)
+        x = oracle.fill_uniform(9, n)
+        for (a, b, A) in ((dl, du, L.Tridiagonal(_t(dl), _t(d), _t(du))), (du, du, L.SymTridiagonal(_t(d), _t(du))),
+                          (None, du, L.Bidiagonal(_t(d), _t(du), "U")), (dl, None, L.Bidiagonal(_t(d), _t(dl), "L"))):
+            want = oracle.tridiag_mv(n, a if n > 1 else None, d, b if n > 1 else None, x)
+            ring = (A @ _t(x)).cpu().numpy()
+            h.set_tuning(tri_force_shuffle=1)
+            try:
+                shf = (A @ _t(x)).cpu().numpy()
+            finally:
+                h.set_tuning(tri_force_shuffle=0)
+            assert np.max(np.abs(ring - want)) <= tol_rows(np.float64, 3, 1.0, 1.0)
+            assert np.max(np.abs(shf - want)) <= tol_rows(np.float64, 3, 1.0, 1.0)
+    for tune in ({"tri_tile": 256, "tri_stages": 1, "tri_ctas_per_sm": 1}, {"tri_tile": 2048, "tri_stages": 3, "tri_ctas_per_sm": 2}):
+        h.set_tuning(**tune)
+        try:
+            n = 700001
+            dl, d, du = _mk(oracle, n, torch.float64, 5)
+            x = oracle.fill_uniform(9, n)
+            got = (L.Tridiagonal(_t(dl), _t(d), _t(du)) @ _t(x)).cpu().numpy()
+        finally:
+            h.set_tuning(**{k: 0 for k in tune})
+        assert np.max(np.abs(got - oracle.tridiag_mv(n, dl, d, du, x))) <= tol_rows(np.float64, 3, 1.0, 1.0)
+
+
 def test_structured_scalar_fallback_matches(L, oracle):
     n = 50001
     dl, d, du = _mk(oracle, n, torch.float64, 3)

@@ -18,13 +18,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _oracle_local_gbmv(y_own, shard, xbuf, alpha, beta):
+def _oracle_local_gbmv(y, data, m, n, kl, ku, x, alpha, beta):
     from oracle import oracle as O
-    p = shard.plan
-    A = np.asfortranarray(shard.data.numpy().T)
-    out = O.gbmv("N", p.m_loc, p.n_loc, p.kl_loc, p.ku_loc, alpha, A, xbuf.numpy(), beta, y_own.numpy())
-    y_own.copy_(torch.from_numpy(out))
-    return y_own
+    A = np.asfortranarray(data.numpy().T)
+    out = O.gbmv("N", m, n, kl, ku, alpha, A, x.numpy(), beta, y.numpy(), lda=A.shape[0])
+    y.copy_(torch.from_numpy(out))
+    return y
 
 
 def _worker(rank, world, port, n, bands, q):
@@ -55,6 +54,11 @@ def _worker(rank, world, port, n, bands, q):
         y = torch.zeros(f.plan.m_loc, dtype=torch.float64)
         f.mul_(y, xbuf, local_gbmv=_oracle_local_gbmv)
         out["single"] = (f.plan.r0, y.numpy().copy())
+        y_no = torch.zeros(f.plan.m_loc, dtype=torch.float64)      # non-overlapped path, same answer
+        f.mul_(y_no, xbuf, local_gbmv=_oracle_local_gbmv, overlap=False)
+        assert torch.equal(y_no, y)
+        a, b = f.interior_rows()
+        assert 0 <= a <= b <= f.plan.m_loc and (f.plan.left == 0 or a >= f.plan.l) and a % 4 == 0
         # ghosts really were filled from the neighbours
         assert np.array_equal(xbuf.numpy(), x_full[f.plan.c0:f.plan.c1])
         # lazy chain: y = F1 (F2 (... x))
