@@ -54,8 +54,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="M,C1,C2,C3,C4,C5")
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="1 warm-up + 1 timed launch per config (profiling runs)")
     a = ap.parse_args()
     only = a.only.split(",")
+    if a.quick:
+        global timeit
+        _t = timeit
+        timeit = lambda fn, reps=1, warm=1: _t(fn, 1, 1)  # noqa: E731
     sh = 3 if a.small else 0
     h = L.handle_for(0)
 
@@ -109,14 +114,15 @@ def main():
         x = vec(g * g, 5)
         y = torch.empty_like(x)
         best = None
-        for tr, tc in ((256, 16), (256, 32), (512, 16), (128, 32), (1024, 8), (256, 8), (512, 32)):
+        for tr, tc in (() if a.quick else ((256, 16), (256, 32), (512, 16), (128, 32), (1024, 8), (256, 8), (512, 32))):
             h.set_tuning(kron_tr=tr, kron_tc=tc)
             ms = timeit(lambda: Lap.mul_(y, x))
             emit(f"C3 2-D Laplacian kronsum {g}x{g} tile {tr}x{tc}", ms, 16 * g * g)
             if best is None or ms < best[0]:
                 best = (ms, tr, tc)
         h.set_tuning(kron_tr=0, kron_tc=0)
-        emit(f"C3 2-D Laplacian kronsum {g}x{g} default", timeit(lambda: Lap.mul_(y, x)), 16 * g * g, best_tile=best[1:])
+        emit(f"C3 2-D Laplacian kronsum {g}x{g} default", timeit(lambda: Lap.mul_(y, x)), 16 * g * g,
+             best_tile=best[1:] if best else None)
         del x, y
         torch.cuda.empty_cache()
 
@@ -127,12 +133,27 @@ def main():
             L.fill_uniform(f, 1 + i)
         byts = batch * 4 * n * (9 + 9 + 9 + 25)
         flops = batch * 2 * n * (9 * 9 + 17 * 9)
-        for tile in (64, 128, 256, 512):
+        for tile in ((128,) if a.quick else (64, 128, 256, 512)):
             h.set_tuning(chain_tile=tile)
             emit(f"C5 fused chain A*B*C f32 batch={batch} n=4096 (4,4)^3 tile={tile}",
                  timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2), byts, flops)
         h.set_tuning(chain_tile=0)
         del fs
+        torch.cuda.empty_cache()
+
+    if "PEAK" in only:
+        # FP64 denominator: cuBLAS DGEMM (library call, measurement only) + a plain device copy
+        N = 8192
+        a_ = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        b_ = torch.randn(N, N, dtype=torch.float64, device="cuda")
+        c_ = torch.empty_like(a_)
+        ms = timeit(lambda: torch.matmul(a_, b_, out=c_), 5, 2)
+        emit("PEAK cuBLAS DGEMM 8192^3 (FP64 denominator)", ms, None, 2 * N**3)
+        del a_, b_, c_
+        src = torch.empty(1 << 29, dtype=torch.float64, device="cuda")
+        dst = torch.empty_like(src)
+        emit("PEAK torch copy 4 GiB f64 (HBM denominator)", timeit(lambda: dst.copy_(src)), 2 * src.numel() * 8)
+        del src, dst
         torch.cuda.empty_cache()
 
     if "C4" in only:
@@ -142,11 +163,16 @@ def main():
         Cm = L.BandedMatrix(torch.empty((n, 513), dtype=torch.float64, device="cuda"), n, 256, 256)
         flops = 2 * n * 257 * 257
         byts = 8 * n * (257 + 257 + 513)
-        for force in (1, 0):
+        for force in ((0,) if a.quick else (1, 0)):
             h.set_tuning(gbmm_force=force)
             ms = timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1)
             emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 gbmm_force={force}", ms, byts, flops)
         h.set_tuning(gbmm_force=0)
+        if not a.quick:
+            for v, nm in ((2, "3-stage, 3 CTAs/SM"), (3, "2-stage, 5 CTAs/SM")):
+                h.set_tuning(gbmm_variant=v)
+                emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant {v} ({nm})", timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
+            h.set_tuning(gbmm_variant=0)
 
 
 if __name__ == "__main__":

@@ -283,21 +283,54 @@ __global__ void __launch_bounds__(CH_NT + 32) gbmm_chain3_reg_kernel(int64_t n, 
     T *Dg = D + b * sD_;
 
     // ---- stage operand tiles (coalesced global reads -> split-column smem), zero outside [0,n)
-    for (int e = tid; e < G::NP * G::LDA; e += nthr) {
-        const int lc = e / G::LDA, f = e - lc * G::LDA;
-        const int64_t c = p0 + lc;
-        sA[((lc & 3) * G::HA4 + (lc >> 2)) * G::PA + f] = (c >= 0 && c < n) ? Ag[c * G::LDA + f] : (T)0;
-    }
-    for (int e = tid; e < G::NQ * G::LDB; e += nthr) {
-        const int lc = e / G::LDB, f = e - lc * G::LDB;
-        const int64_t c = q0 + lc;
-        sB[((lc & 3) * G::HB4 + (lc >> 2)) * G::PB + f] = (c >= 0 && c < n) ? Bg[c * G::LDB + f] : (T)0;
-    }
-    for (int e = tid; e < CH_TCOL * G::LDC; e += nthr) {
-        const int lc = e / G::LDC, f = e - lc * G::LDC;
-        const int64_t c = j0 + lc;
-        sC[((lc & 3) * G::HC4 + (lc >> 2)) * G::PC + f] = (c < n) ? Cg[c * G::LDC + f] : (T)0;
-    }
+    // All 128-bit loads of a tile are issued back to back (one latency exposure per operand);
+    // tile starts are multiples of 4 columns, so with n % 4 == 0 every vector is 16-byte aligned
+    // and lies wholly inside or wholly outside the matrix.
+    auto stage = [&](T *dst, const T *src_item, int64_t c_first, int ncols_tile, int ld, int pitch, int h4) {
+        const int total = ncols_tile * ld;                       // elements of the tile (multiple of 4)
+        const int64_t e_lo = (c_first < 0 ? -c_first : 0) * (int64_t)ld;            // first valid tile element
+        const int64_t c_end = c_first + ncols_tile < n ? c_first + ncols_tile : n;
+        const int64_t e_hi = (c_end - c_first) * (int64_t)ld;                        // one past the last valid
+        const T *src = src_item + c_first * ld;                   // tile element e lives at src[e]
+        constexpr int VPT = 8;                                    // vectors per thread per batch
+        constexpr int EPVL = 16 / (int)sizeof(T);
+        using V = typename vec16<T>::type;
+        const bool vec_ok = (n % EPVL == 0) && lbm_aligned16_dev(src_item) && (total % EPVL == 0);
+        if (vec_ok) {
+            for (int base = 0; base < total / EPVL; base += VPT * nthr) {
+                V v[VPT];
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const int vi = base + k * nthr + tid;
+                    const int64_t e = (int64_t)vi * EPVL;
+                    const bool ok = vi < total / EPVL && e >= e_lo && e + EPVL <= e_hi;
+                    if (ok) v[k] = ld_stream(reinterpret_cast<const V *>(src + e));
+                    else v[k] = V{};
+                }
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const int vi = base + k * nthr + tid;
+                    if (vi < total / EPVL) {
+                        const T *pv = reinterpret_cast<const T *>(&v[k]);
+#pragma unroll
+                        for (int w = 0; w < EPVL; ++w) {
+                            const int e = vi * EPVL + w;
+                            const int lc = e / ld, f = e - lc * ld;
+                            dst[((lc & 3) * h4 + (lc >> 2)) * pitch + f] = pv[w];
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int e = tid; e < total; e += nthr) {
+                const int lc = e / ld, f = e - lc * ld;
+                dst[((lc & 3) * h4 + (lc >> 2)) * pitch + f] = (e >= e_lo && e < e_hi) ? src[e] : (T)0;
+            }
+        }
+    };
+    stage(sA, Ag, p0, G::NP, G::LDA, G::PA, G::HA4);
+    stage(sB, Bg, q0, G::NQ, G::LDB, G::PB, G::HB4);
+    stage(sC, Cg, j0, CH_TCOL, G::LDC, G::PC, G::HC4);
     __syncthreads();
 
     // ---- phase 1: AB[:, q0 + 4u + w], w = 0..3, for u = tid < NQ/4 --------------------------
@@ -410,12 +443,29 @@ __global__ void __launch_bounds__(CH_NT + 32) gbmm_chain3_reg_kernel(int64_t n, 
         }
     }
     __syncthreads();
-    // coalesced copy-out of the contiguous D tile
+    // coalesced copy-out of the contiguous D tile (128-bit stores when aligned)
     const int64_t ncol = j0 + CH_TCOL <= n ? CH_TCOL : n - j0;
     T *Dt = Dg + j0 * G::LDD;
-    for (int e = tid; e < (int)ncol * G::LDD; e += nthr) {
-        const int lc = e / G::LDD, r = e - lc * G::LDD;
-        Dt[e] = sD[((lc & 3) * G::HC4 + (lc >> 2)) * G::PD + r];
+    const int totD = (int)ncol * G::LDD;
+    constexpr int EPVD = 16 / (int)sizeof(T);
+    using VD = typename vec16<T>::type;
+    if (totD % EPVD == 0 && lbm_aligned16_dev(Dt)) {
+        for (int vi = tid; vi < totD / EPVD; vi += nthr) {
+            VD v;
+            T *pv = reinterpret_cast<T *>(&v);
+#pragma unroll
+            for (int w = 0; w < EPVD; ++w) {
+                const int e = vi * EPVD + w;
+                const int lc = e / G::LDD, r = e - lc * G::LDD;
+                pv[w] = sD[((lc & 3) * G::HC4 + (lc >> 2)) * G::PD + r];
+            }
+            st_stream(reinterpret_cast<VD *>(Dt) + vi, v);
+        }
+    } else {
+        for (int e = tid; e < totD; e += nthr) {
+            const int lc = e / G::LDD, r = e - lc * G::LDD;
+            Dt[e] = sD[((lc & 3) * G::HC4 + (lc >> 2)) * G::PD + r];
+        }
     }
 }
 

@@ -14,8 +14,8 @@
 //
 // Kernel: a CTA owns a 64x64 tile of C (dense coordinates) that intersects C's band; it sweeps
 // the tile's p-range in chunks of 16, staging zero-padded dense 64x16 (A) and 16x64 (B) tiles in
-// shared memory through a 3-stage cp.async pipeline (8-byte copies with zero-fill do the band
-// masking; pitches 72 / 20 doubles make both the staging writes and the DMMA fragment loads
+// shared memory through a 3-stage cp.async pipeline (16-byte copies, 8-byte zero-filling copies
+// at the band edges do the masking; pitches 72 / 20 doubles make both the staging writes and the DMMA fragment loads
 // bank-conflict-free), and 4 warps each
 // keep a 32x32 block of C (16 DMMA accumulators) in registers.  8x8x4 sub-products whose A or B
 // block lies wholly outside its band are skipped (warp-uniform test), which removes most of
@@ -25,8 +25,8 @@
 namespace {
 
 constexpr int TM = 64, TN = 64, KC = 16, NT = 128;
-constexpr int PA = 72;  // sA[p][i], i fastest
-constexpr int PB = 20;  // sB[j][p], p fastest
+constexpr int PA = 68;  // sA[p][i], i fastest; 2*PA = 8 (mod 32): each half-warp's 16 fragment loads hit 16 bank pairs
+constexpr int PB = 20;  // sB[j][p], p fastest; 2*PB = 8 (mod 32), same property
 
 struct DmmaArgs {
     int64_t m, n, k;
@@ -35,6 +35,7 @@ struct DmmaArgs {
     const double *A;
     const double *B;
     double *C;
+    int64_t gy;  // row tiles per column block
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -55,20 +56,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int NSTAGE = 3;
 constexpr int STAGE_DBL = KC * PA + TN * PB;  // doubles per stage
 
-__global__ void __launch_bounds__(NT, 4) gbmm_dmma_kernel(const DmmaArgs a) {
+template <int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int wi = (warp & 1) * 32, wj = (warp >> 1) * 32;  // warp's 32x32 block inside the tile
 
-    const int64_t j0 = (int64_t)blockIdx.x * TN;
+    // tile order: the tiles of one column block are consecutive CTAs (they share the B tile in
+    // L2) and consecutive column blocks share most of their A rows
+    const int64_t lin = (int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y;
+    const int64_t by = lin % a.gy;
+    const int64_t j0 = (lin / a.gy) * TN;
+    if (j0 >= a.n) return;
     int64_t I0 = floordiv(j0 - a.kuc, TM);
     if (I0 < 0) I0 = 0;
-    const int64_t i0 = (I0 + blockIdx.y) * TM;
+    const int64_t i0 = (I0 + by) * TM;
     if (i0 >= a.m || i0 > j0 + TN - 1 + a.klc) return;
 
     // p-range of the tile
@@ -86,45 +92,80 @@ __global__ void __launch_bounds__(NT, 4) gbmm_dmma_kernel(const DmmaArgs a) {
         for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
 
     // ---- staging maps (all offsets relative to the tile: 32-bit) ---------------------------
-    // A: ii = tid % 64, pp = tid / 64 + 2q (q < 8).  A[i,p] = Ad[(kua + i) + (lda-1)*p], valid for
-    //    p in [i - kla, i + kua], p < k, i < m.
-    // B: pp = tid % 16, jj = tid / 16 + 8q (q < 8).  B[p,j] = Bd[(kub + p) + (ldb-1)*j], valid for
-    //    p in [j - kub, j + klb], p < k, j < n.
-    const int a_ii = tid & 63, a_p0 = tid >> 6;
-    const int b_pp = tid & 15, b_j0 = tid >> 4;
-    const bool a_row_ok = (i0 + a_ii) < a.m;
-    const int a_lo = (int)(i0 + a_ii - a.kla - plo);  // valid relative p range for this thread's row
-    const int a_hi = (int)(i0 + a_ii + a.kua - plo);
+    // Elements are staged in PAIRS along the direction that is contiguous in global memory:
+    // one 16-byte cp.async when both are in-band and the source is 16-byte aligned (always the
+    // case for odd lda with even ku, e.g. l=u=128), else two 8-byte zero-filling copies.
+    // A: rows (2*ii2, 2*ii2+1), ii2 = tid % 32; p = tid / 32 + 4q (q < 4).
+    //    A[i,p] = Ad[(kua + i) + (lda-1)*p], valid for p in [i - kla, i + kua], p < k, i < m.
+    // B: p pair (2*pp2, 2*pp2+1), pp2 = tid % 8; j = tid / 8 + 16q (q < 4).
+    //    B[p,j] = Bd[(kub + p) + (ldb-1)*j], valid for p in [j - kub, j + klb], p < k, j < n.
+    const int a_ii = 2 * (tid & 31), a_p0 = tid >> 5;
+    const int b_pp = 2 * (tid & 7), b_j0 = tid >> 3;
     const int kmax = (int)(a.k - 1 - plo);             // relative p must be <= kmax
+    const bool a_ok0 = (i0 + a_ii) < a.m, a_ok1 = (i0 + a_ii + 1) < a.m;
+    const int a_lo0 = (int)(i0 + a_ii - a.kla - plo);  // valid relative p range of row a_ii (row a_ii+1: +1)
+    const int a_hi0 = (int)(i0 + a_ii + a.kua - plo);
     const double *a_ptr = a.A + (a.kua + i0 + a_ii) + (a.lda - 1) * plo;  // + (lda-1)*prel
     const int64_t a_step = a.lda - 1;
-    int b_lo[8], b_hi[8];
-    bool b_col_ok[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int64_t j = j0 + b_j0 + 8 * q;
-        b_col_ok[q] = j < a.n;
-        b_lo[q] = (int)(j - a.kub - plo);
-        b_hi[q] = (int)(j + a.klb - plo);
-    }
-    const double *b_ptr = a.B + (a.kub + plo + b_pp) + (a.ldb - 1) * (j0 + b_j0);  // + prel + (ldb-1)*8q
-    const int64_t b_step = (a.ldb - 1) * 8;
+    const int b_lo0 = (int)(j0 + b_j0 - a.kub - plo);  // valid relative p range of column b_j0 (+16q for q)
+    const int b_hi0 = (int)(j0 + b_j0 + a.klb - plo);
+    const int b_ncol = (int)((a.n - j0 - b_j0 + 15) / 16);  // q < b_ncol  <=>  column j0 + b_j0 + 16q < n
+    const double *b_ptr = a.B + (a.kub + plo + b_pp) + (a.ldb - 1) * (j0 + b_j0);  // + prel + (ldb-1)*16q
+    const int64_t b_step = (a.ldb - 1) * 16;
+
+    auto cp16 = [&](double *dst, const double *src) {
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    };
+    auto stage_pair = [&](double *dst, const double *src, bool ok0, bool ok1, const double *safe) {
+        if (ok0 && ok1 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+            cp16(dst, src);
+        } else {
+            cp_async8_zfill(dst, ok0 ? src : safe, ok0);
+            cp_async8_zfill(dst + 1, ok1 ? src + 1 : safe, ok1);
+        }
+    };
+    // 16-byte alignment of every pair source (true for l=u=128: lda-1, ldb-1 and ku even)
+    const bool a_al = ((reinterpret_cast<uintptr_t>(a_ptr) & 15u) == 0) && ((a_step & 1) == 0);
+    const bool b_al = ((reinterpret_cast<uintptr_t>(b_ptr) & 15u) == 0) && (((a.ldb - 1) & 1) == 0);
+    // tile-level band limits (relative p) for the "whole chunk in band" fast paths
+    const int ti0 = (int)(i0 - plo), tj0 = (int)(j0 - plo);
+    const bool rows_in = i0 + TM <= a.m, cols_in = j0 + TN <= a.n;
+    const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
 
     auto issue = [&](int ch) {
         double *sA = smem + (ch % NSTAGE) * STAGE_DBL;
         double *sB = sA + KC * PA;
         const int pr = ch * KC;  // relative p of the chunk start
+        const bool p_in = pr + KC - 1 <= kmax;
+        // every (i,p) of the 64 x 16 A tile in band  <=>  ti0+63 - pr <= kla  and  ti0 - (pr+15) >= -kua
+        if (a_al && rows_in && p_in && ti0 + TM - 1 - pr <= kla && ti0 - (pr + KC - 1) >= -kua) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int p = pr + a_p0 + 2 * q;
-            const bool ok = a_row_ok && p >= a_lo && p <= a_hi && p <= kmax;
-            cp_async8_zfill(sA + (a_p0 + 2 * q) * PA + a_ii, ok ? a_ptr + a_step * p : a.A, ok);
+            for (int q = 0; q < 4; ++q) cp16(sA + (a_p0 + 4 * q) * PA + a_ii, a_ptr + a_step * (pr + a_p0 + 4 * q));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int p = pr + a_p0 + 4 * q;
+                const bool pk = p <= kmax;
+                const bool ok0 = a_ok0 && pk && p >= a_lo0 && p <= a_hi0;
+                const bool ok1 = a_ok1 && pk && p >= a_lo0 + 1 && p <= a_hi0 + 1;
+                stage_pair(sA + (a_p0 + 4 * q) * PA + a_ii, a_ptr + a_step * p, ok0, ok1, a.A);
+            }
         }
-        const int pb = pr + b_pp;
+        // every (p,j) of the 16 x 64 B tile in band  <=>  (pr+15) - tj0 <= klb  and  pr - (tj0+63) >= -kub
+        if (b_al && cols_in && p_in && (pr + KC - 1) - tj0 <= klb && pr - (tj0 + TN - 1) >= -kub) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const bool ok = b_col_ok[q] && pb >= b_lo[q] && pb <= b_hi[q] && pb <= kmax;
-            cp_async8_zfill(sB + (b_j0 + 8 * q) * PB + b_pp, ok ? b_ptr + pr + b_step * q : a.B, ok);
+            for (int q = 0; q < 4; ++q) cp16(sB + (b_j0 + 16 * q) * PB + b_pp, b_ptr + pr + b_step * q);
+        } else {
+            const int pb = pr + b_pp;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool cok = q < b_ncol;
+                const int lo = b_lo0 + 16 * q, hi = b_hi0 + 16 * q;
+                const bool ok0 = cok && pb >= lo && pb <= hi && pb <= kmax;
+                const bool ok1 = cok && pb + 1 >= lo && pb + 1 <= hi && pb + 1 <= kmax;
+                stage_pair(sB + (b_j0 + 16 * q) * PB + b_pp, b_ptr + pr + b_step * q, ok0, ok1, a.B);
+            }
         }
     };
 
@@ -138,7 +179,8 @@ __global__ void __launch_bounds__(NT, 4) gbmm_dmma_kernel(const DmmaArgs a) {
     const int fr = lane >> 2, fc = lane & 3;  // fragment row / col of this lane
     // skip-test constants: block x of A covers rows ia..ia+7, block y of B covers cols jb..jb+7
     const int ia0 = (int)(i0 + wi - plo), jb0 = (int)(j0 + wj - plo);
-    const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
+    const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + 8*x
+    const int fb_off = (wj + fr) * PB + fc;     // + 8*x*PB + 4*ks
 
     for (int ch = 0; ch < nch; ++ch) {
         cp_async_wait<NSTAGE - 2>();  // chunk ch has landed (this thread's copies)
@@ -147,29 +189,61 @@ __global__ void __launch_bounds__(NT, 4) gbmm_dmma_kernel(const DmmaArgs a) {
         cp_async_commit();
         const double *sA = smem + (ch % NSTAGE) * STAGE_DBL;
         const double *sB = sA + KC * PA;
+        const int pr = ch * KC;
+        constexpr bool DB = (MINB <= 3);  // double-buffer fragments only where registers allow it
+        double fa[DB ? 2 : 1][4], fb[DB ? 2 : 1][4];
+        if (DB) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                fa[0][x] = sA[fa_off + 8 * x];
+                fb[0][x] = sB[fb_off + 8 * x * PB];
+            }
+        }
+        // whole 32 x 16 (A) and 16 x 32 (B) warp panels inside their bands: no per-block tests
+        const bool full = (ia0 + 31 - pr <= kla) && (ia0 - (pr + KC - 1) >= -kua) &&
+                          ((pr + KC - 1) - jb0 <= klb) && (pr - (jb0 + 31) >= -kub);
 #pragma unroll
         for (int ks = 0; ks < KC / 4; ++ks) {
-            const int p = ch * KC + 4 * ks;  // relative
-            unsigned ma = 0, mb = 0;
+            const int cur = DB ? (ks & 1) : 0, nxt = DB ? (cur ^ 1) : 0;
+            if (DB) {
+                if (ks + 1 < KC / 4) {  // fragments of the next k-step are in flight during this one's MMAs
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int ia = ia0 + 8 * x;
-                if (ia - (p + 3) <= kla && (ia + 7) - p >= -kua) ma |= 1u << x;
-                const int jb = jb0 + 8 * x;
-                if ((p + 3) - jb >= -kub && p - (jb + 7) <= klb) mb |= 1u << x;
+                    for (int x = 0; x < 4; ++x) {
+                        fa[nxt][x] = sA[fa_off + 4 * (ks + 1) * PA + 8 * x];
+                        fb[nxt][x] = sB[fb_off + 8 * x * PB + 4 * ks + 4];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    fa[0][x] = sA[fa_off + 4 * ks * PA + 8 * x];
+                    fb[0][x] = sB[fb_off + 8 * x * PB + 4 * ks];
+                }
             }
-            if (ma == 0 || mb == 0) continue;
-            double fa[4], fb[4];
+            if (full) {
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                fa[x] = sA[(4 * ks + fc) * PA + wi + 8 * x + fr];
-                fb[x] = sB[(wj + 8 * x + fr) * PB + 4 * ks + fc];
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], fa[cur][x], fb[cur][y]);
+            } else {
+                const int p = pr + 4 * ks;  // relative
+                unsigned ma = 0, mb = 0;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int ia = ia0 + 8 * x;
+                    if (ia - (p + 3) <= kla && (ia + 7) - p >= -kua) ma |= 1u << x;
+                    const int jb = jb0 + 8 * x;
+                    if ((p + 3) - jb >= -kub && p - (jb + 7) <= klb) mb |= 1u << x;
+                }
+                if (ma != 0 && mb != 0) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)
+                            if ((ma >> x & 1u) && (mb >> y & 1u))
+                                dmma884(acc[x][y][0], acc[x][y][1], fa[cur][x], fb[cur][y]);
+                }
             }
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    if ((ma >> x & 1u) && (mb >> y & 1u)) dmma884(acc[x][y][0], acc[x][y][1], fa[x], fb[y]);
         }
     }
     cp_async_wait<0>();
@@ -234,19 +308,32 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     int64_t gy = (klc + kuc + TN - 1) / TM + 2;
     const int64_t mt = (m + TM - 1) / TM;
     if (gy > mt) gy = mt;
-    if (gy > 65535) return lbm_fail_arg(h, 15, "C band too wide for the DMMA tile grid");
     if (beta == 0.0) {
         gbmm_zero_corners_kernel<<<64, 256, 0, h->stream>>>(m, n, klc, kuc, C, ldc);
         LBM_LAUNCH_CHECK(h, "gbmm_zero_corners_kernel");
     }
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    const size_t smem = (size_t)NSTAGE * STAGE_DBL * sizeof(double);
-    static int configured_dev_mask = 0;
-    if (!(configured_dev_mask & (1 << h->device))) {
-        LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_dev_mask |= (1 << h->device);
-    }
-    gbmm_dmma_kernel<<<grid, NT, smem, h->stream>>>(a);
+    a.gy = gy;
+    const int64_t total = gx * gy;
+    const int64_t gxx = total < 1048576 ? total : 1048576;
+    dim3 grid((unsigned)gxx, (unsigned)((total + gxx - 1) / gxx));
+    // default: 2-stage ring, 4 CTAs (16 warps) per SM -- occupancy beats ring depth here
+    // (profiles/configs_r01.md); gbmm_variant = 2: 3-stage / 3 CTAs, 3: 2-stage / 5 CTAs
+    const int variant = (int)h->tune.gbmm_variant;
+    static int configured_dev_mask[3] = {0, 0, 0};
+#define LBM_DMMA_LAUNCH(IDX, NS, MB)                                                                         \
+    do {                                                                                                      \
+        const size_t smem = (size_t)(NS) * STAGE_DBL * sizeof(double);                                        \
+        if (!(configured_dev_mask[IDX] & (1 << h->device))) {                                                 \
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<NS, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                     \
+            configured_dev_mask[IDX] |= (1 << h->device);                                                     \
+        }                                                                                                     \
+        gbmm_dmma_kernel<NS, MB><<<grid, NT, smem, h->stream>>>(a);                                           \
+    } while (0)
+    if (variant == 2) LBM_DMMA_LAUNCH(0, 3, 3);
+    else if (variant == 3) LBM_DMMA_LAUNCH(2, 2, 5);
+    else LBM_DMMA_LAUNCH(1, 2, 4);
+#undef LBM_DMMA_LAUNCH
     LBM_LAUNCH_CHECK(h, "gbmm_dmma_kernel");
     return 0;
 }

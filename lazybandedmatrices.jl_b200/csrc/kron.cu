@@ -150,17 +150,22 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
     const uint32_t col_bytes = (uint32_t)((re - rs) * (int64_t)sizeof(T));
     const int roff = (int)(rs - (r0 - a.hp));  // smem row offset of rs
 
-    auto issue = [&](int64_t q, int s) {  // thread 0 only
+    // Warp 0 issues a chunk: lane 0 arms the byte count, the lanes issue one per-column bulk copy
+    // each IN PARALLEL (one instruction for up to 32 copies), lane 0 arrives.
+    auto issue = [&](int64_t q, int s) {  // all 32 lanes of warp 0
+        const int lane = tid & 31;
         const int64_t c0 = q * a.g;
         int64_t ca = c0 - a.kla > 0 ? c0 - a.kla : 0;
         int64_t cb = c0 + a.g + a.kua < a.n1 ? c0 + a.g + a.kua : a.n1;
         T *st = sbase + (int64_t)s * stage_elems;
-        mbar_add_tx(&bars[s], (uint32_t)(cb - ca) * col_bytes);
-        for (int64_t c = ca; c < cb; ++c)
+        if (lane == 0) mbar_add_tx(&bars[s], (uint32_t)(cb - ca) * col_bytes);
+        __syncwarp();
+        for (int64_t c = ca + lane; c < cb; c += 32)
             bulk_g2s(st + (c - (c0 - a.kla)) * a.seg + roff, a.x + c * a.n2 + rs, col_bytes, &bars[s]);
-        mbar_arrive(&bars[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[s]);
     };
-    if (tid == 0) {
+    if (tid < 32) {
         const int64_t pro = mine < S ? mine : S;
         for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
     }
@@ -205,44 +210,63 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
         T cnext = (T)0;
         if (kk + 1 < mine) cnext = load_coef(q + step);  // in flight during this chunk's compute
         mbar_wait(&bars[s], parity);
-#pragma unroll 2
-        for (int cc = 0; cc < gq; ++cc) {
-            const int64_t c = c0 + cc;
-            T cav[NBA];
+        const int seg = a.seg;
+        const T *xrow = st + tid + a.hp;                 // X[r0+tid, c0-kla] of this stage
+        T *yp = a.y + (r0 + tid) + a.n2 * c0;             // Y[r0+tid, c0]; += n2 per column
+        if (!edge) {
+            // interior chunk: no index tests, 32-bit smem offsets, one pointer bump per column
+#pragma unroll 4
+            for (int cc = 0; cc < gq; ++cc) {
+                T cav[NBA];
 #pragma unroll
-            for (int t = 0; t < NBA; ++t) cav[t] = ca[cc * NBA + t];
+                for (int t = 0; t < NBA; ++t) cav[t] = ca[cc * NBA + t];
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                const int rr = tid + 256 * k;
-                const int64_t r = r0 + rr;
-                if (r >= a.n2) continue;
-                const T *xa = st + (int64_t)cc * a.seg + rr + a.hp;              // X[r, c-kla+t] at xa[t*seg]
-                const T *xb = st + (int64_t)(cc + a.kla) * a.seg + rr + a.hp - a.klb;  // X[r-klb+t, c] at xb[t]
-                T acc = 0;
-                if (!edge) {
+                for (int k = 0; k < RPT; ++k) {
+                    const T *xa = xrow + cc * seg + 256 * k;                // X[r, c-kla+t] at xa[t*seg]
+                    const T *xb = xa + a.kla * seg - a.klb;                 // X[r-klb+t, c] at xb[t]
+                    T acc = 0;
 #pragma unroll
-                    for (int t = 0; t < NBA; ++t) acc = fma(cav[t], xa[(int64_t)t * a.seg], acc);
+                    for (int t = 0; t < NBA; ++t) acc = fma(cav[t], xa[t * seg], acc);
 #pragma unroll
                     for (int t = 0; t < NBB; ++t) acc = fma(cbv[k][t], xb[t], acc);
-                } else {
+                    T *yo = yp + 256 * k;
+                    *yo = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *yo, a.alpha * acc);
+                }
+                yp += a.n2;
+            }
+        } else {
+            for (int cc = 0; cc < gq; ++cc) {
+                const int64_t c = c0 + cc;
+                T cav[NBA];
 #pragma unroll
-                    for (int t = 0; t < NBA; ++t) {
-                        const int64_t qq = c - a.kla + t;
-                        if (qq >= 0 && qq < a.n1) acc = fma(cav[t], xa[(int64_t)t * a.seg], acc);
-                    }
+                for (int t = 0; t < NBA; ++t) cav[t] = ca[cc * NBA + t];
 #pragma unroll
-                    for (int t = 0; t < NBB; ++t) {
-                        const int64_t p = r - a.klb + t;
-                        if (p >= 0 && p < a.n2) acc = fma(cbv[k][t], xb[t], acc);
+                for (int k = 0; k < RPT; ++k) {
+                    const int64_t r = r0 + tid + 256 * k;
+                    if (r < a.n2) {
+                        const T *xa = xrow + cc * seg + 256 * k;
+                        const T *xb = xa + a.kla * seg - a.klb;
+                        T acc = 0;
+#pragma unroll
+                        for (int t = 0; t < NBA; ++t) {
+                            const int64_t qq = c - a.kla + t;
+                            if (qq >= 0 && qq < a.n1) acc = fma(cav[t], xa[t * seg], acc);
+                        }
+#pragma unroll
+                        for (int t = 0; t < NBB; ++t) {
+                            const int64_t p = r - a.klb + t;
+                            if (p >= 0 && p < a.n2) acc = fma(cbv[k][t], xb[t], acc);
+                        }
+                        T *yo = yp + 256 * k;
+                        *yo = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *yo, a.alpha * acc);
                     }
                 }
-                const int64_t o = r + a.n2 * c;
-                a.y[o] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[o], a.alpha * acc);
+                yp += a.n2;
             }
         }
         if (kk + 1 < mine && tid < ncoef) sCA[((kk + 1) & 1) * ncoef + tid] = cnext;
         __syncthreads();
-        if (tid == 0 && kk + S < mine) issue(first + (kk + S) * step, s);
+        if (tid < 32 && kk + S < mine) issue(first + (kk + S) * step, s);
     }
 }
 
@@ -302,7 +326,7 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     while (cps > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --cps;
     a.stages = (int)stages;
     const int64_t nstrips = (n2 + tr - 1) / tr;
-    int64_t phases = ((int64_t)h->sm_count * cps + nstrips - 1) / nstrips;
+    int64_t phases = ((int64_t)h->sm_count * cps) / nstrips;  // floor: every CTA resident, one wave
     if (phases > a.nchunks) phases = a.nchunks;
     if (phases > 65535) phases = 65535;
     if (phases < 1) phases = 1;

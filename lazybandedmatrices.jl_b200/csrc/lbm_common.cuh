@@ -34,6 +34,7 @@ struct lbm_tuning {
     // gbmm
     int64_t gbmm_force;       // 0 auto, 1 generic, 2 dmma
     int64_t gbmm_tile;
+    int64_t gbmm_variant;     // DMMA kernel: 0 = 3-stage/3 CTAs per SM, 1 = 2-stage/4 CTAs per SM
     int64_t chain_tile;
     int64_t chain_force_generic;
 };
@@ -85,6 +86,8 @@ static inline bool lbm_aligned16(const void *p) { return (reinterpret_cast<uintp
 
 #ifdef __CUDACC__
 namespace lbm {
+
+__device__ __forceinline__ bool lbm_aligned16_dev(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -58,15 +58,15 @@ def test_gbmm_dmma_tensor_path(L, oracle):
         B_np, B = _band(L, oracle, k, n, klb, kub, 32 + s, torch.float64)
         want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
         tol = tol_rows(np.float64, min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
-        for f in (force, 1):
-            h.set_tuning(gbmm_force=f)
+        for f, variant in ((force, 0), (force, 2), (force, 3), (1, 0)):
+            h.set_tuning(gbmm_force=f, gbmm_variant=variant)
             try:
                 before = h.launch_count()
                 C = A @ B
                 torch.cuda.synchronize()
                 nl = h.launch_count() - before
             finally:
-                h.set_tuning(gbmm_force=0)
+                h.set_tuning(gbmm_force=0, gbmm_variant=0)
             assert nl == (2 if f != 1 else 1)      # zero-corners + DMMA tile kernel vs the single diag kernel
             _cmp_band(oracle, C, want, m, kla + klb, kua + kub, tol)
     # alpha/beta and an output band wider than the product band, tensor path
