@@ -45,50 +45,94 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a
+    thread (nvidia-smi's loop is too slow for a 40 ms region); falls back to nvidia-smi."""
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.proc = None
+        self.sm, self.reasons, self.mx = [], set(), None
+        self._stop = threading.Event()
+        self.t = None
+        self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            hdl = None
+            if uuid:
+                for cand in ("GPU-" + uuid, uuid):
+                    try:
+                        hdl = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        hdl = None
+            if hdl is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+                hdl = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(hdl, pynvml.NVML_CLOCK_SM))
+            R = pynvml
+            names = {"hw_slowdown": R.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": R.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": R.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": R.nvmlClocksThrottleReasonSwPowerCap}
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM)))
+                        m = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hdl)
+                        for k, bit in names.items():
+                            if m & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+            self.how = "nvml"
+        except Exception:
+            self.how = "nvidia-smi"
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                              "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+
+                def rd():
+                    for line in self.proc.stdout:
+                        f = [t.strip() for t in line.split(",")]
+                        try:
+                            self.sm.append(float(f[0]))
+                            self.mx = float(f[1])
+                        except Exception:
+                            continue
+                        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                            if v.lower().startswith("active"):
+                                self.reasons.add(name)
+                self.t = threading.Thread(target=rd, daemon=True)
+                self.t.start()
+            except Exception:
+                self.how = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for s in self.samples:
-            f = [t.strip() for t in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self.how == "nvidia-smi":
+            time.sleep(0.05)
+            self.proc.terminate()
+        if self.t:
+            self.t.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.how}
 
 
 # --------------------------------------------------------------------------------------------
@@ -167,7 +211,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import lbm_b200 as L
-    from lbm_b200.shard import ShardedBanded
+    from lbm_b200.shard import ShardedBanded, init_comm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +221,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     h = L.handle_for(local)
+    if world > 1 and not args.torch_p2p:
+        init_comm(local)      # ghost exchange inside the library: one C call per sharded mul!
     n = 1 << (args.log2n or LOG2N)
     K, W = args.steps, max(3, args.warmup)
 
@@ -312,6 +358,7 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"mul!(y,A,x), A=brand(n,n,l,u) f64, n=2^{args.log2n or LOG2N}, l=u in {{1,8}}, "
                                    f"row-sharded over {world} GPU(s), NCCL ghost exchange in the timed region",
+                       "exchange": "none (1 GPU)" if world == 1 else ("torch.distributed P2P" if args.torch_p2p else "in-library ncclSend/ncclRecv, overlapped with interior rows"),
                        "l2": "inputs (3.2 GB and 18.3 GB slabs) far larger than the 126 MB L2; no flush needed",
                        "algorithmic_bytes_per_step": step_bytes},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -398,6 +445,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=0, help="override n = 2^k (testing only; metric is 2^27)")
     ap.add_argument("--no-wide", action="store_true", help="skip the l=u=128 breakdown point")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--torch-p2p", action="store_true", help="N>1: exchange ghosts through torch.distributed P2P "
+                    "instead of the library's own NCCL communicator")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

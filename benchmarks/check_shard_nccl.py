@@ -12,7 +12,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import lbm_b200 as L  # noqa: E402
-from lbm_b200.shard import ShardedBanded, sharded_chain_mul_  # noqa: E402
+from lbm_b200.shard import ShardedBanded, init_comm, sharded_chain_mul_  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
@@ -22,6 +22,18 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     eps = np.finfo(np.float64).eps
+    for use_lib_comm in (False, True):   # torch.distributed P2P path, then the in-library NCCL path
+        if use_lib_comm:
+            init_comm(local)
+            assert L.handle_for(local).comm_world == world
+        _check(rank, world, dev, eps)
+    dist.barrier()
+    if rank == 0:
+        print(f"OK sharded mul!/chain on {world} GPUs match the oracle (torch P2P path and in-library NCCL path)")
+    dist.destroy_process_group()
+
+
+def _check(rank, world, dev, eps):
     for n, bands in ((200003, [(1, 1), (1, 1)]), (100000, [(8, 8), (2, 5), (1, 1)]), (50000, [(128, 128), (3, 0)])):
         x_full = O.fill_uniform(0x9, n)
         factors = [ShardedBanded.brand(n, l, u, rank, world, device=dev, seed=0x1 + i) for i, (l, u) in enumerate(bands)]
@@ -47,10 +59,6 @@ def main():
             scale *= (l + u + 1)
         err = np.max(np.abs(y2.cpu().numpy() - v[factors[0].plan.r0:factors[0].plan.r1]))
         assert err <= 4 * eps * scale * len(bands), (n, bands, "chain", err)
-    dist.barrier()
-    if rank == 0:
-        print(f"OK sharded mul!/chain on {world} GPUs match the oracle")
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

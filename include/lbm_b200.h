@@ -142,6 +142,25 @@ int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
                    int64_t klb, int64_t kub, const double *B, int64_t ldb,
                    double alpha, const double *x, double beta, double *y);
 
+/* ---- row-sharded mul! across the GPUs of one box (one process per GPU) ------------------- */
+/* Rank r of `world` owns rows [r0,r1) of a square n x n operator and stores the COLUMN slice
+ * [c0,c1) = [max(0,r0-kl), min(n,r1+ku)) of the diagonal-major array (same lda); x lives in a
+ * ghost-cell vector [left | owned | right] of length c1-c0.  lbm_shard_plan writes
+ * {r0, r1, c0, c1, left, right, kl_loc, ku_loc} (pure integers, no GPU).  The communicator is
+ * NCCL (dlopen'ed): rank 0 calls lbm_comm_unique_id, the host broadcasts the 128 bytes, every
+ * rank calls lbm_comm_init.  lbm_?gbmv_sharded = ghost exchange (ncclSend/ncclRecv over
+ * NVLink on a private stream) overlapped with the interior rows, then the <= kl+ku boundary
+ * rows: y_own <- alpha*A[r0:r1,:]*x + beta*y_own.  No all-reduce/all-gather on the path. */
+int lbm_shard_plan(int64_t n, int64_t kl, int64_t ku, int rank, int world, int64_t *out8);
+int lbm_comm_unique_id(void *id128);
+int lbm_comm_init(lbm_handle_t h, const void *id128, int rank, int world);
+int lbm_comm_destroy(lbm_handle_t h);
+int lbm_halo_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *xbuf, int elem_bytes);
+int lbm_dgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, double alpha, const double *A_slab,
+                      int64_t lda, double *xbuf, double beta, double *y_own, int overlap);
+int lbm_sgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, float alpha, const float *A_slab,
+                      int64_t lda, float *xbuf, float beta, float *y_own, int overlap);
+
 /* ---- structure helpers (pure integer, host side, no GPU needed) ------------------------ */
 /* bandwidths(ApplyMatrix(*, F1..Fnf)) = min.(size-1, (sum kl, sum ku))  ([up] LazyArrays;
  * reference README.md:13-26 shows (1,1)*(1,1) -> (2,2)). */

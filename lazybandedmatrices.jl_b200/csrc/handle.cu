@@ -75,6 +75,8 @@ int lbm_create(lbm_handle_t *out, int device) {
     }
     h->stream = h->own_stream;
     h->err[0] = 0;
+    h->rank = 0;
+    h->world = 1;
     *out = h;
     return 0;
 }
@@ -83,6 +85,7 @@ int lbm_destroy(lbm_handle_t h) {
     if (!h) return 0;
     lbm_device_guard g(h->device);
     cudaStreamSynchronize(h->stream);
+    lbm_comm_destroy(h);
     if (h->scratch) cudaFree(h->scratch);
     for (int i = 0; i < 4; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);

@@ -52,6 +52,11 @@ struct lbm_handle_s {
     size_t scratch_bytes;
     void *stage[4];           // device staging for *_host entry points
     size_t stage_bytes[4];
+    // multi-GPU: one process per GPU; NCCL communicator owned by the handle (dist.cu)
+    void *nccl_comm;
+    int rank, world;
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_ready, ev_halo;
 };
 
 int lbm_fail_cuda(lbm_handle_t h, cudaError_t e, const char *what);

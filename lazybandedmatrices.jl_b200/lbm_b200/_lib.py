@@ -53,10 +53,16 @@ def _sigs():
         "lbm_sfill_uniform": (C.c_int, [H, u64, i64, i64, vp]),
         "lbm_prod_bandwidths": (C.c_int, [i64, i64, C.c_int, C.POINTER(i64), C.POINTER(i64),
                                           C.POINTER(i64), C.POINTER(i64)]),
+        "lbm_shard_plan": (C.c_int, [i64, i64, i64, C.c_int, C.c_int, C.POINTER(i64)]),
+        "lbm_comm_unique_id": (C.c_int, [vp]),
+        "lbm_comm_init": (C.c_int, [H, vp, C.c_int, C.c_int]),
+        "lbm_comm_destroy": (C.c_int, [H]),
+        "lbm_halo_exchange": (C.c_int, [H, i64, i64, i64, vp, C.c_int]),
     }
     for p, ft in (("d", f64), ("s", f32)):
         s[f"lbm_{p}gbmv"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
         s[f"lbm_{p}gbmv_host"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
+        s[f"lbm_{p}gbmv_sharded"] = (C.c_int, [H, i64, i64, i64, ft, vp, i64, vp, ft, vp, C.c_int])
         s[f"lbm_{p}tridiag_mv"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}bidiag_mv"] = (C.c_int, [H, ch, i64, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}gbmm"] = (C.c_int, [H, i64, i64, i64, ft, i64, i64, vp, i64, i64, i64, vp, i64, ft,
@@ -111,6 +117,7 @@ class Handle:
             raise LbmCudaError(rc, f"lbm_create(device={device}) failed: {msg} "
                                    "(liblbm_b200 has no CPU fallback)")
         self.device = int(device)
+        self.comm_world = 1  # > 1 once init_comm() has created the library's NCCL communicator
 
     @property
     def ptr(self):

@@ -21,6 +21,34 @@ import torch.distributed as dist
 from .errors import LbmArgumentError
 
 
+def init_comm(device: int, group=None):
+    """Collective: create the library's own NCCL communicator for this process group, so that a
+    sharded mul! (ghost exchange + interior + boundary kernels) is ONE C call
+    (lbm_?gbmv_sharded).  Rank 0 draws the NCCL unique id, torch.distributed broadcasts its
+    128 bytes, every rank joins."""
+    import ctypes as C
+
+    from . import _lib
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    h = _lib.handle_for(device)
+    if world == 1:
+        return h
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        rc = _lib.lib().lbm_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc:
+            raise RuntimeError(f"lbm_comm_unique_id failed ({rc}): is libnccl.so.2 loadable?")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda(device)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().tolist())
+    idb = (C.c_ubyte * 128).from_buffer_copy(raw)
+    h.check(_lib.lib().lbm_comm_init(h.ptr, C.cast(idb, C.c_void_p), rank, world), "lbm_comm_init")
+    h.comm_world = world
+    return h
+
+
 def split_rows(n: int, world: int, rank: int, align: int = 4):
     """Contiguous near-equal row blocks whose starts are multiples of `align` (keeps every
     shard's slab and vectors 16-byte aligned for the bulk-TMA path)."""
@@ -182,6 +210,18 @@ class ShardedBanded:
         if not (exchange and p.world > 1):
             self._apply_rows(y_own, xbuf, 0, p.m_loc, alpha, beta, local_gbmv)
             return y_own
+        if local_gbmv is None and group is None and xbuf.is_cuda:
+            # product fast path: exchange + kernels inside the library (needs init_comm())
+            from . import _lib
+            from .banded import _ft, _pfx, _ptr
+            h = _lib.handle_of(self.data)
+            if h.comm_world == p.world:
+                fn = getattr(_lib.lib(), f"lbm_{_pfx(self.data.dtype)}gbmv_sharded")
+                ft = _ft(self.data.dtype)
+                assert xbuf.is_contiguous() and y_own.is_contiguous() and xbuf.shape[0] == p.n_loc
+                h.check(fn(h.ptr, p.n, p.l, p.u, ft(alpha), _ptr(self.data), p.l + p.u + 1, _ptr(xbuf), ft(beta),
+                           _ptr(y_own), 1 if overlap else 0), "lbm_gbmv_sharded")
+                return y_own
         if not overlap:
             p.exchange(xbuf, group)
             self._apply_rows(y_own, xbuf, 0, p.m_loc, alpha, beta, local_gbmv)

@@ -132,3 +132,14 @@ def test_plan_geometry():
     from lbm_b200.errors import LbmArgumentError
     with pytest.raises(LbmArgumentError):
         RowShard.plan(64, 128, 128, 0, 4)
+    # the C library's plan (used by lbm_?gbmv_sharded) is the same function, bit for bit
+    import ctypes as C
+    import lbm_b200
+    lib = lbm_b200.lib()
+    out = (C.c_int64 * 8)()
+    for (nn, ll, uu, ww) in [(1 << 27, 8, 8, 8), (1003, 1, 1, 3), (4099, 128, 128, 2), (64, 0, 1, 2), (10, 2, 3, 1)]:
+        for r in range(ww):
+            pl = RowShard.plan(nn, ll, uu, r, ww)
+            assert lib.lbm_shard_plan(nn, ll, uu, r, ww, out) == 0
+            assert list(out) == [pl.r0, pl.r1, pl.c0, pl.c1, pl.left, pl.right, pl.kl_loc, pl.ku_loc]
+    assert lib.lbm_shard_plan(10, 1, 1, 3, 3, out) == -4
