@@ -16,8 +16,9 @@
 //    (i - R0) mod NT with its accumulator in a register for the ~(kl+ku+C)/C chunks that
 //    touch it, so each element of A is read from smem by exactly one thread, lanes read
 //    consecutive addresses, and completed rows retire as coalesced stores.
-//  * gbmv_wide_t_kernel (wide bands, op = T): one warp per output; the column of A is a
-//    contiguous vector, read coalesced, reduced with warp shuffles.
+//  * gbmv_wide_t_ring_kernel (wide bands, op = T): column chunks (contiguous) + x window through
+//    the same TMA ring; one warp reduces a whole column from smem with a shuffle tree.
+//  * gbmv_wide_t_kernel: unaligned fallback of the above, reading global memory directly.
 //  * gbmv_direct_kernel: any alignment / any lda fallback, thread per output, L1/L2 served.
 #include "lbm_common.cuh"
 
@@ -261,8 +262,98 @@ __global__ void __launch_bounds__(1024) gbmv_wide_n_kernel(const GbmvWideArgs<T>
 }
 
 // ------------------------------------------------------------------------------------------
-// wide bands, op = T: warp per output, coalesced column read + shuffle reduction
+// wide bands, op = T, aligned: column chunks through the TMA ring, warp per column from smem
 // ------------------------------------------------------------------------------------------
+// y[j] = sum_r A[r, j] * x[j + r - ku].  A CTA owns a contiguous run of output columns; chunks of
+// C columns (contiguous in the diagonal-major array) and the matching x window
+// [cb - ku, cb + C + kl) arrive by bulk TMA; lane <-> column, warp <-> slice of the band rows
+// (one smem read of A per FMA, conflict-free for odd lda), partial sums combined per chunk.
+template <typename T>
+__global__ void __launch_bounds__(256) gbmv_wide_t_ring_kernel(const GbmvWideArgs<T> a) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.stages;
+    const int64_t stage_elems = a.sA_elems + a.sx_elems;
+    const int C = a.chunk;
+    const int nb = (int)(a.kl + a.ku + 1);
+
+    const int64_t J0 = (int64_t)blockIdx.x * a.run;            // run is a multiple of EPV
+    const int64_t J1 = J0 + a.run < a.n ? J0 + a.run : a.n;
+    if (J0 >= J1) return;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t nchunks = (J1 - J0 + C - 1) / C;
+
+    auto issue = [&](int64_t q, int s) {  // thread 0 only
+        const int64_t cb = J0 + q * C;
+        const int64_t cq = cb + C < J1 ? C : J1 - cb;
+        int64_t x0 = cb - a.ku > 0 ? cb - a.ku : 0;
+        x0 &= ~(int64_t)(EPV - 1);
+        int64_t x1 = cb + cq + a.kl < a.m ? cb + cq + a.kl : a.m;
+        if (x1 < x0) x1 = x0;
+        T *sA = sbase + (int64_t)s * stage_elems;
+        T *sx = sA + a.sA_elems;
+        mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cq * a.lda) + stage_bytes_bulk<T>(x1 - x0));
+        stage_issue<T>(sA, a.A + cb * a.lda, cq * a.lda, &bars[s]);
+        stage_issue<T>(sx, a.x + x0, x1 - x0, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+    if (tid == 0) {
+        const int64_t pro = nchunks < S ? nchunks : S;
+        for (int64_t q = 0; q < pro; ++q) issue(q, (int)q);
+    }
+    const int lda = (int)a.lda;
+    const int rw = (nb + 7) / 8;                             // band rows per warp
+    T *spart = sbase + (int64_t)S * stage_elems;             // [8][C] partial sums
+    for (int64_t q = 0; q < nchunks; ++q) {
+        const int s = (int)(q % S);
+        const uint32_t parity = (uint32_t)((q / S) & 1);
+        const int64_t cb = J0 + q * C;
+        const int cq = (int)(cb + C < J1 ? C : J1 - cb);
+        int64_t x0 = cb - a.ku > 0 ? cb - a.ku : 0;
+        x0 &= ~(int64_t)(EPV - 1);
+        const T *sA = sbase + (int64_t)s * stage_elems;
+        const T *sx = sA + a.sA_elems;
+        mbar_wait(&bars[s], parity);
+        // lane <-> column (stride lda between lanes: conflict-free for odd lda), warp <-> a slice
+        // of the band rows; the 8 partial sums per column meet in smem once per chunk.
+        for (int jj = lane; jj < cq; jj += 32) {
+            const int64_t j = cb + jj;
+            const T *col = sA + jj * lda;
+            const int xoff = (int)(j - a.ku - x0);            // sx index of row i = j - ku (r = 0)
+            int rlo = (int)(a.ku - j > 0 ? a.ku - j : 0);     // valid band rows: 0 <= j + r - ku < m
+            int rhi = (int)(a.m - 1 - j + a.ku < nb - 1 ? a.m - 1 - j + a.ku : nb - 1);
+            const int w0 = warp * rw, w1 = w0 + rw - 1;
+            if (rlo < w0) rlo = w0;
+            if (rhi > w1) rhi = w1;
+            T acc0 = 0, acc1 = 0;
+            int r = rlo;
+            for (; r + 1 <= rhi; r += 2) {
+                acc0 = fma(col[r], sx[xoff + r], acc0);
+                acc1 = fma(col[r + 1], sx[xoff + r + 1], acc1);
+            }
+            if (r <= rhi) acc0 = fma(col[r], sx[xoff + r], acc0);
+            spart[warp * C + jj] = acc0 + acc1;
+        }
+        __syncthreads();
+        if (tid < cq) {
+            T acc = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += spart[w * C + tid];
+            const int64_t j = cb + tid;
+            a.y[j] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[j], a.alpha * acc);
+        }
+        __syncthreads();
+        if (tid == 0 && q + S < nchunks) issue(q + S, s);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gbmv_wide_t_kernel(int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha,
                                                          const T *__restrict__ A, int64_t lda,
@@ -385,12 +476,13 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
     const int64_t min_stage_bytes = ((GBMV_NT + nb) * (lda + 1) + 2 * EPV) * (int64_t)sizeof(T);
     bool narrow_ok = aligned && min_stage_bytes <= 100 * 1024 && lda <= 4 * nb + 8;
     bool wide_ok = aligned && !tr && (nb + 32) <= 1024 && (32 * lda + 64) * (int64_t)sizeof(T) <= smem_cap;
-    int path;  // 1 direct, 2 narrow, 3 wide-n, 4 wide-t
+    int path;  // 1 direct, 2 narrow, 3 wide-n, 4 wide-t (warp per output, global), 5 wide-t (TMA ring)
     if (force == 1) path = 1;
     else if (force == 2 && narrow_ok) path = 2;
     else if (force == 3 && wide_ok) path = 3;
     else if (narrow_ok) path = 2;
     else if (wide_ok) path = 3;
+    else if (tr && nb >= 32 && aligned && force != 4 && (32 * lda + 64 + 32 + nb) * (int64_t)sizeof(T) <= smem_cap) path = 5;
     else if (tr && nb >= 32) path = 4;
     else path = 1;
 
@@ -483,6 +575,48 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         }
         kern<<<(unsigned)grid, (unsigned)nt, (size_t)smem_cta, h->stream>>>(a);
         LBM_LAUNCH_CHECK(h, "gbmv_wide_n_kernel");
+        return 0;
+    }
+
+    if (path == 5) {
+        GbmvWideArgs<T> a;
+        a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda;
+        a.alpha = alpha; a.beta = beta; a.A = A; a.x = x; a.y = y;
+        int64_t chunk = h->tune.gbmvw_chunk > 0 ? h->tune.gbmvw_chunk : 32;
+        chunk = round_up(chunk, 32);
+        if (chunk > 256) chunk = 256;
+        auto sbytes = [&](int64_t c) { return (round_up(c * lda + EPV, EPV) + round_up(c + nb + 2 * EPV, EPV)) * (int64_t)sizeof(T); };
+        while (chunk > 32 && sbytes(chunk) + 128 > smem_cap) chunk -= 32;
+        a.chunk = (int)chunk;
+        a.sA_elems = round_up(chunk * lda + EPV, EPV);
+        a.sx_elems = round_up(chunk + nb + 2 * EPV, EPV);
+        const int64_t stage_bytes = sbytes(chunk);
+        // one CTA per SM with 66 KB chunks: the ring must keep >= 2 chunks in flight behind the one
+        // being reduced, i.e. 3 stages
+        int64_t stages = h->tune.gbmvw_stages > 0 ? h->tune.gbmvw_stages : 3;
+        if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+        while (stages > 1 && stages * stage_bytes + 128 > smem_cap) --stages;
+        a.stages = (int)stages;
+        while (stages > 1 && stages * stage_bytes + 128 + 8 * chunk * (int64_t)sizeof(T) > smem_cap) --stages;
+        a.stages = (int)stages;
+        const int64_t smem_cta = stages * stage_bytes + 128 + 8 * chunk * (int64_t)sizeof(T);
+        int64_t ctas = h->tune.gbmvw_ctas_per_sm > 0 ? h->tune.gbmvw_ctas_per_sm : (227 * 1024) / (smem_cta + 1024);
+        if (ctas < 1) ctas = 1;
+        if (ctas > 8) ctas = 8;
+        int64_t grid = (int64_t)h->sm_count * ctas;
+        int64_t run = (n + grid - 1) / grid;
+        if (run < chunk) run = chunk;
+        run = round_up(run, 32);
+        grid = (n + run - 1) / run;
+        a.run = run;
+        static int configured_dev_mask = 0;
+        auto kern = gbmv_wide_t_ring_kernel<T>;
+        if (!(configured_dev_mask & (1 << h->device))) {
+            LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+            configured_dev_mask |= (1 << h->device);
+        }
+        kern<<<(unsigned)grid, 256, (size_t)smem_cta, h->stream>>>(a);
+        LBM_LAUNCH_CHECK(h, "gbmv_wide_t_ring_kernel");
         return 0;
     }
 

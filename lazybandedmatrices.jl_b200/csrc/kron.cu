@@ -195,8 +195,21 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
             cbv[k][t] = (r < a.n2 && p >= 0 && p < a.n2) ? a.B[(a.kub + a.klb - t) + a.ldb * p] : (T)0;
         }
     }
-    const bool row_edge = (r0 - a.klb < 0) || (r0 + a.tr + a.kub > a.n2);
-    __syncthreads();  // sCA[0] visible
+    // Halo rows outside the grid (first / last strip) are never written by the bulk copies:
+    // zero them once in every stage.  With B's out-of-matrix coefficients already zero this makes
+    // the unmasked interior path exact for edge strips too (0 * 0, never 0 * garbage), so only a
+    // PARTIAL last strip or the first/last column chunk needs the predicated path.
+    {
+        const int rows_in = (int)(re - rs);
+        const int nz = a.seg - rows_in;  // rows [0, roff) and [roff + rows_in, seg)
+        for (int e = tid; e < S * scols * nz; e += 256) {
+            const int col = e / nz, z = e - col * nz;
+            const int row = z < roff ? z : rows_in + z;
+            sbase[(int64_t)col * a.seg + row] = (T)0;
+        }
+    }
+    const bool row_edge = r0 + a.tr > a.n2;  // partial strip: some threads own no row
+    __syncthreads();  // sCA[0] and the zeroed halo rows visible
 
     for (int64_t kk = 0; kk < mine; ++kk) {
         const int s = (int)(kk % S);

@@ -56,10 +56,14 @@ def test_gbmv_shapes(L, oracle, dt, trans):
     print(f"max err/tol = {worst:.3f}")
 
 
-@pytest.mark.parametrize("force", [1, 2, 3])
+@pytest.mark.parametrize("force", [1, 2, 3, 4])
 def test_gbmv_every_kernel_path(L, oracle, force):
-    """direct (1), streamed-tile (2) and wide column-streaming (3) kernels on the same inputs."""
-    for (m, n, kl, ku) in [(5000, 5000, 1, 1), (4100, 4100, 8, 8), (9000, 9100, 16, 16), (3000, 3000, 2, 7)]:
+    """direct (1), streamed-tile (2), wide column-streaming (3) and the non-ring wide-T warp kernel (4)
+    on the same inputs."""
+    shapes = [(5000, 5000, 1, 1), (4100, 4100, 8, 8), (9000, 9100, 16, 16), (3000, 3000, 2, 7)]
+    if force == 4:
+        shapes = [(3000, 3100, 40, 40), (2000, 1900, 128, 128), (700, 700, 300, 20)]
+    for (m, n, kl, ku) in shapes:
         for trans in ("N", "T"):
             _run(L, oracle, torch.float64, trans, m, n, kl, ku, 1.5, 0.5, 31, tune={"gbmv_force": force})
 
