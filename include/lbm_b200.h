@@ -142,6 +142,15 @@ int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
                    int64_t klb, int64_t kub, const double *B, int64_t ldb,
                    double alpha, const double *x, double beta, double *y);
 
+/* y <- alpha*(A (x) B (x) C)*x + beta*y on a full n x n x n tensor (k fastest): the three mode
+ * products of /root/reference/src/blockkron.jl:441-450 (A on dim 3, B on dim 2, C on dim 1), i.e.
+ * the arithmetic of KronTrav(A,B,C)*DiagTrav(X) before the DiagTrav re-ordering. */
+int lbm_dkron3d_mv(lbm_handle_t h, int64_t n,
+                   int64_t kla, int64_t kua, const double *A, int64_t lda,
+                   int64_t klb, int64_t kub, const double *B, int64_t ldb,
+                   int64_t klc, int64_t kuc, const double *C, int64_t ldc,
+                   double alpha, const double *x, double beta, double *y);
+
 /* ---- row-sharded mul! across the GPUs of one box (one process per GPU) ------------------- */
 /* Rank r of `world` owns rows [r0,r1) of a square n x n operator and stores the COLUMN slice
  * [c0,c1) = [max(0,r0-kl), min(n,r1+ku)) of the diagonal-major array (same lda); x lives in a

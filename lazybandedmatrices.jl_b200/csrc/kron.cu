@@ -34,6 +34,7 @@ struct KronArgs {
     int pitch;        // smem pitch of the X tile (rows incl. halo, padded)
     int offCA, offCB; // smem offsets (elements)
     int useA, useB;   // which terms to apply
+    int64_t batch_stride;  // elements between consecutive (n2 x n1) slices (blockIdx.z)
 };
 
 template <typename T>
@@ -46,6 +47,8 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
     const int nba = a.kla + a.kua + 1, nbb = a.klb + a.kub + 1;
     const int64_t r0 = (int64_t)blockIdx.x * a.tr;
     const int64_t c0 = (int64_t)blockIdx.y * a.tc;
+    const T *xs = a.x + (int64_t)blockIdx.z * a.batch_stride;
+    T *ys = a.y + (int64_t)blockIdx.z * a.batch_stride;
     const int trn = (int)(r0 + a.tr < a.n2 ? a.tr : a.n2 - r0);
     const int tcn = (int)(c0 + a.tc < a.n1 ? a.tc : a.n1 - c0);
     const int hl = a.useB ? a.klb : 0, hu = a.useB ? a.kub : 0;   // row halo
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
         const int64_t r = r0 - hl + rr;
         const int64_t c = c0 - wl + cc;
         T v = 0;
-        if (r >= 0 && r < a.n2 && c >= 0 && c < a.n1) v = a.x[r + a.n2 * c];
+        if (r >= 0 && r < a.n2 && c >= 0 && c < a.n1) v = xs[r + a.n2 * c];
         sX[rr + a.pitch * cc] = v;
     }
     if (a.useA)
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
                 for (int t = 0; t < nbb; ++t) acc = fma(cb[t], xb[t], acc);
             }
             const int64_t o = r + a.n2 * (c0 + cc);
-            a.y[o] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[o], a.alpha * acc);
+            ys[o] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, ys[o], a.alpha * acc);
         }
     }
 }
@@ -356,8 +359,10 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
 
 template <typename T>
 int kron_launch(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda, int64_t klb,
-                int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int useA, int useB) {
+                int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int useA, int useB,
+                int64_t batch = 1, int64_t batch_stride = 0) {
     KronArgs<T> a;
+    a.batch_stride = batch_stride;
     a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
     a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
     a.useA = useA; a.useB = useB;
@@ -389,7 +394,8 @@ int kron_launch(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
         configured_dev_mask |= (1 << h->device);
     }
-    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (batch > 65535) return lbm_fail_arg(h, 2, "batch too large for the tile grid");
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
     kern<<<grid, 256, (size_t)smem, h->stream>>>(a);
     LBM_LAUNCH_CHECK(h, "kron_tile_kernel");
     return 0;
@@ -450,5 +456,37 @@ int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     rc = kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, 1.0, x, 0.0, (double *)z, 0, 1);
     if (rc) return rc;
     return kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, (const double *)z, beta, y, 1, 0);
+}
+
+// Y = (A (x) B (x) C) applied to a full n x n x n tensor X (k fastest, then j, then l) as the three
+// mode products of /root/reference/src/blockkron.jl:441-450: A along dim 3, B along dim 2, C along
+// dim 1 -- the arithmetic of KronTrav(A,B,C)*DiagTrav(X) before the DiagTrav re-ordering.
+int lbm_dkron3d_mv(lbm_handle_t h, int64_t n, int64_t kla, int64_t kua, const double *A, int64_t lda, int64_t klb,
+                   int64_t kub, const double *B, int64_t ldb, int64_t klc, int64_t kuc, const double *C, int64_t ldc,
+                   double alpha, const double *x, double beta, double *y) {
+    if (!h) return -1;
+    if (n < 0) return lbm_fail_arg(h, 2, "n < 0");
+    if (kla < 0 || kua < 0 || lda < kla + kua + 1) return lbm_fail_arg(h, 6, "bad band of A");
+    if (klb < 0 || kub < 0 || ldb < klb + kub + 1) return lbm_fail_arg(h, 10, "bad band of B");
+    if (klc < 0 || kuc < 0 || ldc < klc + kuc + 1) return lbm_fail_arg(h, 14, "bad band of C");
+    if (n == 0) return 0;
+    if (!A) return lbm_fail_arg(h, 5, "A == NULL");
+    if (!B) return lbm_fail_arg(h, 9, "B == NULL");
+    if (!C) return lbm_fail_arg(h, 13, "C == NULL");
+    if (!x) return lbm_fail_arg(h, 16, "x == NULL");
+    if (!y) return lbm_fail_arg(h, 18, "y == NULL");
+    lbm_device_guard g(h->device);
+    void *z1v, *z2v;
+    int rc;
+    const size_t bytes = (size_t)(n * n * n) * sizeof(double);
+    if ((rc = lbm_scratch(h, 2 * bytes, &z1v))) return rc;
+    double *z1 = (double *)z1v, *z2 = z1 + n * n * n;
+    (void)z2v;
+    // mode 3: X as (n^2 x n) matrix, Z1 = X * A^T
+    if ((rc = kron_launch<double>(h, n, n * n, kla, kua, A, lda, 0, 0, A, lda, 1.0, x, 0.0, z1, 1, 0))) return rc;
+    // mode 2: each l-slice (n x n): Z2[:,:,l] = Z1[:,:,l] * B^T   (batched over l)
+    if ((rc = kron_launch<double>(h, n, n, klb, kub, B, ldb, 0, 0, B, ldb, 1.0, z1, 0.0, z2, 1, 0, n, n * n))) return rc;
+    // mode 1: Z2 as (n x n^2) matrix, Y = alpha * C * Z2 + beta * Y
+    return kron_launch<double>(h, n * n, n, 0, 0, C, ldc, klc, kuc, C, ldc, alpha, z2, beta, y, 0, 1);
 }
 }

@@ -159,11 +159,104 @@ class KronSum:
         return self.mul_(y, x)
 
 
+def _diagtrav_index(shape):
+    """Flat (column-major) indices of an array's entries in DiagTrav order: anti-diagonal blocks
+    K = 1.., inside a block k descending (/root/reference/src/blockkron.jl:14-24, :101-133; 3-D order
+    pinned by test/test_blockkron.jl:53-57).  Host integer logic only."""
+    if len(shape) == 2:
+        m, n = shape
+        out = []
+        for K in range(1, max(m, n) + 1):
+            for j in range(1, K + 1):
+                k = K + 1 - j
+                if k <= m and j <= n:
+                    out.append((k - 1) + m * (j - 1))
+        return out
+    if len(shape) == 3:
+        n = shape[0]
+        if not (shape[1] == n and shape[2] == n):
+            raise LbmArgumentError("3-D DiagTrav needs a cubic array")
+        out = []
+        for K in range(1, n + 1):
+            for k in range(K, 0, -1):
+                for j in range(K + 1 - k, 0, -1):
+                    l = K + 2 - k - j
+                    out.append((k - 1) + n * (j - 1) + n * n * (l - 1))
+        return out
+    raise LbmArgumentError("DiagTrav supports 2-D and 3-D arrays")
+
+
+class DiagTrav:
+    """`DiagTrav(X)`: a matrix / cubic tensor viewed as a block vector by anti-diagonal traversal.
+    The constructor zeroes the bottom-right part (zero_bottomright, src/blockkron.jl:27-64).
+    `array` is a device tensor indexed [k, j(, l)]; storage is column-major (k fastest)."""
+
+    def __init__(self, array: torch.Tensor):
+        if array.dim() == 2:
+            m, n = array.shape
+            k = torch.arange(m, device=array.device).view(m, 1)
+            j = torch.arange(n, device=array.device).view(1, n)
+            keep = (k + j) <= (max(m, n) - 1)
+        elif array.dim() == 3:
+            n = array.shape[0]
+            r = torch.arange(n, device=array.device)
+            keep = (r.view(n, 1, 1) + r.view(1, n, 1) + r.view(1, 1, n)) <= (n - 1)
+        else:
+            raise LbmArgumentError("DiagTrav supports 2-D and 3-D arrays")
+        self.array = torch.where(keep, array, torch.zeros((), dtype=array.dtype, device=array.device))
+        self._idx = None
+
+    def colmajor(self) -> torch.Tensor:
+        """vec(array) with k fastest (the layout the Kronecker kernels take)."""
+        return self.array.permute(*reversed(range(self.array.dim()))).contiguous().view(-1)
+
+    def vector(self) -> torch.Tensor:
+        """The block vector (what `Vector(DiagTrav(X))` returns in the reference)."""
+        if self._idx is None:
+            self._idx = torch.tensor(_diagtrav_index(tuple(self.array.shape)), dtype=torch.int64,
+                                     device=self.array.device)
+        return self.colmajor().index_select(0, self._idx)
+
+    @classmethod
+    def from_colmajor(cls, v: torch.Tensor, shape):
+        arr = v.view(*reversed(shape)).permute(*reversed(range(len(shape))))
+        return cls(arr)
+
+
 class KronTrav:
-    """Structure of `KronTrav(A, B[, C])` (Kronecker product in DiagTrav ordering)."""
+    """`KronTrav(A, B[, C])`: Kronecker product in DiagTrav ordering -- structure queries plus the
+    never-materialised apply `K*DiagTrav(X) = DiagTrav(B*X*A')` (src/blockkron.jl:433-440) and its
+    3-D version by mode products (:441-450)."""
 
     def __init__(self, *args):
         self.args = args
+
+    def mul_diagtrav(self, X: "DiagTrav") -> "DiagTrav":
+        arr = X.array
+        if arr.dtype != torch.float64:
+            raise LbmArgumentError("the device KronTrav apply is Float64")
+        h = _lib.handle_of(arr)
+        x = X.colmajor()
+        y = torch.empty_like(x)
+        bm = [a.as_banded(arr.dtype, arr.device) if isinstance(a, Eye) else a for a in self.args]
+        if len(bm) == 2 and arr.dim() == 2:
+            A, B = bm
+            n2, n1 = arr.shape                      # X is size(B,2) x size(A,2)
+            if (A.shape[1], B.shape[1]) != (n1, n2):
+                raise DimensionMismatch(f"KronTrav factors {A.shape}, {B.shape} do not match DiagTrav array {tuple(arr.shape)}")
+            h.check(_lib.lib().lbm_dkron2d_mv(h.ptr, n1, n2, A.l, A.u, _ptr(A.data), A.lda, B.l, B.u, _ptr(B.data),
+                                              B.lda, 1.0, _ptr(x), 0.0, _ptr(y)), "lbm_dkron2d_mv")
+            return DiagTrav.from_colmajor(y, (n2, n1))
+        if len(bm) == 3 and arr.dim() == 3:
+            A, B, Cm = bm
+            n = arr.shape[0]
+            if not all(f.shape == (n, n) for f in bm):
+                raise DimensionMismatch("3-factor KronTrav apply needs n x n factors and an n^3 tensor")
+            h.check(_lib.lib().lbm_dkron3d_mv(h.ptr, n, A.l, A.u, _ptr(A.data), A.lda, B.l, B.u, _ptr(B.data), B.lda,
+                                              Cm.l, Cm.u, _ptr(Cm.data), Cm.lda, 1.0, _ptr(x), 0.0, _ptr(y)),
+                    "lbm_dkron3d_mv")
+            return DiagTrav.from_colmajor(y, (n, n, n))
+        raise LbmArgumentError("KronTrav apply is defined for 2 factors x matrix or 3 factors x cubic tensor")
 
     def blockbandwidths(self):
         # _krontrav_blockbandwidths: broadcast(+, map(bandwidths, A)...)  (src/blockkron.jl:355,358)

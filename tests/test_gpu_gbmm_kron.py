@@ -261,3 +261,69 @@ def test_blockkron_apply(L, oracle):
         if n1 * n2 <= 2000:
             dense = np.kron(oracle.band_to_dense(A_np, n1, la, ua), oracle.band_to_dense(B_np, n2, lb, ub)) @ x_np
             assert np.max(np.abs(got - dense)) <= tol
+
+
+def _dense_banded(L, M):
+    """Dense numpy matrix -> full-band BandedMatrix on the device."""
+    m, n = M.shape
+    data = np.zeros((m + n - 1, n), order="F")
+    l, u = m - 1, n - 1
+    for j in range(n):
+        for i in range(m):
+            data[u + i - j, j] = M[i, j]
+    return L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(data.T)).cuda(), m, l, u)
+
+
+def test_krontrav_apply_reference_kats(L, oracle, kats):
+    """The reference's own KATs for KronTrav*DiagTrav, computed on the GPU without forming K."""
+    k = next(k for k in kats if k["kind"] == "krontrav_mul")            # test/test_blockkron.jl:139-148
+    A, B, X, Y = (np.array(k[s], dtype=np.float64) for s in "ABXY")
+    K = L.KronTrav(_dense_banded(L, A), _dense_banded(L, B))
+    for Z in (X, Y):                                                       # K*DiagTrav(X) == K*DiagTrav(Y)
+        got = K.mul_diagtrav(L.DiagTrav(torch.from_numpy(Z).cuda())).vector().cpu().tolist()
+        assert got == [211.0, 291.0, 533.0]
+    for k in [k for k in kats if k["kind"] == "diagtrav"]:                 # DiagTrav index map on the device
+        Xn = np.array(k["X"], dtype=np.float64)
+        if max(Xn.shape) == min(Xn.shape) or True:
+            got = L.DiagTrav(torch.from_numpy(Xn).cuda()).vector().cpu().tolist()
+            want = oracle.diagtrav(oracle.zero_bottomright(Xn.copy())).tolist()
+            assert got == want, k["src"]
+    k = next(k for k in kats if k["kind"] == "krontrav3_matrix")           # explicit 4x4 KronTrav(A,B,C), :154-164
+    A, B, Cm = (np.array(k[s], dtype=np.float64) for s in "ABC")
+    K3 = L.KronTrav(_dense_banded(L, A), _dense_banded(L, B), _dense_banded(L, Cm))
+    n = 2
+    order = oracle.diagtrav(np.arange(n**3).reshape(n, n, n))
+    cols = []
+    for flat in order:
+        Xt = np.zeros((n, n, n))
+        Xt[np.unravel_index(int(flat), (n, n, n))] = 1.0
+        cols.append(K3.mul_diagtrav(L.DiagTrav(torch.from_numpy(Xt).cuda())).vector().cpu().numpy())
+    assert np.stack(cols, axis=1).astype(int).tolist() == k["expect"]
+    for k in [k for k in kats if k["kind"] == "krontrav_laplace2d"]:       # A*DiagTrav(X) == DiagTrav(X*D'), :201-207
+        n = k["n"]
+        D = L.banded_from_diagonals(n, {0: float(k["diag"]), 1: float(k["off"]), -1: float(k["off"])})
+        Dd = D.to_dense().cpu().numpy()
+        Xn = np.triu(np.random.default_rng(0).standard_normal((n, n)))[:, ::-1].copy()
+        Xg = L.DiagTrav(torch.from_numpy(Xn).cuda())
+        if "X * Δ'" in k["snippet"]:
+            got = L.KronTrav(D, L.Eye(n)).mul_diagtrav(Xg).vector().cpu().numpy()
+            want = oracle.diagtrav(Xn @ Dd.T)
+        else:
+            got = L.KronTrav(L.Eye(n), D).mul_diagtrav(Xg).vector().cpu().numpy()
+            want = oracle.diagtrav(Dd @ Xn)
+        assert np.array_equal(got, want), k["src"]                        # exact for the +-1/-2 stencil
+
+
+def test_kron3d_mode_products(L, oracle):
+    """lbm_dkron3d_mv == the three mode-product sweeps of src/blockkron.jl:441-450 (numpy einsum),
+    and KronTrav(A,B,C)*DiagTrav(X) == the oracle's restatement including the DiagTrav ordering."""
+    rng = np.random.default_rng(2)
+    for n, bw in ((4, (1, 1)), (9, (2, 1)), (33, (1, 1)), (64, (3, 3))):
+        facs = [_band(L, oracle, n, n, bw[0], bw[1], 40 + i, torch.float64) for i in range(3)]
+        dA, dB, dC = (oracle.band_to_dense(f[0], n, *bw) for f in facs)
+        X = rng.standard_normal((n, n, n))
+        K3 = L.KronTrav(facs[0][1], facs[1][1], facs[2][1])
+        out = K3.mul_diagtrav(L.DiagTrav(torch.from_numpy(X).cuda()))
+        want_vec = oracle.krontrav3_mul_diagtrav(dA, dB, dC, X)
+        tol = tol_rows(np.float64, (bw[0] + bw[1] + 1) ** 3, 1.0, float(np.abs(X).max()))
+        assert np.max(np.abs(out.vector().cpu().numpy() - want_vec)) <= tol
