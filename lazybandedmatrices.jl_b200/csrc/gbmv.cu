@@ -640,6 +640,11 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
     }
 }
 
+// Host-buffer entry point: H2D(A, x) + kernel + D2H(y), pipelined.  op = N streams A in column
+// chunks on a copy stream; as soon as the columns a block of rows needs have landed, that block's
+// sub-slab (again a rectangular banded matrix: same lda, shifted bandwidths) is applied on the
+// compute stream and its piece of y goes back on a third stream -- so kernels and the D2H hide under
+// the H2D, which is the PCIe-bound critical path.
 template <typename T>
 int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha, const T *A,
                    int64_t lda, const T *x, T beta, T *y) {
@@ -653,18 +658,65 @@ int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl,
     const int64_t nout = tr ? n : m, nin = tr ? m : n;
     if (nout == 0) return 0;
     lbm_device_guard g(h->device);
-    void *dA, *dx, *dy;
+    void *dAv, *dxv, *dyv;
     int rc;
-    if ((rc = lbm_stage(h, 0, (size_t)(lda * n) * sizeof(T) + 16, &dA))) return rc;
-    if ((rc = lbm_stage(h, 1, (size_t)nin * sizeof(T) + 16, &dx))) return rc;
-    if ((rc = lbm_stage(h, 2, (size_t)nout * sizeof(T) + 16, &dy))) return rc;
-    if (lda * n > 0) LBM_CUDA(h, cudaMemcpyAsync(dA, A, (size_t)(lda * n) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    if (nin) LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    rc = gbmv_impl<T>(h, trans, m, n, kl, ku, alpha, (const T *)dA, lda, (const T *)dx, beta, (T *)dy);
-    if (rc) return rc;
-    LBM_CUDA(h, cudaMemcpyAsync(y, dy, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-    LBM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if ((rc = lbm_stage(h, 0, (size_t)(lda * n) * sizeof(T) + 16, &dAv))) return rc;
+    if ((rc = lbm_stage(h, 1, (size_t)nin * sizeof(T) + 16, &dxv))) return rc;
+    if ((rc = lbm_stage(h, 2, (size_t)nout * sizeof(T) + 16, &dyv))) return rc;
+    T *dA = (T *)dAv, *dx = (T *)dxv, *dy = (T *)dyv;
+    const int64_t chunk_cols = ((int64_t)256 << 20) / (lda * (int64_t)sizeof(T));  // ~256 MB of A per chunk
+    const bool pipelined = !tr && n > 2 * chunk_cols && chunk_cols > 4 * (kl + ku + 1);
+    if (!pipelined) {
+        if (lda * n > 0) LBM_CUDA(h, cudaMemcpyAsync(dA, A, (size_t)(lda * n) * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        if (nin) LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        rc = gbmv_impl<T>(h, trans, m, n, kl, ku, alpha, dA, lda, dx, beta, dy);
+        if (rc) return rc;
+        LBM_CUDA(h, cudaMemcpyAsync(y, dy, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        LBM_CUDA(h, cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (!h->h2d_stream) {
+        LBM_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+        LBM_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        LBM_CUDA(h, cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        LBM_CUDA(h, cudaEventCreateWithFlags(&h->ev_kern, cudaEventDisableTiming));
+    }
+    cudaStream_t sc = h->h2d_stream, sk = h->stream, so = h->d2h_stream;
+    // order the pipeline after whatever is already queued on the handle's stream
+    LBM_CUDA(h, cudaEventRecord(h->ev_kern, sk));
+    LBM_CUDA(h, cudaStreamWaitEvent(sc, h->ev_kern, 0));
+    LBM_CUDA(h, cudaStreamWaitEvent(so, h->ev_kern, 0));
+    LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, sc));
+    if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, sc));
+    int64_t r_done = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += chunk_cols) {
+        const int64_t c1 = c0 + chunk_cols < n ? c0 + chunk_cols : n;
+        LBM_CUDA(h, cudaMemcpyAsync(dA + c0 * lda, A + c0 * lda, (size_t)((c1 - c0) * lda) * sizeof(T),
+                                    cudaMemcpyHostToDevice, sc));
+        LBM_CUDA(h, cudaEventRecord(h->ev_copy, sc));
+        // rows whose columns [i-kl, i+ku] all lie in [0, c1): i < c1 - ku (all remaining rows once c1 == n)
+        int64_t r_hi = c1 == n ? m : c1 - ku;
+        r_hi &= ~(int64_t)3;                   // keep sub-slabs 16-byte aligned
+        if (c1 == n) r_hi = m;
+        if (r_hi > m) r_hi = m;
+        if (r_hi <= r_done) continue;
+        LBM_CUDA(h, cudaStreamWaitEvent(sk, h->ev_copy, 0));
+        const int64_t a0 = r_done, b0 = r_hi;
+        const int64_t cc0 = a0 - kl > 0 ? a0 - kl : 0;
+        const int64_t cc1 = b0 + ku < n ? b0 + ku : n;
+        const int64_t shift = a0 - cc0;
+        rc = gbmv_impl<T>(h, 'N', b0 - a0, cc1 - cc0, kl - shift, ku + shift, alpha, dA + cc0 * lda, lda, dx + cc0, beta,
+                          dy + a0);
+        if (rc) return rc;
+        LBM_CUDA(h, cudaEventRecord(h->ev_kern, sk));
+        LBM_CUDA(h, cudaStreamWaitEvent(so, h->ev_kern, 0));
+        LBM_CUDA(h, cudaMemcpyAsync(y + a0, dy + a0, (size_t)(b0 - a0) * sizeof(T), cudaMemcpyDeviceToHost, so));
+        r_done = r_hi;
+    }
+    LBM_CUDA(h, cudaStreamSynchronize(so));
+    LBM_CUDA(h, cudaStreamSynchronize(sk));
+    LBM_CUDA(h, cudaStreamSynchronize(sc));
     return 0;
 }
 

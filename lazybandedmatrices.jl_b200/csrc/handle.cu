@@ -86,6 +86,12 @@ int lbm_destroy(lbm_handle_t h) {
     lbm_device_guard g(h->device);
     cudaStreamSynchronize(h->stream);
     lbm_comm_destroy(h);
+    if (h->h2d_stream) {
+        cudaStreamDestroy(h->h2d_stream);
+        cudaStreamDestroy(h->d2h_stream);
+        cudaEventDestroy(h->ev_copy);
+        cudaEventDestroy(h->ev_kern);
+    }
     if (h->scratch) cudaFree(h->scratch);
     for (int i = 0; i < 4; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);

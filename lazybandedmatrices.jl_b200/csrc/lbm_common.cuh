@@ -52,6 +52,9 @@ struct lbm_handle_s {
     size_t scratch_bytes;
     void *stage[4];           // device staging for *_host entry points
     size_t stage_bytes[4];
+    // *_host pipeline: copy-in / copy-out streams and their events (created on first use)
+    cudaStream_t h2d_stream, d2h_stream;
+    cudaEvent_t ev_copy, ev_kern;
     // multi-GPU: one process per GPU; NCCL communicator owned by the handle (dist.cu)
     void *nccl_comm;
     int rank, world;

@@ -147,6 +147,23 @@ def test_gbmv_host_entry_point(L, oracle):
     assert np.max(np.abs(y_np - want)) <= tol_rows(np.float64, kl + ku + 1, 1.0, 1.0)
 
 
+def test_gbmv_host_entry_point_pipelined(L, oracle):
+    """Large host operands take the 3-stream chunked pipeline (H2D of A overlapped with the
+    sub-slab kernels and the D2H of y); result identical to the oracle's full sweep."""
+    import ctypes as C
+    for (n, kl, ku, beta) in (((1 << 25) + 3, 1, 1, 0.0), (12_000_001, 2, 3, 0.5)):
+        A_np = oracle.brand(n, n, kl, ku, seed=21)
+        x_np = oracle.fill_uniform(22, n)
+        y0 = oracle.fill_uniform(23, n)
+        y_np = y0.copy()
+        h = L.handle_for(0)
+        rc = L.lib().lbm_dgbmv_host(h.ptr, b"N", n, n, kl, ku, 1.5, A_np.ctypes.data_as(C.c_void_p), kl + ku + 1,
+                                    x_np.ctypes.data_as(C.c_void_p), beta, y_np.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        want = oracle.gbmv("N", n, n, kl, ku, 1.5, A_np, x_np, beta, y0)
+        assert np.max(np.abs(y_np - want)) <= tol_rows(np.float64, kl + ku + 1, 1.0, 1.0, 1.5, beta, 1.0)
+
+
 def test_gbmv_large_linearity_and_sampled_rows(L, oracle):
     """At a size the oracle cannot sweep quickly: sampled rows vs the oracle's definition
     (regenerating only the needed entries from the counter-based stream) + linearity."""
