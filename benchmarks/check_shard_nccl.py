@@ -12,7 +12,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import lbm_b200 as L  # noqa: E402
-from lbm_b200.shard import ShardedBanded, init_comm, sharded_chain_mul_  # noqa: E402
+from lbm_b200.shard import RowShard, ShardedBanded, ShardedKronSum, GbmmColumnShard, init_comm, sharded_chain_mul_  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
@@ -27,10 +27,42 @@ def main():
             init_comm(local)
             assert L.handle_for(local).comm_world == world
         _check(rank, world, dev, eps)
+    _check_kron_gbmm(rank, world, dev, eps)
     dist.barrier()
     if rank == 0:
         print(f"OK sharded mul!/chain on {world} GPUs match the oracle (torch P2P path and in-library NCCL path)")
     dist.destroy_process_group()
+
+
+def _check_kron_gbmm(rank, world, dev, eps):
+    """C3 (grid-column partition, in-library ghost-column exchange) and C4 (column-partitioned gbmm)."""
+    for (n1, n2, (kla, kua), (klb, kub)) in ((4096, 2048, (1, 1), (1, 1)), (1000, 516, (2, 2), (1, 1)), (300, 70, (1, 2), (3, 0))):
+        A = O.brand(n1, n1, kla, kua, seed=3)
+        Bn = O.brand(n2, n2, klb, kub, seed=4)
+        x = O.fill_uniform(5, n1 * n2)
+        want = O.kronsum2d_mv(n1, n2, A, kla, kua, Bn, klb, kub, x, 1.5, 0.0).reshape(n1, n2)
+        p = RowShard.plan(n1, kla, kua, rank, world)
+        Bg = L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(Bn.T)).to(dev), n2, klb, kub)
+        sh = ShardedKronSum(n1, n2, kla, kua, torch.from_numpy(np.ascontiguousarray(A.T[p.c0:p.c1])).to(dev), Bg, rank, world)
+        xbuf = sh.new_buffer(torch.float64, dev)
+        sh.owned(xbuf).copy_(torch.from_numpy(x.reshape(n1, n2)[p.r0:p.r1]))
+        for overlap in (True, False):
+            y = torch.full((p.m_loc, n2), float("nan"), dtype=torch.float64, device=dev)
+            sh.mul_(y, xbuf, alpha=1.5, overlap=overlap)
+            err = np.max(np.abs(y.cpu().numpy() - want[p.r0:p.r1]))
+            assert err <= 4 * eps * 1.5 * (kla + kua + klb + kub + 2), ("kronsum", n1, n2, overlap, err)
+    for (n, la, ua, lb, ub) in ((5000, 1, 1, 1, 1), (3000, 128, 128, 128, 128), (2000, 8, 3, 2, 5)):
+        A, B = O.brand(n, n, la, ua, seed=1), O.brand(n, n, lb, ub, seed=2)
+        want = O.gbmm(n, n, n, A, la, ua, B, lb, ub)
+        p = GbmmColumnShard.plan(n, la, ua, lb, ub, rank, world)
+        Cs = p.local_gbmm(torch.from_numpy(np.ascontiguousarray(A.T[p.pa:p.pb])).to(dev),
+                          torch.from_numpy(np.ascontiguousarray(B.T[p.c0:p.c1])).to(dev))
+        got = np.zeros_like(want)
+        got[:, p.c0:p.c1] = Cs.cpu().numpy().T
+        ref = np.zeros_like(want)
+        ref[:, p.c0:p.c1] = want[:, p.c0:p.c1]
+        dg, dw = O.band_to_dense(got, n, la + lb, ua + ub), O.band_to_dense(ref, n, la + lb, ua + ub)
+        assert np.max(np.abs(dg - dw)) <= 4 * eps * min(la + ua + 1, lb + ub + 1), ("gbmm shard", n, la)
 
 
 def _check(rank, world, dev, eps):

@@ -170,6 +170,17 @@ int lbm_dgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, double 
 int lbm_sgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, float alpha, const float *A_slab,
                       int64_t lda, float *xbuf, float beta, float *y_own, int overlap);
 
+/* kron(A,I)+kron(I,B) partitioned by grid columns: plan = lbm_shard_plan(n1, kla, kua, ...) over COLUMNS
+ * of X; A_slab = columns [c0,c1) of A's band array; xbuf = n2 x (c1-c0) ghost-cell buffer
+ * [left ghost columns | owned | right ghost columns]; y_own = n2 x (r1-r0).  Ghost columns travel by
+ * ncclSend/ncclRecv while the interior columns are computed; B*X is rank-local. */
+int lbm_dkronsum2d_mv_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua,
+                              const double *A_slab, int64_t lda, int64_t klb, int64_t kub, const double *B,
+                              int64_t ldb, double alpha, double *xbuf, double beta, double *y_own, int overlap);
+int lbm_skronsum2d_mv_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua,
+                              const float *A_slab, int64_t lda, int64_t klb, int64_t kub, const float *B,
+                              int64_t ldb, float alpha, float *xbuf, float beta, float *y_own, int overlap);
+
 /* ---- structure helpers (pure integer, host side, no GPU needed) ------------------------ */
 /* bandwidths(ApplyMatrix(*, F1..Fnf)) = min.(size-1, (sum kl, sum ku))  ([up] LazyArrays;
  * reference README.md:13-26 shows (1,1)*(1,1) -> (2,2)). */

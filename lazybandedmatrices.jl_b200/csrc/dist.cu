@@ -88,7 +88,7 @@ Plan make_plan(int64_t n, int64_t kl, int64_t ku, int rank, int world) {
     return p;
 }
 
-int exchange(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int eb) {
+int exchange(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb) {
     // sends read / recvs write xbuf: order them after everything already queued on the main stream
     LBM_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
     LBM_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
@@ -164,6 +164,18 @@ int gbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, T alpha, con
 }
 
 }  // namespace
+
+// internal (kron.cu): plan over `n` units of `unit_bytes` each + ghost exchange; the main stream does
+// NOT wait -- the caller overlaps interior work and then waits on h->ev_halo.
+int lbm_internal_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int64_t *plan8) {
+    const Plan p = make_plan(n, kl, ku, h->rank, h->world);
+    plan8[0] = p.r0; plan8[1] = p.r1; plan8[2] = p.c0; plan8[3] = p.c1;
+    plan8[4] = p.left; plan8[5] = p.right; plan8[6] = p.kl_loc; plan8[7] = p.ku_loc;
+    if (h->world == 1) return 0;
+    if (!h->nccl_comm) return lbm_fail_arg(h, 1, "lbm_comm_init has not been called on this handle");
+    if (p.m_loc < (kl > ku ? kl : ku)) return lbm_fail_arg(h, 2, "shard narrower than the halo max(kl,ku): use fewer ranks");
+    return exchange(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes);
+}
 
 extern "C" {
 

@@ -18,6 +18,8 @@
 //    the tile's coefficient rows of A and B with out-of-matrix slots masked to zero BY INDEX.
 #include "lbm_common.cuh"
 
+int lbm_internal_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int64_t *plan8);
+
 namespace {
 
 template <typename T>
@@ -35,6 +37,9 @@ struct KronArgs {
     int offCA, offCB; // smem offsets (elements)
     int useA, useB;   // which terms to apply
     int64_t batch_stride;  // elements between consecutive (n2 x n1) slices (blockIdx.z)
+    // sharded use: X has n1_in columns, output column c reads input column c + xoff; only output
+    // columns [c_begin, c_end) are produced.  Unsharded: n1_in = n1, xoff = 0, range = [0, n1).
+    int64_t n1_in, xoff, c_begin, c_end;
 };
 
 template <typename T>
@@ -46,11 +51,11 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
     const int tid = threadIdx.x;
     const int nba = a.kla + a.kua + 1, nbb = a.klb + a.kub + 1;
     const int64_t r0 = (int64_t)blockIdx.x * a.tr;
-    const int64_t c0 = (int64_t)blockIdx.y * a.tc;
+    const int64_t c0 = a.c_begin + (int64_t)blockIdx.y * a.tc;
     const T *xs = a.x + (int64_t)blockIdx.z * a.batch_stride;
     T *ys = a.y + (int64_t)blockIdx.z * a.batch_stride;
     const int trn = (int)(r0 + a.tr < a.n2 ? a.tr : a.n2 - r0);
-    const int tcn = (int)(c0 + a.tc < a.n1 ? a.tc : a.n1 - c0);
+    const int tcn = (int)(c0 + a.tc < a.c_end ? a.tc : a.c_end - c0);
     const int hl = a.useB ? a.klb : 0, hu = a.useB ? a.kub : 0;   // row halo
     const int wl = a.useA ? a.kla : 0, wu = a.useA ? a.kua : 0;   // column halo
     const int rows_h = trn + hl + hu;
@@ -61,9 +66,9 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
         const int cc = e / rows_h;
         const int rr = e - cc * rows_h;
         const int64_t r = r0 - hl + rr;
-        const int64_t c = c0 - wl + cc;
+        const int64_t c = c0 + a.xoff - wl + cc;  // input column
         T v = 0;
-        if (r >= 0 && r < a.n2 && c >= 0 && c < a.n1) v = xs[r + a.n2 * c];
+        if (r >= 0 && r < a.n2 && c >= 0 && c < a.n1_in) v = xs[r + a.n2 * c];
         sX[rr + a.pitch * cc] = v;
     }
     if (a.useA)
@@ -71,8 +76,8 @@ __global__ void __launch_bounds__(256) kron_tile_kernel(const KronArgs<T> a) {
             const int cc = e / nba;
             const int t = e - cc * nba;
             const int64_t c = c0 + cc;
-            const int64_t q = c - a.kla + t;  // A[c,q] = Ad[(kua + c - q) + lda*q]
-            sCA[e] = (q >= 0 && q < a.n1) ? a.A[(a.kua + c - q) + a.lda * q] : (T)0;
+            const int64_t q = c + a.xoff - a.kla + t;  // input column; A[c,q] sits at band row kua+kla-t of slab column q
+            sCA[e] = (q >= 0 && q < a.n1_in) ? a.A[(a.kua + a.kla - t) + a.lda * q] : (T)0;
         }
     if (a.useB)
         for (int e = tid; e < trn * nbb; e += 256) {
@@ -126,6 +131,7 @@ struct KronRingArgs {
     int seg;       // smem elements per staged grid column = tr + 2*hp
     int stages;
     int64_t nchunks;
+    int64_t n1_in, xoff, c_begin, c_end;  // see KronArgs
 };
 
 template <typename T, int NBA, int NBB, int RPT>
@@ -157,14 +163,20 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
     // each IN PARALLEL (one instruction for up to 32 copies), lane 0 arrives.
     auto issue = [&](int64_t q, int s) {  // all 32 lanes of warp 0
         const int lane = tid & 31;
-        const int64_t c0 = q * a.g;
-        int64_t ca = c0 - a.kla > 0 ? c0 - a.kla : 0;
-        int64_t cb = c0 + a.g + a.kua < a.n1 ? c0 + a.g + a.kua : a.n1;
+        const int64_t c0 = a.c_begin + q * a.g;
+        const int64_t ci0 = c0 + a.xoff - a.kla;  // first INPUT column of the stage
+        int64_t ca = ci0 > 0 ? ci0 : 0;
+        int64_t cb = ci0 + a.g + a.kla + a.kua < a.n1_in ? ci0 + a.g + a.kla + a.kua : a.n1_in;
+        if (c0 + a.g > a.c_end) {  // last (short) chunk of the range: no columns beyond its halo
+            const int64_t lim = a.c_end + a.xoff + a.kua;
+            if (cb > lim) cb = lim;
+        }
+        if (cb < ca) cb = ca;
         T *st = sbase + (int64_t)s * stage_elems;
         if (lane == 0) mbar_add_tx(&bars[s], (uint32_t)(cb - ca) * col_bytes);
         __syncwarp();
         for (int64_t c = ca + lane; c < cb; c += 32)
-            bulk_g2s(st + (c - (c0 - a.kla)) * a.seg + roff, a.x + c * a.n2 + rs, col_bytes, &bars[s]);
+            bulk_g2s(st + (c - ci0) * a.seg + roff, a.x + c * a.n2 + rs, col_bytes, &bars[s]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[s]);
     };
@@ -181,9 +193,9 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
     auto load_coef = [&](int64_t q) -> T {
         if (tid >= ncoef) return (T)0;
         const int cc = tid / NBA, t = tid - cc * NBA;
-        const int64_t c = q * a.g + cc;
-        const int64_t qq = c - a.kla + t;
-        return (c < a.n1 && qq >= 0 && qq < a.n1) ? a.A[(a.kua + a.kla - t) + a.lda * qq] : (T)0;
+        const int64_t c = a.c_begin + q * a.g + cc;
+        const int64_t qq = c + a.xoff - a.kla + t;  // input column
+        return (c < a.c_end && qq >= 0 && qq < a.n1_in) ? a.A[(a.kua + a.kla - t) + a.lda * qq] : (T)0;
     };
     if (mine > 0 && tid < ncoef) sCA[tid] = load_coef(first);
 
@@ -218,11 +230,11 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
         const int s = (int)(kk % S);
         const uint32_t parity = (uint32_t)((kk / S) & 1);
         const int64_t q = first + kk * step;
-        const int64_t c0 = q * a.g;
-        const int gq = (int)(c0 + a.g < a.n1 ? a.g : a.n1 - c0);
+        const int64_t c0 = a.c_begin + q * a.g;
+        const int gq = (int)(c0 + a.g < a.c_end ? a.g : a.c_end - c0);
         const T *st = sbase + (int64_t)s * stage_elems;
         const T *ca = sCA + (kk & 1) * ncoef;
-        const bool edge = row_edge || (c0 - a.kla < 0) || (c0 + gq + a.kua > a.n1);
+        const bool edge = row_edge || (c0 + a.xoff - a.kla < 0) || (c0 + a.xoff + gq + a.kua > a.n1_in);
         T cnext = (T)0;
         if (kk + 1 < mine) cnext = load_coef(q + step);  // in flight during this chunk's compute
         mbar_wait(&bars[s], parity);
@@ -265,8 +277,8 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
                         T acc = 0;
 #pragma unroll
                         for (int t = 0; t < NBA; ++t) {
-                            const int64_t qq = c - a.kla + t;
-                            if (qq >= 0 && qq < a.n1) acc = fma(cav[t], xa[t * seg], acc);
+                            const int64_t qq = c + a.xoff - a.kla + t;
+                            if (qq >= 0 && qq < a.n1_in) acc = fma(cav[t], xa[t * seg], acc);
                         }
 #pragma unroll
                         for (int t = 0; t < NBB; ++t) {
@@ -311,19 +323,24 @@ int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_
 // returns true (and the launch status in *rc) when the ring kernel took the call
 template <typename T>
 bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda,
-                   int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc) {
+                   int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc,
+                   int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0, int64_t c_end = -1) {
+    if (n1_in < 0) n1_in = n1;
+    if (c_end < 0) c_end = n1;
+    if (c_end <= c_begin) { *rc = 0; return true; }
     constexpr int EPV = 16 / (int)sizeof(T);
     const int64_t nba = kla + kua + 1, nbb = klb + kub + 1;
     const bool shape_ok = (nba == 3 || nba == 1 || nba == 5) && (nbb == 3 || nbb == 1 || nbb == 5) &&
                           !(nba == 5 && nbb == 1) && !(nba == 1 && nbb == 5) && !(nba == 1 && nbb == 1);
-    if (!shape_ok || n2 % EPV != 0 || !lbm_aligned16(x) || n2 < 512 || n1 < 8 || h->tune.kron_force_tile) return false;
+    if (!shape_ok || n2 % EPV != 0 || !lbm_aligned16(x) || n2 < 512 || (c_end < 0 ? n1 : c_end) - c_begin < 1 || h->tune.kron_force_tile) return false;
     KronRingArgs<T> a;
     a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
     a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
+    a.n1_in = n1_in; a.xoff = xoff; a.c_begin = c_begin; a.c_end = c_end;
     int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
     tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
     int64_t g = h->tune.kron_tc > 0 ? h->tune.kron_tc : 16;
-    if (g > n1) g = n1;
+    if (g > c_end - c_begin) g = c_end - c_begin;
     if (g * nba > 256) g = 256 / nba;  // one A coefficient per thread per chunk
     const int64_t hmax = klb > kub ? klb : kub;
     a.hp = (int)((hmax + EPV - 1) / EPV * EPV);
@@ -334,7 +351,7 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     auto stage_bytes = [&](int64_t gg) { return (gg + kla + kua) * (int64_t)a.seg * (int64_t)sizeof(T); };
     while (g > 2 && stages * stage_bytes(g) + 4096 > sm_smem) g /= 2;
     a.g = (int)g;
-    a.nchunks = (n1 + g - 1) / g;
+    a.nchunks = (c_end - c_begin + g - 1) / g;
     int64_t cps = h->tune.kron_ctas_per_sm > 0 ? h->tune.kron_ctas_per_sm : (200 * 1024) / (stages * stage_bytes(g) + 256);
     if (cps < 1) cps = 1;
     if (cps > 8) cps = 8;
@@ -360,9 +377,15 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
 template <typename T>
 int kron_launch(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda, int64_t klb,
                 int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int useA, int useB,
-                int64_t batch = 1, int64_t batch_stride = 0) {
+                int64_t batch = 1, int64_t batch_stride = 0, int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0,
+                int64_t c_end = -1) {
     KronArgs<T> a;
     a.batch_stride = batch_stride;
+    a.n1_in = n1_in < 0 ? n1 : n1_in;
+    a.xoff = xoff;
+    a.c_begin = c_begin;
+    a.c_end = c_end < 0 ? n1 : c_end;
+    if (a.c_end <= a.c_begin) return 0;
     a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
     a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
     a.useA = useA; a.useB = useB;
@@ -386,7 +409,7 @@ int kron_launch(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua
     const int64_t smem = layout(tr, tc, pitch, oCA, oCB);
     if (smem > smem_cap) return lbm_fail_arg(h, 4, "bands too wide for the fused Kronecker kernel");
     a.tr = (int)tr; a.tc = (int)tc; a.pitch = pitch; a.offCA = oCA; a.offCB = oCB;
-    const int64_t gx = (n2 + tr - 1) / tr, gy = (n1 + tc - 1) / tc;
+    const int64_t gx = (n2 + tr - 1) / tr, gy = (a.c_end - a.c_begin + tc - 1) / tc;
     if (gy > 65535) return lbm_fail_arg(h, 2, "n1 too large for the tile grid");
     static int configured_dev_mask = 0;
     auto kern = kron_tile_kernel<T>;
@@ -431,9 +454,60 @@ int kronsum_impl(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t ku
     return kron_launch<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y, 1, 1);
 }
 
+// Column-partitioned kron(A,I) + kron(I,B): rank r owns grid columns
+// [r0,r1) of X (contiguous memory), stores the column slice [c0,c1) of A's band array, and keeps X
+// in a ghost-cell buffer [kla ghost columns | owned | kua ghost columns].  The B*X term is rank
+// local; only the ghost columns (n2 elements each) travel.  Interior columns overlap the exchange.
+template <typename T>
+int kronsum_range(lbm_handle_t h, int64_t m_loc, int64_t n_loc, int64_t left, int64_t n2, int64_t kla, int64_t kua,
+                  const T *A, int64_t lda, int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *xbuf, T beta,
+                  T *y, int64_t cb, int64_t ce) {
+    if (ce <= cb) return 0;
+    int rc = 0;
+    if (kron_ring_try<T>(h, m_loc, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, xbuf, beta, y, &rc, n_loc, left, cb, ce))
+        return rc;
+    return kron_launch<T>(h, m_loc, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, xbuf, beta, y, 1, 1, 1, 0, n_loc, left,
+                          cb, ce);
+}
+
+template <typename T>
+int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A_slab, int64_t lda,
+                    int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, T *xbuf, T beta, T *y_own, int overlap) {
+    int rc = kron_check<T>(h, n1, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, xbuf, y_own);
+    if (rc || n1 == 0 || n2 == 0) return rc;
+    lbm_device_guard g(h->device);
+    int64_t pl[8];
+    if ((rc = lbm_internal_exchange(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T), pl))) return rc;
+    const int64_t m_loc = pl[1] - pl[0], n_loc = pl[3] - pl[2], left = pl[4], right = pl[5];
+    if (m_loc == 0) return 0;
+    if (h->world == 1)
+        return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc);
+    if (!overlap) {
+        LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+        return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc);
+    }
+    int64_t a = left == 0 ? 0 : kla, b = right == 0 ? m_loc : m_loc - kua;
+    if (a > m_loc) a = m_loc;
+    if (b < a) b = a;
+    if ((rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, a, b))) return rc;
+    LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+    if ((rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, a))) return rc;
+    return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, b, m_loc);
+}
+
 }  // namespace
 
 extern "C" {
+int lbm_dkronsum2d_mv_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const double *A_slab,
+                              int64_t lda, int64_t klb, int64_t kub, const double *B, int64_t ldb, double alpha,
+                              double *xbuf, double beta, double *y_own, int overlap) {
+    return kronsum_sharded<double>(h, n1, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, overlap);
+}
+int lbm_skronsum2d_mv_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const float *A_slab,
+                              int64_t lda, int64_t klb, int64_t kub, const float *B, int64_t ldb, float alpha, float *xbuf,
+                              float beta, float *y_own, int overlap) {
+    return kronsum_sharded<float>(h, n1, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, overlap);
+}
 int lbm_dkronsum2d_mv(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const double *A, int64_t lda,
                       int64_t klb, int64_t kub, const double *B, int64_t ldb, double alpha, const double *x,
                       double beta, double *y) {

@@ -71,6 +71,8 @@ def _sigs():
                                                       vp, i64, vp, i64, vp, i64, vp, i64])
         s[f"lbm_{p}kronsum2d_mv"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, ft,
                                                vp, ft, vp])
+        s[f"lbm_{p}kronsum2d_mv_sharded"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, ft,
+                                                       vp, ft, vp, C.c_int])
     s["lbm_dkron2d_mv"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, f64, vp, f64, vp])
     s["lbm_dkron3d_mv"] = (C.c_int, [H, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, f64, vp, f64, vp])
     return s

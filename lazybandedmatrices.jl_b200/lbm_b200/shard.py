@@ -249,3 +249,151 @@ def sharded_chain_mul_(y_own, factors, xbuf, tmp_bufs, group=None, local_gbmv=No
         f.mul_(consumer.plan.owned(t), v, group=group, local_gbmv=local_gbmv)
         v = t
     return order[-1].mul_(y_own, v, group=group, local_gbmv=local_gbmv)
+
+
+# ------------------------------------------------------------------------------------------------
+# banded x banded materialise, column-partitioned: no communication
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class GbmmColumnShard:
+    """Rank r owns the COLUMNS [c0,c1) of C = A*B (n x n, bands (la,ua) x (lb,ub)).  It needs
+    B[:, c0:c1] and the columns [pa,pb) = [c0-ub, c1+lb) of A (a one-time, static halo).  Taken as
+    they lie in the diagonal-major arrays (same ld, same band-row index), those column slices ARE
+    banded matrices of a smaller product with shifted bandwidths:
+        rows   [ra, rb) = [c0-uc, c1+lc) ∩ [0,n)        (uc = ua+ub, lc = la+lb)
+        A_sub  (rb-ra) x (pb-pa),  bandwidths (la - (ra-pa), ua + (ra-pa))
+        B_sub  (pb-pa) x (c1-c0),  bandwidths (lb - (pa-c0), ub + (pa-c0))
+        C_sub  (rb-ra) x (c1-c0),  bandwidths (lc - (ra-c0), uc + (ra-c0))
+    so the local work is one ordinary lbm_?gbmm call and C's column slice is written in place."""
+    n: int
+    la: int
+    ua: int
+    lb: int
+    ub: int
+    rank: int
+    world: int
+    c0: int
+    c1: int
+
+    @classmethod
+    def plan(cls, n, la, ua, lb, ub, rank, world):
+        c0, c1 = split_rows(n, world, rank)
+        return cls(n, la, ua, lb, ub, rank, world, c0, c1)
+
+    @property
+    def lc(self):
+        return self.la + self.lb
+
+    @property
+    def uc(self):
+        return self.ua + self.ub
+
+    @property
+    def pa(self):
+        return max(0, self.c0 - self.ub)
+
+    @property
+    def pb(self):
+        return min(self.n, self.c1 + self.lb)
+
+    @property
+    def ra(self):
+        return max(0, self.c0 - self.uc)
+
+    @property
+    def rb(self):
+        return min(self.n, self.c1 + self.lc)
+
+    def sub_bandwidths(self):
+        """((klA,kuA), (klB,kuB), (klC,kuC)) of the local sub-product."""
+        sa, sb, sc = self.ra - self.pa, self.pa - self.c0, self.ra - self.c0
+        return ((self.la - sa, self.ua + sa), (self.lb - sb, self.ub + sb), (self.lc - sc, self.uc + sc))
+
+    def local_gbmm(self, A_slab: torch.Tensor, B_slab: torch.Tensor, C_slab: torch.Tensor = None, gbmm_fn=None):
+        """A_slab = data_A[pa:pb] ((pb-pa) x (la+ua+1)), B_slab = data_B[c0:c1]; returns / fills
+        C_slab = data_C[c0:c1] ((c1-c0) x (lc+uc+1))."""
+        (kla, kua), (klb, kub), (klc, kuc) = self.sub_bandwidths()
+        m_loc, k_loc, n_loc = self.rb - self.ra, self.pb - self.pa, self.c1 - self.c0
+        if C_slab is None:
+            C_slab = torch.empty((n_loc, self.lc + self.uc + 1), dtype=A_slab.dtype, device=A_slab.device)
+        if gbmm_fn is None:
+            from .banded import BandedMatrix, gbmm
+            gbmm(BandedMatrix(A_slab, m_loc, kla, kua), BandedMatrix(B_slab, k_loc, klb, kub),
+                 out=BandedMatrix(C_slab, m_loc, klc, kuc))
+        else:
+            gbmm_fn(m_loc, n_loc, k_loc, A_slab, kla, kua, B_slab, klb, kub, C_slab, klc, kuc)
+        return C_slab
+
+
+def split_batch(batch: int, world: int, rank: int):
+    """Batched independent products (config C5) are replicas: contiguous batch ranges, no communication."""
+    per = -(-batch // world)
+    b0 = min(batch, rank * per)
+    return b0, min(batch, b0 + per)
+
+
+# ------------------------------------------------------------------------------------------------
+# kron(A,I) + kron(I,B) partitioned by grid columns (SURVEY.md 8e, config C3)
+# ------------------------------------------------------------------------------------------------
+class ShardedKronSum:
+    """Rank r owns grid columns [r0,r1) of X (n2 x n1, column-major: a contiguous range of
+    x = vec(X)); plan = RowShard.plan(n1, kla, kua) over COLUMNS.  It stores A's column slice
+    [c0,c1) (a_slab: (c1-c0) x (kla+kua+1)) and all of B; X lives in a ghost-cell buffer of
+    n2 x (c1-c0) columns.  Only the ghost columns (n2 values each) are exchanged; B*X is local."""
+
+    def __init__(self, n1, n2, kla, kua, a_slab, B, rank, world):
+        self.plan = RowShard.plan(n1, kla, kua, rank, world)
+        self.n1, self.n2, self.kla, self.kua = n1, n2, kla, kua
+        if tuple(a_slab.shape) != (self.plan.n_loc, kla + kua + 1):
+            raise LbmArgumentError(f"A slab must be ({self.plan.n_loc}, {kla + kua + 1})")
+        self.a_slab = a_slab.contiguous()
+        self.B = B
+
+    def new_buffer(self, dtype, device):
+        return torch.zeros((self.plan.n_loc, self.n2), dtype=dtype, device=device)   # column c = row c (n2 contiguous)
+
+    def owned(self, xbuf):
+        p = self.plan
+        return xbuf[p.left: p.left + p.m_loc]
+
+    def exchange(self, xbuf, group=None):
+        p = self.plan
+        flat = xbuf.view(-1)
+        ops, n2 = [], self.n2
+        own0 = p.left * n2
+        if p.rank > 0:
+            cnt = min(p.u, p.m_loc) * n2
+            if cnt:
+                ops.append(dist.P2POp(dist.isend, flat[own0: own0 + cnt], p.rank - 1, group))
+            if p.left:
+                ops.append(dist.P2POp(dist.irecv, flat[: own0], p.rank - 1, group))
+        if p.rank < p.world - 1:
+            cnt = min(p.l, p.m_loc) * n2
+            end = own0 + p.m_loc * n2
+            if cnt:
+                ops.append(dist.P2POp(dist.isend, flat[end - cnt: end], p.rank + 1, group))
+            if p.right:
+                ops.append(dist.P2POp(dist.irecv, flat[end:], p.rank + 1, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def mul_(self, y_own, xbuf, alpha=1.0, beta=0.0, group=None, local_apply=None, overlap=True):
+        """y_own ((r1-r0) x n2 tensor = n2 x (r1-r0) column-major) <- alpha*(X A^T + B X)[:, r0:r1] + beta*y_own."""
+        p = self.plan
+        if local_apply is None and group is None and xbuf.is_cuda:
+            from . import _lib
+            from .banded import _ft, _pfx, _ptr
+            h = _lib.handle_of(xbuf)
+            if p.world == 1 or h.comm_world == p.world:
+                fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}kronsum2d_mv_sharded")
+                ft = _ft(xbuf.dtype)
+                B = self.B
+                h.check(fn(h.ptr, self.n1, self.n2, self.kla, self.kua, _ptr(self.a_slab), self.kla + self.kua + 1,
+                           B.l, B.u, _ptr(B.data), B.lda, ft(alpha), _ptr(xbuf), ft(beta), _ptr(y_own),
+                           1 if overlap else 0), "lbm_kronsum2d_mv_sharded")
+                return y_own
+            raise LbmArgumentError("call lbm_b200.shard.init_comm() first (or pass a local_apply for host-logic tests)")
+        if p.world > 1:
+            self.exchange(xbuf, group)
+        return local_apply(y_own, self, xbuf, alpha, beta)

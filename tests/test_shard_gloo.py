@@ -143,3 +143,103 @@ def test_plan_geometry():
             assert lib.lbm_shard_plan(nn, ll, uu, r, ww, out) == 0
             assert list(out) == [pl.r0, pl.r1, pl.c0, pl.c1, pl.left, pl.right, pl.kl_loc, pl.ku_loc]
     assert lib.lbm_shard_plan(10, 1, 1, 3, 3, out) == -4
+
+
+def test_gbmm_column_partition_matches_global(oracle):
+    """C = A*B column-partitioned over ranks with a static halo of A and
+    NO communication -- each rank's sub-product (shifted bandwidths) reproduces its column slice of
+    the global product bit-exactly (host logic of lbm_b200.shard.GbmmColumnShard, oracle as kernel)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "lazybandedmatrices.jl_b200"))
+    from lbm_b200.shard import GbmmColumnShard, split_batch
+
+    def oracle_gbmm(m, n, k, A, kla, kua, B, klb, kub, Cs, klc, kuc):
+        out = oracle.gbmm(m, n, k, np.asfortranarray(A.numpy().T), kla, kua, np.asfortranarray(B.numpy().T), klb, kub,
+                          klc=klc, kuc=kuc)
+        Cs.copy_(torch.from_numpy(np.ascontiguousarray(out.T)))
+
+    for (n, la, ua, lb, ub, world) in [(200, 1, 1, 1, 1, 2), (333, 8, 3, 2, 5, 4), (1500, 128, 128, 128, 128, 3),
+                                       (64, 0, 2, 3, 0, 2)]:
+        A = oracle.brand(n, n, la, ua, seed=1)
+        B = oracle.brand(n, n, lb, ub, seed=2)
+        want = oracle.gbmm(n, n, n, A, la, ua, B, lb, ub)                 # (lc+uc+1) x n
+        got = np.zeros_like(want)
+        At, Bt = torch.from_numpy(np.ascontiguousarray(A.T)), torch.from_numpy(np.ascontiguousarray(B.T))
+        for r in range(world):
+            p = GbmmColumnShard.plan(n, la, ua, lb, ub, r, world)
+            (kla, kua), (klb, kub), (klc, kuc) = p.sub_bandwidths()
+            assert min(kla, kua, klb, kub, klc, kuc) >= 0
+            Cs = p.local_gbmm(At[p.pa:p.pb], Bt[p.c0:p.c1], gbmm_fn=oracle_gbmm)
+            got[:, p.c0:p.c1] = Cs.numpy().T
+        # in-matrix entries identical (same summation order); out-of-matrix slots are zero in both
+        assert np.array_equal(oracle.band_to_dense(got, n, la + lb, ua + ub), oracle.band_to_dense(want, n, la + lb, ua + ub))
+    assert [split_batch(4096, 8, r) for r in (0, 7)] == [(0, 512), (3584, 4096)]
+    assert [split_batch(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+
+
+def _kron_worker(rank, world, port, n1, n2, bands, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "lazybandedmatrices.jl_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from lbm_b200.shard import ShardedKronSum
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        (kla, kua), (klb, kub) = bands
+        A = O.brand(n1, n1, kla, kua, seed=3)
+        Bn = O.brand(n2, n2, klb, kub, seed=4)
+        Bd = O.band_to_dense(Bn, n2, klb, kub)
+        x = O.fill_uniform(5, n1 * n2).reshape(n1, n2)          # row c = grid column c
+
+        class _B:                                               # only .l/.u/.data/.lda are consulted on GPU
+            pass
+
+        def local_apply(y_own, sh, xbuf, alpha, beta):
+            p = sh.plan
+            slab = np.asfortranarray(sh.a_slab.numpy().T)
+            Aloc = O.band_to_dense(slab, p.m_loc, p.kl_loc, p.ku_loc)      # (r1-r0) x (c1-c0)
+            Xext = xbuf.numpy().T                                           # n2 x (c1-c0)
+            Y = Xext @ Aloc.T + Bd @ Xext[:, p.left:p.left + p.m_loc]
+            y_own.copy_(torch.from_numpy(np.ascontiguousarray((alpha * Y).T)) + beta * y_own)
+            return y_own
+
+        from lbm_b200.shard import RowShard
+        p = RowShard.plan(n1, kla, kua, rank, world)
+        sh = ShardedKronSum(n1, n2, kla, kua, torch.from_numpy(np.ascontiguousarray(A.T[p.c0:p.c1])), _B(), rank, world)
+        xbuf = sh.new_buffer(torch.float64, "cpu")
+        sh.owned(xbuf).copy_(torch.from_numpy(x[p.r0:p.r1]))
+        y = torch.zeros((p.m_loc, n2), dtype=torch.float64)
+        sh.mul_(y, xbuf, local_apply=local_apply)
+        assert np.array_equal(xbuf.numpy(), x[p.c0:p.c1])       # ghost columns filled from the neighbours
+        q.put((rank, p.r0, y.numpy().copy()))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n1,n2,bands", [(2, 40, 16, ((1, 1), (1, 1))), (3, 50, 12, ((2, 1), (0, 2)))])
+def test_kronsum_column_partition_gloo(world, n1, n2, bands, oracle):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_kron_worker, args=(r, world, port, n1, n2, bands, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = np.zeros((n1, n2))
+    for _ in range(world):
+        rank, r0, yy = q.get(timeout=120)
+        got[r0:r0 + yy.shape[0]] = yy
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (kla, kua), (klb, kub) = bands
+    A = oracle.brand(n1, n1, kla, kua, seed=3)
+    Bn = oracle.brand(n2, n2, klb, kub, seed=4)
+    x = oracle.fill_uniform(5, n1 * n2)
+    want = oracle.kronsum2d_mv(n1, n2, A, kla, kua, Bn, klb, kub, x).reshape(n1, n2)
+    assert np.max(np.abs(got - want)) <= 4 * np.finfo(np.float64).eps * (kla + kua + klb + kub + 2)
