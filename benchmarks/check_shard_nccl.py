@@ -12,7 +12,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import lbm_b200 as L  # noqa: E402
-from lbm_b200.shard import RowShard, ShardedBanded, ShardedKronSum, GbmmColumnShard, init_comm, sharded_chain_mul_  # noqa: E402
+from lbm_b200.shard import (RowShard, ShardedBanded, ShardedKronSum, ShardedTridiagonal, GbmmColumnShard, init_comm,  # noqa: E402
+                            sharded_chain_mul_)
 from oracle import oracle as O  # noqa: E402
 
 
@@ -51,6 +52,22 @@ def _check_kron_gbmm(rank, world, dev, eps):
             sh.mul_(y, xbuf, alpha=1.5, overlap=overlap)
             err = np.max(np.abs(y.cpu().numpy() - want[p.r0:p.r1]))
             assert err <= 4 * eps * 1.5 * (kla + kua + klb + kub + 2), ("kronsum", n1, n2, overlap, err)
+    for kind in ("tri", "sym", "biU", "biL"):                       # C2: row-sharded structured mat-vec
+        n = 400003
+        d, dl, du, x = O.fill_uniform(1, n), O.fill_uniform(2, n - 1), O.fill_uniform(3, n - 1), O.fill_uniform(4, n)
+        if kind == "sym":
+            dl = du
+        has_l, has_u = kind != "biU", kind != "biL"
+        c0, c1 = ShardedTridiagonal.slices(n, int(has_l), int(has_u), rank, world)
+        t = lambda a: torch.from_numpy(a.copy()).to(dev)  # noqa: E731
+        sh = ShardedTridiagonal(n, t(dl[c0:c1 - 1]) if has_l else None, t(d[c0:c1]), t(du[c0:c1 - 1]) if has_u else None, rank, world)
+        xbuf = sh.plan.new_vector(torch.float64, dev)
+        sh.plan.owned(xbuf).copy_(t(x[sh.plan.r0:sh.plan.r1]))
+        y = torch.full((sh.plan.m_loc,), float("nan"), dtype=torch.float64, device=dev)
+        sh.mul_(y, xbuf)
+        want = O.tridiag_mv(n, dl if has_l else None, d, du if has_u else None, x)
+        err = np.max(np.abs(y.cpu().numpy() - want[sh.plan.r0:sh.plan.r1]))
+        assert err <= 4 * eps * 3, ("sharded " + kind, err)
     for (n, la, ua, lb, ub) in ((5000, 1, 1, 1, 1), (3000, 128, 128, 128, 128), (2000, 8, 3, 2, 5)):
         A, B = O.brand(n, n, la, ua, seed=1), O.brand(n, n, lb, ub, seed=2)
         want = O.gbmm(n, n, n, A, la, ua, B, lb, ub)

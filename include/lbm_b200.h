@@ -87,6 +87,12 @@ int lbm_dtridiag_mv(lbm_handle_t h, int64_t n, const double *dl, const double *d
 int lbm_stridiag_mv(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du,
                     float alpha, const float *X, int64_t ldx, int64_t nrhs,
                     float beta, float *Y, int64_t ldy);
+/* mat-vec restricted to rows [row_begin,row_end): y[i-row_begin] <- alpha*(A x)[i] + beta*y[i-row_begin].
+ * Used by row shards: the rank applies its ghost-extended square system and keeps the owned rows. */
+int lbm_dtridiag_mv_rows(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du,
+                         double alpha, const double *x, double beta, double *y, int64_t row_begin, int64_t row_end);
+int lbm_stridiag_mv_rows(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du,
+                         float alpha, const float *x, float beta, float *y, int64_t row_begin, int64_t row_end);
 int lbm_dbidiag_mv(lbm_handle_t h, char uplo, int64_t n, const double *dv, const double *ev,
                    double alpha, const double *X, int64_t ldx, int64_t nrhs,
                    double beta, double *Y, int64_t ldy);

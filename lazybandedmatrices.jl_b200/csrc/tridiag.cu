@@ -147,6 +147,8 @@ struct TriRingArgs {
     int64_t tile, ntiles;
     int stages;
     int64_t seg;  // smem elements per staged array (tile + 2*EPV, multiple of EPV)
+    int64_t row_begin, row_end;  // only rows [row_begin,row_end) are produced, y[i - row_begin]
+    int64_t tile0;               // index of the first tile (tiles stay aligned to multiples of `tile`)
 };
 
 // smem stage layout: [ d | x | lo | hi ], each `seg` elements, all windows starting at the
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
     const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
     const int64_t noff = a.n - 1;  // length of the off-diagonals actually read
 
-    auto issue = [&](int64_t t, int s) {  // thread 0 only
+    auto issue = [&](int64_t tt, int s) {  // thread 0 only
+        const int64_t t = a.tile0 + tt;
         const int64_t i0 = t * a.tile;
         const int64_t i1 = i0 + a.tile < a.n ? i0 + a.tile : a.n;
         const int64_t w0 = i0 >= EPV ? i0 - EPV : 0;
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
     for (int64_t k = 0; k < mine; ++k) {
         const int s = (int)(k % S);
         const uint32_t parity = (uint32_t)((k / S) & 1);
-        const int64_t t = first + k * step;
+        const int64_t t = a.tile0 + first + k * step;
         const int64_t i0 = t * a.tile;
         const int64_t i1 = i0 + a.tile < a.n ? i0 + a.tile : a.n;
         const int64_t w0 = i0 >= EPV ? i0 - EPV : 0;
@@ -208,13 +211,16 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         const T *slo = sx + a.seg;                                  // dl window (HAS_DL)
         const T *shi = (HAS_DL && HAS_DU && !SYM) ? slo + a.seg : slo;  // du window
         mbar_wait(&bars[s], parity);
-        for (int64_t i = i0 + tid; i < i1; i += TRI_NT) {
+        const int64_t ie = i1 < a.row_end ? i1 : a.row_end;
+        for (int64_t i = i0 + tid; i < ie; i += TRI_NT) {
+            if (i < a.row_begin) continue;
             const int r = (int)(i - w0);
             T acc = 0;
             if (HAS_DL && i > 0) acc = slo[r - 1] * sx[r - 1];
             acc = fma(sd[r], sx[r], acc);
             if (HAS_DU && i < a.n - 1) acc = fma(shi[r], sx[r + 1], acc);
-            a.y[i] = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, a.y[i], a.alpha * acc);
+            T *yo = a.y + (i - a.row_begin);
+            *yo = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *yo, a.alpha * acc);
         }
         __syncthreads();
         if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
@@ -259,9 +265,14 @@ __global__ void __launch_bounds__(256) tridiag_mv_scalar_kernel(int64_t n, const
 
 template <typename T>
 int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du, T alpha, const T *X, int64_t ldx,
-                 int64_t nrhs, T beta, T *Y, int64_t ldy) {
+                 int64_t nrhs, T beta, T *Y, int64_t ldy, int64_t row_begin = 0, int64_t row_end = -1) {
     if (!h) return -1;
     if (n < 0) return lbm_fail_arg(h, 2, "n < 0");
+    if (row_end < 0) row_end = n;
+    const bool ranged = !(row_begin == 0 && row_end == n);
+    if (ranged && (row_begin < 0 || row_end > n || row_begin > row_end)) return lbm_fail_arg(h, 13, "bad row range");
+    if (ranged && nrhs != 1) return lbm_fail_arg(h, 9, "row ranges are mat-vec only");
+    if (ranged && row_begin == row_end) return 0;
     if (nrhs < 0) return lbm_fail_arg(h, 9, "nrhs < 0");
     if (n == 0 || nrhs == 0) return 0;
     if (!d) return lbm_fail_arg(h, 4, "d == NULL");
@@ -274,6 +285,8 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
     const bool aligned = lbm_aligned16(d) && lbm_aligned16(X) && lbm_aligned16(Y) && (!dl || lbm_aligned16(dl)) &&
                          (!du || lbm_aligned16(du)) && (nrhs == 1 || (ldx % VN == 0 && ldy % VN == 0));
     const int64_t ctas = h->tune.tri_ctas_per_sm > 0 ? h->tune.tri_ctas_per_sm : 16;
+    if ((!aligned || h->tune.tri_force_scalar) && ranged)
+        return lbm_fail_arg(h, 13, "row-ranged tridiagonal apply needs 16-byte aligned operands");
     if (!aligned || h->tune.tri_force_scalar) {
         int64_t blocks = (n + 255) / 256;
         if (blocks > (int64_t)h->sm_count * ctas) blocks = (int64_t)h->sm_count * ctas;
@@ -281,7 +294,7 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
         LBM_LAUNCH_CHECK(h, "tridiag_mv_scalar_kernel");
         return 0;
     }
-    if (nrhs == 1 && !h->tune.tri_force_shuffle) {
+    if (nrhs == 1 && (!h->tune.tri_force_shuffle || ranged)) {
         constexpr int EPV = VN;
         TriRingArgs<T> a;
         a.n = n; a.dl = dl; a.d = d; a.du = du; a.x = X; a.y = Y; a.alpha = alpha; a.beta = beta;
@@ -290,7 +303,10 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
         int64_t tile = h->tune.tri_tile > 0 ? h->tune.tri_tile : 1024;
         tile = (tile + TRI_NT - 1) / TRI_NT * TRI_NT;
         a.tile = tile;
-        a.ntiles = (n + tile - 1) / tile;
+        a.row_begin = row_begin;
+        a.row_end = row_end;
+        a.tile0 = row_begin / tile;
+        a.ntiles = (row_end + tile - 1) / tile - a.tile0;
         a.seg = tile + 2 * EPV;
         const int64_t stage_bytes = a.seg * narr * (int64_t)sizeof(T);
         int64_t stages = h->tune.tri_stages > 0 ? h->tune.tri_stages : 2;
@@ -343,6 +359,14 @@ int lbm_dbidiag_mv(lbm_handle_t h, char uplo, int64_t n, const double *dv, const
     if (uplo == 'U' || uplo == 'u') return tridiag_impl<double>(h, n, nullptr, dv, ev, alpha, X, ldx, nrhs, beta, Y, ldy);
     if (uplo == 'L' || uplo == 'l') return tridiag_impl<double>(h, n, ev, dv, nullptr, alpha, X, ldx, nrhs, beta, Y, ldy);
     return lbm_fail_arg(h, 2, "uplo must be 'U' or 'L'");
+}
+int lbm_dtridiag_mv_rows(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du, double alpha,
+                         const double *x, double beta, double *y, int64_t row_begin, int64_t row_end) {
+    return tridiag_impl<double>(h, n, dl, d, du, alpha, x, n, 1, beta, y, n, row_begin, row_end);
+}
+int lbm_stridiag_mv_rows(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du, float alpha,
+                         const float *x, float beta, float *y, int64_t row_begin, int64_t row_end) {
+    return tridiag_impl<float>(h, n, dl, d, du, alpha, x, n, 1, beta, y, n, row_begin, row_end);
 }
 int lbm_sbidiag_mv(lbm_handle_t h, char uplo, int64_t n, const float *dv, const float *ev, float alpha,
                    const float *X, int64_t ldx, int64_t nrhs, float beta, float *Y, int64_t ldy) {

@@ -65,6 +65,7 @@ def _sigs():
         s[f"lbm_{p}gbmv_sharded"] = (C.c_int, [H, i64, i64, i64, ft, vp, i64, vp, ft, vp, C.c_int])
         s[f"lbm_{p}tridiag_mv"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}bidiag_mv"] = (C.c_int, [H, ch, i64, vp, vp, ft, vp, i64, i64, ft, vp, i64])
+        s[f"lbm_{p}tridiag_mv_rows"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, ft, vp, i64, i64])
         s[f"lbm_{p}gbmm"] = (C.c_int, [H, i64, i64, i64, ft, i64, i64, vp, i64, i64, i64, vp, i64, ft,
                                        i64, i64, vp, i64])
         s[f"lbm_{p}gbmm_chain3_batched"] = (C.c_int, [H, i64, i64, C.POINTER(i64), C.POINTER(i64),

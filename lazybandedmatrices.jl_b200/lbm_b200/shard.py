@@ -397,3 +397,65 @@ class ShardedKronSum:
         if p.world > 1:
             self.exchange(xbuf, group)
         return local_apply(y_own, self, xbuf, alpha, beta)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tridiagonal / SymTridiagonal / Bidiagonal mat-vec, row-sharded (BASELINE config 2)
+# ------------------------------------------------------------------------------------------------
+class ShardedTridiagonal:
+    """Rank r owns rows [r0,r1) of an n x n Tridiagonal(dl,d,du) (SymTridiagonal: dl is du;
+    Bidiagonal: one of them None).  It keeps the slices of the diagonals over the ghost-extended
+    index range [c0,c1) = [r0-1, r1+1) ∩ [0,n) and x in a ghost-cell vector of the same range; after
+    the one-element ghost exchange the local apply is the ordinary SQUARE tridiagonal kernel on the
+    extended range -- its owned rows are exact, its (at most two) ghost rows are discarded."""
+
+    def __init__(self, n, dl_ext, d_ext, du_ext, rank, world):
+        self.plan = RowShard.plan(n, 1 if dl_ext is not None else 0, 1 if du_ext is not None else 0, rank, world)
+        p = self.plan
+        if d_ext.shape[0] != p.n_loc:
+            raise LbmArgumentError(f"d slice must cover [c0,c1) = {p.n_loc} entries")
+        for off in (dl_ext, du_ext):
+            if off is not None and off.shape[0] != max(p.n_loc - 1, 0):
+                raise LbmArgumentError(f"off-diagonal slices must have {max(p.n_loc - 1, 0)} entries")
+        self.dl, self.d, self.du = dl_ext, d_ext, du_ext
+        self._ybuf = None
+
+    @classmethod
+    def slices(cls, n, l, u, rank, world):
+        """(c0, c1): global index range of the d / x slices this rank holds; off-diagonal slices are
+        dl[c0 : c1-1], du[c0 : c1-1] (dl[i] = A[i+1,i], du[i] = A[i,i+1])."""
+        p = RowShard.plan(n, l, u, rank, world)
+        return p.c0, p.c1
+
+    def mul_(self, y_own, xbuf, alpha=1.0, beta=0.0, group=None, local_apply=None):
+        p = self.plan
+        if local_apply is None and group is None and xbuf.is_cuda:
+            from . import _lib
+            from .banded import _ft, _pfx, _ptr
+            h = _lib.handle_of(xbuf)
+            if p.world > 1:
+                if h.comm_world != p.world:
+                    raise LbmArgumentError("call lbm_b200.shard.init_comm() first")
+                h.check(_lib.lib().lbm_halo_exchange(h.ptr, p.n, p.l, p.u, C_void(xbuf), xbuf.element_size()),
+                        "lbm_halo_exchange")
+            # the extended square system, restricted to the owned rows: written straight into y_own
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}tridiag_mv_rows")
+            ft = _ft(xbuf.dtype)
+            h.check(fn(h.ptr, p.n_loc, _ptr(self.dl), _ptr(self.d), _ptr(self.du), ft(alpha), _ptr(xbuf), ft(beta),
+                       _ptr(y_own), p.left, p.left + p.m_loc), "lbm_tridiag_mv_rows")
+            return y_own
+        if self._ybuf is None or self._ybuf.shape[0] != p.n_loc or self._ybuf.device != xbuf.device:
+            self._ybuf = torch.empty(p.n_loc, dtype=xbuf.dtype, device=xbuf.device)
+        yb = self._ybuf
+        if beta != 0.0:
+            yb[p.left: p.left + p.m_loc].copy_(y_own)
+        if p.world > 1:
+            p.exchange(xbuf, group)
+        local_apply(yb, p.n_loc, self.dl, self.d, self.du, xbuf, alpha, beta)
+        y_own.copy_(yb[p.left: p.left + p.m_loc])
+        return y_own
+
+
+def C_void(t):
+    import ctypes as C
+    return C.c_void_p(t.data_ptr())

@@ -157,3 +157,25 @@ def test_structured_scalar_fallback_matches(L, oracle):
     got = (A @ xv).cpu().numpy()
     want = oracle.tridiag_mv(n, dl, d, du, xv.cpu().numpy())
     assert np.max(np.abs(got - want)) <= tol_rows(np.float64, 3, 1.0, 1.0)
+
+
+def test_tridiag_row_ranges(L, oracle):
+    """lbm_?tridiag_mv_rows: only rows [a,b) are produced, written at y[i-a] (used by row shards)."""
+    import ctypes as C
+    h = L.handle_for(0)
+    n = 70003
+    dl, d, du = _mk(oracle, n, torch.float64, 3)
+    x = oracle.fill_uniform(9, n)
+    want = oracle.tridiag_mv(n, dl, d, du, x, 2.0, 0.0)
+    g = [_t(a) for a in (dl, d, du, x)]
+    for (a, b) in ((0, n), (1, n - 1), (1, 1025), (1023, 1024), (4096, 4096), (5000, n), (33333, 66001)):
+        y = torch.full((max(b - a, 1),), float("nan"), dtype=torch.float64, device="cuda")
+        rc = L.lib().lbm_dtridiag_mv_rows(h.ptr, n, C.c_void_p(g[0].data_ptr()), C.c_void_p(g[1].data_ptr()),
+                                          C.c_void_p(g[2].data_ptr()), 2.0, C.c_void_p(g[3].data_ptr()), 0.0,
+                                          C.c_void_p(y.data_ptr()), a, b)
+        assert rc == 0
+        torch.cuda.synchronize()
+        if b > a:
+            assert np.max(np.abs(y.cpu().numpy()[: b - a] - want[a:b])) <= tol_rows(np.float64, 3, 1.0, 1.0, 2.0)
+    assert L.lib().lbm_dtridiag_mv_rows(h.ptr, n, None, C.c_void_p(g[1].data_ptr()), None, 1.0,
+                                        C.c_void_p(g[3].data_ptr()), 0.0, C.c_void_p(g[3].data_ptr()), 5, 3) == -13

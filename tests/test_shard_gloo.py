@@ -243,3 +243,63 @@ def test_kronsum_column_partition_gloo(world, n1, n2, bands, oracle):
     x = oracle.fill_uniform(5, n1 * n2)
     want = oracle.kronsum2d_mv(n1, n2, A, kla, kua, Bn, klb, kub, x).reshape(n1, n2)
     assert np.max(np.abs(got - want)) <= 4 * np.finfo(np.float64).eps * (kla + kua + klb + kub + 2)
+
+
+def _tri_worker(rank, world, port, n, kind, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "lazybandedmatrices.jl_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from lbm_b200.shard import RowShard, ShardedTridiagonal
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d, dl, du, x = O.fill_uniform(1, n), O.fill_uniform(2, n - 1), O.fill_uniform(3, n - 1), O.fill_uniform(4, n)
+        if kind == "sym":
+            dl = du
+        has_l, has_u = kind != "biU", kind != "biL"
+        c0, c1 = ShardedTridiagonal.slices(n, int(has_l), int(has_u), rank, world)
+        t = lambda a: torch.from_numpy(a.copy())
+        sh = ShardedTridiagonal(n, t(dl[c0:c1 - 1]) if has_l else None, t(d[c0:c1]), t(du[c0:c1 - 1]) if has_u else None,
+                                rank, world)
+        p = sh.plan
+        xbuf = p.new_vector(torch.float64, "cpu")
+        p.owned(xbuf).copy_(t(x[p.r0:p.r1]))
+
+        def local_apply(yb, nl, a, dd, b, xb, alpha, beta):
+            out = O.tridiag_mv(nl, None if a is None else a.numpy(), dd.numpy(), None if b is None else b.numpy(),
+                               xb.numpy(), alpha, beta, yb.numpy())
+            yb.copy_(torch.from_numpy(out))
+
+        y = torch.zeros(p.m_loc, dtype=torch.float64)
+        sh.mul_(y, xbuf, local_apply=local_apply)
+        q.put((rank, p.r0, y.numpy().copy()))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["tri", "sym", "biU", "biL"])
+def test_sharded_tridiagonal_gloo(kind, oracle):
+    world, n = 3, 1003
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tri_worker, args=(r, world, port, n, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = np.zeros(n)
+    for _ in range(world):
+        rank, r0, yy = q.get(timeout=120)
+        got[r0:r0 + len(yy)] = yy
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d, dl, du, x = oracle.fill_uniform(1, n), oracle.fill_uniform(2, n - 1), oracle.fill_uniform(3, n - 1), oracle.fill_uniform(4, n)
+    if kind == "sym":
+        dl = du
+    want = oracle.tridiag_mv(n, dl if kind != "biU" else None, d, du if kind != "biL" else None, x)
+    assert np.array_equal(got, want)
