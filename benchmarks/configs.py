@@ -169,7 +169,8 @@ def main():
             emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 gbmm_force={force}", ms, byts, flops)
         h.set_tuning(gbmm_force=0)
         if not a.quick:
-            for v, nm in ((2, "3-stage, 3 CTAs/SM"), (3, "2-stage, 5 CTAs/SM")):
+            for v, nm in ((2, "3-stage, 3 CTAs/SM"), (3, "2-stage, 5 CTAs/SM"), (4, "column-persistent 2-stage, 4 CTAs/SM"),
+                          (5, "column-persistent 3-stage, 3 CTAs/SM")):
                 h.set_tuning(gbmm_variant=v)
                 emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant {v} ({nm})", timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
             h.set_tuning(gbmm_variant=0)

@@ -266,6 +266,216 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
             }
 }
 
+// ------------------------------------------------------------------------------------------
+// column-block persistent variant: one CTA owns ALL row tiles of a 64-column block and runs the
+// cp.async ring straight across tile boundaries (no pipeline fill/drain per 64x64 tile; the B
+// column block is re-read from L1/L2 by the same CTA).
+// ------------------------------------------------------------------------------------------
+struct TileIter {            // walks (tile, chunk) of one column block; warp-uniform
+    int64_t i0, pc, phi;     // current tile's first row, current chunk's first p, tile's last p
+    int t, ntiles;
+    bool valid;
+};
+
+template <int NSTAGE, int MINB>
+__global__ void __launch_bounds__(NT, MINB) gbmm_dmma_col_kernel(const DmmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wi = (warp & 1) * 32, wj = (warp >> 1) * 32;
+    const int64_t j0 = ((int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y) * TN;
+    if (j0 >= a.n) return;
+    int64_t I0 = floordiv(j0 - a.kuc, TM);
+    if (I0 < 0) I0 = 0;
+    // number of row tiles of this column block: i0 < m and i0 <= j0 + TN - 1 + klc
+    int64_t last = j0 + TN - 1 + a.klc < a.m - 1 ? j0 + TN - 1 + a.klc : a.m - 1;
+    const int ntiles = last >= I0 * TM ? (int)(last / TM - I0 + 1) : 0;
+    const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
+
+    auto tile_range = [&](int t, int64_t &i0, int64_t &plo, int64_t &phi) {
+        i0 = (I0 + t) * TM;
+        plo = i0 - a.kla > j0 - a.kub ? i0 - a.kla : j0 - a.kub;
+        phi = i0 + TM - 1 + a.kua < j0 + TN - 1 + a.klb ? i0 + TM - 1 + a.kua : j0 + TN - 1 + a.klb;
+        if (plo < 0) plo = 0;
+        if (phi > a.k - 1) phi = a.k - 1;
+        plo &= ~(int64_t)3;
+    };
+    auto iter_seek = [&](TileIter &it) {  // move to the first non-empty tile at or after it.t
+        it.valid = false;
+        while (it.t < it.ntiles) {
+            int64_t plo;
+            tile_range(it.t, it.i0, plo, it.phi);
+            if (it.phi >= plo) {
+                it.pc = plo;
+                it.valid = true;
+                return;
+            }
+            ++it.t;
+        }
+    };
+    auto iter_next = [&](TileIter &it) {
+        it.pc += KC;
+        if (it.pc > it.phi) {
+            ++it.t;
+            iter_seek(it);
+        }
+    };
+
+    // staging maps (see gbmm_dmma_kernel): pairs along the contiguous direction
+    const int a_ii = 2 * (tid & 31), a_p0 = tid >> 5;
+    const int b_pp = 2 * (tid & 7), b_j0 = tid >> 3;
+    const int64_t a_step = a.lda - 1, b_step = a.ldb - 1;
+    const bool a_al = ((reinterpret_cast<uintptr_t>(a.A) & 15u) == 0) && ((a_step & 1) == 0) && ((a.kua & 1) == 0);
+    const bool b_al = ((reinterpret_cast<uintptr_t>(a.B) & 15u) == 0) && ((b_step & 1) == 0) && ((a.kub & 1) == 0);
+    const bool cols_in = j0 + TN <= a.n;
+
+    auto cp16 = [&](double *dst, const double *src) {
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    };
+    auto issue = [&](const TileIter &it, int slot) {
+        double *sA = smem + slot * STAGE_DBL;
+        double *sB = sA + KC * PA;
+        const int64_t i0 = it.i0, pc = it.pc;
+        const bool p_in = pc + KC <= a.k;
+        const int di = (int)(i0 - pc), dj = (int)(pc - j0);
+        // A: rows i0 + a_ii (+1), p = pc + a_p0 + 4q;  A[i,p] = Ad[(kua + i) + (lda-1)*p]
+        const double *ap = a.A + (a.kua + i0 + a_ii) + a_step * (pc + a_p0);
+        if (a_al && p_in && i0 + TM <= a.m && di + TM - 1 <= kla && di - (KC - 1) >= -kua) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cp16(sA + (a_p0 + 4 * q) * PA + a_ii, ap + a_step * 4 * q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int pp = a_p0 + 4 * q;
+                const int d0 = di + a_ii - pp;  // i - p for the pair's first row
+                const bool pk = pc + pp < a.k;
+                const bool ok0 = pk && i0 + a_ii < a.m && d0 <= kla && d0 >= -kua;
+                const bool ok1 = pk && i0 + a_ii + 1 < a.m && d0 + 1 <= kla && d0 + 1 >= -kua;
+                double *dst = sA + pp * PA + a_ii;
+                const double *src = ap + a_step * 4 * q;
+                if (ok0 && ok1 && a_al) cp16(dst, src);
+                else {
+                    cp_async8_zfill(dst, ok0 ? src : a.A, ok0);
+                    cp_async8_zfill(dst + 1, ok1 ? src + 1 : a.A, ok1);
+                }
+            }
+        }
+        // B: p = pc + b_pp (+1), j = j0 + b_j0 + 16q;  B[p,j] = Bd[(kub + p) + (ldb-1)*j]
+        const double *bp = a.B + (a.kub + pc + b_pp) + b_step * (j0 + b_j0);
+        if (b_al && p_in && cols_in && dj + KC - 1 <= klb && dj - (TN - 1) >= -kub) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cp16(sB + (b_j0 + 16 * q) * PB + b_pp, bp + b_step * 16 * q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int jj = b_j0 + 16 * q;
+                const int d0 = dj + b_pp - jj;  // p - j for the pair's first p
+                const bool jk = j0 + jj < a.n;
+                const bool ok0 = jk && pc + b_pp < a.k && d0 <= klb && d0 >= -kub;
+                const bool ok1 = jk && pc + b_pp + 1 < a.k && d0 + 1 <= klb && d0 + 1 >= -kub;
+                double *dst = sB + jj * PB + b_pp;
+                const double *src = bp + b_step * 16 * q;
+                if (ok0 && ok1 && b_al) cp16(dst, src);
+                else {
+                    cp_async8_zfill(dst, ok0 ? src : a.B, ok0);
+                    cp_async8_zfill(dst + 1, ok1 ? src + 1 : a.B, ok1);
+                }
+            }
+        }
+    };
+
+    TileIter P;  // producer
+    P.t = 0;
+    P.ntiles = ntiles;
+    iter_seek(P);
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (P.valid) {
+            issue(P, s);
+            iter_next(P);
+        }
+        cp_async_commit();
+    }
+
+    const int fr = lane >> 2, fc = lane & 3;
+    const int fa_off = fc * PA + wi + fr;
+    const int fb_off = (wj + fr) * PB + fc;
+    int g = 0;  // consumed chunks so far (ring position)
+    for (int t = 0; t < ntiles; ++t) {
+        int64_t i0, plo, phi;
+        tile_range(t, i0, plo, phi);
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+        for (int64_t pc = plo; pc <= phi; pc += KC, ++g) {
+            cp_async_wait<NSTAGE - 2>();
+            __syncthreads();
+            if (P.valid) {
+                issue(P, (g + NSTAGE - 1) % NSTAGE);
+                iter_next(P);
+            }
+            cp_async_commit();
+            const double *sA = smem + (g % NSTAGE) * STAGE_DBL;
+            const double *sB = sA + KC * PA;
+            const int ia0 = (int)(i0 + wi - pc), jb0 = (int)(j0 + wj - pc);  // relative to the chunk start
+            const bool full = (ia0 + 31 <= kla) && (ia0 - (KC - 1) >= -kua) && ((KC - 1) - jb0 <= klb) && (-(jb0 + 31) >= -kub);
+#pragma unroll
+            for (int ks = 0; ks < KC / 4; ++ks) {
+                double fa[4], fb[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    fa[x] = sA[fa_off + 4 * ks * PA + 8 * x];
+                    fb[x] = sB[fb_off + 8 * x * PB + 4 * ks];
+                }
+                if (full) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], fa[x], fb[y]);
+                } else {
+                    const int p = 4 * ks;  // relative to the chunk start
+                    unsigned ma = 0, mb = 0;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int ia = ia0 + 8 * x;
+                        if (ia - (p + 3) <= kla && (ia + 7) - p >= -kua) ma |= 1u << x;
+                        const int jb = jb0 + 8 * x;
+                        if ((p + 3) - jb >= -kub && p - (jb + 7) <= klb) mb |= 1u << x;
+                    }
+                    if (ma != 0 && mb != 0) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y)
+                                if ((ma >> x & 1u) && (mb >> y & 1u)) dmma884(acc[x][y][0], acc[x][y][1], fa[x], fb[y]);
+                    }
+                }
+            }
+        }
+        // epilogue of tile t
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t i = i0 + wi + 8 * x + fr;
+                    const int64_t j = j0 + wj + 8 * y + 2 * fc + e;
+                    const int64_t f = a.kuc + i - j;
+                    if (i < a.m && j < a.n && f >= 0 && f <= a.klc + a.kuc) {
+                        double *c = a.C + f + a.ldc * j;
+                        const double v = a.alpha * acc[x][y][e];
+                        *c = (a.beta == 0.0) ? v : fma(a.beta, *c, v);
+                    }
+                }
+    }
+    cp_async_wait<0>();
+}
+
 // out-of-matrix slots of C's band (first kuc / last klc columns) are written 0 when beta == 0
 __global__ void __launch_bounds__(256) gbmm_zero_corners_kernel(int64_t m, int64_t n, int64_t klc, int64_t kuc,
                                                                double *C, int64_t ldc) {
@@ -330,7 +540,27 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         }                                                                                                     \
         gbmm_dmma_kernel<NS, MB><<<grid, NT, smem, h->stream>>>(a);                                           \
     } while (0)
-    if (variant == 2) LBM_DMMA_LAUNCH(0, 3, 3);
+    if (variant == 4 || variant == 5) {
+        // column-block persistent kernels: one CTA per 64-column block
+        const int64_t gcol = gx < 1048576 ? gx : 1048576;
+        dim3 gridc((unsigned)gcol, (unsigned)((gx + gcol - 1) / gcol));
+        static int cfg_col[2] = {0, 0};
+        if (variant == 4) {
+            const size_t smem = (size_t)2 * STAGE_DBL * sizeof(double);
+            if (!(cfg_col[0] & (1 << h->device))) {
+                LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_col_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg_col[0] |= (1 << h->device);
+            }
+            gbmm_dmma_col_kernel<2, 4><<<gridc, NT, smem, h->stream>>>(a);
+        } else {
+            const size_t smem = (size_t)3 * STAGE_DBL * sizeof(double);
+            if (!(cfg_col[1] & (1 << h->device))) {
+                LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_col_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg_col[1] |= (1 << h->device);
+            }
+            gbmm_dmma_col_kernel<3, 3><<<gridc, NT, smem, h->stream>>>(a);
+        }
+    } else if (variant == 2) LBM_DMMA_LAUNCH(0, 3, 3);
     else if (variant == 3) LBM_DMMA_LAUNCH(2, 2, 5);
     else LBM_DMMA_LAUNCH(1, 2, 4);
 #undef LBM_DMMA_LAUNCH

@@ -98,6 +98,20 @@ def test_gbmv_padded_lda_and_unaligned(L, oracle):
     assert np.max(np.abs(y.cpu().numpy() - want)) <= tol_rows(np.float64, 3, 1.0, 1.0)
 
 
+def test_gbmv_wide_padded_lda_rectangular(L, oracle):
+    """Wide-band kernels (column-streaming N, ring T, warp T) with lda > kl+ku+1 and m != n."""
+    for (m, n, kl, ku, pad) in [(3000, 3100, 70, 60, 2), (2500, 2400, 128, 128, 7), (900, 1500, 200, 10, 1), (1500, 900, 10, 200, 4)]:
+        for trans in ("N", "T"):
+            for dt in (torch.float64, torch.float32):
+                _run(L, oracle, dt, trans, m, n, kl, ku, 1.25, 0.5, 77, lda_pad=pad)
+    _run(L, oracle, torch.float64, "T", 3000, 3100, 70, 60, 1.0, 0.0, 78, lda_pad=3, tune={"gbmv_force": 4})
+    # tall / wide matrices whose trailing rows (columns) see no band at all: y <- beta*y there
+    _run(L, oracle, torch.float64, "N", 5000, 100, 40, 40, 2.0, 0.5, 79)
+    _run(L, oracle, torch.float64, "T", 100, 5000, 40, 40, 2.0, 0.5, 79)
+    _run(L, oracle, torch.float64, "N", 5000, 100, 2, 2, 2.0, 0.5, 80)
+    _run(L, oracle, torch.float64, "T", 100, 5000, 2, 2, 2.0, 0.5, 80)
+
+
 def test_gbmv_masks_by_index_not_value(L, oracle):
     """Out-of-matrix storage slots hold NaN, y holds NaN and beta == 0: nothing may leak."""
     for (m, n, kl, ku) in [(3000, 3000, 2, 3), (2000, 2000, 128, 128), (700, 900, 5, 1)]:
