@@ -9,14 +9,14 @@ from .errors import DimensionMismatch, LbmArgumentError, LbmCudaError, LbmLibrar
 from ._lib import Handle, handle_for, lib, SO_PATH  # noqa: F401
 from .banded import BandedMatrix, TransposedBanded, brand, banded_from_diagonals, fill_uniform, gbmm, gbmv_  # noqa: F401
 from .tridiag import Tridiagonal, SymTridiagonal, Bidiagonal  # noqa: F401
-from .lazy import ApplyMatrix, chain3_batched  # noqa: F401
+from .lazy import ApplyMatrix, BroadcastMatrix, chain3_batched  # noqa: F401
 from .blockkron import BlockKron, KronSum, KronTrav, DiagTrav, Eye  # noqa: F401
 from .blockconcat import BlockVcat, BlockHcat, BlockBroadcastArray, BlockBandedSpec, unitblocks, zeros_spec  # noqa: F401
 from .linalg import mul_, matmul, bandwidths, blockbandwidths, subblockbandwidths  # noqa: F401
 
 __all__ = [
     "BandedMatrix", "brand", "banded_from_diagonals", "Tridiagonal", "SymTridiagonal", "Bidiagonal",
-    "ApplyMatrix", "chain3_batched", "BlockKron", "KronSum", "KronTrav", "DiagTrav", "Eye", "BlockVcat", "BlockHcat",
+    "ApplyMatrix", "BroadcastMatrix", "chain3_batched", "BlockKron", "KronSum", "KronTrav", "DiagTrav", "Eye", "BlockVcat", "BlockHcat",
     "BlockBroadcastArray", "BlockBandedSpec", "unitblocks", "zeros_spec", "mul_", "matmul", "bandwidths",
     "blockbandwidths", "subblockbandwidths", "DimensionMismatch", "LbmArgumentError", "LbmCudaError",
     "Handle", "handle_for", "lib", "fill_uniform", "gbmm", "gbmv_",

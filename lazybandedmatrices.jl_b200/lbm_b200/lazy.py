@@ -80,6 +80,44 @@ class ApplyMatrix:
         return self.mul_(y, x)
 
 
+class BroadcastMatrix:
+    """`BroadcastArray(+, A, B, ...)` / `BroadcastArray(-, A, B)` of banded operands (the
+    `BroadcastBandedLayout` the reference imports at /root/reference/src/LazyBandedMatrices.jl:20;
+    used for the Laplacian sum at test/test_blockkron.jl:303,345).  `bandwidths` is the union band;
+    `mul!` applies term by term, accumulating into y with beta = 1 (`A*x + B*x`), which is how the
+    reference's `Mul{BroadcastBandedLayout{+}}` simplifies."""
+
+    def __init__(self, f, *args):
+        if f not in ("+", "-"):
+            raise LbmArgumentError("only BroadcastArray(+/-, ...) of banded operands is on the B200 path")
+        if f == "-" and len(args) != 2:
+            raise LbmArgumentError("BroadcastArray(-) takes two operands")
+        for a in args[1:]:
+            if tuple(a.shape) != tuple(args[0].shape):
+                raise DimensionMismatch(f"arrays could not be broadcast to a common size: {tuple(args[0].shape)} and {tuple(a.shape)}")
+        self.f = f
+        self.args = tuple(args)
+
+    @property
+    def shape(self):
+        return tuple(self.args[0].shape)
+
+    def bandwidths(self):
+        ls, us = zip(*[a.bandwidths() for a in self.args])
+        return (max(ls), max(us))
+
+    def mul_(self, y, x, alpha=1.0, beta=0.0):
+        from .linalg import mul_ as _mul
+        sign = [1.0] + [(-1.0 if self.f == "-" else 1.0)] * (len(self.args) - 1)
+        for k, (a, sg) in enumerate(zip(self.args, sign)):
+            _mul(y, a, x, alpha * sg, beta if k == 0 else 1.0)
+        return y
+
+    def __matmul__(self, x):
+        y = torch.empty((self.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        return self.mul_(y, x)
+
+
 def _as_banded(a) -> BandedMatrix:
     if isinstance(a, BandedMatrix):
         return a

@@ -327,3 +327,31 @@ def test_kron3d_mode_products(L, oracle):
         want_vec = oracle.krontrav3_mul_diagtrav(dA, dB, dC, X)
         tol = tol_rows(np.float64, (bw[0] + bw[1] + 1) ** 3, 1.0, float(np.abs(X).max()))
         assert np.max(np.abs(out.vector().cpu().numpy() - want_vec)) <= tol
+
+
+def test_broadcast_sum_of_banded(L, oracle):
+    """BroadcastArray(+/-, banded...)*x == A*x +/- B*x (union band), incl. mixed structured kinds and
+    a lazy product inside the sum (test/test_blockkron.jl:345-346 pattern)."""
+    n = 5000
+    A_np, A = _band(L, oracle, n, n, 2, 1, 1, torch.float64)
+    B_np, B = _band(L, oracle, n, n, 0, 3, 2, torch.float64)
+    d, e = oracle.fill_uniform(3, n), oracle.fill_uniform(4, n - 1)
+    S = L.SymTridiagonal(torch.from_numpy(d).cuda(), torch.from_numpy(e).cuda())
+    x_np = oracle.fill_uniform(9, n)
+    x = torch.from_numpy(x_np).cuda()
+    Ax = oracle.gbmv("N", n, n, 2, 1, 1.0, A_np, x_np)
+    Bx = oracle.gbmv("N", n, n, 0, 3, 1.0, B_np, x_np)
+    Sx = oracle.tridiag_mv(n, e, d, e, x_np)
+    M = L.BroadcastMatrix("+", A, B, S)
+    assert M.bandwidths() == (2, 3)
+    assert np.max(np.abs((M @ x).cpu().numpy() - (Ax + Bx + Sx))) <= tol_rows(np.float64, 4 + 4 + 3, 1.0, 1.0)
+    Mm = L.BroadcastMatrix("-", A, B)
+    y0 = oracle.fill_uniform(5, n)
+    y = torch.from_numpy(y0.copy()).cuda()
+    Mm.mul_(y, x, 2.0, 0.5)
+    assert np.max(np.abs(y.cpu().numpy() - (2.0 * (Ax - Bx) + 0.5 * y0))) <= tol_rows(np.float64, 8, 1.0, 1.0, 2.0, 0.5, 1.0)
+    P = L.BroadcastMatrix("+", L.ApplyMatrix("*", A, B), S)          # (A*B + S) x
+    want = oracle.gbmv("N", n, n, 2, 1, 1.0, A_np, Bx) + Sx
+    assert np.max(np.abs((P @ x).cpu().numpy() - want)) <= 2 * tol_rows(np.float64, 4, 1.0, 4.0) + tol_rows(np.float64, 3, 1.0, 1.0)
+    with pytest.raises(L.DimensionMismatch):
+        L.BroadcastMatrix("+", A, L.brand(n + 1, n + 1, 1, 1))
