@@ -138,6 +138,11 @@ def main():
             emit(f"C5 fused chain A*B*C f32 batch={batch} n=4096 (4,4)^3 tile={tile}",
                  timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2), byts, flops)
         h.set_tuning(chain_tile=0)
+        if not a.quick:
+            for v, nm in ((2, "transposed-smem kernel, 204 regs / 2 CTAs"), (3, "transposed-smem kernel, 128 regs / 3 CTAs")):
+                h.set_tuning(chain_variant=v)
+                emit(f"C5 fused chain variant {v} ({nm})", timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2), byts, flops)
+            h.set_tuning(chain_variant=0)
         del fs
         torch.cuda.empty_cache()
 

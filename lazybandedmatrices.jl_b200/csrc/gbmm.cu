@@ -469,6 +469,232 @@ __global__ void __launch_bounds__(CH_NT + 32) gbmm_chain3_reg_kernel(int64_t n, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// "transposed" fused chain (variant for compile-time bands, Float32; chain_variant = 2/3): the shared operands A and
+// A*B live in shared memory as [band row][column] so the 12 columns a thread needs of one band
+// row are 3 LDS.128 (consecutive threads -> consecutive 16 bytes: conflict-free, 5x fewer loads);
+// B's and C's coefficients for the thread's own 4 columns go global -> registers directly
+// (LDB x LDG.128, no staging), and D leaves the registers as 25 x STG.128 (a thread's 4 columns
+// are 4*LDD contiguous values).  Two __syncthreads per 512-column tile.
+// ------------------------------------------------------------------------------------------
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC, int MINB>
+__global__ void __launch_bounds__(CH_NT + 32, MINB) gbmm_chain3_t_kernel(int64_t n, const T *__restrict__ A, int64_t sA_,
+                                                                     const T *__restrict__ B, int64_t sB_,
+                                                                     const T *__restrict__ C, int64_t sC_,
+                                                                     T *__restrict__ D, int64_t sD_) {
+    using G = ChainGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    static_assert(sizeof(T) == 4, "the transposed chain kernel is the Float32 path");
+    constexpr int PAT = G::NP + 4;   // pitch of sA  [LDA ][NP]  (multiple of 4: LDS.128 aligned)
+    constexpr int PQT = G::NQ;       // pitch of sAB [LD01][NQ]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sA = reinterpret_cast<T *>(smem_raw);
+    T *sAB = sA + G::LDA * PAT;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int64_t b = blockIdx.y;
+    const int64_t j0 = (int64_t)blockIdx.x * CH_TCOL;
+    const int64_t q0 = j0 - G::HQ, p0 = j0 - G::HP;
+    const T *Ag = A + b * sA_;
+    const T *Bg = B + b * sB_;
+    const T *Cg = C + b * sC_;
+    T *Dg = D + b * sD_;
+    // tiles that can touch the matrix boundary take the index-masked coefficient / store paths
+    const bool edge = (p0 - G::L3 - G::U3 < 0) || (j0 + CH_TCOL + G::HP + G::L3 + G::U3 > n);
+
+    // B and C tiles are consumed two phases later: start them towards L2 now so the coefficient
+    // loads of phases 1 and 2 do not each pay a full DRAM latency
+    {
+        const int64_t qa = q0 < 0 ? 0 : q0, qb_ = q0 + G::NQ < n ? q0 + G::NQ : n;
+        const char *bp = reinterpret_cast<const char *>(Bg + qa * G::LDB);
+        const int64_t bbytes = (qb_ - qa) * G::LDB * (int64_t)sizeof(T);
+        for (int64_t o = (int64_t)tid * 128; o < bbytes; o += (int64_t)nthr * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + o));
+        const int64_t je = j0 + CH_TCOL < n ? j0 + CH_TCOL : n;
+        const char *cp = reinterpret_cast<const char *>(Cg + j0 * G::LDC);
+        const int64_t cbytes = (je - j0) * G::LDC * (int64_t)sizeof(T);
+        for (int64_t o = (int64_t)tid * 128; o < cbytes; o += (int64_t)nthr * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o));
+    }
+
+    // ---- stage A (global, column-major) -> sA[f][col]; zero outside [0,n) -------------------
+    {
+        constexpr int total4 = G::NP * G::LDA / 4;
+        const int64_t e_lo = (p0 < 0 ? -p0 : 0) * (int64_t)G::LDA;
+        const int64_t c_end = p0 + G::NP < n ? p0 + G::NP : n;
+        const int64_t e_hi = (c_end - p0) * (int64_t)G::LDA;
+        const T *src = Ag + p0 * G::LDA;
+        constexpr int VPT = (total4 + CH_NT + 31) / (CH_NT + 32);
+        float4 v[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int vi = k * nthr + tid;
+            const int64_t e = (int64_t)vi * 4;
+            v[k] = (vi < total4 && e >= e_lo && e + 4 <= e_hi) ? ld_stream(reinterpret_cast<const float4 *>(src + e)) : float4{0.f, 0.f, 0.f, 0.f};
+        }
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int vi = k * nthr + tid;
+            if (vi < total4) {
+                const float *pv = reinterpret_cast<const float *>(&v[k]);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int e = vi * 4 + w;
+                    const int lc = e / G::LDA, f = e - lc * G::LDA;
+                    sA[f * PAT + lc] = pv[w];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: AB[:, q0 + 4u + w] for u = tid < NQ/4 --------------------------------------
+    if (tid < G::NQ / 4) {
+        const int u = tid;
+        const int64_t qb = q0 + 4 * u;             // first of the thread's 4 columns (multiple of 4)
+        const bool qok = qb >= 0 && qb < n;         // n % 4 == 0: all four columns valid or none
+        T acc[4][G::LD01];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int r = 0; r < G::LD01; ++r) acc[w][r] = (T)0;
+        T bco[4 * G::LDB];                          // B band entries of the 4 columns, [w*LDB + ep]
+        if (qok) {
+#pragma unroll
+            for (int k = 0; k < G::LDB; ++k) {
+                const float4 t4 = ld_stream(reinterpret_cast<const float4 *>(Bg + qb * G::LDB) + k);
+                bco[4 * k] = t4.x; bco[4 * k + 1] = t4.y; bco[4 * k + 2] = t4.z; bco[4 * k + 3] = t4.w;
+            }
+            if (edge) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+#pragma unroll
+                    for (int ep = 0; ep < G::LDB; ++ep) {
+                        const int64_t pp = qb + w + ep - KUB;
+                        if (pp < 0 || pp >= n) bco[w * G::LDB + ep] = (T)0;
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4 * G::LDB; ++k) bco[k] = (T)0;
+        }
+        // A columns needed: local index 4u + v, v in [V0, V0 + 4 + KLB + KUB); loaded as aligned float4s
+        constexpr int V0 = (G::HP - G::HQ) - KUB;
+        constexpr int V0F = (V0 >= 0 ? V0 / 4 : -((-V0 + 3) / 4)) * 4;
+        constexpr int NV4 = (V0 + 4 + KLB + KUB - V0F + 3) / 4;
+#pragma unroll
+        for (int f = 0; f < G::LDA; ++f) {
+            T av[4 * NV4];
+#pragma unroll
+            for (int k = 0; k < NV4; ++k) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(sA + f * PAT + 4 * u + V0F + 4 * k);
+                av[4 * k] = t4.x; av[4 * k + 1] = t4.y; av[4 * k + 2] = t4.z; av[4 * k + 3] = t4.w;
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int e = -KUB; e <= KLB; ++e) {
+                    // A column p = q + e  <->  v = (HP-HQ) + w + e;  AB band row r = U01 - KUA + e + f
+                    acc[w][G::U01 - KUA + e + f] = fma(av[(G::HP - G::HQ) + w + e - V0F], bco[w * G::LDB + e + KUB], acc[w][G::U01 - KUA + e + f]);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < G::LD01; ++r) {
+            float4 o;
+            o.x = qok ? acc[0][r] : 0.f; o.y = qok ? acc[1][r] : 0.f; o.z = qok ? acc[2][r] : 0.f; o.w = qok ? acc[3][r] : 0.f;
+            *reinterpret_cast<float4 *>(sAB + r * PQT + 4 * u) = o;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: D[:, j0 + 4t + w] = sum_e AB[:, j+e] * C[j+e, j] ---------------------------
+    if (tid < CH_NT) {
+        const int t = tid;
+        const int64_t jb = j0 + 4 * t;
+        if (jb >= n) return;                        // whole thread beyond the matrix (n % 4 == 0)
+        T dacc[4][G::LDD];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int r = 0; r < G::LDD; ++r) dacc[w][r] = (T)0;
+        T cco[4 * G::LDC];
+#pragma unroll
+        for (int k = 0; k < G::LDC; ++k) {
+            const float4 t4 = ld_stream(reinterpret_cast<const float4 *>(Cg + jb * G::LDC) + k);
+            cco[4 * k] = t4.x; cco[4 * k + 1] = t4.y; cco[4 * k + 2] = t4.z; cco[4 * k + 3] = t4.w;
+        }
+        if (edge) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int ep = 0; ep < G::LDC; ++ep) {
+                    const int64_t qq = jb + w + ep - KUC;
+                    if (qq < 0 || qq >= n) cco[w * G::LDC + ep] = (T)0;
+                }
+        }
+        constexpr int V0 = G::HQ - KUC;
+        constexpr int V0F = (V0 >= 0 ? V0 / 4 : -((-V0 + 3) / 4)) * 4;
+        constexpr int NV4 = (V0 + 4 + KLC + KUC - V0F + 3) / 4;
+#pragma unroll
+        for (int f = 0; f < G::LD01; ++f) {
+            T av[4 * NV4];
+#pragma unroll
+            for (int k = 0; k < NV4; ++k) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(sAB + f * PQT + 4 * t + V0F + 4 * k);
+                av[4 * k] = t4.x; av[4 * k + 1] = t4.y; av[4 * k + 2] = t4.z; av[4 * k + 3] = t4.w;
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int e = -KUC; e <= KLC; ++e)
+                    dacc[w][G::U3 - G::U01 + e + f] = fma(av[G::HQ + w + e - V0F], cco[w * G::LDC + e + KUC], dacc[w][G::U3 - G::U01 + e + f]);
+        }
+        // D: the thread's 4 columns are 4*LDD contiguous values -> LDD x STG.128
+        T *Dt = Dg + jb * G::LDD;
+#pragma unroll
+        for (int k = 0; k < G::LDD; ++k) {
+            float o[4];
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int idx = 4 * k + z;
+                const int w = idx / G::LDD, r = idx - w * G::LDD;
+                T val = dacc[w][r];
+                if (edge) {
+                    const int64_t i = jb + w + r - G::U3;
+                    if (i < 0 || i >= n) val = (T)0;
+                }
+                o[z] = val;
+            }
+            st_stream(reinterpret_cast<float4 *>(Dt) + k, float4{o[0], o[1], o[2], o[3]});
+        }
+    }
+}
+
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC, int MINB>
+int chain3_t_launch2(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int64_t sA, const T *B, int64_t sB, const T *C,
+                     int64_t sC, T *D, int64_t sD) {
+    using G = ChainGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    constexpr size_t smem = (size_t)(G::LDA * (G::NP + 4) + G::LD01 * G::NQ) * sizeof(T);
+    static int configured_dev_mask = 0;
+    auto kern = gbmm_chain3_t_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC, MINB>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_dev_mask |= (1 << h->device);
+    }
+    dim3 grid((unsigned)((n + CH_TCOL - 1) / CH_TCOL), (unsigned)batch);
+    kern<<<grid, CH_NT + 32, smem, h->stream>>>(n, A, sA, B, sB, C, sC, D, sD);
+    LBM_LAUNCH_CHECK(h, "gbmm_chain3_t_kernel");
+    return 0;
+}
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
+int chain3_t_launch(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int64_t sA, const T *B, int64_t sB, const T *C,
+                    int64_t sC, T *D, int64_t sD) {
+    // chain_variant 2: 204 registers (2 CTAs/SM); 3: 128 registers (3 CTAs/SM)
+    if (h->tune.chain_variant == 2)
+        return chain3_t_launch2<T, KLA, KUA, KLB, KUB, KLC, KUC, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+    return chain3_t_launch2<T, KLA, KUA, KLB, KUB, KLC, KUC, 3>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+}
+
 template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
 int chain3_reg_launch(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int64_t sA, const T *B, int64_t sB,
                       const T *C, int64_t sC, T *D, int64_t sD) {
@@ -509,6 +735,15 @@ int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, con
         auto all = [&](int64_t l, int64_t u) {
             return kl[0] == l && kl[1] == l && kl[2] == l && ku[0] == u && ku[1] == u && ku[2] == u;
         };
+        if constexpr (sizeof(T) == 4) {
+            // chain_variant: 0/1 = split-column register kernel (fastest measured, profiles/configs_r01_final.jsonl),
+            // 2/3 = transposed-smem kernel (204 / 128 registers)
+            const bool t_ok = (h->tune.chain_variant == 2 || h->tune.chain_variant == 3) && n % 4 == 0 && sA % 4 == 0 && sB % 4 == 0 && sC % 4 == 0 &&
+                              sD % 4 == 0 && lbm_aligned16(A) && lbm_aligned16(B) && lbm_aligned16(C) && lbm_aligned16(D);
+            if (t_ok && all(4, 4)) return chain3_t_launch<T, 4, 4, 4, 4, 4, 4>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+            if (t_ok && all(1, 1)) return chain3_t_launch<T, 1, 1, 1, 1, 1, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+            if (t_ok && all(2, 2)) return chain3_t_launch<T, 2, 2, 2, 2, 2, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+        }
         if (all(4, 4)) return chain3_reg_launch<T, 4, 4, 4, 4, 4, 4>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
         if (all(1, 1)) return chain3_reg_launch<T, 1, 1, 1, 1, 1, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
         if (all(2, 2)) return chain3_reg_launch<T, 2, 2, 2, 2, 2, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);

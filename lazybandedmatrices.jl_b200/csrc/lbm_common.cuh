@@ -37,6 +37,7 @@ struct lbm_tuning {
     int64_t gbmm_variant;     // DMMA kernel: 0 = 3-stage/3 CTAs per SM, 1 = 2-stage/4 CTAs per SM
     int64_t chain_tile;
     int64_t chain_force_generic;
+    int64_t chain_variant;    // 0/1 split-column register kernel (default), 2/3 transposed-smem kernel (204/128 regs)
 };
 
 struct lbm_handle_s {

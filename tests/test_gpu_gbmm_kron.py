@@ -129,7 +129,8 @@ def test_chain3_batched(L, oracle, dt):
     npdt = NP[dt]
     for (batch, n, kl, ku) in [(5, 300, [4, 4, 4], [4, 4, 4]), (3, 1000, [1, 2, 0], [0, 1, 3]), (2, 70, [0, 0, 0], [0, 0, 0]),
                                (7, 4096, [4, 4, 4], [4, 4, 4]), (3, 1000, [1, 1, 1], [1, 1, 1]), (2, 513, [2, 2, 2], [2, 2, 2]),
-                               (4, 37, [4, 4, 4], [4, 4, 4]), (2, 1027, [4, 4, 4], [4, 4, 4]), (1, 3, [4, 4, 4], [4, 4, 4])]:
+                               (4, 37, [4, 4, 4], [4, 4, 4]), (2, 1027, [4, 4, 4], [4, 4, 4]), (1, 3, [4, 4, 4], [4, 4, 4]),
+                               (3, 1024, [2, 2, 2], [2, 2, 2]), (2, 516, [1, 1, 1], [1, 1, 1]), (2, 8, [4, 4, 4], [4, 4, 4]), (2, 4, [1, 1, 1], [1, 1, 1])]:
         fs = [oracle.fill_uniform(1 + i, batch * n * (kl[i] + ku[i] + 1), npdt).reshape(batch, n, kl[i] + ku[i] + 1)
               for i in range(3)]
         want = oracle.gbmm_chain3_batched(n, kl, ku, *fs)
@@ -163,12 +164,12 @@ def test_chain3_register_kernel_vs_generic_and_nan_corners(L, oracle):
     gs = [torch.from_numpy(f).cuda() for f in fs]
     tol = tol_rows(np.float32, 9, 1.0, 1.0) * 9 + tol_rows(np.float32, 9, 9.0, 1.0)
     outs = []
-    for force in (0, 1):
-        h.set_tuning(chain_force_generic=force)
+    for force, variant in ((0, 0), (0, 2), (0, 3), (1, 0)):     # split-column, transposed (2 variants), generic
+        h.set_tuning(chain_force_generic=force, chain_variant=variant)
         try:
             outs.append(L.chain3_batched(*gs, kl, ku).cpu().numpy())
         finally:
-            h.set_tuning(chain_force_generic=0)
+            h.set_tuning(chain_force_generic=0, chain_variant=0)
     for got in outs:
         for b in range(batch):
             dg = oracle.band_to_dense(np.asfortranarray(got[b].T), n, 12, 12)
