@@ -135,6 +135,17 @@ def test_chain3_batched(L, oracle, dt):
               for i in range(3)]
         want = oracle.gbmm_chain3_batched(n, kl, ku, *fs)
         got = L.chain3_batched(*[torch.from_numpy(f).cuda() for f in fs], kl, ku).cpu().numpy()
+        if dt == torch.float32:   # the transposed-smem variant must give the same in-matrix entries
+            hh = L.handle_for(0)
+            hh.set_tuning(chain_variant=3)
+            try:
+                got3 = L.chain3_batched(*[torch.from_numpy(f).cuda() for f in fs], kl, ku).cpu().numpy()
+            finally:
+                hh.set_tuning(chain_variant=0)
+            for b in range(batch):
+                assert np.max(np.abs(oracle.band_to_dense(np.asfortranarray(got3[b].T), n, sum(kl), sum(ku))
+                                     - oracle.band_to_dense(np.asfortranarray(want[b].T), n, sum(kl), sum(ku)))) <= \
+                    tol_rows(npdt, kl[0] + ku[0] + 1, 1.0, 1.0) * (kl[2] + ku[2] + 1) + tol_rows(npdt, kl[2] + ku[2] + 1, float(kl[0] + ku[0] + 1), 1.0)
         nb = [kl[i] + ku[i] + 1 for i in range(3)]
         # per-stage bounds: stage 1 terms <= nb0 (entries <= 1), stage 2 terms <= nb2 with |AB| <= nb0
         tol = tol_rows(npdt, nb[0], 1.0, 1.0) * nb[2] + tol_rows(npdt, nb[2], float(nb[0]), 1.0)
