@@ -138,64 +138,79 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: OpenBLAS ?gbmv -- the BLAS routine the reference's gbmv! ccalls
 # --------------------------------------------------------------------------------------------
-def cpu_gbmv_sample(log2n_sample, repeats):
-    """Times scipy.linalg.blas.dgbmv (OpenBLAS, all host threads) and the repo's OpenMP oracle on
-    a bounded sample of the workload; returns GB/s of the faster with the sample description."""
-    import numpy as np
-    from scipy.linalg import blas
-    from oracle import oracle as O
-    n = 1 << log2n_sample
-    tot_bytes, t_blas, t_orc = 0, 0.0, 0.0
-    for (l, u) in BANDS:
-        A = O.brand(n, n, l, u, seed=1)
-        x = O.fill_uniform(9, n)
-        y = np.zeros(n)
-        blas.dgbmv(n, n, l, u, 1.0, A, x, beta=0.0, y=y, overwrite_y=1)   # warm
-        best_b = best_o = 1e30
-        for _ in range(repeats):
+class CpuGbmvSample:
+    """The reference's CPU path for this workload on the box's host cores: OpenBLAS ?gbmv through scipy -- the BLAS
+    routine BandedMatrices.gbmv! ccalls -- with every host thread, on a bounded sample (same bands, reduced n);
+    the repo's OpenMP oracle port is timed beside it.  Inputs are generated once; `step()` times one pass."""
+
+    def __init__(self, log2n_sample):
+        import numpy as np
+        from oracle import oracle as O
+        self.n = 1 << log2n_sample
+        self.log2n = log2n_sample
+        self.ops = []
+        for (l, u) in BANDS:
+            self.ops.append((l, u, O.brand(self.n, self.n, l, u, seed=1), O.fill_uniform(9, self.n), np.zeros(self.n)))
+        self.bytes = sum(alg_bytes(self.n, l, u) for (l, u) in BANDS)
+        self.cores = os.cpu_count() or 1
+        try:
+            from threadpoolctl import threadpool_info
+            self.blas_threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+        except Exception:
+            self.blas_threads = None
+        self.omp_threads = O.num_threads()
+
+    def step(self):
+        from scipy.linalg import blas
+        from oracle import oracle as O
+        tb = to = 0.0
+        for (l, u, A, x, y) in self.ops:
             t0 = time.perf_counter()
-            blas.dgbmv(n, n, l, u, 1.0, A, x, beta=0.0, y=y, overwrite_y=1)
-            best_b = min(best_b, time.perf_counter() - t0)
+            blas.dgbmv(self.n, self.n, l, u, 1.0, A, x, beta=0.0, y=y, overwrite_y=1)
+            tb += time.perf_counter() - t0
             t0 = time.perf_counter()
-            O.gbmv("N", n, n, l, u, 1.0, A, x)
-            best_o = min(best_o, time.perf_counter() - t0)
-        tot_bytes += alg_bytes(n, l, u)
-        t_blas += best_b
-        t_orc += best_o
-        del A
-    cores = os.cpu_count() or 1
-    return {
-        "openblas_gbs": tot_bytes / t_blas / 1e9, "oracle_omp_gbs": tot_bytes / t_orc / 1e9,
-        "seconds_blas": t_blas, "seconds_oracle": t_orc, "cores": cores,
-        "sample": f"dgbmv f64 n=2^{log2n_sample}, l=u in {{1,8}} (same workload at reduced n; best of {repeats})",
-    }
+            O.gbmv("N", self.n, self.n, l, u, 1.0, A, x)
+            to += time.perf_counter() - t0
+        return tb, to
+
+    def describe(self, reps):
+        return (f"dgbmv f64 n=2^{self.log2n}, l=u in {{1,8}} (same workload at reduced n; {reps} passes; "
+                f"OpenBLAS threads={self.blas_threads}, OpenMP threads={self.omp_threads})")
+
+
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all host threads."""
+    n = str(os.cpu_count() or 1)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = n
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    log2n = 24
-    # warm-up + K timed steps, each step = one pass over the bounded sample
-    cpu_gbmv_sample(log2n, 1)
-    vals, secs, omp = [], [], []
-    for _ in range(max(1, args.steps)):
-        r = cpu_gbmv_sample(log2n, 1)
-        vals.append(r["openblas_gbs"])
-        omp.append(r["oracle_omp_gbs"])
-        secs.append(r["seconds_blas"])
-    v = sum(vals) / len(vals)
+    _use_all_host_threads()          # before numpy / scipy / libgomp are loaded
+    sample = CpuGbmvSample(24)
+    for _ in range(max(1, args.warmup)):
+        sample.step()
+    tb = to = 0.0
+    K = max(1, args.steps)
+    for _ in range(K):
+        a, b = sample.step()
+        tb += a
+        to += b
+    v = sample.bytes * K / tb / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tb / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"gbmv f64 l=u in {{1,8}}, bounded sample n=2^{log2n} of the n=2^27 workload",
+        "config": {"workload": "gbmv f64 l=u in {1,8}, bounded sample n=2^24 of the n=2^27 workload",
                    "note": "reference is pure Julia (not runnable here); timed = OpenBLAS dgbmv (scipy.linalg.blas, "
                            "all host threads): the BLAS routine BandedMatrices.gbmv! ccalls, i.e. what the reference "
                            "executes for this path (BASELINE.md section 4). The repo's own OpenMP oracle port is "
                            "timed beside it as cpu_baseline.oracle_omp_gbs."},
-        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
-                         "which": "openblas_dgbmv", "oracle_omp_gbs": sum(omp) / len(omp)},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": sample.cores, "kind": "port", "sample": sample.describe(K),
+                         "which": "openblas_dgbmv", "oracle_omp_gbs": sample.bytes * K / to / 1e9},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -346,10 +361,16 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_gbmv_sample(24, 2)
-        cpu = {"value": r["openblas_gbs"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
-               "which": "openblas_dgbmv (the routine the reference's gbmv! ccalls)",
-               "oracle_omp_gbs": r["oracle_omp_gbs"]}
+        sample = CpuGbmvSample(24)
+        sample.step()
+        tb = to = 0.0
+        for _ in range(3):
+            a_, b_ = sample.step()
+            tb += a_
+            to += b_
+        cpu = {"value": sample.bytes * 3 / tb / 1e9, "unit": "GB/s", "cores": sample.cores, "kind": "port",
+               "sample": sample.describe(3), "which": "openblas_dgbmv (the routine the reference's gbmv! ccalls)",
+               "oracle_omp_gbs": sample.bytes * 3 / to / 1e9}
 
     if rank == 0:
         line = {

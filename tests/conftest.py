@@ -31,5 +31,11 @@ def oracle():
 def L():
     """The product package; GPU tests fail loudly (not skip) if the CUDA extension is missing."""
     import lbm_b200
+    if not os.path.exists(lbm_b200.SO_PATH):
+        # not built yet in this checkout: build in-tree (nvcc cross-compiles without a GPU).  This is
+        # building the product, not falling back: if the build fails the tests fail.
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "lazybandedmatrices.jl_b200"), "-j8"], check=True,
+                       stdout=subprocess.DEVNULL)
     lbm_b200.lib()
     return lbm_b200
