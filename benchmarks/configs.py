@@ -133,16 +133,14 @@ def main():
             L.fill_uniform(f, 1 + i)
         byts = batch * 4 * n * (9 + 9 + 9 + 25)
         flops = batch * 2 * n * (9 * 9 + 17 * 9)
-        for tile in ((128,) if a.quick else (64, 128, 256, 512)):
-            h.set_tuning(chain_tile=tile)
-            emit(f"C5 fused chain A*B*C f32 batch={batch} n=4096 (4,4)^3 tile={tile}",
-                 timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2), byts, flops)
-        h.set_tuning(chain_tile=0)
-        if not a.quick:
-            for v, nm in ((2, "transposed-smem kernel, 204 regs / 2 CTAs"), (3, "transposed-smem kernel, 128 regs / 3 CTAs")):
-                h.set_tuning(chain_variant=v)
-                emit(f"C5 fused chain variant {v} ({nm})", timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2), byts, flops)
-            h.set_tuning(chain_variant=0)
+        variants = ((0, "default = warp-autonomous TMA kernel"),) if a.quick else (
+            (0, "default = warp-autonomous TMA kernel"), (1, "split-column register kernel"),
+            (2, "transposed-smem kernel, 204 regs / 2 CTAs"), (3, "transposed-smem kernel, 128 regs / 3 CTAs"))
+        for v, nm in variants:
+            h.set_tuning(chain_variant=v)
+            emit(f"C5 fused chain A*B*C f32 batch={batch} n=4096 (4,4)^3 variant {v} ({nm})",
+                 timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 10, 3), byts, flops)
+        h.set_tuning(chain_variant=0)
         del fs
         torch.cuda.empty_cache()
 

@@ -13,6 +13,9 @@
 //  * wide bands (FP64 DMMA tiles) live in gbmm_dmma.cu.
 #include "lbm_common.cuh"
 
+int lbm_chain3_warp_f32(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, const int64_t *ku, const float *A,
+                        int64_t sA, const float *B, int64_t sB, const float *C, int64_t sC, float *D, int64_t sD,
+                        bool *handled);
 int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double alpha, int64_t kla, int64_t kua,
                       const double *A, int64_t lda, int64_t klb, int64_t kub, const double *B, int64_t ldb,
                       double beta, int64_t klc, int64_t kuc, double *C, int64_t ldc, bool *handled);
@@ -736,8 +739,13 @@ int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, con
             return kl[0] == l && kl[1] == l && kl[2] == l && ku[0] == u && ku[1] == u && ku[2] == u;
         };
         if constexpr (sizeof(T) == 4) {
-            // chain_variant: 0/1 = split-column register kernel (fastest measured, profiles/configs_r01_final.jsonl),
-            // 2/3 = transposed-smem kernel (204 / 128 registers)
+            // chain_variant: 0 = auto / 4 = warp-autonomous TMA kernel (gbmm_chain_warp.cu) when the shape is covered,
+            // 1 = split-column register kernel, 2/3 = transposed-smem kernel (204 / 128 registers)
+            if (h->tune.chain_variant == 0 || h->tune.chain_variant == 4) {
+                bool handled = false;
+                int rc = lbm_chain3_warp_f32(h, batch, n, kl, ku, A, sA, B, sB, C, sC, D, sD, &handled);
+                if (handled) return rc;
+            }
             const bool t_ok = (h->tune.chain_variant == 2 || h->tune.chain_variant == 3) && n % 4 == 0 && sA % 4 == 0 && sB % 4 == 0 && sC % 4 == 0 &&
                               sD % 4 == 0 && lbm_aligned16(A) && lbm_aligned16(B) && lbm_aligned16(C) && lbm_aligned16(D);
             if (t_ok && all(4, 4)) return chain3_t_launch<T, 4, 4, 4, 4, 4, 4>(h, batch, n, A, sA, B, sB, C, sC, D, sD);

@@ -37,7 +37,7 @@ struct lbm_tuning {
     int64_t gbmm_variant;     // DMMA kernel: 0 = 3-stage/3 CTAs per SM, 1 = 2-stage/4 CTAs per SM
     int64_t chain_tile;
     int64_t chain_force_generic;
-    int64_t chain_variant;    // 0/1 split-column register kernel (default), 2/3 transposed-smem kernel (204/128 regs)
+    int64_t chain_variant;    // 0 auto (= 4 when covered), 1 split-column register kernel, 2/3 transposed-smem kernel, 4 warp-autonomous TMA kernel
 };
 
 struct lbm_handle_s {

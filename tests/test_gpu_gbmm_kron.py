@@ -135,9 +135,9 @@ def test_chain3_batched(L, oracle, dt):
               for i in range(3)]
         want = oracle.gbmm_chain3_batched(n, kl, ku, *fs)
         got = L.chain3_batched(*[torch.from_numpy(f).cuda() for f in fs], kl, ku).cpu().numpy()
-        if dt == torch.float32:   # the transposed-smem variant must give the same in-matrix entries
+        for variant in ((1, 3) if dt == torch.float32 else ()):   # split-column / transposed-smem variants: same in-matrix entries
             hh = L.handle_for(0)
-            hh.set_tuning(chain_variant=3)
+            hh.set_tuning(chain_variant=variant)
             try:
                 got3 = L.chain3_batched(*[torch.from_numpy(f).cuda() for f in fs], kl, ku).cpu().numpy()
             finally:
@@ -175,7 +175,7 @@ def test_chain3_register_kernel_vs_generic_and_nan_corners(L, oracle):
     gs = [torch.from_numpy(f).cuda() for f in fs]
     tol = tol_rows(np.float32, 9, 1.0, 1.0) * 9 + tol_rows(np.float32, 9, 9.0, 1.0)
     outs = []
-    for force, variant in ((0, 0), (0, 2), (0, 3), (1, 0)):     # split-column, transposed (2 variants), generic
+    for force, variant in ((0, 0), (0, 1), (0, 2), (0, 3), (1, 0)):     # warp-autonomous (default), split-column, transposed x2, generic
         h.set_tuning(chain_force_generic=force, chain_variant=variant)
         try:
             outs.append(L.chain3_batched(*gs, kl, ku).cpu().numpy())
@@ -187,6 +187,35 @@ def test_chain3_register_kernel_vs_generic_and_nan_corners(L, oracle):
             dw = oracle.band_to_dense(np.asfortranarray(want[b].T), n, 12, 12)
             assert not np.isnan(dg).any()
             assert np.max(np.abs(dg - dw)) <= tol
+
+
+def test_chain3_warp_kernel_persistent_loop(L, oracle):
+    """More tiles than resident warps (148 SMs x 8 warps): every warp walks several tiles, so the
+    mbarrier parities, the A*B/D slab aliasing and the next-tile prefetch are all exercised; ragged
+    last tiles (n/4 not a multiple of the tile's 30 column groups); out-of-matrix slots of D are 0."""
+    for (batch, n, k) in ((96, 4096, 4), (300, 1000, 4), (700, 516, 2), (1500, 128, 1), (40, 4, 1)):
+        kl = ku = [k, k, k]
+        ld = 2 * k + 1
+        fs = [oracle.fill_uniform(11 + i, batch * n * ld, np.float32).reshape(batch, n, ld) for i in range(3)]
+        gs = [torch.from_numpy(f).cuda() for f in fs]
+        got = L.chain3_batched(*gs, kl, ku).cpu().numpy()
+        h = L.handle_for(0)
+        h.set_tuning(chain_variant=1)
+        try:
+            ref_gpu = L.chain3_batched(*gs, kl, ku).cpu().numpy()
+        finally:
+            h.set_tuning(chain_variant=0)
+        tol = tol_rows(np.float32, ld, 1.0, 1.0) * ld + tol_rows(np.float32, ld, float(ld), 1.0)
+        # the split-column kernel also stores 0 in out-of-matrix slots: whole arrays are comparable
+        assert np.max(np.abs(got - ref_gpu)) <= tol, (batch, n, k)
+        for b in (0, batch // 2, batch - 1):
+            want = oracle.gbmm_chain3_batched(n, kl, ku, *[f[b:b + 1] for f in fs])[0]
+            dg = oracle.band_to_dense(np.asfortranarray(got[b].T), n, 3 * k, 3 * k)
+            dw = oracle.band_to_dense(np.asfortranarray(want.T), n, 3 * k, 3 * k)
+            assert np.max(np.abs(dg - dw)) <= tol, (batch, n, k, b)
+        j = np.arange(n)[:, None]
+        i = j + np.arange(6 * k + 1)[None, :] - 3 * k
+        assert np.all(got[:, (i < 0) | (i >= n)] == 0.0)
 
 
 def _lap(L, n, dtype=torch.float64):
