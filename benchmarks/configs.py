@@ -52,7 +52,7 @@ def vec(n, seed, dt=torch.float64):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="M,C1,C2,C3,C4,C5")
+    ap.add_argument("--only", default="M,C1,C2,C3,MM,C4,C5")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--quick", action="store_true", help="1 warm-up + 1 timed launch per config (profiling runs)")
     a = ap.parse_args()
@@ -126,6 +126,23 @@ def main():
         del x, y
         torch.cuda.empty_cache()
 
+    if "MM" in only:
+        # banded x dense (north_star "mat-mat applies"): 8 right-hand sides share one pass over A
+        n, nrhs = 1 << (24 - sh), 8
+        for l in (1, 8):
+            A = L.brand(n, n, l, l, seed=1)
+            X = torch.empty((nrhs, n), dtype=torch.float64, device="cuda")
+            L.fill_uniform(X, 9)
+            Y = torch.empty_like(X)
+            byts = 8 * n * ((2 * l + 1) + 2 * nrhs)
+            ms = timeit(lambda: L.mul_(Y.t(), A, X.t()))
+            emit(f"MM banded*dense f64 n=2^{24 - sh} l=u={l} nrhs={nrhs} (lbm_dgbmv_multi, one pass over A)", ms, byts)
+            ms1 = timeit(lambda: [L.mul_(Y[c], A, X[c]) for c in range(nrhs)])
+            emit(f"MM banded*dense f64 n=2^{24 - sh} l=u={l} nrhs={nrhs} (column by column, {nrhs} gbmv launches)", ms1, byts,
+                 note="same algorithmic bytes credited; A re-read per column")
+            del A, X, Y
+        torch.cuda.empty_cache()
+
     if "C5" in only:
         batch, n = 4096 >> sh, 4096
         fs = [torch.empty((batch, n, 9), dtype=torch.float32, device="cuda") for _ in range(3)]
@@ -172,8 +189,10 @@ def main():
             emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 gbmm_force={force}", ms, byts, flops)
         h.set_tuning(gbmm_force=0)
         if not a.quick:
-            for v, nm in ((2, "3-stage, 3 CTAs/SM"), (3, "2-stage, 5 CTAs/SM"), (4, "column-persistent 2-stage, 4 CTAs/SM"),
-                          (5, "column-persistent 3-stage, 3 CTAs/SM")):
+            for v, nm in ((1, "2-stage, 4 CTAs/SM"), (2, "3-stage, 3 CTAs/SM"), (3, "2-stage, 5 CTAs/SM"), (4, "column-persistent 2-stage, 4 CTAs/SM"),
+                          (5, "column-persistent 3-stage, 3 CTAs/SM"), (6, "3-stage, 4 CTAs/SM"), (7, "4-stage, 3 CTAs/SM"),
+                          (8, "3-stage, 4 CTAs/SM, rotated quadrants"), (9, "3-stage, 4 CTAs/SM, interleaved p-halves"), (10, "3-stage, 4 CTAs/SM, both"),
+                          (11, "3-stage, 4 CTAs/SM, single launch over all tiles"), (12, "2-stage, 6 CTAs/SM")):
                 h.set_tuning(gbmm_variant=v)
                 emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant {v} ({nm})", timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
             h.set_tuning(gbmm_variant=0)

@@ -70,6 +70,15 @@ int lbm_dgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
               double alpha, const double *A, int64_t lda, const double *x, double beta, double *y);
 int lbm_sgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
               float alpha, const float *A, int64_t lda, const float *x, float beta, float *y);
+/* banded * dense, `mul!(C, A::BandedMatrix, B::Matrix, alpha, beta)` ([up] BandedMatrices; exercised by the reference
+ * at test/test_tridiag.jl:253 for the structured kinds): Y[:,c] <- alpha*op(A)*X[:,c] + beta*Y[:,c], c < nrhs, X / Y
+ * column-major with leading dimensions ldx / ldy.  Narrow bands share ONE pass over A between up to 8 columns. */
+int lbm_dgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
+                    const double *A, int64_t lda, const double *X, int64_t ldx, double beta, double *Y, int64_t ldy,
+                    int64_t nrhs);
+int lbm_sgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha,
+                    const float *A, int64_t lda, const float *X, int64_t ldx, float beta, float *Y, int64_t ldy,
+                    int64_t nrhs);
 /* same, HOST pointers (pageable or pinned): H2D(A,x[,y]) + kernel + D2H(y) + sync. */
 int lbm_dgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
                    double alpha, const double *A, int64_t lda, const double *x, double beta, double *y);

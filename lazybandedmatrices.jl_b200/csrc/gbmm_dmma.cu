@@ -36,6 +36,7 @@ struct DmmaArgs {
     const double *B;
     double *C;
     int64_t gy;  // row tiles per column block
+    int flags;   // 1: rotate the warp -> quadrant map per CTA, 2: interleave the two halves of the p-range
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -58,17 +59,59 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int STAGE_DBL = KC * PA + TN * PB;  // doubles per stage
 
-template <int NSTAGE, int MINB>
+// Warp -> block map inside the 64x64 tile: warp (a,b) owns the 8-row blocks a0 + BSX*x and the 8-column blocks
+// b0 + BSX*y (x, y < 4).  BSX = 1: quadrants.  BSX = 2 interleaves the warps' blocks so that all four warps see the
+// same band-edge pattern in the ramp chunks (busiest warp +6 % over the mean instead of +26 %), but fewer chunks then
+// take the unmasked path; measured 18.5 vs 19.9 TFLOP/s, so quadrants stay (profiles/dmma_r01_notes.md).
+constexpr int BSX = 1;
+// Block-validity masks of a warp panel for one chunk.  Bit 4*ks + x stands for the 8x4 (A) / 4x8 (B) DMMA operand
+// block x of k-step ks; with t = 2*BSX*x - ks in [-3, 6*BSX] the block touches the band iff tlo <= t <= thi, where
+// tlo / thi are two integers per chunk (see the kernel).  MASK_GE[c + 3] = {t >= c}, c in [-3, 6*BSX + 1];
+// MASK_LE[c + 4] = {t <= c}, c in [-4, 6*BSX].
+constexpr int TMAX = 6 * BSX;
+constexpr unsigned mask_cmp(int c, bool ge) {
+    unsigned m = 0;
+    for (int ks = 0; ks < 4; ++ks)
+        for (int x = 0; x < 4; ++x) {
+            const int t = 2 * BSX * x - ks;
+            if (ge ? (t >= c) : (t <= c)) m |= 1u << (4 * ks + x);
+        }
+    return m;
+}
+struct MaskTables {
+    unsigned short ge[TMAX + 5], le[TMAX + 5];
+};
+constexpr MaskTables make_tables() {
+    MaskTables t{};
+    for (int c = -3; c <= TMAX + 1; ++c) t.ge[c + 3] = (unsigned short)mask_cmp(c, true);
+    for (int c = -4; c <= TMAX; ++c) t.le[c + 4] = (unsigned short)mask_cmp(c, false);
+    return t;
+}
+__constant__ MaskTables MASKS = make_tables();
+__device__ __forceinline__ int fdiv4(int a) { return a >> 2; }             // floor(a / 4)
+__device__ __forceinline__ int cdiv4(int a) { return (a + 3) >> 2; }       // ceil(a / 4)
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// blocks with  lo4 <= 4t <= hi4
+__device__ __forceinline__ unsigned band_mask(int lo4, int hi4) {
+    return (unsigned)MASKS.ge[clampi(cdiv4(lo4), -3, TMAX + 1) + 3] & (unsigned)MASKS.le[clampi(fdiv4(hi4), -4, TMAX) + 4];
+}
+
+// MODE 0: every tile (one launch).  MODE 1: interior tiles only -- the lean instantiation (no zero-filling staging,
+// no per-block tests) that carries ~all of the work; MODE 2: the remaining corner tiles.
+template <int NSTAGE, int MINB, int MODE>
 __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wi = (warp & 1) * 32, wj = (warp >> 1) * 32;  // warp's 32x32 block inside the tile
-
     // tile order: the tiles of one column block are consecutive CTAs (they share the B tile in
     // L2) and consecutive column blocks share most of their A rows
     const int64_t lin = (int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y;
+    // warp's 32x32 quadrant of the tile; rotated per CTA so that the quadrant that is busiest in the ramp chunks
+    // does not always land on the same SM sub-core (warp w of every resident CTA shares sub-core w % 4)
+    const int role = (a.flags & 1) ? ((warp + (int)(lin & 3)) & 3) : warp;
+    constexpr int WOFF = BSX == 1 ? 32 : 8, BST = 8 * BSX, SPAN = 24 * BSX + 7;  // first block, block stride, panel span - 1
+    const int wi = (role & 1) * WOFF, wj = (role >> 1) * WOFF;
     const int64_t by = lin % a.gy;
     const int64_t j0 = (lin / a.gy) * TN;
     if (j0 >= a.n) return;
@@ -84,6 +127,16 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
     if (phi > a.k - 1) phi = a.k - 1;
     plo &= ~(int64_t)3;
     const int nch = phi >= plo ? (int)((phi - plo + KC) / KC) : 0;
+    // Interior tiles (all but the matrix corners): every dense position (i,p) / (p,j) the chunks touch -- in band or
+    // not -- is an address inside the arrays, so the tiles are staged RAW with unpredicated 16-byte copies and the
+    // band edges are masked in registers (partial chunks only).  Corner tiles keep the zero-filling staging.
+    const bool interior_t = i0 + TM <= a.m && j0 >= 4 && j0 + TN + 4 <= a.n && plo >= 4 && plo + (int64_t)nch * KC + 4 <= a.k &&
+                          a.lda >= 33 && a.ldb >= 33 && ((a.lda - 1) & 1) == 0 && ((a.ldb - 1) & 1) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(a.A + a.kua + i0 + (a.lda - 1) * plo) & 15u) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(a.B + a.kub + plo + (a.ldb - 1) * j0) & 15u) == 0);
+    if (MODE == 1 && !interior_t) return;
+    if (MODE == 2 && interior_t) return;
+    const bool interior = MODE == 1 ? true : (MODE == 2 ? false : interior_t);
 
     double acc[4][4][2];
 #pragma unroll
@@ -133,10 +186,23 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
     const bool rows_in = i0 + TM <= a.m, cols_in = j0 + TN <= a.n;
     const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
 
-    auto issue = [&](int ch) {
-        double *sA = smem + (ch % NSTAGE) * STAGE_DBL;
+    // chunk visiting order: it -> chunk.  Interleaving the two halves of the p-range pairs every cheap ramp chunk
+    // (few blocks in band) with an expensive mid-range chunk, which keeps the prefetch distance useful.
+    const int half = (nch + 1) >> 1;
+    const bool reorder = (a.flags & 2) != 0;
+    auto chunk_of = [&](int it) { return reorder ? ((it & 1) ? half + (it >> 1) : (it >> 1)) : it; };
+    auto issue = [&](int it) {
+        const int ch = chunk_of(it);
+        double *sA = smem + (it % NSTAGE) * STAGE_DBL;
         double *sB = sA + KC * PA;
         const int pr = ch * KC;  // relative p of the chunk start
+        if (interior) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cp16(sA + (a_p0 + 4 * q) * PA + a_ii, a_ptr + a_step * (pr + a_p0 + 4 * q));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cp16(sB + (b_j0 + 16 * q) * PB + b_pp, b_ptr + pr + b_step * q);
+            return;
+        }
         const bool p_in = pr + KC - 1 <= kmax;
         // every (i,p) of the 64 x 16 A tile in band  <=>  ti0+63 - pr <= kla  and  ti0 - (pr+15) >= -kua
         if (a_al && rows_in && p_in && ti0 + TM - 1 - pr <= kla && ti0 - (pr + KC - 1) >= -kua) {
@@ -179,29 +245,62 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
     const int fr = lane >> 2, fc = lane & 3;  // fragment row / col of this lane
     // skip-test constants: block x of A covers rows ia..ia+7, block y of B covers cols jb..jb+7
     const int ia0 = (int)(i0 + wi - plo), jb0 = (int)(j0 + wj - plo);
-    const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + 8*x
-    const int fb_off = (wj + fr) * PB + fc;     // + 8*x*PB + 4*ks
+    const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + BST*x
+    const int fb_off = (wj + fr) * PB + fc;     // + BST*x*PB + 4*ks
 
-    for (int ch = 0; ch < nch; ++ch) {
-        cp_async_wait<NSTAGE - 2>();  // chunk ch has landed (this thread's copies)
-        __syncthreads();              // ... everyone's; and everyone is done computing chunk ch-1
-        if (ch + NSTAGE - 1 < nch) issue(ch + NSTAGE - 1);
+    for (int it = 0; it < nch; ++it) {
+        cp_async_wait<NSTAGE - 2>();  // chunk `it` has landed (this thread's copies)
+        __syncthreads();              // ... everyone's; and everyone is done computing chunk it-1
+        if (it + NSTAGE - 1 < nch) issue(it + NSTAGE - 1);
         cp_async_commit();
-        const double *sA = smem + (ch % NSTAGE) * STAGE_DBL;
+        const double *sA = smem + (it % NSTAGE) * STAGE_DBL;
         const double *sB = sA + KC * PA;
-        const int pr = ch * KC;
+        const int pr = chunk_of(it) * KC;
         constexpr bool DB = (MINB <= 3);  // double-buffer fragments only where registers allow it
+        // whole 32 x 16 (A) and 16 x 32 (B) warp panels inside their bands: no per-block tests
+        const bool full = (ia0 + SPAN - pr <= kla) && (ia0 - (pr + KC - 1) >= -kua) &&
+                          ((pr + KC - 1) - jb0 <= klb) && (pr - (jb0 + SPAN) >= -kub);
+        if (interior && !full) {
+            // raw-staged partial chunk.  da = (first row of the warp panel) - (first p of the chunk); A block (x,ks)
+            // holds i - p = da + BST*x - 4ks + [-3, 7]; db likewise for B with p - j = -(db + BST*y - 4ks) + [-7, 3]
+            const int da = ia0 - pr, db = jb0 - pr;
+            const unsigned mA = band_mask(-kua - 7 - da, kla + 3 - da);   // blocks touching A's band
+            const unsigned mB = band_mask(-klb - 7 - db, kub + 3 - db);   // blocks touching B's band
+            if (mA != 0 && mB != 0) {
+                // per-lane element test: (unsigned)(d + kua) <= kla + kua  with d = i - p of the lane's element
+                const int va = da + fr - fc + kua, wa = kla + kua;
+                const int vb = -db + fc - fr + kub, wb = klb + kub;
+#pragma unroll
+                for (int ks = 0; ks < KC / 4; ++ks) {
+                    const unsigned ma = (mA >> (4 * ks)) & 15u, mb = (mB >> (4 * ks)) & 15u;
+                    if (ma == 0 || mb == 0) continue;
+                    double ga[4], gb[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double ra = sA[fa_off + 4 * ks * PA + BST * x];
+                        const double rb = sB[fb_off + BST * x * PB + 4 * ks];
+                        ga[x] = (unsigned)(va + BST * x - 4 * ks) <= (unsigned)wa ? ra : 0.0;
+                        gb[x] = (unsigned)(vb - BST * x + 4 * ks) <= (unsigned)wb ? rb : 0.0;
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        if (!(ma >> x & 1u)) continue;
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)
+                            if (mb >> y & 1u) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
+                    }
+                }
+            }
+            continue;
+        }
         double fa[DB ? 2 : 1][4], fb[DB ? 2 : 1][4];
         if (DB) {
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                fa[0][x] = sA[fa_off + 8 * x];
-                fb[0][x] = sB[fb_off + 8 * x * PB];
+                fa[0][x] = sA[fa_off + BST * x];
+                fb[0][x] = sB[fb_off + BST * x * PB];
             }
         }
-        // whole 32 x 16 (A) and 16 x 32 (B) warp panels inside their bands: no per-block tests
-        const bool full = (ia0 + 31 - pr <= kla) && (ia0 - (pr + KC - 1) >= -kua) &&
-                          ((pr + KC - 1) - jb0 <= klb) && (pr - (jb0 + 31) >= -kub);
 #pragma unroll
         for (int ks = 0; ks < KC / 4; ++ks) {
             const int cur = DB ? (ks & 1) : 0, nxt = DB ? (cur ^ 1) : 0;
@@ -209,15 +308,15 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
                 if (ks + 1 < KC / 4) {  // fragments of the next k-step are in flight during this one's MMAs
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
-                        fa[nxt][x] = sA[fa_off + 4 * (ks + 1) * PA + 8 * x];
-                        fb[nxt][x] = sB[fb_off + 8 * x * PB + 4 * ks + 4];
+                        fa[nxt][x] = sA[fa_off + 4 * (ks + 1) * PA + BST * x];
+                        fb[nxt][x] = sB[fb_off + BST * x * PB + 4 * ks + 4];
                     }
                 }
             } else {
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
-                    fa[0][x] = sA[fa_off + 4 * ks * PA + 8 * x];
-                    fb[0][x] = sB[fb_off + 8 * x * PB + 4 * ks];
+                    fa[0][x] = sA[fa_off + 4 * ks * PA + BST * x];
+                    fb[0][x] = sB[fb_off + BST * x * PB + 4 * ks];
                 }
             }
             if (full) {
@@ -230,9 +329,9 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
                 unsigned ma = 0, mb = 0;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
-                    const int ia = ia0 + 8 * x;
+                    const int ia = ia0 + BST * x;
                     if (ia - (p + 3) <= kla && (ia + 7) - p >= -kua) ma |= 1u << x;
-                    const int jb = jb0 + 8 * x;
+                    const int jb = jb0 + BST * x;
                     if ((p + 3) - jb >= -kub && p - (jb + 7) <= klb) mb |= 1u << x;
                 }
                 if (ma != 0 && mb != 0) {
@@ -255,8 +354,8 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
         for (int y = 0; y < 4; ++y)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int64_t i = i0 + wi + 8 * x + fr;
-                const int64_t j = j0 + wj + 8 * y + 2 * fc + e;
+                const int64_t i = i0 + wi + BST * x + fr;
+                const int64_t j = j0 + wj + BST * y + 2 * fc + e;
                 const int64_t f = a.kuc + i - j;
                 if (i < a.m && j < a.n && f >= 0 && f <= a.klc + a.kuc) {
                     double *c = a.C + f + a.ldc * j;
@@ -523,22 +622,35 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         LBM_LAUNCH_CHECK(h, "gbmm_zero_corners_kernel");
     }
     a.gy = gy;
+    a.flags = 0;
     const int64_t total = gx * gy;
     const int64_t gxx = total < 1048576 ? total : 1048576;
     dim3 grid((unsigned)gxx, (unsigned)((total + gxx - 1) / gxx));
-    // default: 2-stage ring, 4 CTAs (16 warps) per SM -- occupancy beats ring depth here
-    // (profiles/configs_r01.md); gbmm_variant = 2: 3-stage / 3 CTAs, 3: 2-stage / 5 CTAs
+    // gbmm_variant: 0 = default (2-stage / 5 CTAs per SM, lean interior instantiation + corner instantiation),
+    // 1: 2-stage / 4 CTAs, 2: 3-stage / 3 CTAs, 3: = 0, 4/5: column-persistent kernels, 6: 3-stage / 4 CTAs,
+    // 7: 4-stage / 3 CTAs, 8-10: 6 + rotated quadrants / interleaved p-halves, 11: 6 as one launch, 12: 2-stage / 6 CTAs
+    // (measured in profiles/configs_r01_*.jsonl; everything lands between 17 and 21 TFLOP/s)
     const int variant = (int)h->tune.gbmm_variant;
-    static int configured_dev_mask[3] = {0, 0, 0};
+    static int configured_dev_mask[6] = {0, 0, 0, 0, 0, 0};
 #define LBM_DMMA_LAUNCH(IDX, NS, MB)                                                                         \
     do {                                                                                                      \
         const size_t smem = (size_t)(NS) * STAGE_DBL * sizeof(double);                                        \
         if (!(configured_dev_mask[IDX] & (1 << h->device))) {                                                 \
-            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<NS, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<NS, MB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                     \
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<NS, MB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                     \
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<NS, MB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem));                                                     \
             configured_dev_mask[IDX] |= (1 << h->device);                                                     \
         }                                                                                                     \
-        gbmm_dmma_kernel<NS, MB><<<grid, NT, smem, h->stream>>>(a);                                           \
+        if (variant == 11) {                                                                                  \
+            gbmm_dmma_kernel<NS, MB, 0><<<grid, NT, smem, h->stream>>>(a);                                    \
+        } else {                                                                                              \
+            gbmm_dmma_kernel<NS, MB, 1><<<grid, NT, smem, h->stream>>>(a);                                    \
+            LBM_LAUNCH_CHECK(h, "gbmm_dmma_kernel<interior>");                                                \
+            gbmm_dmma_kernel<NS, MB, 2><<<grid, NT, smem, h->stream>>>(a);                                    \
+        }                                                                                                     \
     } while (0)
     if (variant == 4 || variant == 5) {
         // column-block persistent kernels: one CTA per 64-column block
@@ -562,7 +674,13 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         }
     } else if (variant == 2) LBM_DMMA_LAUNCH(0, 3, 3);
     else if (variant == 3) LBM_DMMA_LAUNCH(2, 2, 5);
-    else LBM_DMMA_LAUNCH(1, 2, 4);
+    else if (variant == 6) LBM_DMMA_LAUNCH(3, 3, 4);
+    else if (variant == 12) LBM_DMMA_LAUNCH(5, 2, 6);
+    else if (variant >= 8 && variant <= 10) { a.flags = variant - 7; LBM_DMMA_LAUNCH(3, 3, 4); }
+    else if (variant == 7) LBM_DMMA_LAUNCH(4, 4, 3);
+    else if (variant == 1) LBM_DMMA_LAUNCH(1, 2, 4);
+    else if (variant == 11) LBM_DMMA_LAUNCH(3, 3, 4);   // 3-stage / 4 CTAs as ONE launch over all tiles
+    else LBM_DMMA_LAUNCH(2, 2, 5);   // default: 2-stage ring at 5 CTAs (20 warps) per SM -- occupancy beats ring depth: 3-stage ring at 4 CTAs (16 warps) per SM -- 4 x (55.5 + 1) KB just fits
 #undef LBM_DMMA_LAUNCH
     LBM_LAUNCH_CHECK(h, "gbmm_dmma_kernel");
     return 0;

@@ -406,6 +406,113 @@ __global__ void __launch_bounds__(256) scale_kernel(int64_t n, T beta, T *__rest
 }
 
 // ------------------------------------------------------------------------------------------
+// banded x dense (several right-hand sides):  Y[:, c] <- alpha*op(A)*X[:, c] + beta*Y[:, c]
+// ------------------------------------------------------------------------------------------
+// `mul!(C, A::BandedMatrix, B::Matrix, alpha, beta)`.  Same streamed-tile scheme as gbmv_tile_kernel, but a
+// stage carries the slab of A ONCE plus the x-windows of R columns (R bulk copies), and a thread keeps R
+// accumulators per output row -- so A is read from HBM once per R right-hand sides instead of once per column.
+template <typename T>
+struct GbmvMultiArgs {
+    int64_t m, n, kl, ku, lda, nout;
+    T alpha, beta;
+    const T *A;
+    const T *X;
+    T *Y;
+    int64_t ldx, ldy;
+    int64_t tile, ntiles;
+    int stages;
+    int64_t sA_elems, sx_elems;   // per stage: sA_elems + R * sx_elems
+};
+
+template <typename T, int R, bool TRANS>
+__global__ void __launch_bounds__(GBMV_NT) gbmv_multi_kernel(const GbmvMultiArgs<T> a) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int S = a.stages;
+    const int nb = (int)(a.kl + a.ku + 1);
+    const int64_t stage_elems = a.sA_elems + R * a.sx_elems;
+    const int sxe = (int)a.sx_elems;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
+    const int64_t nin = TRANS ? a.m : a.n;
+
+    auto ranges = [&](int64_t t, int64_t &o0, int64_t &o1, int64_t &c0, int64_t &c1, int64_t &x0, int64_t &x1) {
+        o0 = t * a.tile;
+        o1 = o0 + a.tile < a.nout ? o0 + a.tile : a.nout;
+        const int64_t lo = TRANS ? a.ku : a.kl, hi = TRANS ? a.kl : a.ku;
+        x0 = o0 - lo > 0 ? o0 - lo : 0;
+        x1 = o1 + hi < nin ? o1 + hi : nin;
+        if (x0 > nin) x0 = nin;
+        if (x1 < x0) x1 = x0;
+        if (!TRANS) { c0 = x0; c1 = x1; } else { c0 = o0; c1 = o1; }
+    };
+    auto issue = [&](int64_t t, int s) {  // thread 0 only
+        int64_t o0, o1, c0, c1, x0, x1;
+        ranges(t, o0, o1, c0, c1, x0, x1);
+        const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        const int64_t cntA = c1 * a.lda - e0a;
+        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        const int64_t cntx = x1 - x0a;
+        T *sA = sbase + (int64_t)s * stage_elems;
+        T *sx = sA + a.sA_elems;
+        mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + R * stage_bytes_bulk<T>(cntx));
+        stage_issue<T>(sA, a.A + e0a, cntA, &bars[s]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) stage_issue<T>(sx + r * a.sx_elems, a.X + r * a.ldx + x0a, cntx, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+    if (tid == 0) {
+        const int64_t pro = mine < S ? mine : S;
+        for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
+    }
+    const int lda = (int)a.lda;
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = (int)(k % S);
+        const uint32_t parity = (uint32_t)((k / S) & 1);
+        int64_t o0, o1, c0, c1, x0, x1;
+        ranges(first + k * step, o0, o1, c0, c1, x0, x1);
+        const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        const T *sA = sbase + (int64_t)s * stage_elems;
+        const T *sx = sA + a.sA_elems;
+        mbar_wait(&bars[s], parity);
+        for (int64_t o = o0 + tid; o < o1; o += GBMV_NT) {
+            T acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = (T)0;
+            // N: terms j = o-kl+q, band row ku+o-j;  T: terms i = o-ku+q, band row ku+i-o.  Masked by index.
+            const int64_t t0 = o - (TRANS ? a.ku : a.kl);
+            const int xb = (int)(t0 - x0a);
+            const int ab = TRANS ? (int)(o * a.lda - e0a) : (int)((a.kl + a.ku) + t0 * a.lda - e0a);
+            const int astep = TRANS ? 1 : lda - 1;
+            int q0 = t0 < 0 ? (int)-t0 : 0;
+            int q1 = t0 + nb > nin ? (int)(nin - t0) : nb;
+            for (int q = q0; q < q1; ++q) {
+                const T av = sA[ab + q * astep];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + xb + q], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                T *yp = a.Y + r * a.ldy + o;
+                *yp = (a.beta == (T)0) ? a.alpha * acc[r] : fma(a.beta, *yp, a.alpha * acc[r]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
@@ -640,6 +747,89 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
     }
 }
 
+template <typename T, int R, bool TRANS>
+int launch_multi(lbm_handle_t h, const GbmvMultiArgs<T> &a, int grid, size_t smem) {
+    static int configured_dev_mask = 0;
+    auto kern = gbmv_multi_kernel<T, R, TRANS>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        configured_dev_mask |= (1 << h->device);
+    }
+    kern<<<grid, GBMV_NT, smem, h->stream>>>(a);
+    LBM_LAUNCH_CHECK(h, "gbmv_multi_kernel");
+    return 0;
+}
+
+// Y <- alpha*op(A)*X + beta*Y, X/Y column-major with leading dimensions ldx/ldy.  Narrow bands: groups of up to 8
+// columns share one pass over A (gbmv_multi_kernel); wide bands / unaligned operands: one gbmv per column.
+template <typename T>
+int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha, const T *A,
+                    int64_t lda, const T *X, int64_t ldx, T beta, T *Y, int64_t ldy, int64_t nrhs) {
+    if (!h) return -1;
+    const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
+    if (!tr && !(trans == 'N' || trans == 'n')) return lbm_fail_arg(h, 2, "trans must be N, T or C");
+    if (m < 0) return lbm_fail_arg(h, 3, "m < 0");
+    if (n < 0) return lbm_fail_arg(h, 4, "n < 0");
+    if (kl < 0) return lbm_fail_arg(h, 5, "kl < 0");
+    if (ku < 0) return lbm_fail_arg(h, 6, "ku < 0");
+    if (lda < kl + ku + 1) return lbm_fail_arg(h, 9, "lda < kl+ku+1");
+    if (nrhs < 0) return lbm_fail_arg(h, 15, "nrhs < 0");
+    const int64_t nout = tr ? n : m, nin = tr ? m : n;
+    if (nrhs > 1 && ldx < nin) return lbm_fail_arg(h, 11, "ldx < rows of X");
+    if (nrhs > 1 && ldy < nout) return lbm_fail_arg(h, 14, "ldy < rows of Y");
+    if (nrhs == 0 || nout == 0) return 0;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int64_t nb = kl + ku + 1;
+    const int64_t smem_cap = h->max_smem_optin - 1024;
+    const bool fused_ok = nrhs >= 2 && nin > 0 && alpha != (T)0 && A && X && Y && nb <= 33 && lda <= 4 * nb + 8 &&
+                          lbm_aligned16(A) && lbm_aligned16(X) && lbm_aligned16(Y) && ldx % EPV == 0 &&
+                          h->tune.gbmv_force != 1;
+    int64_t c = 0;
+    if (fused_ok) {
+        lbm_device_guard g(h->device);
+        while (nrhs - c >= 2) {
+            const int R = nrhs - c >= 8 ? 8 : (nrhs - c >= 4 ? 4 : 2);
+            GbmvMultiArgs<T> a;
+            a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda; a.nout = nout; a.alpha = alpha; a.beta = beta;
+            a.A = A; a.X = X + c * ldx; a.Y = Y + c * ldy; a.ldx = ldx; a.ldy = ldy;
+            auto stage_elems = [&](int64_t tl, int64_t &sa, int64_t &sx) {
+                sa = round_up((tl + kl + ku) * lda + EPV, EPV);
+                sx = round_up(tl + kl + ku + EPV, EPV);
+            };
+            int64_t sa, sx, tile = GBMV_NT;
+            for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {
+                stage_elems(tl, sa, sx);
+                if ((sa + R * sx) * (int64_t)sizeof(T) <= 40 * 1024) tile = tl;
+            }
+            stage_elems(tile, sa, sx);
+            a.tile = tile; a.ntiles = (nout + tile - 1) / tile; a.sA_elems = sa; a.sx_elems = sx;
+            const int64_t stage_bytes = (sa + R * sx) * (int64_t)sizeof(T);
+            if (stage_bytes + 128 > smem_cap) break;       // cannot happen for nb <= 33; falls back below
+            int64_t stages = 2;
+            int64_t ctas = (200 * 1024) / (stages * stage_bytes + 256);
+            if (ctas < 1) ctas = 1;
+            if (ctas > 8) ctas = 8;
+            while (stages > 1 && ctas * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --stages;
+            while (ctas > 1 && ctas * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --ctas;
+            a.stages = (int)stages;
+            int64_t grid = (int64_t)h->sm_count * ctas;
+            if (grid > a.ntiles) grid = a.ntiles;
+            const size_t smem = (size_t)(128 + stages * stage_bytes);
+            int rc;
+            if (R == 8) rc = tr ? launch_multi<T, 8, true>(h, a, (int)grid, smem) : launch_multi<T, 8, false>(h, a, (int)grid, smem);
+            else if (R == 4) rc = tr ? launch_multi<T, 4, true>(h, a, (int)grid, smem) : launch_multi<T, 4, false>(h, a, (int)grid, smem);
+            else rc = tr ? launch_multi<T, 2, true>(h, a, (int)grid, smem) : launch_multi<T, 2, false>(h, a, (int)grid, smem);
+            if (rc) return rc;
+            c += R;
+        }
+    }
+    for (; c < nrhs; ++c) {
+        int rc = gbmv_impl<T>(h, trans, m, n, kl, ku, alpha, A, lda, X ? X + c * ldx : X, beta, Y ? Y + c * ldy : Y);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 // Host-buffer entry point: H2D(A, x) + kernel + D2H(y), pipelined.  op = N streams A in column
 // chunks on a copy stream; as soon as the columns a block of rows needs have landed, that block's
 // sub-slab (again a rectangular banded matrix: same lda, shifted bandwidths) is applied on the
@@ -730,6 +920,16 @@ int lbm_dgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
 int lbm_sgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha, const float *A,
               int64_t lda, const float *x, float beta, float *y) {
     return gbmv_impl<float>(h, trans, m, n, kl, ku, alpha, A, lda, x, beta, y);
+}
+int lbm_dgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
+                    const double *A, int64_t lda, const double *X, int64_t ldx, double beta, double *Y, int64_t ldy,
+                    int64_t nrhs) {
+    return gbmv_multi_impl<double>(h, trans, m, n, kl, ku, alpha, A, lda, X, ldx, beta, Y, ldy, nrhs);
+}
+int lbm_sgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha,
+                    const float *A, int64_t lda, const float *X, int64_t ldx, float beta, float *Y, int64_t ldy,
+                    int64_t nrhs) {
+    return gbmv_multi_impl<float>(h, trans, m, n, kl, ku, alpha, A, lda, X, ldx, beta, Y, ldy, nrhs);
 }
 int lbm_dgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
                    const double *A, int64_t lda, const double *x, double beta, double *y) {

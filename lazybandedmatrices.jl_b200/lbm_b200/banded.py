@@ -173,16 +173,31 @@ def gbmv_(y, A: BandedMatrix, x, alpha=1.0, beta=0.0, trans="N"):
     fn = getattr(_lib.lib(), f"lbm_{_pfx(A.dtype)}gbmv")
     ft = _ft(A.dtype)
     if x.dim() == 1:
-        cols = [(x, y)]
-    else:
-        cols = [(x[:, c], y[:, c]) for c in range(x.shape[1])]
-    for xc, yc in cols:
-        xcc = xc if xc.is_contiguous() else xc.contiguous()
-        ycc = yc if yc.is_contiguous() else yc.contiguous()
+        xcc = x if x.is_contiguous() else x.contiguous()
+        ycc = y if y.is_contiguous() else y.contiguous()
         h.check(fn(h.ptr, trans.encode(), m, n, A.l, A.u, ft(alpha), _ptr(A.data), A.lda, _ptr(xcc), ft(beta),
                    _ptr(ycc)), "lbm_gbmv")
-        if ycc is not yc:
-            yc.copy_(ycc)
+        if ycc is not y:
+            y.copy_(ycc)
+        return y
+    # mat-mat: X, Y are torch (rows, nrhs) tensors; the ABI wants column-major storage with a leading dimension,
+    # i.e. the transposed tensor with unit inner stride (a padded outer stride is passed through as ldx / ldy)
+    nrhs = x.shape[1]
+
+    def colmajor(t, rows):
+        tt = t.t()
+        ok = tt.stride(1) == 1 and (nrhs == 1 or tt.stride(0) >= max(1, rows))
+        return (tt, True) if ok else (tt.contiguous(), False)
+
+    xt, _ = colmajor(x, nin)
+    yt, y_direct = colmajor(y, nout)
+    ldx = xt.stride(0) if nrhs > 1 else max(1, nin)
+    ldy = yt.stride(0) if nrhs > 1 else max(1, nout)
+    fm = getattr(_lib.lib(), f"lbm_{_pfx(A.dtype)}gbmv_multi")
+    h.check(fm(h.ptr, trans.encode(), m, n, A.l, A.u, ft(alpha), _ptr(A.data), A.lda, _ptr(xt), ldx, ft(beta),
+               _ptr(yt), ldy, nrhs), "lbm_gbmv_multi")
+    if not y_direct:
+        y.copy_(yt.t())
     return y
 
 

@@ -200,3 +200,43 @@ def test_gbmv_large_linearity_and_sampled_rows(L, oracle):
     # linearity: A(2x) == 2 A x exactly (power-of-two scaling)
     y2 = A @ (2.0 * x)
     assert torch.equal(y2, 2.0 * y)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_gbmv_multi_banded_times_dense(L, oracle, dt):
+    """`mul!(C, A::BandedMatrix, B::Matrix, alpha, beta)` -> lbm_?gbmv_multi: groups of 8/4/2 columns share one
+    pass over A (narrow bands), wide bands go column by column; both ops, ragged nrhs, padded ldx/ldy, and NaNs
+    parked in A's out-of-matrix slots."""
+    npdt = NP[dt]
+    cases = [  # (m, n, kl, ku, nrhs, pad)
+        (1000, 1000, 1, 1, 8, 0), (3001, 2999, 4, 2, 11, 4), (777, 777, 8, 8, 3, 0), (5000, 5003, 16, 16, 5, 8),
+        (40, 33, 5, 2, 2, 0), (9, 9, 3, 0, 7, 0), (2000, 2000, 128, 128, 3, 0), (70001, 70001, 2, 2, 13, 0), (5, 5, 1, 1, 1, 0),
+        (300, 300, 0, 0, 4, 0),
+    ]
+    for s, (m, n, kl, ku, nrhs, pad) in enumerate(cases):
+        lda = kl + ku + 1
+        A_np = np.asfortranarray(oracle.fill_uniform(200 + s, lda * n, npdt).reshape((lda, n), order="F"))
+        Ap = A_np.copy()
+        r = np.arange(lda)[:, None]
+        i = np.arange(n)[None, :] + r - ku
+        Ap[(i < 0) | (i >= m)] = np.nan
+        A = L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(Ap.T)).cuda(), m, kl, ku)
+        for trans in ("N", "T"):
+            nin, nout = (n, m) if trans == "N" else (m, n)
+            ldx, ldy = nin + pad, nout + pad
+            X_np = oracle.fill_uniform(300 + s, ldx * nrhs, npdt).reshape(nrhs, ldx)     # row c = column c of X
+            Y_np = oracle.fill_uniform(400 + s, ldy * nrhs, npdt).reshape(nrhs, ldy)
+            for alpha, beta in ((1.0, 0.0), (-1.5, 0.5)):
+                Xd = torch.from_numpy(X_np).cuda()
+                Yd = torch.from_numpy(Y_np.copy()).cuda()
+                # column-major views with padded leading dimensions: no copies inside the host layer
+                L.mul_(Yd[:, :nout].t(), A if trans == "N" else A.T, Xd[:, :nin].t(), alpha, beta)
+                got = Yd.cpu().numpy()
+                tol = tol_rows(npdt, lda, 1.0, 1.0, alpha, beta, 1.0)
+                for c in range(nrhs):
+                    want = oracle.gbmv(trans, m, n, kl, ku, alpha, A_np, X_np[c, :nin].copy(), beta, Y_np[c, :nout].copy())
+                    assert np.max(np.abs(got[c, :nout] - want)) <= tol, (m, n, kl, ku, nrhs, trans, c)
+                    if pad:
+                        assert np.array_equal(got[c, nout:], Y_np[c, nout:])           # padding rows untouched
+    with pytest.raises(L.DimensionMismatch):
+        L.mul_(torch.empty(5, 3, dtype=dt, device="cuda"), L.brand(5, 5, 1, 1, dtype=dt), torch.empty(5, 4, dtype=dt, device="cuda"))
