@@ -52,7 +52,7 @@ def vec(n, seed, dt=torch.float64):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="M,C1,C2,C3,MM,C4,C5")
+    ap.add_argument("--only", default="M,C1,C2,C3,MM,BC,RD,C4,C5")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--quick", action="store_true", help="1 warm-up + 1 timed launch per config (profiling runs)")
     a = ap.parse_args()
@@ -141,6 +141,31 @@ def main():
             emit(f"MM banded*dense f64 n=2^{24 - sh} l=u={l} nrhs={nrhs} (column by column, {nrhs} gbmv launches)", ms1, byts,
                  note="same algorithmic bytes credited; A re-read per column")
             del A, X, Y
+        torch.cuda.empty_cache()
+
+    if "RD" in only:
+        # single-pass reductions on the structured kinds (8(f) rank 3)
+        n = 1 << (28 - sh)
+        S = L.SymTridiagonal(vec(n, 2), vec(n - 1, 3))
+        x, y = vec(n, 4), vec(n, 5)
+        emit(f"RD dot(x, SymTridiagonal, y) f64 n=2^{28 - sh}", timeit(lambda: S.dot(x, y)), 8 * 4 * n)
+        emit(f"RD sum(SymTridiagonal; dims=1) f64 n=2^{28 - sh}", timeit(lambda: S.sum(1)), 8 * 3 * n)
+        emit(f"RD sum(SymTridiagonal) f64 n=2^{28 - sh}", timeit(lambda: S.sum()), 8 * 2 * n)
+        del S, x, y
+        torch.cuda.empty_cache()
+
+    if "BC" in only:
+        # BroadcastArray(+, A1, A2) * x, fused (lbm_dgbmv2) vs term by term (two gbmv, y read + written twice)
+        n = 1 << (27 - sh)
+        A1 = L.brand(n, n, 1, 1, seed=1)
+        A2 = L.brand(n, n, 1, 1, seed=2)
+        x, y = vec(n, 9), torch.empty(n, dtype=torch.float64, device="cuda")
+        M = L.BroadcastMatrix("+", A1, A2)
+        byts = 8 * n * (3 + 3 + 2)
+        emit(f"BC (A1+A2)*x f64 n=2^{27 - sh} (1,1)+(1,1) fused lbm_dgbmv2", timeit(lambda: M.mul_(y, x)), byts)
+        emit(f"BC (A1+A2)*x f64 n=2^{27 - sh} (1,1)+(1,1) term by term (2 gbmv)",
+             timeit(lambda: (L.mul_(y, A1, x), L.mul_(y, A2, x, 1.0, 1.0))), byts, note="same algorithmic bytes credited")
+        del A1, A2, x, y
         torch.cuda.empty_cache()
 
     if "C5" in only:

@@ -79,6 +79,14 @@ int lbm_dgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
 int lbm_sgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha,
                     const float *A, int64_t lda, const float *X, int64_t ldx, float beta, float *Y, int64_t ldy,
                     int64_t nrhs);
+/* fused broadcast sum, `mul!(y, BroadcastArray(+/-, A1, A2), x)` (BroadcastBandedLayout, reference
+ * src/LazyBandedMatrices.jl:20; test/test_misc.jl:21-40, test/test_blockkron.jl:303,345):
+ * y <- alpha1*A1*x + alpha2*A2*x + beta*y without forming A1 +- A2 and with ONE pass over x and y. */
+int lbm_dgbmv2(lbm_handle_t h, int64_t m, int64_t n, double alpha1, int64_t kl1, int64_t ku1, const double *A1, int64_t lda1,
+               double alpha2, int64_t kl2, int64_t ku2, const double *A2, int64_t lda2, const double *x, double beta,
+               double *y);
+int lbm_sgbmv2(lbm_handle_t h, int64_t m, int64_t n, float alpha1, int64_t kl1, int64_t ku1, const float *A1, int64_t lda1,
+               float alpha2, int64_t kl2, int64_t ku2, const float *A2, int64_t lda2, const float *x, float beta, float *y);
 /* same, HOST pointers (pageable or pinned): H2D(A,x[,y]) + kernel + D2H(y) + sync. */
 int lbm_dgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku,
                    double alpha, const double *A, int64_t lda, const double *x, double beta, double *y);
@@ -110,6 +118,19 @@ int lbm_sbidiag_mv(lbm_handle_t h, char uplo, int64_t n, const float *dv, const 
                    float beta, float *Y, int64_t ldy);
 
 /* ---- banded * banded -> banded:  C <- alpha*A*B + beta*C ------------------------------ */
+/* ---- single-pass reductions over the structured kinds --------- */
+/* dot(x, A, y) = x' A y for A = Tridiagonal(dl,d,du) (reference src/tridiag.jl:665-682); SymTridiagonal passes
+ * dl == du == ev, Bidiagonal passes NULL for the missing diagonal.  *result is a DEVICE scalar, written by a
+ * deterministic two-stage reduction (no atomics).  n == 0 -> 0. */
+int lbm_dtridiag_dot(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du, const double *x,
+                     const double *y, double *result);
+int lbm_stridiag_dot(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du, const float *x,
+                     const float *y, float *result);
+/* Base._sum(A, dims) (reference src/tridiag.jl:594-660, src/bidiag.jl:396-435): dims = 1 -> out[j] = sum_i A[i,j]
+ * (n values), dims = 2 -> out[i] = sum_j A[i,j] (n values), dims = 0 -> the scalar sum(A) (Colon). */
+int lbm_dtridiag_sum(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du, int dims, double *out);
+int lbm_stridiag_sum(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du, int dims, float *out);
+
 /* Materialises ApplyMatrix(*, A, B) (reference README.md:8-26; [up] BandedMatrices gbmm!).
  * A m x k (kla,kua), B k x n (klb,kub), C m x n stored with band (klc,kuc) which must
  * cover the product band clipped to the matrix: klc >= min(kla+klb, m-1),

@@ -424,7 +424,7 @@ struct GbmvMultiArgs {
     int64_t sA_elems, sx_elems;   // per stage: sA_elems + R * sx_elems
 };
 
-template <typename T, int R, bool TRANS>
+template <typename T, int R, bool TRANS, int NBU>   // NBU: compile-time unroll bound >= kl+ku+1
 __global__ void __launch_bounds__(GBMV_NT) gbmv_multi_kernel(const GbmvMultiArgs<T> a) {
     constexpr int EPV = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_multi_kernel(const GbmvMultiArgs
         const T *sA = sbase + (int64_t)s * stage_elems;
         const T *sx = sA + a.sA_elems;
         mbar_wait(&bars[s], parity);
+        const bool interior = o0 - (TRANS ? a.ku : a.kl) >= 0 && o1 - 1 + (TRANS ? a.kl : a.ku) < nin;
         for (int64_t o = o0 + tid; o < o1; o += GBMV_NT) {
             T acc[R];
 #pragma unroll
@@ -494,18 +495,143 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_multi_kernel(const GbmvMultiArgs
             const int xb = (int)(t0 - x0a);
             const int ab = TRANS ? (int)(o * a.lda - e0a) : (int)((a.kl + a.ku) + t0 * a.lda - e0a);
             const int astep = TRANS ? 1 : lda - 1;
-            int q0 = t0 < 0 ? (int)-t0 : 0;
-            int q1 = t0 + nb > nin ? (int)(nin - t0) : nb;
-            for (int q = q0; q < q1; ++q) {
-                const T av = sA[ab + q * astep];
+            if (interior) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + xb + q], acc[r]);
+                for (int q = 0; q < NBU; ++q) {
+                    if (q < nb) {
+                        const T av = sA[ab + q * astep];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + xb + q], acc[r]);
+                    }
+                }
+            } else {
+                const int q0 = t0 < 0 ? (int)-t0 : 0;
+                const int q1 = t0 + nb > nin ? (int)(nin - t0) : nb;
+                for (int q = q0; q < q1; ++q) {
+                    const T av = sA[ab + q * astep];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + xb + q], acc[r]);
+                }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 T *yp = a.Y + r * a.ldy + o;
                 *yp = (a.beta == (T)0) ? a.alpha * acc[r] : fma(a.beta, *yp, a.alpha * acc[r]);
             }
+        }
+        __syncthreads();
+        if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused broadcast sum:  y <- alpha1*A1*x + alpha2*A2*x + beta*y   (BroadcastArray(+/-, A1, A2) * x)
+// ------------------------------------------------------------------------------------------
+// `Mul{BroadcastBandedLayout{+}}` (reference src/LazyBandedMatrices.jl:20; used for D_xx +- D at
+// test/test_misc.jl:21-40 and the Laplacian sum test/test_blockkron.jl:303,345) applied WITHOUT forming the sum
+// and without a second pass over y: a stage carries both slabs and ONE x-window (the union band's).
+template <typename T>
+struct Gbmv2Args {
+    int64_t m, n;
+    int64_t kl[2], ku[2], lda[2];
+    T alpha[2], beta;
+    const T *A[2];
+    const T *x;
+    T *y;
+    int64_t tile, ntiles;
+    int stages;
+    int64_t sA_elems[2], sx_elems;
+};
+
+template <typename T, int NBU>   // NBU: compile-time unroll bound >= both band widths
+__global__ void __launch_bounds__(GBMV_NT) gbmv2_tile_kernel(const Gbmv2Args<T> a) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int S = a.stages;
+    const int64_t stage_elems = a.sA_elems[0] + a.sA_elems[1] + a.sx_elems;
+    const int64_t klm = a.kl[0] > a.kl[1] ? a.kl[0] : a.kl[1], kum = a.ku[0] > a.ku[1] ? a.ku[0] : a.ku[1];
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
+
+    // column range [c0, c1) operand f needs for the output rows [o0, o1)
+    auto cols = [&](int64_t o0, int64_t o1, int64_t kl, int64_t ku, int64_t &c0, int64_t &c1) {
+        c0 = o0 - kl > 0 ? o0 - kl : 0;
+        c1 = o1 + ku < a.n ? o1 + ku : a.n;
+        if (c0 > a.n) c0 = a.n;
+        if (c1 < c0) c1 = c0;
+    };
+    auto issue = [&](int64_t t, int s) {  // thread 0 only
+        const int64_t o0 = t * a.tile, o1 = o0 + a.tile < a.m ? o0 + a.tile : a.m;
+        T *dst = sbase + (int64_t)s * stage_elems;
+        uint32_t bytes = 0;
+        int64_t e0[2], cnt[2], x0, x1;
+        for (int f = 0; f < 2; ++f) {
+            int64_t c0, c1;
+            cols(o0, o1, a.kl[f], a.ku[f], c0, c1);
+            e0[f] = (c0 * a.lda[f]) & ~(int64_t)(EPV - 1);
+            cnt[f] = c1 * a.lda[f] - e0[f];
+            bytes += stage_bytes_bulk<T>(cnt[f]);
+        }
+        cols(o0, o1, klm, kum, x0, x1);
+        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        bytes += stage_bytes_bulk<T>(x1 - x0a);
+        mbar_add_tx(&bars[s], bytes);
+        stage_issue<T>(dst, a.A[0] + e0[0], cnt[0], &bars[s]);
+        stage_issue<T>(dst + a.sA_elems[0], a.A[1] + e0[1], cnt[1], &bars[s]);
+        stage_issue<T>(dst + a.sA_elems[0] + a.sA_elems[1], a.x + x0a, x1 - x0a, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+    if (tid == 0) {
+        const int64_t pro = mine < S ? mine : S;
+        for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
+    }
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = (int)(k % S);
+        const uint32_t parity = (uint32_t)((k / S) & 1);
+        const int64_t t = first + k * step;
+        const int64_t o0 = t * a.tile, o1 = o0 + a.tile < a.m ? o0 + a.tile : a.m;
+        const T *sA0 = sbase + (int64_t)s * stage_elems;
+        const T *sA[2] = {sA0, sA0 + a.sA_elems[0]};
+        const T *sx = sA0 + a.sA_elems[0] + a.sA_elems[1];
+        int64_t e0[2], x0, x1;
+        for (int f = 0; f < 2; ++f) {
+            int64_t c0, c1;
+            cols(o0, o1, a.kl[f], a.ku[f], c0, c1);
+            e0[f] = (c0 * a.lda[f]) & ~(int64_t)(EPV - 1);
+        }
+        cols(o0, o1, klm, kum, x0, x1);
+        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        mbar_wait(&bars[s], parity);
+        const bool interior = o0 - klm >= 0 && o1 - 1 + kum < a.n;   // no index masks needed
+        for (int64_t o = o0 + tid; o < o1; o += GBMV_NT) {
+            T tot = (T)0;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const int nb = (int)(a.kl[f] + a.ku[f] + 1), lda = (int)a.lda[f];
+                const int64_t j0 = o - a.kl[f];
+                const int xb = (int)(j0 - x0a);
+                const int ab = (int)((a.kl[f] + a.ku[f]) + j0 * a.lda[f] - e0[f]);
+                T acc = (T)0;
+                if (interior) {
+#pragma unroll
+                    for (int q = 0; q < NBU; ++q)
+                        if (q < nb) acc = fma(sA[f][ab + q * (lda - 1)], sx[xb + q], acc);
+                } else {
+                    const int q0 = j0 < 0 ? (int)-j0 : 0;
+                    const int q1 = j0 + nb > a.n ? (int)(a.n - j0) : nb;
+                    for (int q = q0; q < q1; ++q) acc = fma(sA[f][ab + q * (lda - 1)], sx[xb + q], acc);
+                }
+                tot = fma(a.alpha[f], acc, tot);
+            }
+            a.y[o] = (a.beta == (T)0) ? tot : fma(a.beta, a.y[o], tot);
         }
         __syncthreads();
         if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
@@ -747,10 +873,10 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
     }
 }
 
-template <typename T, int R, bool TRANS>
-int launch_multi(lbm_handle_t h, const GbmvMultiArgs<T> &a, int grid, size_t smem) {
+template <typename T, int R, bool TRANS, int NBU>
+int launch_multi2(lbm_handle_t h, const GbmvMultiArgs<T> &a, int grid, size_t smem) {
     static int configured_dev_mask = 0;
-    auto kern = gbmv_multi_kernel<T, R, TRANS>;
+    auto kern = gbmv_multi_kernel<T, R, TRANS, NBU>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         configured_dev_mask |= (1 << h->device);
@@ -758,6 +884,14 @@ int launch_multi(lbm_handle_t h, const GbmvMultiArgs<T> &a, int grid, size_t sme
     kern<<<grid, GBMV_NT, smem, h->stream>>>(a);
     LBM_LAUNCH_CHECK(h, "gbmv_multi_kernel");
     return 0;
+}
+
+template <typename T, int R, bool TRANS>
+int launch_multi(lbm_handle_t h, const GbmvMultiArgs<T> &a, int grid, size_t smem) {
+    const int64_t nb = a.kl + a.ku + 1;
+    if (nb <= 3) return launch_multi2<T, R, TRANS, 3>(h, a, grid, smem);
+    if (nb <= 17) return launch_multi2<T, R, TRANS, 17>(h, a, grid, smem);
+    return launch_multi2<T, R, TRANS, 33>(h, a, grid, smem);
 }
 
 // Y <- alpha*op(A)*X + beta*Y, X/Y column-major with leading dimensions ldx/ldy.  Narrow bands: groups of up to 8
@@ -828,6 +962,81 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
         if (rc) return rc;
     }
     return 0;
+}
+
+template <typename T, int NBU>
+int launch_gbmv2(lbm_handle_t h, const Gbmv2Args<T> &a, int grid, size_t smem) {
+    static int configured_dev_mask = 0;
+    auto kern = gbmv2_tile_kernel<T, NBU>;
+    if (!(configured_dev_mask & (1 << h->device))) {
+        LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        configured_dev_mask |= (1 << h->device);
+    }
+    kern<<<grid, GBMV_NT, smem, h->stream>>>(a);
+    LBM_LAUNCH_CHECK(h, "gbmv2_tile_kernel");
+    return 0;
+}
+
+// y <- alpha1*A1*x + alpha2*A2*x + beta*y.  Fused when both bands are narrow and everything is 16-byte aligned;
+// otherwise two gbmv calls (the second accumulating with beta = 1).
+template <typename T>
+int gbmv2_impl(lbm_handle_t h, int64_t m, int64_t n, T alpha1, int64_t kl1, int64_t ku1, const T *A1, int64_t lda1, T alpha2,
+               int64_t kl2, int64_t ku2, const T *A2, int64_t lda2, const T *x, T beta, T *y) {
+    if (!h) return -1;
+    if (m < 0) return lbm_fail_arg(h, 2, "m < 0");
+    if (n < 0) return lbm_fail_arg(h, 3, "n < 0");
+    if (kl1 < 0 || ku1 < 0) return lbm_fail_arg(h, 5, "kl1/ku1 < 0");
+    if (lda1 < kl1 + ku1 + 1) return lbm_fail_arg(h, 8, "lda1 < kl1+ku1+1");
+    if (kl2 < 0 || ku2 < 0) return lbm_fail_arg(h, 10, "kl2/ku2 < 0");
+    if (lda2 < kl2 + ku2 + 1) return lbm_fail_arg(h, 13, "lda2 < kl2+ku2+1");
+    if (m == 0) return 0;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int64_t nb1 = kl1 + ku1 + 1, nb2 = kl2 + ku2 + 1;
+    const int64_t klm = kl1 > kl2 ? kl1 : kl2, kum = ku1 > ku2 ? ku1 : ku2;
+    auto stage_elems = [&](int64_t tl, int64_t &s1, int64_t &s2, int64_t &sx) {
+        s1 = round_up((tl + kl1 + ku1) * lda1 + EPV, EPV);
+        s2 = round_up((tl + kl2 + ku2) * lda2 + EPV, EPV);
+        sx = round_up(tl + klm + kum + EPV, EPV);
+    };
+    int64_t s1, s2, sx;
+    stage_elems(GBMV_NT, s1, s2, sx);
+    const bool fused = n > 0 && A1 && A2 && x && y && alpha1 != (T)0 && alpha2 != (T)0 && nb1 <= 33 && nb2 <= 33 &&
+                       lda1 <= 4 * nb1 + 8 && lda2 <= 4 * nb2 + 8 && lbm_aligned16(A1) && lbm_aligned16(A2) && lbm_aligned16(x) &&
+                       (s1 + s2 + sx) * (int64_t)sizeof(T) <= 100 * 1024 && h->tune.gbmv_force != 1;
+    if (!fused) {
+        int rc = gbmv_impl<T>(h, 'N', m, n, kl1, ku1, alpha1, A1, lda1, x, beta, y);
+        if (rc) return rc;
+        rc = gbmv_impl<T>(h, 'N', m, n, kl2, ku2, alpha2, A2, lda2, x, (T)1, y);
+        return rc < 0 ? (rc <= -5 ? rc - 5 : rc) : rc;   // argument numbers of the second operand
+    }
+    lbm_device_guard g(h->device);
+    Gbmv2Args<T> a;
+    a.m = m; a.n = n; a.kl[0] = kl1; a.ku[0] = ku1; a.lda[0] = lda1; a.kl[1] = kl2; a.ku[1] = ku2; a.lda[1] = lda2;
+    a.alpha[0] = alpha1; a.alpha[1] = alpha2; a.beta = beta; a.A[0] = A1; a.A[1] = A2; a.x = x; a.y = y;
+    int64_t tile = GBMV_NT;
+    for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {
+        stage_elems(tl, s1, s2, sx);
+        if ((s1 + s2 + sx) * (int64_t)sizeof(T) <= 40 * 1024) tile = tl;
+    }
+    stage_elems(tile, s1, s2, sx);
+    a.tile = tile; a.ntiles = (m + tile - 1) / tile; a.sA_elems[0] = s1; a.sA_elems[1] = s2; a.sx_elems = sx;
+    const int64_t stage_bytes = (s1 + s2 + sx) * (int64_t)sizeof(T);
+    int64_t stages = 2;
+    int64_t ctas = (200 * 1024) / (stages * stage_bytes + 256);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 8) ctas = 8;
+    while (stages > 1 && ctas * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --stages;
+    while (ctas > 1 && ctas * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --ctas;
+    a.stages = (int)stages;
+    int64_t grid = (int64_t)h->sm_count * ctas;
+    if (grid > a.ntiles) grid = a.ntiles;
+    const size_t smem = (size_t)(128 + stages * stage_bytes);
+    const int64_t nbm = nb1 > nb2 ? nb1 : nb2;
+    if (nbm <= 3) return launch_gbmv2<T, 3>(h, a, (int)grid, smem);
+    if (nbm <= 5) return launch_gbmv2<T, 5>(h, a, (int)grid, smem);
+    if (nbm <= 9) return launch_gbmv2<T, 9>(h, a, (int)grid, smem);
+    if (nbm <= 17) return launch_gbmv2<T, 17>(h, a, (int)grid, smem);
+    return launch_gbmv2<T, 33>(h, a, (int)grid, smem);
 }
 
 // Host-buffer entry point: H2D(A, x) + kernel + D2H(y), pipelined.  op = N streams A in column
@@ -930,6 +1139,15 @@ int lbm_sgbmv_multi(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
                     const float *A, int64_t lda, const float *X, int64_t ldx, float beta, float *Y, int64_t ldy,
                     int64_t nrhs) {
     return gbmv_multi_impl<float>(h, trans, m, n, kl, ku, alpha, A, lda, X, ldx, beta, Y, ldy, nrhs);
+}
+int lbm_dgbmv2(lbm_handle_t h, int64_t m, int64_t n, double alpha1, int64_t kl1, int64_t ku1, const double *A1, int64_t lda1,
+               double alpha2, int64_t kl2, int64_t ku2, const double *A2, int64_t lda2, const double *x, double beta,
+               double *y) {
+    return gbmv2_impl<double>(h, m, n, alpha1, kl1, ku1, A1, lda1, alpha2, kl2, ku2, A2, lda2, x, beta, y);
+}
+int lbm_sgbmv2(lbm_handle_t h, int64_t m, int64_t n, float alpha1, int64_t kl1, int64_t ku1, const float *A1, int64_t lda1,
+               float alpha2, int64_t kl2, int64_t ku2, const float *A2, int64_t lda2, const float *x, float beta, float *y) {
+    return gbmv2_impl<float>(h, m, n, alpha1, kl1, ku1, A1, lda1, alpha2, kl2, ku2, A2, lda2, x, beta, y);
 }
 int lbm_dgbmv_host(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
                    const double *A, int64_t lda, const double *x, double beta, double *y) {

@@ -62,6 +62,9 @@ def _sigs():
     for p, ft in (("d", f64), ("s", f32)):
         s[f"lbm_{p}gbmv"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
         s[f"lbm_{p}gbmv_multi"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, i64, ft, vp, i64, i64])
+        s[f"lbm_{p}gbmv2"] = (C.c_int, [H, i64, i64, ft, i64, i64, vp, i64, ft, i64, i64, vp, i64, vp, ft, vp])
+        s[f"lbm_{p}tridiag_dot"] = (C.c_int, [H, i64, vp, vp, vp, vp, vp, vp])
+        s[f"lbm_{p}tridiag_sum"] = (C.c_int, [H, i64, vp, vp, vp, C.c_int, vp])
         s[f"lbm_{p}gbmv_host"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
         s[f"lbm_{p}gbmv_sharded"] = (C.c_int, [H, i64, i64, i64, ft, vp, i64, vp, ft, vp, C.c_int])
         s[f"lbm_{p}tridiag_mv"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, i64, i64, ft, vp, i64])

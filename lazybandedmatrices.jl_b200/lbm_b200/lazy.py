@@ -109,6 +109,21 @@ class BroadcastMatrix:
     def mul_(self, y, x, alpha=1.0, beta=0.0):
         from .linalg import mul_ as _mul
         sign = [1.0] + [(-1.0 if self.f == "-" else 1.0)] * (len(self.args) - 1)
+        if x.shape[0] != self.shape[1]:
+            raise DimensionMismatch(
+                f"second entry of size(A)={self.shape} and first entry of size(B) = {tuple(x.shape)} must match.")
+        if y.shape[0] != self.shape[0]:
+            raise DimensionMismatch(f"sizes size(A)={self.shape} and size(C) = {tuple(y.shape)} must match at first entry.")
+        if (len(self.args) == 2 and all(isinstance(a, BandedMatrix) for a in self.args) and x.dim() == 1
+                and x.is_contiguous() and y.is_contiguous() and self.args[0].dtype == self.args[1].dtype == x.dtype):
+            # fused: one pass over x and y, the sum is never formed (lbm_?gbmv2)
+            A1, A2 = self.args
+            h = _lib.handle_of(A1.data)
+            ft = _lib.f64 if A1.dtype == torch.float64 else _lib.f32
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(A1.dtype)}gbmv2")
+            h.check(fn(h.ptr, A1.m, A1.n, ft(alpha * sign[0]), A1.l, A1.u, _ptr(A1.data), A1.lda, ft(alpha * sign[1]),
+                       A2.l, A2.u, _ptr(A2.data), A2.lda, _ptr(x), ft(beta), _ptr(y)), "lbm_gbmv2")
+            return y
         for k, (a, sg) in enumerate(zip(self.args, sign)):
             _mul(y, a, x, alpha * sg, beta if k == 0 else 1.0)
         return y

@@ -65,6 +65,36 @@ class _Structured:
     def size(self, d=None):
         return self.shape if d is None else self.shape[d - 1]
 
+    def _diagonals(self):
+        """(dl, d, du) as the C ABI wants them: None for a diagonal the kind does not have."""
+        raise NotImplementedError
+
+    def dot(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """`dot(x, A, y)` = x' A y as a 0-d device tensor (/root/reference/src/tridiag.jl:665-682); one pass."""
+        if not (x.shape[0] == self.n == y.shape[0]) or x.dim() != 1 or y.dim() != 1:
+            raise DimensionMismatch(f"dot(x, A, y): lengths {tuple(x.shape)}, {self.shape}, {tuple(y.shape)}")
+        dl, d, du = self._diagonals()
+        out = torch.empty((), dtype=d.dtype, device=d.device)
+        h = _lib.handle_of(d)
+        fn = getattr(_lib.lib(), f"lbm_{_pfx(d.dtype)}tridiag_dot")
+        h.check(fn(h.ptr, self.n, _ptr(dl), _ptr(d), _ptr(du), _ptr(x.contiguous()), _ptr(y.contiguous()), _ptr(out)),
+                "lbm_tridiag_dot")
+        return out
+
+    def sum(self, dims=None) -> torch.Tensor:
+        """`sum(A)` (0-d), `sum(A; dims=1)` (1 x n) or `sum(A; dims=2)` (n x 1): Base._sum of the reference
+        (src/tridiag.jl:594-660, src/bidiag.jl:396-435)."""
+        if dims not in (None, 1, 2):
+            raise LbmArgumentError("dims must be None, 1 or 2 on the B200 path")
+        dl, d, du = self._diagonals()
+        out = torch.empty(() if dims is None else (self.n,), dtype=d.dtype, device=d.device)
+        h = _lib.handle_of(d)
+        fn = getattr(_lib.lib(), f"lbm_{_pfx(d.dtype)}tridiag_sum")
+        h.check(fn(h.ptr, self.n, _ptr(dl), _ptr(d), _ptr(du), 0 if dims is None else dims, _ptr(out)), "lbm_tridiag_sum")
+        if dims is None:
+            return out
+        return out.reshape(1, self.n) if dims == 1 else out.reshape(self.n, 1)
+
     @property
     def shape(self):
         return (self.n, self.n)
@@ -117,6 +147,9 @@ class Tridiagonal(_Structured):
             A = A + torch.diag(self.dl, -1) + torch.diag(self.du, 1)
         return A
 
+    def _diagonals(self):
+        return (self.dl if self.n > 1 else None, self.d, self.du if self.n > 1 else None)
+
     def mul_(self, y, x, alpha=1.0, beta=0.0):
         return _tridiag_mv_(y, self.n, self.dl if self.n > 1 else None, self.d,
                             self.du if self.n > 1 else None, x, alpha, beta)
@@ -157,6 +190,10 @@ class SymTridiagonal(_Structured):
             e = self.ev[: self.n - 1]
             A = A + torch.diag(e, -1) + torch.diag(e, 1)
         return A
+
+    def _diagonals(self):
+        ev = self.ev if self.n > 1 else None
+        return (ev, self.dv, ev)
 
     def mul_(self, y, x, alpha=1.0, beta=0.0):
         ev = self.ev if self.n > 1 else None
@@ -203,6 +240,10 @@ class Bidiagonal(_Structured):
         if self.n > 1:
             A = A + torch.diag(self.ev, 1 if self.uplo == "U" else -1)
         return A
+
+    def _diagonals(self):
+        ev = self.ev if self.n > 1 else None
+        return (None, self.dv, ev) if self.uplo == "U" else (ev, self.dv, None)
 
     def mul_(self, y, x, alpha=1.0, beta=0.0):
         _check_mul_sizes((self.n, self.n), x, y)

@@ -241,6 +241,27 @@ def tridiag_dot(x, dl, d, du, y):
     return float(fn(_i(len(d)), *[_p(a) for a in arrs]))
 
 
+def tridiag_sum(n, dl, d, du, dims=None):
+    """Base._sum(A, dims) for Tridiagonal(dl,d,du) -- numpy restatement of /root/reference/src/tridiag.jl:594-628
+    (SymTridiagonal: dl = du = ev[:n-1], :630-660; Bidiagonal: the missing diagonal is None, src/bidiag.jl:396-435).
+    dims=None: scalar; dims=1: column sums (1 x n); dims=2: row sums (n x 1)."""
+    d = np.asarray(d)
+    z = np.zeros(max(n - 1, 0), dtype=d.dtype)
+    dl = z if dl is None else np.asarray(dl)[: max(n - 1, 0)]
+    du = z if du is None else np.asarray(du)[: max(n - 1, 0)]
+    if dims is None:
+        return d.sum() + dl.sum() + du.sum()
+    res = d.copy()
+    if n > 1:
+        if dims == 1:      # res[j] = du[j-1] + d[j] + dl[j]
+            res[1:] += du
+            res[:-1] += dl
+        else:              # res[i] = dl[i-1] + d[i] + du[i]
+            res[1:] += dl
+            res[:-1] += du
+    return res.reshape(1, n) if dims == 1 else res.reshape(n, 1)
+
+
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
 

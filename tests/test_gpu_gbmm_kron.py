@@ -420,3 +420,41 @@ def test_broadcast_sum_of_banded(L, oracle):
     assert np.max(np.abs((P @ x).cpu().numpy() - want)) <= 2 * tol_rows(np.float64, 4, 1.0, 4.0) + tol_rows(np.float64, 3, 1.0, 1.0)
     with pytest.raises(L.DimensionMismatch):
         L.BroadcastMatrix("+", A, L.brand(n + 1, n + 1, 1, 1))
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_broadcast_sum_fused_gbmv2(L, oracle, dt):
+    """mul!(y, BroadcastArray(+/-, A1, A2), x) through the fused lbm_?gbmv2 (one pass over x and y) equals
+    alpha*(A1 x +/- A2 x) + beta*y from two oracle gbmv's; rectangular, different bands, wide-band fallback,
+    NaNs in out-of-matrix slots, and exactly ONE kernel launch on the fused path."""
+    npdt = NP[dt]
+    h = L.handle_for(0)
+    cases = [  # (m, n, (kl1, ku1), (kl2, ku2), fused?)
+        (5000, 5000, (2, 1), (0, 3), True), (100003, 100003, (1, 1), (1, 1), True), (3000, 3100, (8, 8), (1, 0), True),
+        (3100, 3000, (0, 0), (4, 2), True), (7, 7, (1, 1), (2, 2), True), (4000, 4000, (16, 16), (16, 16), False),   # f64 stage > 100 KB: two launches
+        (2000, 2000, (128, 128), (1, 1), False), (1, 1, (0, 0), (0, 0), True),
+    ]
+    for s, (m, n, (kl1, ku1), (kl2, ku2), fused) in enumerate(cases):
+        mats = []
+        for f, (kl, ku) in enumerate(((kl1, ku1), (kl2, ku2))):
+            lda = kl + ku + 1
+            A_np = np.asfortranarray(oracle.fill_uniform(500 + 2 * s + f, lda * n, npdt).reshape((lda, n), order="F"))
+            Ap = A_np.copy()
+            i = np.arange(n)[None, :] + np.arange(lda)[:, None] - ku
+            Ap[(i < 0) | (i >= m)] = np.nan
+            mats.append((A_np, L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(Ap.T)).cuda(), m, kl, ku)))
+        x_np = oracle.fill_uniform(600 + s, n, npdt)
+        y_np = oracle.fill_uniform(700 + s, m, npdt)
+        x = torch.from_numpy(x_np).cuda()
+        for op, sg in (("+", 1.0), ("-", -1.0)):
+            for alpha, beta in ((1.0, 0.0), (2.0, 0.5)):
+                y = torch.from_numpy(y_np.copy()).cuda()
+                before = h.launch_count()
+                L.BroadcastMatrix(op, mats[0][1], mats[1][1]).mul_(y, x, alpha, beta)
+                torch.cuda.synchronize()
+                if fused:
+                    assert h.launch_count() - before == 1
+                want = (oracle.gbmv("N", m, n, kl1, ku1, alpha, mats[0][0], x_np, beta, y_np)
+                        + oracle.gbmv("N", m, n, kl2, ku2, sg * alpha, mats[1][0], x_np))
+                tol = tol_rows(npdt, kl1 + ku1 + 1 + kl2 + ku2 + 1, 1.0, 1.0, alpha, beta, 1.0)
+                assert np.max(np.abs(y.cpu().numpy() - want)) <= tol, (m, n, kl1, ku1, kl2, ku2, op, alpha, beta)

@@ -179,3 +179,49 @@ def test_tridiag_row_ranges(L, oracle):
             assert np.max(np.abs(y.cpu().numpy()[: b - a] - want[a:b])) <= tol_rows(np.float64, 3, 1.0, 1.0, 2.0)
     assert L.lib().lbm_dtridiag_mv_rows(h.ptr, n, None, C.c_void_p(g[1].data_ptr()), None, 1.0,
                                         C.c_void_p(g[3].data_ptr()), 0.0, C.c_void_p(g[3].data_ptr()), 5, 3) == -13
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_dot_and_sum_reductions(L, oracle, dt):
+    """dot(x, A, y) (src/tridiag.jl:665-682) and Base._sum(A[, dims]) (src/tridiag.jl:594-660, src/bidiag.jl:396-435)
+    as single-pass device reductions, all three kinds.  dims sums add <= 3 terms: tolerance 4*eps*3; scalar
+    reductions are compared with a float64 / math.fsum evaluation under 4*eps*(sum of |terms|) (tree summation is
+    at least as accurate as the reference's sequential loop, whose own bound is n*eps*(sum of |terms|))."""
+    import math
+    npdt = np.float64 if dt == torch.float64 else np.float32
+    eps = float(np.finfo(npdt).eps)
+    for n in (0, 1, 2, 3, 257, 100003, 1 << 20):
+        d = oracle.fill_uniform(21, n, npdt) - 0.5
+        lo = oracle.fill_uniform(22, max(n - 1, 0), npdt) - 0.5
+        up = oracle.fill_uniform(23, max(n - 1, 0), npdt) - 0.5
+        x = oracle.fill_uniform(24, n, npdt) - 0.5
+        y = oracle.fill_uniform(25, n, npdt) - 0.5
+        g = lambda a: torch.from_numpy(a).cuda()
+        kinds = [
+            (L.Tridiagonal(g(lo), g(d), g(up)), lo, up),
+            (L.SymTridiagonal(g(d), g(up)), up, up),
+            (L.Bidiagonal(g(d), g(up), "U"), None, up),
+            (L.Bidiagonal(g(d), g(lo), "L"), lo, None),
+        ]
+        for A, l_np, u_np in kinds:
+            # dims sums
+            for dims in (1, 2):
+                got = A.sum(dims).cpu().numpy()
+                want = oracle.tridiag_sum(n, l_np, d, u_np, dims)
+                assert got.shape == want.shape
+                assert np.max(np.abs(got - want), initial=0.0) <= 4 * eps * 3
+            # scalar sum
+            terms = [d.astype(np.float64)] + [t.astype(np.float64) for t in (l_np, u_np) if t is not None]
+            want = math.fsum(np.concatenate(terms)) if n else 0.0
+            bound = 4 * eps * float(sum(np.abs(t).sum() for t in terms)) + 1e-300
+            assert abs(float(A.sum()) - want) <= bound, (n, type(A).__name__)
+            # dot(x, A, y)
+            zl = np.zeros(max(n - 1, 0), npdt)
+            l64 = (zl if l_np is None else l_np).astype(np.float64)
+            u64 = (zl if u_np is None else u_np).astype(np.float64)
+            want = oracle.tridiag_dot(x.astype(np.float64), l64, d.astype(np.float64), u64, y.astype(np.float64)) if n else 0.0
+            x64, y64 = np.abs(x.astype(np.float64)), np.abs(y.astype(np.float64))
+            mag = float((np.abs(d) * x64 * y64).sum()) + (float((np.abs(l64) * x64[1:] * y64[:-1]).sum() + (np.abs(u64) * x64[:-1] * y64[1:]).sum()) if n > 1 else 0.0)
+            assert abs(float(A.dot(g(x), g(y))) - want) <= 4 * eps * 3 * mag + 1e-300, (n, type(A).__name__)
+    with pytest.raises(L.DimensionMismatch):
+        L.SymTridiagonal(torch.ones(4, device="cuda"), torch.ones(3, device="cuda")).dot(torch.ones(5, device="cuda"), torch.ones(4, device="cuda"))

@@ -165,6 +165,30 @@ def test_sum_kats(kats, oracle):
     assert dense.sum() == k["expect"]
 
 
+def test_sum_dims_restatement(kats, oracle):
+    """oracle.tridiag_sum (restatement of Base._sum, src/tridiag.jl:594-660, src/bidiag.jl:396-435) reproduces the
+    reference KATs `sum(T) == 24`, `sum(S) == 12` and `sum(T, dims=k) == sum(Matrix(T), dims=k)`
+    (test/test_tridiag.jl:366-374), for all three kinds."""
+    (k,) = _by_kind(kats, "tridiag_sum")
+    dl, d, du = (np.array(k[f], float) for f in ("dl", "d", "du"))
+    n = len(d)
+    assert oracle.tridiag_sum(n, dl, d, du) == k["expect"]
+    dense = oracle.tridiag_mv(n, dl, d, du, np.eye(n))
+    assert np.array_equal(oracle.tridiag_sum(n, dl, d, du, 1), dense.sum(axis=0, keepdims=True))
+    assert np.array_equal(oracle.tridiag_sum(n, dl, d, du, 2), dense.sum(axis=1, keepdims=True))
+    (k,) = _by_kind(kats, "symtridiag_sum")
+    dv, ev = np.array(k["dv"], float), np.array(k["ev"], float)
+    assert oracle.tridiag_sum(n, ev, dv, ev) == k["expect"]
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7):
+        d, e = rng.integers(-5, 6, n).astype(float), rng.integers(-5, 6, max(n - 1, 0)).astype(float)
+        for (lo, up) in ((e, None), (None, e), (e, e)):           # Bidiagonal L, Bidiagonal U, SymTridiagonal
+            dense = np.diag(d) + (np.diag(lo, -1) if lo is not None and n > 1 else 0) + (np.diag(up, 1) if up is not None and n > 1 else 0)
+            assert oracle.tridiag_sum(n, lo, d, up) == dense.sum()
+            assert np.array_equal(oracle.tridiag_sum(n, lo, d, up, 1), dense.sum(axis=0, keepdims=True))
+            assert np.array_equal(oracle.tridiag_sum(n, lo, d, up, 2), dense.sum(axis=1, keepdims=True))
+
+
 def test_krontrav_square(kats, oracle):
     (k,) = _by_kind(kats, "krontrav_square")
     n = k["n"]
