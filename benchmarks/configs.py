@@ -137,6 +137,11 @@ def main():
             byts = 8 * n * ((2 * l + 1) + 2 * nrhs)
             ms = timeit(lambda: L.mul_(Y.t(), A, X.t()))
             emit(f"MM banded*dense f64 n=2^{24 - sh} l=u={l} nrhs={nrhs} (lbm_dgbmv_multi, one pass over A)", ms, byts)
+            if not a.quick:
+                for tile in (256, 512, 768, 1024, 1536):
+                    h.set_tuning(gbmv_tile=tile)
+                    emit(f"MM banded*dense f64 n=2^{24 - sh} l=u={l} nrhs={nrhs} tile={tile}", timeit(lambda: L.mul_(Y.t(), A, X.t())), byts)
+                h.set_tuning(gbmv_tile=0)
             ms1 = timeit(lambda: [L.mul_(Y[c], A, X[c]) for c in range(nrhs)])
             emit(f"MM banded*dense f64 n=2^{24 - sh} l=u={l} nrhs={nrhs} (column by column, {nrhs} gbmv launches)", ms1, byts,
                  note="same algorithmic bytes credited; A re-read per column")
@@ -176,7 +181,8 @@ def main():
         byts = batch * 4 * n * (9 + 9 + 9 + 25)
         flops = batch * 2 * n * (9 * 9 + 17 * 9)
         variants = ((0, "default = warp-autonomous TMA kernel"),) if a.quick else (
-            (0, "default = warp-autonomous TMA kernel"), (1, "split-column register kernel"),
+            (0, "default = warp-autonomous TMA kernel, A/B double-buffered, 6 warps/SM"),
+            (5, "warp-autonomous TMA kernel, single-buffered, 8 warps/SM"), (1, "split-column register kernel"),
             (2, "transposed-smem kernel, 204 regs / 2 CTAs"), (3, "transposed-smem kernel, 128 regs / 3 CTAs"))
         for v, nm in variants:
             h.set_tuning(chain_variant=v)

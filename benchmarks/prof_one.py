@@ -23,5 +23,51 @@ elif which == "C5":
         L.fill_uniform(f, 1 + i)
     for _ in range(2):
         D = L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4])
+elif which == "C3":
+    g = 8192
+    hh = 1.0 / g
+    D = L.banded_from_diagonals(g, {0: -2.0 / hh**2, 1: 1.0 / hh**2, -1: 1.0 / hh**2})
+    Lap = L.KronSum.from_broadcast(L.BlockKron(D, L.Eye(g)), L.BlockKron(L.Eye(g), D))
+    x = torch.empty(g * g, dtype=torch.float64, device="cuda")
+    L.fill_uniform(x, 5)
+    y = torch.empty_like(x)
+    for _ in range(2):
+        Lap.mul_(y, x)
+elif which == "C2":
+    n = 1 << 28
+    dv = torch.empty(n, dtype=torch.float64, device="cuda")
+    ev = torch.empty(n - 1, dtype=torch.float64, device="cuda")
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    for i, t in enumerate((dv, ev, x)):
+        L.fill_uniform(t, 2 + i)
+    y = torch.empty_like(x)
+    S = L.SymTridiagonal(dv, ev)
+    B = L.Bidiagonal(dv, ev, "U")
+    for _ in range(2):
+        S.mul_(y, x)
+        B.mul_(y, x)
+    S.dot(x, y)
+elif which == "M":
+    n = 1 << 27
+    for l in (1, 8):
+        A = L.brand(n, n, l, l, seed=1)
+        x = torch.empty(n, dtype=torch.float64, device="cuda")
+        L.fill_uniform(x, 9)
+        y = torch.empty_like(x)
+        for _ in range(2):
+            L.mul_(y, A, x)
+        del A
+elif which == "MM":
+    n, nrhs = 1 << 24, 8
+    A = L.brand(n, n, 8, 8, seed=1)
+    X = torch.empty((nrhs, n), dtype=torch.float64, device="cuda")
+    L.fill_uniform(X, 9)
+    Y = torch.empty_like(X)
+    A2 = L.brand(n, n, 1, 1, seed=2)
+    A3 = L.brand(n, n, 1, 1, seed=3)
+    M = L.BroadcastMatrix("+", A2, A3)
+    for _ in range(2):
+        L.mul_(Y.t(), A, X.t())
+        M.mul_(Y[0], X[0])
 torch.cuda.synchronize()
 print("ok")

@@ -741,7 +741,7 @@ int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, con
         if constexpr (sizeof(T) == 4) {
             // chain_variant: 0 = auto / 4 = warp-autonomous TMA kernel (gbmm_chain_warp.cu) when the shape is covered,
             // 1 = split-column register kernel, 2/3 = transposed-smem kernel (204 / 128 registers)
-            if (h->tune.chain_variant == 0 || h->tune.chain_variant == 4) {
+            if (h->tune.chain_variant == 0 || h->tune.chain_variant == 4 || h->tune.chain_variant == 5) {
                 bool handled = false;
                 int rc = lbm_chain3_warp_f32(h, batch, n, kl, ku, A, sA, B, sB, C, sC, D, sD, &handled);
                 if (handled) return rc;

@@ -44,7 +44,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 constexpr int r4(int x) { return (x + 3) / 4 * 4; }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC, int ABBUF>
 struct WarpGeom {
     static constexpr int EPV = 16 / (int)sizeof(T);
     static constexpr int LDA = KLA + KUA + 1, LDB = KLB + KUB + 1, LDC = KLC + KUC + 1;
@@ -58,7 +58,9 @@ struct WarpGeom {
     static constexpr int BYTES_A = NP * LDA * (int)sizeof(T), BYTES_B = NQ * LDB * (int)sizeof(T),
                          BYTES_C = ND * LDC * (int)sizeof(T);
     static constexpr int BYTES_AB = NQ * LD01 * (int)sizeof(T), BYTES_D = ND * LDD * (int)sizeof(T);
-    static constexpr int OFF_B = BYTES_A, OFF_C = OFF_B + BYTES_B, OFF_R = OFF_C + BYTES_C;  // R = A*B, later D
+    // slab: [A, B] x ABBUF, C, R (= A*B, later D)
+    static constexpr int BYTES_ABBUF = BYTES_A + BYTES_B;
+    static constexpr int OFF_B = BYTES_A, OFF_C = ABBUF * BYTES_ABBUF, OFF_R = OFF_C + BYTES_C;
     static constexpr int BYTES_WARP = OFF_R + cmax(BYTES_AB, BYTES_D);
     static_assert(GD > 0, "bands too wide for the warp-autonomous chain kernel");
 };
@@ -112,23 +114,24 @@ __device__ __forceinline__ void contract(T (&out)[4 * LD_OUT], const T (&coef)[4
     }
 }
 
-template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC, int NW>
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC, int NW, int ABBUF>
 __global__ void __launch_bounds__(32 * NW, 1)
     gbmm_chain3_warp_kernel(int64_t n, int64_t batch, int tiles_per_item, int groups_base, int groups_rem,
                             const T *__restrict__ A, int64_t sA_, const T *__restrict__ B, int64_t sB_,
                             const T *__restrict__ C, int64_t sC_, T *__restrict__ D, int64_t sD_) {
-    using G = WarpGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    using G = WarpGeom<T, KLA, KUA, KLB, KUB, KLC, KUC, ABBUF>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * NW];
+    __shared__ __align__(8) uint64_t bars[3 * NW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *slab = smem_raw + (size_t)warp * G::BYTES_WARP;
-    T *sA = reinterpret_cast<T *>(slab);
-    T *sB = reinterpret_cast<T *>(slab + G::OFF_B);
     T *sC = reinterpret_cast<T *>(slab + G::OFF_C);
     T *sR = reinterpret_cast<T *>(slab + G::OFF_R);   // A*B tile, then (aliased) the D tile
-    uint64_t *barAB = &bars[2 * warp], *barC = &bars[2 * warp + 1];
+    uint64_t *barAB = &bars[3 * warp], *barC = &bars[3 * warp + 2];   // barAB[0..ABBUF)
+    auto bufA = [&](int bsel) { return reinterpret_cast<T *>(slab + bsel * G::BYTES_ABBUF); };
+    auto bufB = [&](int bsel) { return reinterpret_cast<T *>(slab + bsel * G::BYTES_ABBUF + G::OFF_B); };
     if (lane == 0) {
-        mbar_init(barAB, 1);
+        mbar_init(&barAB[0], 1);
+        mbar_init(&barAB[1], 1);
         mbar_init(barC, 1);
         mbar_fence_init();
     }
@@ -146,7 +149,9 @@ __global__ void __launch_bounds__(32 * NW, 1)
         ng = groups_base + (ti < groups_rem ? 1 : 0);
     };
     // request A and B of a tile: zero-fill the out-of-range operand columns (item edges), then bulk copies
-    auto request_ab = [&](int64_t b, int g0, int ng) {
+    auto request_ab = [&](int64_t b, int g0, int ng, int bsel) {
+        T *sA = bufA(bsel), *sB = bufB(bsel);
+        uint64_t *bar = &barAB[bsel];
         const int nn = (int)n;
         const int q0 = 4 * g0 - G::HQ, p0 = q0 - G::HB;
         const int nq = 4 * ng + 2 * G::HQ, np = nq + 2 * G::HB;        // columns the tile really needs
@@ -163,9 +168,9 @@ __global__ void __launch_bounds__(32 * NW, 1)
         if (lane == 0) {
             const uint32_t ba = (uint32_t)((a_hi - a_lo) * G::LDA * (int)sizeof(T));
             const uint32_t bb = (uint32_t)((b_hi - b_lo) * G::LDB * (int)sizeof(T));
-            mbar_expect_tx(barAB, ba + bb);
-            bulk_g2s(sA + a_lo * G::LDA, A + b * sA_ + (int64_t)(p0 + a_lo) * G::LDA, ba, barAB);
-            bulk_g2s(sB + b_lo * G::LDB, B + b * sB_ + (int64_t)(q0 + b_lo) * G::LDB, bb, barAB);
+            mbar_expect_tx(bar, ba + bb);
+            bulk_g2s(sA + a_lo * G::LDA, A + b * sA_ + (int64_t)(p0 + a_lo) * G::LDA, ba, bar);
+            bulk_g2s(sB + b_lo * G::LDB, B + b * sB_ + (int64_t)(q0 + b_lo) * G::LDB, bb, bar);
         }
     };
     auto request_c = [&](int64_t b, int g0, int ng) {
@@ -181,24 +186,33 @@ __global__ void __launch_bounds__(32 * NW, 1)
     int g0, ng;
     if (tile < total) {
         decode(tile, b, g0, ng);
-        request_ab(b, g0, ng);
+        request_ab(b, g0, ng, 0);
         request_c(b, g0, ng);
+        if (ABBUF == 2 && tile + stride < total) {
+            decode(tile + stride, b, g0, ng);
+            request_ab(b, g0, ng, 1);
+        }
     }
     uint32_t parity = 0;
-    for (; tile < total; tile += stride) {
+    for (int it = 0; tile < total; tile += stride, ++it) {
+        const int bsel = ABBUF == 2 ? (it & 1) : 0;
+        const uint32_t parAB = ABBUF == 2 ? (uint32_t)((it >> 1) & 1) : parity;
+        const T *sA = bufA(bsel), *sB = bufB(bsel);
         decode(tile, b, g0, ng);
         const int n32 = (int)n;
         const int j0 = 4 * g0, q0 = j0 - G::HQ;
         // masks are only needed where the tile's operand window or result rows leave [0,n): item edges
         constexpr int EDGE_LO = cmax(G::U3, G::HQ + G::HB), EDGE_HI = cmax(G::L3, G::HQ + G::HB);
         const bool edge = j0 < EDGE_LO || j0 + 4 * ng + EDGE_HI > n32;
-        const int64_t nxt = tile + stride;
-        int64_t nb = 0;
-        int ng0 = 0, nng = 0;
+        const int64_t nxt = tile + stride;         // next tile (its C is requested in this iteration)
+        const int64_t nab = tile + ABBUF * stride;   // tile whose A, B are requested in this iteration
+        int64_t nb = 0, ab_b = 0;
+        int ng0 = 0, nng = 0, ab_g0 = 0, ab_ng = 0;
         if (nxt < total) decode(nxt, nb, ng0, nng);
+        if (nab < total) decode(nab, ab_b, ab_g0, ab_ng);
 
         // ---- phase 1: lane u computes columns q0 + 4u .. q0 + 4u + 3 of A*B --------------------
-        mbar_wait(barAB, parity);
+        mbar_wait(&barAB[bsel], parAB);
         const bool p1_active = lane < ng + 2 * G::HQ / 4;
         __align__(16) T acc[4 * G::LD01];
 #pragma unroll
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(32 * NW, 1)
         __syncwarp();
         if (p1_active) store_group<T, G::LD01>(sR, lane, acc);
         __syncwarp();                                   // A, B consumed by every lane; A*B visible to every lane
-        if (nxt < total) request_ab(nb, ng0, nng);
+        if (nab < total) request_ab(ab_b, ab_g0, ab_ng, bsel);
 
         // ---- phase 2: lane t computes columns j0 + 4t .. j0 + 4t + 3 of D ------------------------
         mbar_wait(barC, parity);
@@ -287,15 +301,15 @@ __global__ void __launch_bounds__(32 * NW, 1)
     if (lane == 0) bulk_wait0();
 }
 
-template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC>
+template <typename T, int KLA, int KUA, int KLB, int KUB, int KLC, int KUC, int ABBUF>
 int chain3_warp_launch(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int64_t sA, const T *B, int64_t sB,
                        const T *C, int64_t sC, T *D, int64_t sD) {
-    using G = WarpGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
+    using G = WarpGeom<T, KLA, KUA, KLB, KUB, KLC, KUC, ABBUF>;
     constexpr int NWMAX = (227 * 1024 - 256) / G::BYTES_WARP;
-    constexpr int NW = NWMAX >= 8 ? 8 : (NWMAX >= 4 ? 4 : (NWMAX >= 2 ? 2 : 1));
+    constexpr int NW = NWMAX >= 8 ? 8 : (NWMAX >= 6 ? 6 : (NWMAX >= 4 ? 4 : (NWMAX >= 2 ? 2 : 1)));
     static_assert(NWMAX >= 1, "tile slab exceeds shared memory");
     constexpr size_t smem = (size_t)NW * G::BYTES_WARP;
-    auto kern = gbmm_chain3_warp_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC, NW>;
+    auto kern = gbmm_chain3_warp_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC, NW, ABBUF>;
     static int configured_dev_mask = 0;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -325,9 +339,15 @@ int lbm_chain3_warp_f32(lbm_handle_t h, int64_t batch, int64_t n, const int64_t 
         return kl[0] == l && kl[1] == l && kl[2] == l && ku[0] == u && ku[1] == u && ku[2] == u;
     };
     *handled = true;
-    if (all(4, 4)) return chain3_warp_launch<float, 4, 4, 4, 4, 4, 4>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
-    if (all(2, 2)) return chain3_warp_launch<float, 2, 2, 2, 2, 2, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
-    if (all(1, 1)) return chain3_warp_launch<float, 1, 1, 1, 1, 1, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+    // chain_variant 5: single-buffered A/B (8 warps/SM for (4,4)^3); default: A/B double-buffered, requested a whole
+    // tile ahead (6 warps/SM)
+    const bool single = h->tune.chain_variant == 5;
+    if (all(4, 4)) return single ? chain3_warp_launch<float, 4, 4, 4, 4, 4, 4, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD)
+                                 : chain3_warp_launch<float, 4, 4, 4, 4, 4, 4, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+    if (all(2, 2)) return single ? chain3_warp_launch<float, 2, 2, 2, 2, 2, 2, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD)
+                                 : chain3_warp_launch<float, 2, 2, 2, 2, 2, 2, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
+    if (all(1, 1)) return single ? chain3_warp_launch<float, 1, 1, 1, 1, 1, 1, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD)
+                                 : chain3_warp_launch<float, 1, 1, 1, 1, 1, 1, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
     *handled = false;
     return 0;
 }

@@ -935,12 +935,17 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
                 stage_elems(tl, sa, sx);
                 if ((sa + R * sx) * (int64_t)sizeof(T) <= 40 * 1024) tile = tl;
             }
+            if (h->tune.gbmv_tile > 0) tile = round_up(h->tune.gbmv_tile, GBMV_NT);
             stage_elems(tile, sa, sx);
+            while (tile > GBMV_NT && 2 * (sa + R * sx) * (int64_t)sizeof(T) + 128 > smem_cap) {
+                tile -= GBMV_NT;
+                stage_elems(tile, sa, sx);
+            }
             a.tile = tile; a.ntiles = (nout + tile - 1) / tile; a.sA_elems = sa; a.sx_elems = sx;
             const int64_t stage_bytes = (sa + R * sx) * (int64_t)sizeof(T);
             if (stage_bytes + 128 > smem_cap) break;       // cannot happen for nb <= 33; falls back below
             int64_t stages = 2;
-            int64_t ctas = (200 * 1024) / (stages * stage_bytes + 256);
+            int64_t ctas = (227 * 1024) / (stages * stage_bytes + 128 + 1024);   // as many CTAs as the SM's smem holds
             if (ctas < 1) ctas = 1;
             if (ctas > 8) ctas = 8;
             while (stages > 1 && ctas * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --stages;
