@@ -339,9 +339,10 @@ int lbm_chain3_warp_f32(lbm_handle_t h, int64_t batch, int64_t n, const int64_t 
         return kl[0] == l && kl[1] == l && kl[2] == l && ku[0] == u && ku[1] == u && ku[2] == u;
     };
     *handled = true;
-    // chain_variant 5: single-buffered A/B (8 warps/SM for (4,4)^3); default: A/B double-buffered, requested a whole
-    // tile ahead (6 warps/SM)
-    const bool single = h->tune.chain_variant == 5;
+    // default: single-buffered A/B (8 warps/SM for (4,4)^3); chain_variant 5: A/B double-buffered, requested a whole
+    // tile ahead (6 warps/SM).  Measured equal within noise (0.61-0.64 ms, profiles/configs_r01_final.jsonl): the
+    // kernel sits at the copy-like ceiling of a 53 % read / 47 % write stream, not on load latency.
+    const bool single = h->tune.chain_variant != 5;
     if (all(4, 4)) return single ? chain3_warp_launch<float, 4, 4, 4, 4, 4, 4, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD)
                                  : chain3_warp_launch<float, 4, 4, 4, 4, 4, 4, 2>(h, batch, n, A, sA, B, sB, C, sC, D, sD);
     if (all(2, 2)) return single ? chain3_warp_launch<float, 2, 2, 2, 2, 2, 2, 1>(h, batch, n, A, sA, B, sB, C, sC, D, sD)

@@ -222,9 +222,9 @@ def test_chain3_warp_kernel_persistent_loop(L, oracle):
         ld = 2 * k + 1
         fs = [oracle.fill_uniform(11 + i, batch * n * ld, np.float32).reshape(batch, n, ld) for i in range(3)]
         gs = [torch.from_numpy(f).cuda() for f in fs]
-        got = L.chain3_batched(*gs, kl, ku).cpu().numpy()          # default: A/B double-buffered
+        got = L.chain3_batched(*gs, kl, ku).cpu().numpy()          # default: single-buffered A/B
         h = L.handle_for(0)
-        h.set_tuning(chain_variant=5)                               # single-buffered A/B
+        h.set_tuning(chain_variant=5)                               # A/B double-buffered, a tile ahead
         try:
             got5 = L.chain3_batched(*gs, kl, ku).cpu().numpy()
         finally:
