@@ -236,8 +236,11 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     h = L.handle_for(local)
+    peer_on = False
     if world > 1 and not args.torch_p2p:
-        init_comm(local)      # ghost exchange inside the library: one C call per sharded mul!
+        # ghost exchange inside the library: one C call per sharded mul!; peer-memory mailboxes unless --nccl-exchange
+        init_comm(local, peer=not args.nccl_exchange)
+        peer_on = bool(L._lib.lib().lbm_peer_active(h.ptr))
     n = 1 << (args.log2n or LOG2N)
     K, W = args.steps, max(3, args.warmup)
 
@@ -378,8 +381,10 @@ def run_b200(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"mul!(y,A,x), A=brand(n,n,l,u) f64, n=2^{args.log2n or LOG2N}, l=u in {{1,8}}, "
-                                   f"row-sharded over {world} GPU(s), NCCL ghost exchange in the timed region",
-                       "exchange": "none (1 GPU)" if world == 1 else ("torch.distributed P2P" if args.torch_p2p else "in-library ncclSend/ncclRecv, overlapped with interior rows"),
+                                   f"row-sharded over {world} GPU(s), ghost exchange in the timed region",
+                       "exchange": "none (1 GPU)" if world == 1 else ("torch.distributed P2P" if args.torch_p2p else
+                                                                              ("in-library peer-memory mailboxes (NVLink peer stores + flag handshake kernels), overlapped with interior rows"
+                                                                               if peer_on else "in-library ncclSend/ncclRecv, overlapped with interior rows")),
                        "l2": "inputs (3.2 GB and 18.3 GB slabs) far larger than the 126 MB L2; no flush needed",
                        "algorithmic_bytes_per_step": step_bytes},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -466,6 +471,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=0, help="override n = 2^k (testing only; metric is 2^27)")
     ap.add_argument("--no-wide", action="store_true", help="skip the l=u=128 breakdown point")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N>1: keep the in-library exchange on ncclSend/ncclRecv "
+                    "instead of the peer-memory mailboxes")
     ap.add_argument("--torch-p2p", action="store_true", help="N>1: exchange ghosts through torch.distributed P2P "
                     "instead of the library's own NCCL communicator")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")

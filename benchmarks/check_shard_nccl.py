@@ -23,16 +23,43 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     eps = np.finfo(np.float64).eps
-    for use_lib_comm in (False, True):   # torch.distributed P2P path, then the in-library NCCL path
-        if use_lib_comm:
-            init_comm(local)
-            assert L.handle_for(local).comm_world == world
+    h = L.handle_for(local)
+    _check(rank, world, dev, eps)                       # torch.distributed P2P path (no library communicator yet)
+    init_comm(local)                                    # library communicator + peer-memory mailboxes
+    assert h.comm_world == world
+    peer = bool(L._lib.lib().lbm_peer_active(h.ptr))
+    for mode in ((0, 1) if peer else (1,)):             # peer mailboxes, then in-library ncclSend/ncclRecv
+        h.set_tuning(exchange_mode=mode)
         _check(rank, world, dev, eps)
-    _check_kron_gbmm(rank, world, dev, eps)
+        _check_kron_gbmm(rank, world, dev, eps)
+        _check_epochs(rank, world, dev, eps)
+    h.set_tuning(exchange_mode=0)
     dist.barrier()
     if rank == 0:
-        print(f"OK sharded mul!/chain on {world} GPUs match the oracle (torch P2P path and in-library NCCL path)")
+        print(f"OK sharded mul!/chain/kron/tridiag on {world} GPUs match the oracle (torch P2P, "
+              f"{'peer-memory mailboxes, ' if peer else 'NO peer access: '}in-library NCCL)")
     dist.destroy_process_group()
+
+
+def _check_epochs(rank, world, dev, eps):
+    """Back-to-back applies with x changing every time (scaled by exact powers of two): every epoch must see the
+    neighbours' CURRENT boundary values -- exercises the mailbox double-buffering and the flag handshake."""
+    n, l, u = 300007, 8, 5
+    f = ShardedBanded.brand(n, l, u, rank, world, device=dev, seed=0x21)
+    M = np.asfortranarray(O.fill_uniform(0x21, (l + u + 1) * n).reshape((l + u + 1, n), order="F"))
+    x_full = O.fill_uniform(0x9, n)
+    want = O.gbmv("N", n, n, l, u, 1.0, M, x_full)[f.plan.r0:f.plan.r1]
+    x_own = torch.from_numpy(x_full[f.plan.r0:f.plan.r1]).to(dev)
+    xbuf = f.plan.new_vector(torch.float64, dev)
+    ys = []
+    for k in range(40):
+        f.plan.owned(xbuf).copy_(x_own * float(2 ** (k % 7)))
+        y = torch.empty(f.plan.m_loc, dtype=torch.float64, device=dev)
+        f.mul_(y, xbuf, overlap=bool(k % 2))
+        ys.append(y)
+    for k, y in enumerate(ys):
+        err = np.max(np.abs(y.cpu().numpy() / float(2 ** (k % 7)) - want))
+        assert err <= 4 * eps * (l + u + 1), ("epoch", k, err)
 
 
 def _check_kron_gbmm(rank, world, dev, eps):

@@ -27,6 +27,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         init_comm(local)
+    h = L.handle_for(local)
+    peer = world > 1 and bool(L._lib.lib().lbm_peer_active(h.ptr))
+    # ghost transports to report for the configs that exchange: peer-memory mailboxes (default) and NCCL send/recv
+    modes = ((0, "peer mailboxes"), (1, "ncclSend/Recv")) if peer else ((1, "ncclSend/Recv" if world > 1 else "1 GPU"),)
+
+    def both(name, fn, byts, reps=10, warm=3):
+        for mode, label in modes:
+            h.set_tuning(exchange_mode=mode)
+            emit(f"{name} [{label}]", timeit(fn, reps, warm), byts)
+        h.set_tuning(exchange_mode=0)
 
     def timeit(fn, reps=10, warm=3):
         for _ in range(warm):
@@ -75,7 +85,7 @@ def main():
         xb = p.new_vector(torch.float64, dev)
         p.owned(xb).copy_(vec(p.m_loc, 4, p.r0))
         y = torch.empty(p.m_loc, dtype=torch.float64, device=dev)
-        emit(f"C2 {nm} mul! f64 n=2^28", timeit(lambda: sh.mul_(y, xb)), arrays * 8 * n)
+        both(f"C2 {nm} mul! f64 n=2^28", lambda: sh.mul_(y, xb), arrays * 8 * n)
         del d, e, sh, xb, y
         torch.cuda.empty_cache()
 
@@ -88,7 +98,7 @@ def main():
     xb = sh.new_buffer(torch.float64, dev)
     L.fill_uniform(sh.owned(xb).view(-1), 5, offset=p.r0 * g)
     y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
-    emit("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192", timeit(lambda: sh.mul_(y, xb)), 16 * g * g)
+    both("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192", lambda: sh.mul_(y, xb), 16 * g * g, 20, 5)
     del sh, xb, y
     torch.cuda.empty_cache()
 
@@ -123,7 +133,7 @@ def main():
         xb = sh.plan.new_vector(torch.float64, dev)
         L.fill_uniform(xb, 9, offset=sh.plan.c0)
         y = torch.empty(sh.plan.m_loc, dtype=torch.float64, device=dev)
-        emit("M gbmv f64 n=2^27 l=u=128", timeit(lambda: sh.mul_(y, xb), 5, 2), 8 * n * 259)
+        both("M gbmv f64 n=2^27 l=u=128", lambda: sh.mul_(y, xb), 8 * n * 259, 5, 2)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

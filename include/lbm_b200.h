@@ -200,6 +200,16 @@ int lbm_shard_plan(int64_t n, int64_t kl, int64_t ku, int rank, int world, int64
 int lbm_comm_unique_id(void *id128);
 int lbm_comm_init(lbm_handle_t h, const void *id128, int rank, int world);
 int lbm_comm_destroy(lbm_handle_t h);
+/* Peer-memory ghost transport (optional, one box): after lbm_comm_init every rank calls lbm_peer_alloc (a mailbox
+ * block of 4 slots of slot_bytes each in its own HBM; returns the 64-byte CUDA IPC handle), the host exchanges the
+ * handles (all-gather over the process group), and every rank calls lbm_peer_connect with its neighbours' handles
+ * (NULL at the ends).  From then on the halo exchange of every *_sharded call and of lbm_halo_exchange is two tiny
+ * kernels doing NVLink peer stores + flag handshakes instead of an NCCL send/recv group; halos larger than
+ * slot_bytes, or lbm_set_tuning("exchange_mode", 1), fall back to NCCL.  lbm_peer_active: 1 if the peer path is on. */
+int lbm_peer_alloc(lbm_handle_t h, size_t slot_bytes, void *ipc_handle64);
+int lbm_peer_connect(lbm_handle_t h, const void *left_handle64, const void *right_handle64);
+int lbm_peer_disconnect(lbm_handle_t h);
+int lbm_peer_active(lbm_handle_t h);
 int lbm_halo_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *xbuf, int elem_bytes);
 int lbm_dgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, double alpha, const double *A_slab,
                       int64_t lda, double *xbuf, double beta, double *y_own, int overlap);

@@ -5,6 +5,15 @@
 //   x ready (event) -> [comm stream] ncclGroup{send/recv ghosts} -> event
 //                   -> [main stream] interior rows (need no ghosts, overlap the exchange)
 //                   -> wait event  -> the <= kl+ku boundary rows.
+// Two transports for the ghosts:
+//  * peer mailboxes (default once lbm_peer_connect has run): every rank owns a small mailbox block that its two
+//    neighbours map through CUDA IPC.  `halo_push_kernel` writes this rank's boundary values straight into the
+//    neighbours' mailboxes with NVLink peer stores and then publishes the epoch number in their flag words
+//    (system-scope release); `halo_pull_kernel` spins on the local flags (acquire), then moves the mailbox contents
+//    into the ghost cells.  Mailbox slots are double-buffered by epoch parity, which -- because both directions of a
+//    neighbour pair signal every epoch -- makes an acknowledgement round unnecessary.  Two tiny kernels on the comm
+//    stream replace the NCCL group (~20 us -> a few us per apply; the payloads are latency-, not bandwidth-bound).
+//  * ncclSend/ncclRecv (fallback: no peer access, halo larger than a mailbox slot, exchange_mode = 1).
 // NCCL is dlopen'ed (libnccl.so.2: the copy torch already loaded in-process, else the system
 // one), so the library has no link-time dependency and builds without NCCL headers.
 #include "lbm_common.cuh"
@@ -88,7 +97,142 @@ Plan make_plan(int64_t n, int64_t kl, int64_t ku, int rank, int world) {
     return p;
 }
 
+// ---- peer-mailbox transport -----------------------------------------------------------------------------------------
+constexpr size_t PEER_FLAG_BYTES = 256;   // flags[0] = epoch published by the LEFT neighbour, flags[1] = by the RIGHT one
+
+struct PushArgs {
+    // side 0: to the left neighbour (it receives into its from-RIGHT mailbox), side 1: to the right neighbour
+    const char *src[2];
+    char *dst[2];                 // peer mailbox slot (NULL: no such neighbour)
+    unsigned long long *flag[2];  // peer flag word to publish the epoch in
+    int64_t bytes[2];
+    unsigned long long epoch;
+};
+struct PullArgs {
+    const char *src[2];           // local mailbox slot written by the left / right neighbour
+    char *dst[2];                 // ghost cells (NULL: nothing to receive on that side)
+    const unsigned long long *flag[2];
+    int64_t bytes[2];
+    int wait[2];                  // a neighbour exists on that side
+    unsigned long long epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// grid = 2 CTAs (one per side).  Payload first (peer stores), then fence + barrier, then the flag.
+__global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a) {
+    const int s = blockIdx.x;
+    if (!a.flag[s]) return;
+    const int64_t nb = a.bytes[s];
+    if (nb > 0) {
+        const char *src = a.src[s];
+        char *dst = a.dst[s];
+        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nb) & 15u) == 0) {
+            const int4 *s4 = reinterpret_cast<const int4 *>(src);
+            int4 *d4 = reinterpret_cast<int4 *>(dst);
+            for (int64_t i = threadIdx.x; i < nb / 16; i += blockDim.x) d4[i] = s4[i];
+        } else {
+            for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) dst[i] = src[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(a.flag[s], a.epoch);
+}
+
+// grid = 2 CTAs.  Wait for the neighbour's epoch, then mailbox -> ghost cells (read around L1).
+__global__ void __launch_bounds__(256) halo_pull_kernel(const PullArgs a) {
+    const int s = blockIdx.x;
+    if (!a.wait[s]) return;
+    if (threadIdx.x == 0) {
+        unsigned long long spins = 0;
+        while (ld_acquire_sys(a.flag[s]) < a.epoch) {
+            // a lost neighbour must surface as a CUDA error, never as a hung GPU (~10+ s of polling)
+            if (++spins > (1ull << 25)) __trap();
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const int64_t nb = a.bytes[s];
+    if (nb <= 0 || !a.dst[s]) return;
+    const char *src = a.src[s];
+    char *dst = a.dst[s];
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nb) & 15u) == 0) {
+        const int4 *s4 = reinterpret_cast<const int4 *>(src);
+        int4 *d4 = reinterpret_cast<int4 *>(dst);
+        for (int64_t i = threadIdx.x; i < nb / 16; i += blockDim.x) d4[i] = __ldcg(s4 + i);
+    } else {
+        for (int64_t i = threadIdx.x; i < nb; i += blockDim.x) dst[i] = __ldcg(src + i);
+    }
+}
+
+inline char *peer_slot(void *block, size_t slot_bytes, int from_side, int parity) {
+    return reinterpret_cast<char *>(block) + PEER_FLAG_BYTES + (size_t)(2 * from_side + parity) * slot_bytes;
+}
+
+// same contract as exchange(): ghosts of xbuf valid once h->ev_halo has fired
+int exchange_peer(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb) {
+    LBM_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
+    LBM_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+    const unsigned long long epoch = ++h->peer_epoch;
+    const int par = (int)(epoch & 1);
+    char *own = xbuf + p.left * eb;
+    PushArgs pa;
+    PullArgs pl;
+    memset(&pa, 0, sizeof(pa));
+    memset(&pl, 0, sizeof(pl));
+    pa.epoch = pl.epoch = epoch;
+    unsigned long long *lflags = reinterpret_cast<unsigned long long *>(h->peer_local);
+    if (h->rank > 0) {   // left neighbour: gets my first ku entries (its right ghosts), sends me my left ghosts
+        const int64_t cnt = ku < p.m_loc ? ku : p.m_loc;
+        pa.src[0] = own;
+        pa.dst[0] = peer_slot(h->peer_remote[0], h->peer_slot_bytes, /*from its RIGHT*/ 1, par);
+        pa.flag[0] = reinterpret_cast<unsigned long long *>(h->peer_remote[0]) + 1;
+        pa.bytes[0] = cnt * eb;
+        pl.wait[0] = 1;
+        pl.flag[0] = lflags + 0;
+        pl.src[0] = peer_slot(h->peer_local, h->peer_slot_bytes, 0, par);
+        pl.dst[0] = p.left > 0 ? xbuf : nullptr;
+        pl.bytes[0] = p.left * eb;
+    }
+    if (h->rank < h->world - 1) {   // right neighbour: gets my last kl entries, sends me my right ghosts
+        const int64_t cnt = kl < p.m_loc ? kl : p.m_loc;
+        pa.src[1] = own + (p.m_loc - cnt) * eb;
+        pa.dst[1] = peer_slot(h->peer_remote[1], h->peer_slot_bytes, /*from its LEFT*/ 0, par);
+        pa.flag[1] = reinterpret_cast<unsigned long long *>(h->peer_remote[1]) + 0;
+        pa.bytes[1] = cnt * eb;
+        pl.wait[1] = 1;
+        pl.flag[1] = lflags + 1;
+        pl.src[1] = peer_slot(h->peer_local, h->peer_slot_bytes, 1, par);
+        pl.dst[1] = p.right > 0 ? own + p.m_loc * eb : nullptr;
+        pl.bytes[1] = p.right * eb;
+    }
+    halo_push_kernel<<<2, 256, 0, h->comm_stream>>>(pa);
+    LBM_LAUNCH_CHECK(h, "halo_push_kernel");
+    halo_pull_kernel<<<2, 256, 0, h->comm_stream>>>(pl);
+    LBM_LAUNCH_CHECK(h, "halo_pull_kernel");
+    LBM_CUDA(h, cudaEventRecord(h->ev_halo, h->comm_stream));
+    return 0;
+}
+
+int exchange_nccl(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb);
+
+// transport choice; the halo each way is at most max(kl,ku) units
 int exchange(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb) {
+    const int64_t worst = (kl > ku ? kl : ku) * eb;
+    if (h->peer_on && h->tune.exchange_mode != 1 && (size_t)worst <= h->peer_slot_bytes)
+        return exchange_peer(h, p, kl, ku, xbuf, eb);
+    return exchange_nccl(h, p, kl, ku, xbuf, eb);
+}
+
+int exchange_nccl(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb) {
     // sends read / recvs write xbuf: order them after everything already queued on the main stream
     LBM_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
     LBM_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
@@ -226,8 +370,64 @@ int lbm_comm_init(lbm_handle_t h, const void *id128, int rank, int world) {
     return 0;
 }
 
+// ---- peer-memory transport setup (all three are collective in spirit: every rank of the row partition calls them) ----
+int lbm_peer_alloc(lbm_handle_t h, size_t slot_bytes, void *ipc_handle64) {
+    if (!h) return -1;
+    if (!ipc_handle64) return lbm_fail_arg(h, 3, "ipc_handle64 == NULL");
+    if (slot_bytes == 0 || slot_bytes % 16) return lbm_fail_arg(h, 2, "slot_bytes must be a positive multiple of 16");
+    lbm_device_guard g(h->device);
+    lbm_peer_disconnect(h);
+    const size_t total = PEER_FLAG_BYTES + 4 * slot_bytes;
+    LBM_CUDA(h, cudaMalloc(&h->peer_local, total));
+    LBM_CUDA(h, cudaMemset(h->peer_local, 0, total));
+    LBM_CUDA(h, cudaDeviceSynchronize());
+    h->peer_slot_bytes = slot_bytes;
+    h->peer_epoch = 0;
+    cudaIpcMemHandle_t ih;
+    LBM_CUDA(h, cudaIpcGetMemHandle(&ih, h->peer_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    memcpy(ipc_handle64, &ih, 64);
+    return 0;
+}
+
+int lbm_peer_connect(lbm_handle_t h, const void *left_handle64, const void *right_handle64) {
+    if (!h) return -1;
+    if (!h->peer_local) return lbm_fail_arg(h, 1, "lbm_peer_alloc has not been called on this handle");
+    if (!h->nccl_comm) return lbm_fail_arg(h, 1, "lbm_comm_init has not been called on this handle");
+    if ((h->rank > 0) != (left_handle64 != nullptr)) return lbm_fail_arg(h, 2, "left handle must be given iff rank > 0");
+    if ((h->rank < h->world - 1) != (right_handle64 != nullptr)) return lbm_fail_arg(h, 3, "right handle must be given iff rank < world-1");
+    lbm_device_guard g(h->device);
+    const void *hs[2] = {left_handle64, right_handle64};
+    for (int s = 0; s < 2; ++s) {
+        if (!hs[s]) continue;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, hs[s], 64);
+        LBM_CUDA(h, cudaIpcOpenMemHandle(&h->peer_remote[s], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->peer_on = 1;
+    return 0;
+}
+
+int lbm_peer_disconnect(lbm_handle_t h) {
+    if (!h) return -1;
+    lbm_device_guard g(h->device);
+    if (h->peer_on || h->peer_local) cudaDeviceSynchronize();
+    for (int s = 0; s < 2; ++s) {
+        if (h->peer_remote[s]) cudaIpcCloseMemHandle(h->peer_remote[s]);
+        h->peer_remote[s] = nullptr;
+    }
+    if (h->peer_local) cudaFree(h->peer_local);
+    h->peer_local = nullptr;
+    h->peer_on = 0;
+    h->peer_slot_bytes = 0;
+    return 0;
+}
+
+int lbm_peer_active(lbm_handle_t h) { return h && h->peer_on && h->tune.exchange_mode != 1 ? 1 : 0; }
+
 int lbm_comm_destroy(lbm_handle_t h) {
     if (!h) return -1;
+    lbm_peer_disconnect(h);
     if (h->nccl_comm) {
         lbm_device_guard g(h->device);
         cudaStreamSynchronize(h->comm_stream);

@@ -37,6 +37,7 @@ struct lbm_tuning {
     int64_t gbmm_variant;     // DMMA kernel: 0 = 3-stage/3 CTAs per SM, 1 = 2-stage/4 CTAs per SM
     int64_t chain_tile;
     int64_t chain_force_generic;
+    int64_t exchange_mode;    // multi-GPU ghost exchange: 0 auto (peer mailboxes when connected), 1 force NCCL send/recv
     int64_t chain_variant;    // 0 auto (= 4 when covered), 1 split-column register kernel, 2/3 transposed-smem kernel, 4 warp-autonomous TMA kernel
 };
 
@@ -61,6 +62,13 @@ struct lbm_handle_s {
     int rank, world;
     cudaStream_t comm_stream;
     cudaEvent_t ev_ready, ev_halo;
+    // peer-memory ghost exchange (dist.cu): a mailbox block in THIS GPU's memory that the neighbours write with
+    // NVLink peer stores, and the neighbours' blocks mapped through CUDA IPC
+    void *peer_local;            // [flags 256 B][from-left slots 0,1][from-right slots 0,1]
+    void *peer_remote[2];        // left / right neighbour's block (IPC mapping), NULL at the ends
+    size_t peer_slot_bytes;      // capacity of one mailbox slot
+    uint64_t peer_epoch;         // exchanges done so far (identical on all ranks: SPMD)
+    int peer_on;                 // 1 once lbm_peer_connect succeeded
 };
 
 int lbm_fail_cuda(lbm_handle_t h, cudaError_t e, const char *what);

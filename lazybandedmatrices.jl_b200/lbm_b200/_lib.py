@@ -57,6 +57,10 @@ def _sigs():
         "lbm_comm_unique_id": (C.c_int, [vp]),
         "lbm_comm_init": (C.c_int, [H, vp, C.c_int, C.c_int]),
         "lbm_comm_destroy": (C.c_int, [H]),
+        "lbm_peer_alloc": (C.c_int, [H, sz, vp]),
+        "lbm_peer_connect": (C.c_int, [H, vp, vp]),
+        "lbm_peer_disconnect": (C.c_int, [H]),
+        "lbm_peer_active": (C.c_int, [H]),
         "lbm_halo_exchange": (C.c_int, [H, i64, i64, i64, vp, C.c_int]),
     }
     for p, ft in (("d", f64), ("s", f32)):
