@@ -168,6 +168,11 @@ def main():
         M = L.BroadcastMatrix("+", A1, A2)
         byts = 8 * n * (3 + 3 + 2)
         emit(f"BC (A1+A2)*x f64 n=2^{27 - sh} (1,1)+(1,1) fused lbm_dgbmv2", timeit(lambda: M.mul_(y, x)), byts)
+        if not a.quick:
+            for tile, stages, ctas in ((512, 2, 0), (768, 2, 0), (1024, 2, 0), (1536, 2, 0), (2048, 2, 0), (512, 3, 0), (1024, 3, 0), (1024, 2, 1), (2048, 2, 1), (1024, 4, 1)):
+                h.set_tuning(gbmv_tile=tile, gbmv_stages=stages, gbmv_ctas_per_sm=ctas)
+                emit(f"BC fused tile={tile} stages={stages} ctas={ctas or 'auto'}", timeit(lambda: M.mul_(y, x)), byts)
+            h.set_tuning(gbmv_tile=0, gbmv_stages=0, gbmv_ctas_per_sm=0)
         emit(f"BC (A1+A2)*x f64 n=2^{27 - sh} (1,1)+(1,1) term by term (2 gbmv)",
              timeit(lambda: (L.mul_(y, A1, x), L.mul_(y, A2, x, 1.0, 1.0))), byts, note="same algorithmic bytes credited")
         del A1, A2, x, y
@@ -223,10 +228,20 @@ def main():
             for v, nm in ((1, "2-stage, 4 CTAs/SM"), (2, "3-stage, 3 CTAs/SM"), (3, "2-stage, 5 CTAs/SM"), (4, "column-persistent 2-stage, 4 CTAs/SM"),
                           (5, "column-persistent 3-stage, 3 CTAs/SM"), (6, "3-stage, 4 CTAs/SM"), (7, "4-stage, 3 CTAs/SM"),
                           (8, "3-stage, 4 CTAs/SM, rotated quadrants"), (9, "3-stage, 4 CTAs/SM, interleaved p-halves"), (10, "3-stage, 4 CTAs/SM, both"),
-                          (11, "3-stage, 4 CTAs/SM, single launch over all tiles"), (12, "2-stage, 6 CTAs/SM")):
+                          (11, "3-stage, 4 CTAs/SM, single launch over all tiles"), (12, "2-stage, 6 CTAs/SM"),
+                          (20, "warp-specialised: producer warp + 8 consumer warps, 3-stage, 4 CTAs/SM"),
+                          (21, "warp-specialised, 3-stage, 3 CTAs/SM"), (22, "warp-specialised, 4-stage, 3 CTAs/SM"),
+                          (23, "warp-specialised, 2-stage, 4 CTAs/SM")):
                 h.set_tuning(gbmm_variant=v)
                 emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant {v} ({nm})", timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
-            h.set_tuning(gbmm_variant=0)
+            for tpc in (2, 3, 5, 10):
+                h.set_tuning(gbmm_variant=22, gbmm_tile=tpc)
+                emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant 22 (warp-specialised, 4-stage, 3 CTAs/SM), {tpc} row tiles per CTA",
+                     timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
+                h.set_tuning(gbmm_variant=20, gbmm_tile=tpc)
+                emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant 20 (warp-specialised, 3-stage, 4 CTAs/SM), {tpc} row tiles per CTA",
+                     timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
+            h.set_tuning(gbmm_variant=0, gbmm_tile=0)
 
 
 if __name__ == "__main__":

@@ -26,6 +26,56 @@ __global__ void __launch_bounds__(128) pipes(double *out, int iters, double a0, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the real inner loop of the banded product: per k-step 4 + 4 fragments from shared memory (LDS.64, conflict-free
+// pitches as in gbmm_dmma.cu), 16 DMMAs on 16 distinct accumulators -- no masks, no barriers, no global traffic
+template <int XB, int YB>
+__global__ void __launch_bounds__(128) tile_loop(double *out, int iters) {
+    __shared__ double sA[16 * 68], sB[64 * 20];
+    for (int i = threadIdx.x; i < 16 * 68; i += blockDim.x) sA[i] = 1.0 + i * 1e-9;
+    for (int i = threadIdx.x; i < 64 * 20; i += blockDim.x) sB[i] = 1.0 - i * 1e-9;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int fa_off = fc * 68 + (warp & 1) * 32 + fr, fb_off = ((warp >> 1) * 32 + fr) * 20 + fc;
+    double acc[XB][YB][2];
+    for (int x = 0; x < XB; ++x)
+        for (int y = 0; y < YB; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            double fa[XB], fb[YB];
+#pragma unroll
+            for (int x = 0; x < XB; ++x) fa[x] = sA[fa_off + 4 * ks * 68 + 8 * x];
+#pragma unroll
+            for (int y = 0; y < YB; ++y) fb[y] = sB[fb_off + 8 * y * 20 + 4 * ks];
+#pragma unroll
+            for (int x = 0; x < XB; ++x)
+#pragma unroll
+                for (int y = 0; y < YB; ++y) dmma884(acc[x][y][0], acc[x][y][1], fa[x], fb[y]);
+        }
+    }
+    double s = 0;
+    for (int x = 0; x < XB; ++x)
+        for (int y = 0; y < YB; ++y) s += acc[x][y][0] + acc[x][y][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int XB, int YB>
+void run_tile(const char *name, int ctas_per_sm) {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    double *out; cudaMalloc(&out, sizeof(double) * sms * ctas_per_sm * 128);
+    const int iters = 5000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    tile_loop<XB, YB><<<sms * ctas_per_sm, 128>>>(out, 50);
+    cudaEventRecord(e0);
+    tile_loop<XB, YB><<<sms * ctas_per_sm, 128>>>(out, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = (double)sms * ctas_per_sm * 4 * iters * 4.0 * XB * YB * 512.0;
+    printf("{\"test\": \"%s\", \"ctas_per_sm\": %d, \"ms\": %.3f, \"dmma_tflops\": %.2f}\n", name, ctas_per_sm, ms, fl / ms / 1e9);
+    cudaFree(out);
+}
+
 template <int NACC, int NFMA>
 void run(const char *name, int ctas_per_sm) {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -44,12 +94,38 @@ void run(const char *name, int ctas_per_sm) {
     cudaFree(out);
 }
 
-int main() {
+template <int XB, int YB>
+void run_tile_long(const char *name, int ctas_per_sm, int launches) {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    double *out; cudaMalloc(&out, sizeof(double) * sms * ctas_per_sm * 128);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    tile_loop<XB, YB><<<sms * ctas_per_sm, 128>>>(out, 50);
+    for (int rep = 0; rep < 2; ++rep) {
+        const int nl = rep == 0 ? 1 : launches;
+        cudaEventRecord(e0);
+        for (int l = 0; l < nl; ++l) tile_loop<XB, YB><<<sms * ctas_per_sm, 128>>>(out, 5000);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = (double)nl * sms * ctas_per_sm * 4 * 5000 * 4.0 * XB * YB * 512.0;
+        printf("{\"test\": \"%s\", \"launches\": %d, \"total_ms\": %.1f, \"dmma_tflops\": %.2f}\n", name, nl, ms, fl / ms / 1e9);
+    }
+    cudaFree(out);
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1) {   // "long": sustained load (~2 s) vs a single launch
+        run_tile_long<4, 4>("tile loop 32x32, 4 CTAs/SM", 4, 200);
+        return 0;
+    }
     for (int c : {1, 2, 4}) {
         run<16, 0>("dmma884 x16 independent accumulators", c);
         run<0, 32>("dfma x32 independent", c);
         run<16, 16>("dmma x16 + dfma x16 (128 vs 16 flop-units)", c);
         run<8, 64>("dmma x8 + dfma x64 (equal flops)", c);
+    }
+    for (int c : {1, 2, 4, 5}) {
+        run_tile<4, 4>("tile loop: 8 LDS.64 + 16 DMMA per k-step (32x32 warp tile)", c);
+        run_tile<4, 2>("tile loop: 6 LDS.64 + 8 DMMA per k-step (32x16 warp tile)", c);
     }
     return 0;
 }

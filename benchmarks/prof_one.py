@@ -14,6 +14,7 @@ if which == "C4":
     A = L.brand(n, n, 128, 128, seed=1)
     B = L.brand(n, n, 128, 128, seed=2)
     Cm = L.BandedMatrix(torch.empty((n, 513), dtype=torch.float64, device="cuda"), n, 256, 256)
+    L.handle_for(0).set_tuning(gbmm_variant=int(os.environ.get("LBM_GBMM_VARIANT", "0")))
     for _ in range(2):
         L.gbmm(A, B, out=Cm)
 elif which == "C5":

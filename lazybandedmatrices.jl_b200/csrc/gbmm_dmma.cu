@@ -37,6 +37,7 @@ struct DmmaArgs {
     double *C;
     int64_t gy;  // row tiles per column block
     int flags;   // 1: rotate the warp -> quadrant map per CTA, 2: interleave the two halves of the p-range
+    int tpc;     // warp-specialised kernel: consecutive row tiles per CTA
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -575,6 +576,231 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_col_kernel(const DmmaArgs 
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------
+// warp-specialised variant for interior tiles: a producer warp feeds the cp.async ring, eight consumer warps
+// (32x16 blocks of the 64x64 tile) drift through it independently
+// ------------------------------------------------------------------------------------------
+// Why: in gbmm_dmma_kernel the four warps of a CTA meet at a __syncthreads every chunk although their DMMA counts
+// differ widely in the ramp chunks (24 % of warp time is barrier stall, profiles/ncu_C4_r01.md).  Here the ring is
+// guarded per stage by a `full` mbarrier (armed by the producer lanes' cp.async arrivals) and an `empty` mbarrier
+// (one arrival per consumer warp), so a warp that has nothing to do in a chunk runs ahead by up to NSTAGE-1 chunks
+// instead of waiting, and twice as many (smaller) warps keep the DMMA pipe fed.
+constexpr int WS_CONSUMERS = 8, WS_NT = 32 * (WS_CONSUMERS + 1);
+
+__device__ __forceinline__ void mbar_init_(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive_(uint64_t *bar) {   // arrives once this thread's prior cp.asyncs landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        if (++spins > (1u << 22)) __trap();   // a lost arrival must surface as a CUDA error, not a hang
+        // suspend-time hint: the warp sleeps in hardware (up to ~4 us) instead of burning issue slots that the
+        // DMMA-issuing warps of the same sub-core need (the plain spin loop was 31 % of all executed instructions)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity), "r"(4000u)
+            : "memory");
+    }
+}
+
+template <int NSTAGE, int MINB>
+__global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // a CTA owns `tpc` consecutive row tiles of one 64-column block; the ring runs straight across tile boundaries
+    // (the producer is already fetching the next tile while the consumers finish and store the current one)
+    const int tpc = a.tpc;
+    const int64_t groups = (a.gy + tpc - 1) / tpc;
+    const int64_t lin = (int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y;
+    const int64_t j0 = (lin / groups) * TN;
+    if (j0 >= a.n) return;
+    const int64_t by0 = (lin % groups) * tpc;
+    int64_t I0 = floordiv(j0 - a.kuc, TM);
+    if (I0 < 0) I0 = 0;
+
+    // per-tile parameters; valid = interior tile with work (the corner tiles are left to gbmm_dmma_kernel MODE 2)
+    auto tile_params = [&](int t, int64_t &i0, int64_t &plo, int &nch) -> bool {
+        const int64_t by = by0 + t;
+        if (by >= a.gy) return false;
+        i0 = (I0 + by) * TM;
+        if (i0 >= a.m || i0 > j0 + TN - 1 + a.klc) return false;
+        plo = i0 - a.kla > j0 - a.kub ? i0 - a.kla : j0 - a.kub;
+        int64_t phi = i0 + TM - 1 + a.kua < j0 + TN - 1 + a.klb ? i0 + TM - 1 + a.kua : j0 + TN - 1 + a.klb;
+        if (plo < 0) plo = 0;
+        if (phi > a.k - 1) phi = a.k - 1;
+        plo &= ~(int64_t)3;
+        nch = phi >= plo ? (int)((phi - plo + KC) / KC) : 0;
+        return nch > 0 && i0 + TM <= a.m && j0 >= 4 && j0 + TN + 4 <= a.n && plo >= 4 && plo + (int64_t)nch * KC + 4 <= a.k &&
+               a.lda >= 33 && a.ldb >= 33 && ((a.lda - 1) & 1) == 0 && ((a.ldb - 1) & 1) == 0 &&
+               ((reinterpret_cast<uintptr_t>(a.A + a.kua + i0 + (a.lda - 1) * plo) & 15u) == 0) &&
+               ((reinterpret_cast<uintptr_t>(a.B + a.kub + plo + (a.ldb - 1) * j0) & 15u) == 0);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init_(&bar_full[s], 32);             // the 32 producer lanes' cp.async arrivals
+            mbar_init_(&bar_empty[s], WS_CONSUMERS);  // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int gi = 0;   // chunks issued / consumed so far by this CTA (ring position; identical in every warp)
+    if (warp == WS_CONSUMERS) {
+        // ---------------- producer: raw dense windows, unpredicated 16-byte copies ----------------
+        // A window 64 rows x 16 p: lane owns the row pair 2*lane, one copy per p.  B window 16 p x 64 j: lane owns
+        // the p pair 2*(lane & 7) of columns (lane >> 3) + 4q.
+        const int64_t a_step = a.lda - 1, b_step4 = 4 * (a.ldb - 1);
+        for (int t = 0; t < tpc; ++t) {
+            int64_t i0, plo;
+            int nch;
+            if (!tile_params(t, i0, plo, nch)) continue;
+            const double *a_src = a.A + (a.kua + i0 + 2 * lane) + (a.lda - 1) * plo;
+            const double *b_src = a.B + (a.kub + plo + 2 * (lane & 7)) + (a.ldb - 1) * (j0 + (lane >> 3));
+            for (int it = 0; it < nch; ++it, ++gi) {
+                const int s = gi % NSTAGE;
+                if (gi >= NSTAGE) mbar_wait_(&bar_empty[s], (uint32_t)((gi / NSTAGE - 1) & 1));
+                double *sA = smem + s * STAGE_DBL;
+                double *sB = sA + KC * PA;
+                const uint32_t dA = (uint32_t)__cvta_generic_to_shared(sA + 2 * lane);
+                const uint32_t dB = (uint32_t)__cvta_generic_to_shared(sB + (lane >> 3) * PB + 2 * (lane & 7));
+#pragma unroll
+                for (int q = 0; q < KC; ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dA + (uint32_t)(q * PA * 8)), "l"(a_src + a_step * q) : "memory");
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dB + (uint32_t)(q * 4 * PB * 8)), "l"(b_src + b_step4 * q) : "memory");
+                if (a.flags & 4) {   // experiment: issue every copy twice (2x L2 -> smem traffic, same arithmetic)
+#pragma unroll
+                    for (int q = 0; q < KC; ++q)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dA + (uint32_t)(q * PA * 8)), "l"(a_src + a_step * q) : "memory");
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dB + (uint32_t)(q * 4 * PB * 8)), "l"(b_src + b_step4 * q) : "memory");
+                }
+                mbar_cp_async_arrive_(&bar_full[s]);
+                a_src += a_step * KC;
+                b_src += KC;
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
+    }
+
+    // ---------------- consumers: warp (wa, wb) owns rows 32*wa.., columns 16*wb.. -------------------
+    const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
+    const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + 8*x
+    const int fb_off = (wj + fr) * PB + fc;     // + 8*y*PB + 4*ks
+    for (int t = 0; t < tpc; ++t) {
+        int64_t i0, plo;
+        int nch;
+        if (!tile_params(t, i0, plo, nch)) continue;
+        const int ia0 = (int)(i0 + wi - plo), jb0 = (int)(j0 + wj - plo);
+        double acc[4][2][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+
+        for (int it = 0; it < nch; ++it, ++gi) {
+            const int s = gi % NSTAGE;
+            const int pr = it * KC;
+            // classify the chunk: a warp with nothing in band here only has to release the stage
+            const bool full = (ia0 + 31 - pr <= kla) && (ia0 - (pr + KC - 1) >= -kua) && ((pr + KC - 1) - jb0 <= klb) &&
+                              (pr - (jb0 + 15) >= -kub);
+            unsigned mA = 0xffffu, mB = 0xffffu;
+            if (!full) {
+                const int da = ia0 - pr, db = jb0 - pr;
+                mA = band_mask(-kua - 7 - da, kla + 3 - da);
+                mB = band_mask(-klb - 7 - db, kub + 3 - db) & 0x3333u;   // two column blocks per warp
+            }
+            // every warp observes every phase of full[s] in order (a parity wait only tells adjacent phases apart, so
+            // a warp must not skip one), even when the chunk holds nothing for it
+            mbar_wait_(&bar_full[s], (uint32_t)((gi / NSTAGE) & 1));
+            if (mA != 0 && mB != 0) {
+                const double *sA = smem + s * STAGE_DBL;
+                const double *sB = sA + KC * PA;
+                if (full) {
+#pragma unroll
+                    for (int ks = 0; ks < KC / 4; ++ks) {
+                        double ga[4], gb[2];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) ga[x] = sA[fa_off + 4 * ks * PA + 8 * x];
+#pragma unroll
+                        for (int y = 0; y < 2; ++y) gb[y] = sB[fb_off + 8 * y * PB + 4 * ks];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
+                    }
+                } else {
+                    const int da = ia0 - pr, db = jb0 - pr;
+                    const int va = da + fr - fc + kua, wa = kla + kua;
+                    const int vb = -db + fc - fr + kub, wb = klb + kub;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 4; ++ks) {
+                        const unsigned ma = (mA >> (4 * ks)) & 15u, mb = (mB >> (4 * ks)) & 3u;
+                        if (ma == 0 || mb == 0) continue;
+                        double ga[4], gb[2];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const double ra = sA[fa_off + 4 * ks * PA + 8 * x];
+                            ga[x] = (unsigned)(va + 8 * x - 4 * ks) <= (unsigned)wa ? ra : 0.0;
+                        }
+#pragma unroll
+                        for (int y = 0; y < 2; ++y) {
+                            const double rb = sB[fb_off + 8 * y * PB + 4 * ks];
+                            gb[y] = (unsigned)(vb - 8 * y + 4 * ks) <= (unsigned)wb ? rb : 0.0;
+                        }
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            if (!(ma >> x & 1u)) continue;
+#pragma unroll
+                            for (int y = 0; y < 2; ++y)
+                                if (mb >> y & 1u) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&bar_empty[s]);   // this warp is done with stage s (or never needed it)
+        }
+
+        // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1}) -> band storage; interior tiles need no bounds tests
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t i = i0 + wi + 8 * x + fr;
+                    const int64_t j = j0 + wj + 8 * y + 2 * fc + e;
+                    const int64_t f = a.kuc + i - j;
+                    if (f >= 0 && f <= a.klc + a.kuc) {
+                        double *c = a.C + f + a.ldc * j;
+                        const double v = a.alpha * acc[x][y][e];
+                        *c = (a.beta == 0.0) ? v : fma(a.beta, *c, v);
+                    }
+                }
+    }
+}
+
 // out-of-matrix slots of C's band (first kuc / last klc columns) are written 0 when beta == 0
 __global__ void __launch_bounds__(256) gbmm_zero_corners_kernel(int64_t m, int64_t n, int64_t klc, int64_t kuc,
                                                                double *C, int64_t ldc) {
@@ -623,11 +849,14 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     }
     a.gy = gy;
     a.flags = 0;
+    a.tpc = 1;
     const int64_t total = gx * gy;
     const int64_t gxx = total < 1048576 ? total : 1048576;
     dim3 grid((unsigned)gxx, (unsigned)((total + gxx - 1) / gxx));
-    // gbmm_variant: 0 = default (2-stage / 5 CTAs per SM, lean interior instantiation + corner instantiation),
-    // 1: 2-stage / 4 CTAs, 2: 3-stage / 3 CTAs, 3: = 0, 4/5: column-persistent kernels, 6: 3-stage / 4 CTAs,
+    // gbmm_variant: 0 = default = warp-specialised kernel (producer warp + 8 consumer warps, 3-stage ring, 4 CTAs/SM,
+    // 5 row tiles per CTA) for the interior tiles + the corner instantiation of the plain kernel; 20-23: the same
+    // with other ring depths / occupancies.  Plain kernel (lean interior + corner instantiations): 3: 2-stage / 5 CTAs,
+    // 1: 2-stage / 4 CTAs, 2: 3-stage / 3 CTAs, 4/5: column-persistent kernels, 6: 3-stage / 4 CTAs,
     // 7: 4-stage / 3 CTAs, 8-10: 6 + rotated quadrants / interleaved p-halves, 11: 6 as one launch, 12: 2-stage / 6 CTAs
     // (measured in profiles/configs_r01_*.jsonl; everything lands between 17 and 21 TFLOP/s)
     const int variant = (int)h->tune.gbmm_variant;
@@ -652,7 +881,42 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
             gbmm_dmma_kernel<NS, MB, 2><<<grid, NT, smem, h->stream>>>(a);                                    \
         }                                                                                                     \
     } while (0)
-    if (variant == 4 || variant == 5) {
+    if (variant == 0 || (variant >= 20 && variant <= 23)) {
+        // warp-specialised interior kernel + the corner instantiation of the plain kernel
+        // 20: 3-stage / 4 CTAs, 21: 3-stage / 3 CTAs, 22: 4-stage / 3 CTAs, 23: 2-stage / 4 CTAs
+        static int cfg_ws[4] = {0, 0, 0, 0};
+        // gbmm_tile doubles as "row tiles per CTA" here; default: 5 for the default variant, 1 for the explicit ones
+        a.tpc = h->tune.gbmm_tile > 0 ? (int)(h->tune.gbmm_tile % 100) : (variant == 0 ? 5 : 1);
+        if (a.tpc < 1) a.tpc = 1;
+        if (h->tune.gbmm_tile >= 100) a.flags |= 4;   // (+100: double-copy traffic experiment, results unchanged)
+        const int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
+        const int64_t gws = total_ws < 1048576 ? total_ws : 1048576;
+        dim3 grid_ws((unsigned)gws, (unsigned)((total_ws + gws - 1) / gws));
+#define LBM_WS_LAUNCH(IDX, NS, MB)                                                                                         \
+    do {                                                                                                                   \
+        const size_t smem = (size_t)(NS) * STAGE_DBL * sizeof(double);                                                     \
+        if (!(cfg_ws[IDX] & (1 << h->device))) {                                                                           \
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_ws_kernel<NS, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            cfg_ws[IDX] |= (1 << h->device);                                                                               \
+        }                                                                                                                  \
+        gbmm_dmma_ws_kernel<NS, MB><<<grid_ws, WS_NT, smem, h->stream>>>(a);                                               \
+    } while (0)
+        if (variant == 20 || variant == 0) LBM_WS_LAUNCH(0, 3, 4);
+        else if (variant == 21) LBM_WS_LAUNCH(1, 3, 3);
+        else if (variant == 22) LBM_WS_LAUNCH(2, 4, 3);
+        else LBM_WS_LAUNCH(3, 2, 4);
+#undef LBM_WS_LAUNCH
+        LBM_LAUNCH_CHECK(h, "gbmm_dmma_ws_kernel");
+        {
+            const size_t smem = (size_t)2 * STAGE_DBL * sizeof(double);
+            static int cfg_corner = 0;
+            if (!(cfg_corner & (1 << h->device))) {
+                LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<2, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg_corner |= (1 << h->device);
+            }
+            gbmm_dmma_kernel<2, 5, 2><<<grid, NT, smem, h->stream>>>(a);
+        }
+    } else if (variant == 4 || variant == 5) {
         // column-block persistent kernels: one CTA per 64-column block
         const int64_t gcol = gx < 1048576 ? gx : 1048576;
         dim3 gridc((unsigned)gcol, (unsigned)((gx + gcol - 1) / gcol));
@@ -680,7 +944,7 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     else if (variant == 7) LBM_DMMA_LAUNCH(4, 4, 3);
     else if (variant == 1) LBM_DMMA_LAUNCH(1, 2, 4);
     else if (variant == 11) LBM_DMMA_LAUNCH(3, 3, 4);   // 3-stage / 4 CTAs as ONE launch over all tiles
-    else LBM_DMMA_LAUNCH(2, 2, 5);   // default: 2-stage ring at 5 CTAs (20 warps) per SM -- occupancy beats ring depth: 3-stage ring at 4 CTAs (16 warps) per SM -- 4 x (55.5 + 1) KB just fits
+    else LBM_DMMA_LAUNCH(2, 2, 5);   // variant 3 (and any unknown value): 2-stage ring at 5 CTAs (20 warps) per SM: 3-stage ring at 4 CTAs (16 warps) per SM -- 4 x (55.5 + 1) KB just fits
 #undef LBM_DMMA_LAUNCH
     LBM_LAUNCH_CHECK(h, "gbmm_dmma_kernel");
     return 0;

@@ -1021,13 +1021,20 @@ int gbmv2_impl(lbm_handle_t h, int64_t m, int64_t n, T alpha1, int64_t kl1, int6
     int64_t tile = GBMV_NT;
     for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {
         stage_elems(tl, s1, s2, sx);
-        if ((s1 + s2 + sx) * (int64_t)sizeof(T) <= 40 * 1024) tile = tl;
+        // two CTAs per SM with the largest 2-stage ring that allows: swept in profiles/configs_r01_final.jsonl ("BC fused tile=")
+        if ((s1 + s2 + sx) * (int64_t)sizeof(T) <= 56 * 1024 + 512) tile = tl;
     }
+    if (h->tune.gbmv_tile > 0) tile = round_up(h->tune.gbmv_tile, GBMV_NT);
     stage_elems(tile, s1, s2, sx);
+    while (tile > GBMV_NT && 2 * (s1 + s2 + sx) * (int64_t)sizeof(T) + 128 > h->max_smem_optin - 1024) {
+        tile -= GBMV_NT;
+        stage_elems(tile, s1, s2, sx);
+    }
     a.tile = tile; a.ntiles = (m + tile - 1) / tile; a.sA_elems[0] = s1; a.sA_elems[1] = s2; a.sx_elems = sx;
     const int64_t stage_bytes = (s1 + s2 + sx) * (int64_t)sizeof(T);
-    int64_t stages = 2;
-    int64_t ctas = (200 * 1024) / (stages * stage_bytes + 256);
+    int64_t stages = h->tune.gbmv_stages > 0 ? h->tune.gbmv_stages : 2;
+    if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+    int64_t ctas = h->tune.gbmv_ctas_per_sm > 0 ? h->tune.gbmv_ctas_per_sm : (227 * 1024) / (stages * stage_bytes + 128 + 1024);
     if (ctas < 1) ctas = 1;
     if (ctas > 8) ctas = 8;
     while (stages > 1 && ctas * (stages * stage_bytes + 128 + 1024) > 227 * 1024) --stages;
