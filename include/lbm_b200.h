@@ -187,6 +187,28 @@ int lbm_dkron3d_mv(lbm_handle_t h, int64_t n,
                    int64_t klc, int64_t kuc, const double *C, int64_t ldc,
                    double alpha, const double *x, double beta, double *y);
 
+/* ---- `+` / `-` among structured kinds, and their BandedMatrix storage ----------------------- */
+/* (odl, od, odu) <- alpha*(adl, ad, adu) + beta*(bdl, bd, bdu) + gamma*I on the three diagonals of an n x n
+ * operand in ONE launch: every method of /root/reference/src/special.jl:75-222 (Diagonal / Bidiagonal /
+ * Tridiagonal / SymTridiagonal pairs, and the UniformScaling methods through gamma).  A diagonal a kind does not
+ * have is NULL (sub/super have n-1 entries); an output pointer may be NULL when that diagonal is not wanted
+ * (the reference re-uses the operand's array there, e.g. `Bidiagonal(newdv, A.ev, A.uplo)`, special.jl:85-88).
+ * alpha, beta = +-1 reproduce Julia's `a + b`, `a - b`, `-b` bit for bit. */
+int lbm_dtridiag_axpby(lbm_handle_t h, int64_t n, double alpha, const double *adl, const double *ad, const double *adu,
+                       double beta, const double *bdl, const double *bd, const double *bdu, double gamma,
+                       double *odl, double *od, double *odu);
+int lbm_stridiag_axpby(lbm_handle_t h, int64_t n, float alpha, const float *adl, const float *ad, const float *adu,
+                       float beta, const float *bdl, const float *bd, const float *bdu, float gamma,
+                       float *odl, float *od, float *odu);
+/* AB <- the (kl,ku) diagonal-major array of the structured operand (dl, d, du), zeros on the other band rows:
+ * `BandedMatrix(A, (kl,ku))` with the element definitions of src/tridiag.jl:301-314, :471-484 and
+ * src/bidiag.jl:111-124.  Routes structured x structured products (test/test_special.jl:154-160,
+ * test/test_bidiag.jl:262-267) to lbm_?gbmm. */
+int lbm_dtridiag_pack(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du,
+                      int64_t kl, int64_t ku, double *AB, int64_t lda);
+int lbm_stridiag_pack(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du,
+                      int64_t kl, int64_t ku, float *AB, int64_t lda);
+
 /* ---- row-sharded mul! across the GPUs of one box (one process per GPU) ------------------- */
 /* Rank r of `world` owns rows [r0,r1) of a square n x n operator and stores the COLUMN slice
  * [c0,c1) = [max(0,r0-kl), min(n,r1+ku)) of the diagonal-major array (same lda); x lives in a

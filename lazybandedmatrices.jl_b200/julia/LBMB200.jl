@@ -22,6 +22,7 @@ using LinearAlgebra
 import ArrayLayouts: MemoryLayout, AbstractColumnMajor, MulAdd, materialize!, MatMulVecAdd, MatMulMatAdd,
                      TridiagonalLayout, SymTridiagonalLayout, BidiagonalLayout,
                      diagonaldata, subdiagonaldata, supdiagonaldata
+import BandedMatrices
 import BandedMatrices: BandedMatrix, BandedColumns, bandeddata, bandwidths, bandwidth
 import LazyBandedMatrices
 import LazyBandedMatrices: bidiagonaluplo
@@ -150,6 +151,59 @@ for (T, p) in ((Float64, :d), (Float32, :s))
                         handle().ptr, size(A, 1), size(B, 2), size(A, 2), α, la, ua, dA, size(dA, 1), lb, ub, dB, size(dB, 1),
                         β, lc, uc, dC, size(dC, 1)), "lbm_gbmm")
             C
+        end
+    end
+end
+
+# `+`/`-` among structured kinds (src/special.jl:75-222, src/tridiag.jl:206-208,:570-572, src/bidiag.jl:330-348):
+# the reference's methods are written on the diagonal vectors (`A.dv + B.diag`, `-B.ev`, `A.d .+ B.λ`), so giving
+# DevVector these three operations makes every one of them run on the device unchanged; each is one launch of
+# lbm_?tridiag_axpby on the main-diagonal slot.  `axpby3!` is the fused form (three diagonals, one launch) used by
+# the Tridiagonal +/- Tridiagonal methods below.
+for (T, p) in ((Float64, :d), (Float32, :s))
+    ax = QuoteNode(Symbol(:lbm_, p, :tridiag_axpby)); pk = QuoteNode(Symbol(:lbm_, p, :tridiag_pack))
+    @eval begin
+        function axpby3!(odl, od, odu, α::$T, adl, ad, adu, β::$T, bdl, bd, bdu, γ::$T, n::Integer)
+            P(v) = v === nothing ? Ptr{$T}(C_NULL) : pointer(v)
+            check(ccall(($ax, LIB), Cint,
+                        (Ptr{Cvoid}, Int64, $T, Ptr{$T}, Ptr{$T}, Ptr{$T}, $T, Ptr{$T}, Ptr{$T}, Ptr{$T}, $T, Ptr{$T}, Ptr{$T}, Ptr{$T}),
+                        handle().ptr, n, α, P(adl), P(ad), P(adu), β, P(bdl), P(bd), P(bdu), γ, P(odl), P(od), P(odu)),
+                  "lbm_tridiag_axpby")
+        end
+        function Base.:+(a::DevVector{$T}, b::DevVector{$T})
+            length(a) == length(b) || throw(DimensionMismatch("dimensions must match: a has dims $(axes(a)), b has dims $(axes(b))"))
+            o = similar(a); axpby3!(nothing, o, nothing, one($T), nothing, a, nothing, one($T), nothing, b, nothing, zero($T), length(a)); o
+        end
+        function Base.:-(a::DevVector{$T}, b::DevVector{$T})
+            length(a) == length(b) || throw(DimensionMismatch("dimensions must match: a has dims $(axes(a)), b has dims $(axes(b))"))
+            o = similar(a); axpby3!(nothing, o, nothing, one($T), nothing, a, nothing, -one($T), nothing, b, nothing, zero($T), length(a)); o
+        end
+        Base.:-(a::DevVector{$T}) = (o = similar(a); axpby3!(nothing, o, nothing, -one($T), nothing, a, nothing, zero($T), nothing, nothing, nothing, zero($T), length(a)); o)
+        Base.:*(a::DevVector{$T}, c::Number) = (o = similar(a); axpby3!(nothing, o, nothing, $T(c), nothing, a, nothing, zero($T), nothing, nothing, nothing, zero($T), length(a)); o)
+        Base.:*(c::Number, a::DevVector{$T}) = a * c
+        # `A.d .+ B.λ` / `A.λ .- B.d` of the UniformScaling methods (src/special.jl:183-222)
+        Base.broadcasted(::typeof(+), a::DevVector{$T}, λ::Number) = (o = similar(a); axpby3!(nothing, o, nothing, one($T), nothing, a, nothing, zero($T), nothing, nothing, nothing, $T(λ), length(a)); o)
+        Base.broadcasted(::typeof(+), λ::Number, a::DevVector{$T}) = Base.broadcasted(+, a, λ)
+        Base.broadcasted(::typeof(-), λ::Number, a::DevVector{$T}) = (o = similar(a); axpby3!(nothing, o, nothing, -one($T), nothing, a, nothing, zero($T), nothing, nothing, nothing, $T(λ), length(a)); o)
+        # fused: all three diagonals in one launch (src/tridiag.jl:571-572)
+        function Base.:+(A::LazyBandedMatrices.Tridiagonal{$T,<:DevVector}, B::LazyBandedMatrices.Tridiagonal{$T,<:DevVector})
+            n = size(A, 1); dl, d, du = similar(A.dl), similar(A.d), similar(A.du)
+            axpby3!(dl, d, du, one($T), A.dl, A.d, A.du, one($T), B.dl, B.d, B.du, zero($T), n); LazyBandedMatrices.Tridiagonal(dl, d, du)
+        end
+        function Base.:-(A::LazyBandedMatrices.Tridiagonal{$T,<:DevVector}, B::LazyBandedMatrices.Tridiagonal{$T,<:DevVector})
+            n = size(A, 1); dl, d, du = similar(A.dl), similar(A.d), similar(A.du)
+            axpby3!(dl, d, du, one($T), A.dl, A.d, A.du, -one($T), B.dl, B.d, B.du, zero($T), n); LazyBandedMatrices.Tridiagonal(dl, d, du)
+        end
+        # BandedMatrix(A, (l,u)) of a structured operand: the storage lbm_?gbmm consumes, so structured x structured
+        # products (test/test_special.jl:154-160) reach the banded x banded kernel
+        function BandedMatrices.BandedMatrix(A::Union{LazyBandedMatrices.Tridiagonal{$T,<:DevVector},LazyBandedMatrices.SymTridiagonal{$T,<:DevVector},LazyBandedMatrices.Bidiagonal{$T,<:DevVector}},
+                                             (l, u)::NTuple{2,Integer} = bandwidths(A))
+            n = size(A, 1); data = DevArray{$T}(undef, l + u + 1, n)
+            bl, bu = bandwidths(A)
+            check(ccall(($pk, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{$T}, Ptr{$T}, Ptr{$T}, Int64, Int64, Ptr{$T}, Int64),
+                        handle().ptr, n, bl > 0 ? pointer(subdiagonaldata(A)) : Ptr{$T}(C_NULL), diagonaldata(A),
+                        bu > 0 ? pointer(supdiagonaldata(A)) : Ptr{$T}(C_NULL), l, u, data, l + u + 1), "lbm_tridiag_pack")
+            BandedMatrices._BandedMatrix(data, Base.OneTo(n), l, u)
         end
     end
 end

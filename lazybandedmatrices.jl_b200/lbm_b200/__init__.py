@@ -9,6 +9,7 @@ from .errors import DimensionMismatch, LbmArgumentError, LbmCudaError, LbmLibrar
 from ._lib import Handle, handle_for, lib, SO_PATH  # noqa: F401
 from .banded import BandedMatrix, TransposedBanded, brand, banded_from_diagonals, fill_uniform, gbmm, gbmv_  # noqa: F401
 from .tridiag import Tridiagonal, SymTridiagonal, Bidiagonal  # noqa: F401
+from .special import Diagonal, UniformScaling, add, sub, neg, scale, axpby, to_banded, structured_matmul  # noqa: F401
 from .lazy import ApplyMatrix, BroadcastMatrix, chain3_batched  # noqa: F401
 from .blockkron import BlockKron, KronSum, KronTrav, DiagTrav, Eye  # noqa: F401
 from .blockconcat import BlockVcat, BlockHcat, BlockBroadcastArray, BlockBandedSpec, unitblocks, zeros_spec  # noqa: F401
@@ -16,6 +17,7 @@ from .linalg import mul_, matmul, bandwidths, blockbandwidths, subblockbandwidth
 
 __all__ = [
     "BandedMatrix", "brand", "banded_from_diagonals", "Tridiagonal", "SymTridiagonal", "Bidiagonal",
+    "Diagonal", "UniformScaling", "add", "sub", "neg", "scale", "axpby", "to_banded", "structured_matmul",
     "ApplyMatrix", "BroadcastMatrix", "chain3_batched", "BlockKron", "KronSum", "KronTrav", "DiagTrav", "Eye", "BlockVcat", "BlockHcat",
     "BlockBroadcastArray", "BlockBandedSpec", "unitblocks", "zeros_spec", "mul_", "matmul", "bandwidths",
     "blockbandwidths", "subblockbandwidths", "DimensionMismatch", "LbmArgumentError", "LbmCudaError",

@@ -31,6 +31,10 @@ def matmul(A, other):
         return mul_(y, A, other)
     if isinstance(A, BandedMatrix) and isinstance(other, BandedMatrix):
         return gbmm(A, other)
+    from .special import structured_matmul
+    from .tridiag import _Structured
+    if isinstance(A, (BandedMatrix, _Structured)) and isinstance(other, (BandedMatrix, _Structured)):
+        return structured_matmul(A, other)  # all-pairs products of test/test_special.jl:154-160
     raise LbmArgumentError(f"* is not defined for {type(A).__name__} and {type(other).__name__}")
 
 

@@ -379,3 +379,70 @@ def krontrav3_mul_diagtrav(A, B, Cm, X):
     Z = np.einsum("jm,kml->kjl", B, Y)
     Y = np.einsum("km,mjl->kjl", Cm, Z)
     return diagtrav(Y)
+
+
+# ---- structured-kind `+` / `-` (numpy restatement of /root/reference/src/special.jl:75-222) ---------------
+# A structured operand is a tuple (kind, dl, d, du) with kind in {"D","BU","BL","S","T"} and None for a diagonal
+# the kind does not have; "S" carries ev as both dl and du.  UniformScaling is ("I", lam).
+def _sp_join(ka, kb):
+    """Return kind of `A +/- B`: Diagonal is absorbed (special.jl:75-142), equal kinds are kept
+    (src/tridiag.jl:206-207,:571-572; src/bidiag.jl:330-346 same uplo), anything else is Tridiagonal
+    (special.jl:117-178; src/bidiag.jl:334-336 opposite uplo)."""
+    if ka == "D":
+        return kb
+    if kb == "D":
+        return ka
+    return ka if ka == kb else "T"
+
+
+def special_axpby(sa, A, sb, B):
+    """`sa*A + sb*B` on diagonals for sa, sb in {+1,-1}: every method of special.jl:75-178 is an instance
+    (e.g. :92-95 `Diagonal - Bidiagonal` = Bidiagonal(A.diag - B.dv, -B.ev, B.uplo)).  With B = ("I", lam) or
+    A = ("I", lam) it is the UniformScaling family :180-222 (`newd = A.d .+ B.lam`, `A.lam .- B.d`, `-B.ev`)."""
+    def diag_of(X, k, n):
+        v = X[1 + k]
+        return None if v is None else np.asarray(v)[: (n if k == 1 else max(n - 1, 0))]
+
+    if A[0] == "I" or B[0] == "I":
+        lam, sl, X, sx = (A[1], sa, B, sb) if A[0] == "I" else (B[1], sb, A, sa)
+        n = len(X[2])
+        out = []
+        for k in range(3):
+            v = diag_of(X, k, n)
+            if v is None:
+                out.append(None)
+            elif k == 1:
+                out.append(sx * v + sl * lam)
+            else:
+                out.append(sx * v)
+        return (X[0], out[0], out[1], out[2])
+    n = len(A[2])
+    kind = _sp_join(A[0], B[0])
+    want = {"D": (0, 1, 0), "BU": (0, 1, 1), "BL": (1, 1, 0), "S": (1, 1, 1), "T": (1, 1, 1)}[kind]
+    out = []
+    for k in range(3):
+        a, b = diag_of(A, k, n), diag_of(B, k, n)
+        if not want[k]:
+            out.append(None)
+        elif a is not None and b is not None:
+            out.append(sa * a + sb * b)
+        elif a is not None:
+            out.append(sa * a)
+        elif b is not None:
+            out.append(sb * b)
+        else:
+            out.append(np.zeros(n if k == 1 else max(n - 1, 0), dtype=np.asarray(A[2]).dtype))
+    return (kind, out[0], out[1], out[2])
+
+
+def special_dense(X):
+    """`Matrix(A)` of a structured tuple (element definitions src/tridiag.jl:301-314,:471-484; src/bidiag.jl:111-124)."""
+    _, dl, d, du = X
+    n = len(d)
+    M = np.diag(np.asarray(d))
+    if n > 1:
+        if dl is not None:
+            M = M + np.diag(np.asarray(dl)[: n - 1], -1)
+        if du is not None:
+            M = M + np.diag(np.asarray(du)[: n - 1], 1)
+    return M
