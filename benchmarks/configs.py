@@ -52,7 +52,7 @@ def vec(n, seed, dt=torch.float64):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="M,C1,C2,C3,MM,BC,RD,C4,C5")
+    ap.add_argument("--only", default="M,C1,C2,C3,MM,BC,RD,SP,C4,C5")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--quick", action="store_true", help="1 warm-up + 1 timed launch per config (profiling runs)")
     a = ap.parse_args()
@@ -157,6 +157,26 @@ def main():
         emit(f"RD sum(SymTridiagonal; dims=1) f64 n=2^{28 - sh}", timeit(lambda: S.sum(1)), 8 * 3 * n)
         emit(f"RD sum(SymTridiagonal) f64 n=2^{28 - sh}", timeit(lambda: S.sum()), 8 * 2 * n)
         del S, x, y
+        torch.cuda.empty_cache()
+
+    if "SP" in only:
+        # `+` among structured kinds (src/special.jl:75-222) and their BandedMatrix storage / products
+        n = 1 << (27 - sh)
+        T1 = L.Tridiagonal(vec(n - 1, 1), vec(n, 2), vec(n - 1, 3))
+        T2 = L.Tridiagonal(vec(n - 1, 4), vec(n, 5), vec(n - 1, 6))
+        Bu = L.Bidiagonal(vec(n, 7), vec(n - 1, 8), "U")
+        emit(f"SP Tridiagonal + Tridiagonal f64 n=2^{27 - sh} (lbm_dtridiag_axpby, 3 diagonals in one launch)",
+             timeit(lambda: T1 + T2), 8 * 9 * n)
+        emit(f"SP Bidiagonal - Tridiagonal f64 n=2^{27 - sh}", timeit(lambda: Bu - T2), 8 * (2 + 2 + 2 + 2) * n)
+        del T2, Bu
+        torch.cuda.empty_cache()
+        emit(f"SP BandedMatrix(Tridiagonal) f64 n=2^{27 - sh} (lbm_dtridiag_pack)", timeit(lambda: L.to_banded(T1)), 8 * 6 * n)
+        n2 = 1 << (24 - sh)
+        S = L.SymTridiagonal(vec(n2, 2), vec(n2 - 1, 3))
+        Bl = L.Bidiagonal(vec(n2, 7), vec(n2 - 1, 8), "L")
+        emit(f"SP SymTridiagonal * Bidiagonal -> BandedMatrix (2,1) f64 n=2^{24 - sh} (lbm_dtridiag_mm, one pass)",
+             timeit(lambda: S @ Bl), 8 * n2 * (2 + 2 + 4))
+        del T1, S, Bl
         torch.cuda.empty_cache()
 
     if "BC" in only:

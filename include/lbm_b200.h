@@ -209,6 +209,16 @@ int lbm_dtridiag_pack(lbm_handle_t h, int64_t n, const double *dl, const double 
 int lbm_stridiag_pack(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du,
                       int64_t kl, int64_t ku, float *AB, int64_t lda);
 
+/* C <- A*B for two structured operands, written straight into the diagonal-major array of the product:
+ * bandwidths (la+lb, ua+ub) with la = (adl != NULL), ua = (adu != NULL), ..., leading dimension ldc >= la+lb+ua+ub+1;
+ * out-of-matrix slots are written as zeros.  One pass: each diagonal read once, the band written once
+ * (the all-pairs products of test/test_special.jl:154-160 / test/test_bidiag.jl:262-267; in the reference they go
+ * through ArrayLayouts' banded mul, one generic loop per column). */
+int lbm_dtridiag_mm(lbm_handle_t h, int64_t n, const double *adl, const double *ad, const double *adu,
+                    const double *bdl, const double *bd, const double *bdu, double *C, int64_t ldc);
+int lbm_stridiag_mm(lbm_handle_t h, int64_t n, const float *adl, const float *ad, const float *adu,
+                    const float *bdl, const float *bd, const float *bdu, float *C, int64_t ldc);
+
 /* ---- row-sharded mul! across the GPUs of one box (one process per GPU) ------------------- */
 /* Rank r of `world` owns rows [r0,r1) of a square n x n operator and stores the COLUMN slice
  * [c0,c1) = [max(0,r0-kl), min(n,r1+ku)) of the diagonal-major array (same lda); x lives in a

@@ -70,6 +70,7 @@ def _sigs():
         s[f"lbm_{p}tridiag_dot"] = (C.c_int, [H, i64, vp, vp, vp, vp, vp, vp])
         s[f"lbm_{p}tridiag_sum"] = (C.c_int, [H, i64, vp, vp, vp, C.c_int, vp])
         s[f"lbm_{p}tridiag_axpby"] = (C.c_int, [H, i64, ft, vp, vp, vp, ft, vp, vp, vp, ft, vp, vp, vp])
+        s[f"lbm_{p}tridiag_mm"] = (C.c_int, [H, i64, vp, vp, vp, vp, vp, vp, vp, i64])
         s[f"lbm_{p}tridiag_pack"] = (C.c_int, [H, i64, vp, vp, vp, i64, i64, vp, i64])
         s[f"lbm_{p}gbmv_host"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
         s[f"lbm_{p}gbmv_sharded"] = (C.c_int, [H, i64, i64, i64, ft, vp, i64, vp, ft, vp, C.c_int])

@@ -87,7 +87,8 @@ class BandedMatrix:
         A = torch.zeros(self.m, self.n, dtype=self.dtype, device=self.device)
         for r in range(self.l + self.u + 1):
             k = self.u - r  # diagonal offset j - i
-            j = torch.arange(max(0, k), min(self.n, self.m + k), device=self.device)
+            lo, hi = max(0, k), min(self.n, self.m + k)
+            j = torch.arange(lo, max(lo, hi), device=self.device)
             if j.numel():
                 A[j - k, j] = self.data[j, r]
         return A

@@ -215,6 +215,27 @@ def to_banded(A, l=None, u=None) -> BandedMatrix:
 
 def structured_matmul(A, B) -> BandedMatrix:
     """`A*B` for two structured / banded operands -> BandedMatrix with bandwidths (la+lb, ua+ub)."""
+    if not isinstance(A, BandedMatrix) and not isinstance(B, BandedMatrix):
+        if A.n != B.n:
+            raise DimensionMismatch(
+                f"second entry of size(A)={A.shape} and first entry of size(B) = {B.shape} must match.")
+        if A.dtype != B.dtype or A.device != B.device:
+            raise LbmArgumentError("operands must share element type and device")
+        (la, ua), (lb, ub) = A.bandwidths(), B.bandwidths()
+        rows = la + lb + ua + ub + 1
+        out = torch.empty((A.n, rows), dtype=A.dtype, device=A.device)
+        if A.n:
+            adl, ad, adu = A._diagonals()
+            bdl, bd, bdu = B._diagonals()
+            if A.n == 1:   # no off-diagonal entries: keep the band shape, pass the (empty) diagonals as present
+                z = torch.zeros(1, dtype=A.dtype, device=A.device)
+                adl, adu = (z if la else None), (z if ua else None)
+                bdl, bdu = (z if lb else None), (z if ub else None)
+            h = _lib.handle_of(ad)
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(ad.dtype)}tridiag_mm")
+            h.check(fn(h.ptr, A.n, _ptr(adl), _ptr(ad), _ptr(adu), _ptr(bdl), _ptr(bd), _ptr(bdu), _ptr(out), rows),
+                    "lbm_tridiag_mm")
+        return BandedMatrix(out, A.n, la + lb, ua + ub)
     Ab = A if isinstance(A, BandedMatrix) else to_banded(A)
     Bb = B if isinstance(B, BandedMatrix) else to_banded(B)
     return gbmm(Ab, Bb)
