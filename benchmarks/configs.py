@@ -52,7 +52,7 @@ def vec(n, seed, dt=torch.float64):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="M,C1,C2,C3,MM,BC,RD,SP,C4,C5")
+    ap.add_argument("--only", default="M,C1,C2,C3,GM,MM,BC,RD,SP,C4,C5")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--quick", action="store_true", help="1 warm-up + 1 timed launch per config (profiling runs)")
     a = ap.parse_args()
@@ -124,6 +124,26 @@ def main():
         emit(f"C3 2-D Laplacian kronsum {g}x{g} default", timeit(lambda: Lap.mul_(y, x)), 16 * g * g,
              best_tile=best[1:] if best else None)
         del x, y
+        torch.cuda.empty_cache()
+
+    if "GM" in only:
+        # narrow banded x banded materialise at a size that fills the machine (north-star: >= 70 % of HBM roofline, l,u <= 8)
+        n = 1 << (24 - sh)
+        for dt, w in ((torch.float64, 8), (torch.float32, 4)):
+            for l in (1, 2, 4, 8):
+                A = L.brand(n, n, l, l, dtype=dt, seed=1)
+                B = L.brand(n, n, l, l, dtype=dt, seed=2)
+                Cm = L.BandedMatrix(torch.empty((n, 4 * l + 1), dtype=dt, device="cuda"), n, 2 * l, 2 * l)
+                byts = w * n * ((2 * l + 1) * 2 + 4 * l + 1)
+                flops = 2 * n * (2 * l + 1) ** 2
+                nm = "f64" if w == 8 else "f32"
+                emit(f"GM gbmm {nm} n=2^{24 - sh} ({l},{l})x({l},{l}) register kernel", timeit(lambda: L.gbmm(A, B, out=Cm)), byts, flops)
+                if not a.quick:
+                    h.set_tuning(gbmm_force=1)
+                    emit(f"GM gbmm {nm} n=2^{24 - sh} ({l},{l})x({l},{l}) diagonal-wise kernel (gbmm_force=1)",
+                         timeit(lambda: L.gbmm(A, B, out=Cm), 3, 1), byts, flops)
+                    h.set_tuning(gbmm_force=0)
+                del A, B, Cm
         torch.cuda.empty_cache()
 
     if "MM" in only:

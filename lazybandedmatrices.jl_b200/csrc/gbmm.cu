@@ -20,6 +20,12 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
                       const double *A, int64_t lda, int64_t klb, int64_t kub, const double *B, int64_t ldb,
                       double beta, int64_t klc, int64_t kuc, double *C, int64_t ldc, bool *handled);
 
+// narrow bands (<= 17 stored diagonals per factor): output band in registers, gbmm_reg.cu
+template <typename T>
+int lbm_gbmm_reg(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64_t kla, int64_t kua, const T *A, int64_t lda,
+                 int64_t klb, int64_t kub, const T *B, int64_t ldb, T beta, int64_t klc, int64_t kuc, T *C, int64_t ldc,
+                 bool *handled);
+
 namespace {
 
 using namespace lbm;
@@ -114,6 +120,14 @@ int gbmm_impl(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64_t 
     if (k > 0 && !A) return lbm_fail_arg(h, 8, "A == NULL");
     if (k > 0 && !B) return lbm_fail_arg(h, 12, "B == NULL");
     lbm_device_guard g(h->device);
+
+    // gbmm_force: 0 auto, 1 generic diagonal-wise kernel, 2 DMMA, 3 register kernel; the register kernel wants enough
+    // columns to fill the machine (C1's n = 10^4 stays on the latency-optimised diagonal-wise kernel)
+    if (h->tune.gbmm_force == 3 || (h->tune.gbmm_force == 0 && n >= 256 * (int64_t)h->sm_count)) {
+        bool handled = false;
+        int rc = lbm_gbmm_reg<T>(h, m, n, k, alpha, kla, kua, A, lda, klb, kub, B, ldb, beta, klc, kuc, C, ldc, &handled);
+        if (handled) return rc;
+    }
 
     GbmmArgs<T> a;
     a.m = m; a.n = n; a.k = k; a.kla = kla; a.kua = kua; a.lda = lda; a.klb = klb; a.kub = kub; a.ldb = ldb;

@@ -105,6 +105,79 @@ def test_gbmm_dmma_nan_poisoned_out_of_matrix_slots(L, oracle):
     assert np.max(np.abs(got - oracle.band_to_dense(want, n, 2 * l, 2 * l))) <= tol_rows(np.float64, 2 * l + 1, 1.0, 1.0)
 
 
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_gbmm_register_kernel(L, oracle, dt):
+    """Narrow bands at large n take the register kernel (gbmm_reg.cu); gbmm_force=3 forces it on small, rectangular,
+    asymmetric and template-padded shapes (stored rows 1..17 map onto the {3,5,9,17} instantiations)."""
+    h = L.handle_for(0)
+    cases = [(6, 6, 6, 1, 1, 1, 1), (10, 8, 9, 2, 0, 1, 3), (5, 5, 5, 4, 4, 4, 4), (12, 12, 12, 0, 0, 2, 1), (1, 1, 1, 0, 0, 0, 0),
+             (200, 170, 230, 3, 2, 1, 4), (700, 700, 700, 8, 8, 8, 8), (513, 515, 511, 8, 8, 1, 1), (600, 600, 600, 0, 16, 16, 0),
+             (1000, 1030, 980, 10, 6, 5, 9), (300, 2000, 300, 2, 2, 2, 2), (2000, 300, 2000, 3, 1, 0, 7), (257, 256, 258, 4, 4, 2, 2),
+             (4000, 4000, 4000, 1, 1, 1, 1), (777, 777, 777, 0, 0, 0, 0)]
+    for s, (m, n, k, kla, kua, klb, kub) in enumerate(cases):
+        A_np, A = _band(L, oracle, m, k, kla, kua, 61 + s, dt)
+        B_np, B = _band(L, oracle, k, n, klb, kub, 62 + s, dt)
+        want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
+        h.set_tuning(gbmm_force=3)
+        try:
+            C = A @ B
+            torch.cuda.synchronize()
+        finally:
+            h.set_tuning(gbmm_force=0)
+        tol = tol_rows(NP[dt], min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
+        _cmp_band(oracle, C, want, m, kla + klb, kua + kub, tol)
+    # the auto path at a size that fills the machine agrees with the diagonal-wise kernel bit for bit or within tol
+    n = 1 << 17
+    A_np, A = _band(L, oracle, n, n, 4, 4, 5, dt)
+    B_np, B = _band(L, oracle, n, n, 4, 4, 6, dt)
+    want = oracle.gbmm(n, n, n, A_np, 4, 4, B_np, 4, 4)
+    before = h.launch_count()
+    C = A @ B
+    assert h.launch_count() - before == 1
+    got = np.asfortranarray(C.data.cpu().numpy().T)          # band arrays compared directly (n is too large for dense)
+    r = np.arange(17)[:, None]
+    i = np.arange(n)[None, :] + r - 8
+    inside = (i >= 0) & (i < n)
+    assert np.max(np.abs(np.where(inside, got - want, 0.0))) <= tol_rows(NP[dt], 9, 1.0, 1.0)
+    assert np.all(got[~inside] == 0.0)
+
+
+def test_gbmm_register_kernel_alpha_beta_padded_nan(L, oracle):
+    """alpha/beta, an output band wider than the product band, padded leading dimensions, and NaNs parked in every
+    out-of-matrix slot of A and B (masked by index at staging time)."""
+    h = L.handle_for(0)
+    m = n = k = 900
+    A_np, _ = _band(L, oracle, m, k, 3, 5, 1, torch.float64)
+    B_np, _ = _band(L, oracle, k, n, 6, 2, 2, torch.float64)
+    C0_np, C0 = _band(L, oracle, m, n, 11, 9, 3, torch.float64)      # band wider than (9,7)
+    want = oracle.gbmm(m, n, k, A_np, 3, 5, B_np, 6, 2, klc=11, kuc=9, alpha=-2.0, beta=0.5, Cin=C0_np)
+
+    def poison(M, l, u, rows):
+        P = M.copy()
+        r = np.arange(l + u + 1)[:, None]
+        i = np.arange(P.shape[1])[None, :] + r - u
+        P[(i < 0) | (i >= rows)] = np.nan
+        return P
+
+    def padded(M, extra):   # (n, lda) tensor with lda > l+u+1, junk in the padding rows
+        t = torch.full((M.shape[1], M.shape[0] + extra), float("nan"), dtype=torch.float64, device="cuda")
+        t[:, : M.shape[0]] = torch.from_numpy(np.ascontiguousarray(M.T)).cuda()
+        return t
+
+    A = L.BandedMatrix(padded(poison(A_np, 3, 5, m), 3), m, 3, 5)
+    B = L.BandedMatrix(padded(poison(B_np, 6, 2, k), 1), k, 6, 2)
+    h.set_tuning(gbmm_force=3)
+    try:
+        L.gbmm(A, B, alpha=-2.0, out=C0, beta=0.5)
+        torch.cuda.synchronize()
+    finally:
+        h.set_tuning(gbmm_force=0)
+    got = np.asfortranarray(C0.data.cpu().numpy().T)
+    dg, dw = oracle.band_to_dense(got, m, 11, 9), oracle.band_to_dense(want, m, 11, 9)
+    assert not np.isnan(dg).any()
+    assert np.max(np.abs(dg - dw)) <= tol_rows(np.float64, 9, 1.0, 1.0, 2.0, 0.5, 1.0)
+
+
 def test_gbmm_alpha_beta_and_wider_output_band(L, oracle):
     m = n = k = 500
     A_np, A = _band(L, oracle, m, k, 2, 1, 1, torch.float64)
