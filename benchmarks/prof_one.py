@@ -58,6 +58,26 @@ elif which == "M":
         for _ in range(2):
             L.mul_(y, A, x)
         del A
+elif which == "GM":
+    n = 1 << 24
+    for l in (8, 4, 1):
+        A = L.brand(n, n, l, l, seed=1)
+        B = L.brand(n, n, l, l, seed=2)
+        Cm = L.BandedMatrix(torch.empty((n, 4 * l + 1), dtype=torch.float64, device="cuda"), n, 2 * l, 2 * l)
+        for _ in range(2):
+            L.gbmm(A, B, out=Cm)
+        del A, B, Cm
+elif which == "SP":
+    n = 1 << 26
+    def v(k, s):
+        t = torch.empty(k, dtype=torch.float64, device="cuda")
+        L.fill_uniform(t, s)
+        return t
+    T1 = L.Tridiagonal(v(n - 1, 1), v(n, 2), v(n - 1, 3))
+    T2 = L.Tridiagonal(v(n - 1, 4), v(n, 5), v(n - 1, 6))
+    for _ in range(2):
+        R = T1 + T2
+        P = T1 @ T2
 elif which == "MM":
     n, nrhs = 1 << 24, 8
     A = L.brand(n, n, 8, 8, seed=1)

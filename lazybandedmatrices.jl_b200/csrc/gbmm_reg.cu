@@ -10,17 +10,22 @@
 // A thread owns two adjacent output columns and their NA+NB-1 accumulators each, all in registers (compile-time
 // indices: the loops below are fully unrolled).  The slab column of A at local index 2t+q feeds column 2t with s = q
 // and column 2t+1 with s = q-1, so every value of A read from shared memory is used twice and shared-memory
-// bandwidth (the limiter of a one-column-per-thread version: one LDS per DFMA) stays below the HBM time.
+// bandwidth (the limiter of a one-column-per-thread version: one LDS per FMA) stays below the HBM time.
 //
-// Staging: the slab of A (columns [j0-kub, j0+TC+klb), ONE contiguous range), the tile of B and, on the way out, the
-// tile of C pass through shared memory so every global access is a flat, fully coalesced stream.  Shared-memory
-// columns are laid out in PAIRS with an odd pair pitch (2*P+1 words): lane t reads column 2t+q, i.e. lanes are one
-// pair apart, and an odd pitch makes those LDS.64 / STS.64 conflict-free.  Template row counts NAT >= NA, NBT >= NB come
-// from {3,5,9,17}; missing rows are zero-filled at staging time, which also masks, BY INDEX, every out-of-matrix slot
-// (brand() fills them with random numbers; undef storage may hold NaN).
+// Shared memory holds the slab of A (columns [j0-kub, ...), ONE contiguous range of the band array), the tile of B and,
+// on the way out, the tile of C in exactly the layout they have in HBM (column pitch = row count).  Consequences:
+//   * interior tiles with tight leading dimensions arrive as two 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP)
+//     and leave as one bulk TMA store -- zero staging instructions; edge tiles / padded lda use element-wise cp.async
+//     with zero-fill, which also masks BY INDEX every out-of-matrix slot (brand() fills them with random numbers);
+//   * the row counts NAT, NBT in {3,5,9,17} are odd, so with lanes one column PAIR apart (2*NAT elements) every
+//     2-element vector access (LDS.128 for f64, LDS.64 for f32) is bank-conflict-free, and an element (column 2t+q,
+//     row r) is vector-aligned exactly when q + r is even -- a compile-time fact, so each column is read as NAT/2
+//     vector loads plus one scalar.
 #include "lbm_common.cuh"
 
 namespace {
+
+using namespace lbm;
 
 constexpr int GR_NT = 128;          // threads per CTA
 constexpr int GR_TC = 2 * GR_NT;    // output columns per CTA
@@ -36,8 +41,12 @@ struct GrArgs {
     T *C;
 };
 
+template <typename T> struct vec2;
+template <> struct vec2<double> { using type = double2; };
+template <> struct vec2<float> { using type = float2; };
+
 // resident CTAs per SM the register budget is tuned for: the wide instantiations hold 2*(NAT+NBT-1) accumulators
-constexpr int gr_min_blocks(int nat, int nbt) { return nat + nbt >= 26 ? 3 : (nat + nbt >= 14 ? 5 : (nat + nbt >= 8 ? 8 : 12)); }
+constexpr int gr_min_blocks(int nat, int nbt) { return nat + nbt >= 26 ? 3 : (nat + nbt >= 14 ? 4 : (nat + nbt >= 8 ? 6 : 10)); }
 
 // one element global -> shared, asynchronously (LDGSTS); ok == false writes a zero without touching global memory
 template <typename T>
@@ -48,102 +57,153 @@ __device__ __forceinline__ void cp_async_elem(uint32_t dst, const T *src, bool o
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
+__device__ __forceinline__ void gr_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void gr_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gr_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void gr_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void gr_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// pair-skewed address of (column c, row r) for row pitch P
-template <int P>
-__device__ __forceinline__ int skew(int c, int r) {
-    return (c >> 1) * (2 * P + 1) + (c & 1) * P + r;
+// N consecutive elements starting at p[0]; PAR = parity of the element index of p[0] decides the vector alignment:
+// 2-element vector loads where aligned, scalars at the ragged ends
+template <typename T, int N, int PAR>
+__device__ __forceinline__ void load_run(T *dst, const T *p) {
+    using V = typename vec2<T>::type;
+    if (PAR) dst[0] = p[0];
+#pragma unroll
+    for (int r = PAR; r + 1 < N; r += 2) {
+        const V v = *reinterpret_cast<const V *>(p + r);
+        dst[r] = v.x;
+        dst[r + 1] = v.y;
+    }
+    if ((N - PAR) & 1) dst[N - 1] = p[N - 1];
 }
 
 template <typename T, int NAT, int NBT>
+struct GrGeom {
+    static constexpr int NCT = NAT + NBT - 1;
+    static constexpr int SA_COLS = (GR_TC + NBT + 3) & ~3;          // slab columns (multiple of 4: bulk sizes stay 16-byte multiples)
+    static constexpr int SA_ELEMS = SA_COLS * NAT;
+    static constexpr int SB_ELEMS = GR_TC * NBT;
+    static constexpr int SC_ELEMS = GR_TC * NCT;
+    static constexpr int SM_ELEMS = (SA_ELEMS + SB_ELEMS) > SC_ELEMS ? (SA_ELEMS + SB_ELEMS) : SC_ELEMS;
+    static constexpr size_t SMEM_BYTES = (size_t)SM_ELEMS * sizeof(T) + 16;   // + the mbarrier
+};
+
+template <typename T, int NAT, int NBT>
 __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kernel(const GrArgs<T> a) {
-    constexpr int NCT = NAT + NBT - 1;
-    constexpr int SA_COLS = GR_TC + NBT + 1;                       // slab columns (even count)
-    constexpr int SA_ELEMS = (SA_COLS / 2) * (2 * NAT + 1);
-    constexpr int SB_ELEMS = (GR_TC / 2) * (2 * NBT + 1);
-    constexpr int SC_ELEMS = (GR_TC / 2) * (2 * NCT + 1);
-    constexpr int SM_ELEMS = (SA_ELEMS + SB_ELEMS) > SC_ELEMS ? (SA_ELEMS + SB_ELEMS) : SC_ELEMS;
+    using G = GrGeom<T, NAT, NBT>;
+    using V = typename vec2<T>::type;
+    constexpr int NCT = G::NCT, SA_COLS = G::SA_COLS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sA = reinterpret_cast<T *>(smem_raw);
-    T *sB = sA + SA_ELEMS;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sA = reinterpret_cast<T *>(smem_raw + 16);
+    T *sB = sA + G::SA_ELEMS;
     T *sC = sA;                                                    // aliases sA/sB after the compute phase
-    static_assert(SM_ELEMS >= SC_ELEMS, "smem");
 
     const int tid = threadIdx.x;
     const int NA = a.kla + a.kua + 1, NB = a.klb + a.kub + 1;
     const int64_t ntiles = (a.n + GR_TC - 1) / GR_TC;
+    const bool tight_in = a.lda == NAT && a.ldb == NBT && lbm_aligned16_dev(a.A) && lbm_aligned16_dev(a.B);
+    const int nbc = a.klc + a.kuc + 1;
+    const int off = a.kuc - a.kua - a.kub;                         // C band row of accumulator 0
+    const bool tight_out = nbc == NCT && a.ldc == NCT && off == 0 && a.beta == (T)0 && lbm_aligned16_dev(a.C);
+    uint32_t parity = 0;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t j0 = tile * GR_TC;
         const int cols = (int)((a.n - j0) < GR_TC ? (a.n - j0) : GR_TC);
         const int64_t p0 = j0 - a.kub;                             // global column of slab column 0
         // interior tile: every staged slot is inside the matrix, no index tests needed
-        const bool interior = cols == GR_TC && p0 - a.kua >= 0 && p0 + SA_COLS - 1 + a.kla < a.m && p0 >= 0 &&
-                              p0 + SA_COLS - 1 < a.k && j0 - a.kub >= 0 && j0 + GR_TC - 1 + a.klb < a.k;
+        const bool interior = cols == GR_TC && p0 - a.kua >= 0 && p0 + SA_COLS - 1 + a.kla < a.m && p0 + SA_COLS - 1 < a.k &&
+                              j0 + GR_TC - 1 + a.klb < a.k;
+        const T *Ag = a.A + p0 * a.lda;                            // may point before A for p0 < 0: never dereferenced there
+        const T *Bg = a.B + j0 * a.ldb;
+        const bool tma_in = interior && tight_in && ((p0 * NAT * (int64_t)sizeof(T)) & 15) == 0;
 
-        // ---- stage A slab (pitch NAT, rows >= NA zero) and B tile (pitch NBT) ----
-        // element-wise cp.async (LDGSTS) straight into the skewed layout: nothing waits on a load inside the loop, so
-        // the whole tile (~70 elements per thread) is in flight at once; src-size 0 zero-fills masked / padding slots
-        {
-            const T *Ag = a.A + p0 * a.lda;                        // may point before A for p0 < 0: never dereferenced there
-            const uint32_t sA_u = lbm::smem_u32(sA), sB_u = lbm::smem_u32(sB);
-            // skew<P>(c, r) = c*P + r + (c >> 1) = e + (c >> 1): with a tight leading dimension (lda == NAT) the global
-            // offset is e itself, so an interior element costs one multiply-high, one shift and the copy
-            if (interior && a.lda == NAT) {
-#pragma unroll 4
-                for (int e = tid; e < SA_COLS * NAT; e += GR_NT)
-                    cp_async_elem<T>(sA_u + (uint32_t)((e + ((e / NAT) >> 1)) * (int)sizeof(T)), Ag + e, true);
-            } else {
-                for (int e = tid; e < SA_COLS * NAT; e += GR_NT) {
-                    const int c = e / NAT, r = e - c * NAT;
-                    bool ok = r < NA;
-                    if (ok && !interior) {
-                        const int64_t p = p0 + c, i = p + r - a.kua;
-                        ok = p >= 0 && p < a.k && i >= 0 && i < a.m;
-                    }
-                    cp_async_elem<T>(sA_u + (uint32_t)(skew<NAT>(c, r) * (int)sizeof(T)), ok ? Ag + (r + a.lda * c) : a.A, ok);
-                }
+        // the previous tile's bulk store must have finished READING sC before anything overwrites it
+        if (tid == 0) gr_bulk_wait_read0();
+        __syncthreads();
+
+        // ---- stage the A slab and the B tile, HBM layout kept ----
+        if (tma_in) {
+            if (tid == 0) {
+                gr_fence_proxy_async();                            // earlier generic-proxy accesses of this smem are ordered first
+                mbar_expect_tx(bar, (uint32_t)((G::SA_ELEMS + G::SB_ELEMS) * sizeof(T)));
+                bulk_g2s(sA, Ag, (uint32_t)(G::SA_ELEMS * sizeof(T)), bar);
+                bulk_g2s(sB, Bg, (uint32_t)(G::SB_ELEMS * sizeof(T)), bar);
             }
-            const T *Bg = a.B + j0 * a.ldb;
-            if (interior && a.ldb == NBT) {
-#pragma unroll 4
-                for (int e = tid; e < GR_TC * NBT; e += GR_NT)
-                    cp_async_elem<T>(sB_u + (uint32_t)((e + ((e / NBT) >> 1)) * (int)sizeof(T)), Bg + e, true);
-            } else {
-                for (int e = tid; e < GR_TC * NBT; e += GR_NT) {
-                    const int c = e / NBT, s = e - c * NBT;
-                    bool ok = s < NB && c < cols;
-                    if (ok && !interior) {
-                        const int64_t p = j0 + c + s - a.kub;
-                        ok = p >= 0 && p < a.k;
-                    }
-                    cp_async_elem<T>(sB_u + (uint32_t)(skew<NBT>(c, s) * (int)sizeof(T)), ok ? Bg + (s + a.ldb * c) : a.B, ok);
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            // element-wise cp.async (LDGSTS): nothing waits on a load inside the loop; src-size 0 zero-fills masked slots
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            for (int e = tid; e < G::SA_ELEMS; e += GR_NT) {
+                const int c = e / NAT, r = e - c * NAT;
+                bool ok = r < NA;
+                if (ok && !interior) {
+                    const int64_t p = p0 + c, i = p + r - a.kua;
+                    ok = p >= 0 && p < a.k && i >= 0 && i < a.m;
                 }
+                cp_async_elem<T>(sA_u + (uint32_t)(e * (int)sizeof(T)), ok ? Ag + (r + a.lda * c) : a.A, ok);
+            }
+            for (int e = tid; e < G::SB_ELEMS; e += GR_NT) {
+                const int c = e / NBT, s = e - c * NBT;
+                bool ok = s < NB && c < cols;
+                if (ok && !interior) {
+                    const int64_t p = j0 + c + s - a.kub;
+                    ok = p >= 0 && p < a.k;
+                }
+                cp_async_elem<T>(sB_u + (uint32_t)(e * (int)sizeof(T)), ok ? Bg + (s + a.ldb * c) : a.B, ok);
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---- compute: two columns, NCT accumulators each, everything in registers ----
         T acc0[NCT], acc1[NCT];
 #pragma unroll
         for (int t = 0; t < NCT; ++t) acc0[t] = acc1[t] = (T)0;
         {
-            const T *pa = sA + tid * (2 * NAT + 1);                // pair `tid`; column 2*tid + q lives q/2 pairs further on
-            const T *pb = sB + tid * (2 * NBT + 1);
+            const T *pa = sA + 2 * tid * NAT;                      // column 2*tid + q starts q*NAT further on
+            const T *pb = sB + 2 * tid * NBT;                      // [B column 2*tid (NBT values) | B column 2*tid+1]
+            T b0n = (T)0, b1n = (T)0;                              // second halves of the B vectors, used at odd q
 #pragma unroll
             for (int q = 0; q <= NBT; ++q) {
                 T av[NAT];
-                const T *col = pa + (q >> 1) * (2 * NAT + 1) + (q & 1) * NAT;
-#pragma unroll
-                for (int r = 0; r < NAT; ++r) av[r] = col[r];
+                if ((q & 1) == 0) load_run<T, NAT, 0>(av, pa + q * NAT);   // index (2t+q)*NAT + r is even <=> q + r even
+                else load_run<T, NAT, 1>(av, pa + q * NAT);
+                T b0 = (T)0, b1 = (T)0;
+                if ((q & 1) == 0) {
+                    // elements q, q+1 of column 0 and NBT+q-1, NBT+q of the pair (NBT odd: both vectors are aligned)
+                    if (q + 1 < NBT) {
+                        const V v = *reinterpret_cast<const V *>(pb + q);
+                        b0 = v.x;
+                        b0n = v.y;
+                    } else if (q < NBT) b0 = pb[q];
+                    if (q >= 1) {
+                        const V w = *reinterpret_cast<const V *>(pb + NBT + q - 1);
+                        b1 = w.x;
+                        b1n = w.y;
+                    } else b1n = pb[NBT];
+                } else {
+                    b0 = b0n;
+                    b1 = b1n;
+                }
                 if (q < NBT) {
-                    const T b0 = pb[q];
 #pragma unroll
                     for (int r = 0; r < NAT; ++r) acc0[r + q] = fma(av[r], b0, acc0[r + q]);
                 }
                 if (q >= 1) {
-                    const T b1 = pb[NBT + q - 1];
 #pragma unroll
                     for (int r = 0; r < NAT; ++r) acc1[r + q - 1] = fma(av[r], b1, acc1[r + q - 1]);
                 }
@@ -151,65 +211,61 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
         }
         __syncthreads();                                           // all reads of sA / sB done: sC may overwrite them
 
-        // ---- stage the C tile (pair-skewed, pitch NCT) and stream it out ----
+        // ---- the C tile, HBM layout: [column 2*tid (NCT values) | column 2*tid+1], written as 2-element vectors ----
+        const bool tma_out = tight_out && cols == GR_TC && j0 - a.kuc >= 0 && j0 + GR_TC - 1 + a.klc < a.m;
         {
-            T *pc = sC + tid * (2 * NCT + 1);
+            const T sc = tma_out ? a.alpha : (T)1;                 // the bulk store cannot scale: do it here
+            T *pc = sC + 2 * tid * NCT;
 #pragma unroll
-            for (int t = 0; t < NCT; ++t) {
-                pc[t] = acc0[t];
-                pc[NCT + t] = acc1[t];
+            for (int i = 0; i < NCT; ++i) {
+                const int k0 = 2 * i, k1 = 2 * i + 1;
+                const T lo = k0 < NCT ? acc0[k0 < NCT ? k0 : 0] : acc1[k0 >= NCT ? k0 - NCT : 0];
+                const T hi = k1 < NCT ? acc0[k1 < NCT ? k1 : 0] : acc1[k1 >= NCT ? k1 - NCT : 0];
+                V v;
+                v.x = sc * lo;
+                v.y = sc * hi;
+                *reinterpret_cast<V *>(pc + 2 * i) = v;
             }
         }
-        __syncthreads();
-        {
-            const int nbc = a.klc + a.kuc + 1;
-            const int off = a.kuc - a.kua - a.kub;                 // C band row of accumulator 0
+        T *Cg = a.C + j0 * a.ldc;
+        if (tma_out) {
+            gr_fence_proxy_async();                                // generic-proxy writes -> visible to the bulk store
+            __syncthreads();
+            if (tid == 0) {
+                gr_bulk_s2g(Cg, sC, (uint32_t)(G::SC_ELEMS * sizeof(T)));
+                gr_bulk_commit();
+            }
+        } else {
+            __syncthreads();
             const int NC = NA + NB - 1;
-            T *Cg = a.C + j0 * a.ldc;
             const int total = cols * nbc;
-            const bool fast_out = nbc == NCT && a.ldc == NCT && off == 0 && a.beta == (T)0 && cols == GR_TC &&
-                                  j0 - a.kuc >= 0 && j0 + GR_TC - 1 + a.klc < a.m;
-            if (fast_out) {
-                // tight, fully in-matrix tile: global offset = e, shared index = e + (c >> 1)
-#pragma unroll 4
-                for (int e = tid; e < GR_TC * NCT; e += GR_NT) Cg[e] = a.alpha * sC[e + ((e / NCT) >> 1)];
-            } else {
-                // flat element index e = c*nbc + row, advanced incrementally (no division in the loop)
-                const int dc = GR_NT / nbc, dr = GR_NT - dc * nbc;
-                int c = tid / nbc, row = tid - c * nbc;
-                for (int e = tid; e < total; e += GR_NT) {
-                    const int t = row - off;
-                    const int64_t i = j0 + c + row - a.kuc;
-                    const bool in = i >= 0 && i < a.m;
-                    T v = (T)0;
-                    if (t >= 0 && t < NC && in) v = sC[skew<NCT>(c, t)];
-                    T *dst = Cg + row + a.ldc * c;
-                    if (a.beta == (T)0) *dst = a.alpha * v;
-                    else if (in) *dst = fma(a.beta, *dst, a.alpha * v);
-                    row += dr;
-                    c += dc;
-                    if (row >= nbc) { row -= nbc; ++c; }
-                }
+            // flat element index e = c*nbc + row, advanced incrementally (no division in the loop)
+            const int dc = GR_NT / nbc, dr = GR_NT - dc * nbc;
+            int c = tid / nbc, row = tid - c * nbc;
+            for (int e = tid; e < total; e += GR_NT) {
+                const int t = row - off;
+                const int64_t i = j0 + c + row - a.kuc;
+                const bool in = i >= 0 && i < a.m;
+                T v = (T)0;
+                if (t >= 0 && t < NC && in) v = sC[c * NCT + t];
+                T *dst = Cg + row + a.ldc * c;
+                if (a.beta == (T)0) *dst = a.alpha * v;
+                else if (in) *dst = fma(a.beta, *dst, a.alpha * v);
+                row += dr;
+                c += dc;
+                if (row >= nbc) { row -= nbc; ++c; }
             }
         }
-        __syncthreads();                                           // sC aliases the next tile's sA / sB
     }
-}
-
-template <int NAT, int NBT, typename T>
-constexpr size_t gr_smem_bytes() {
-    constexpr int NCT = NAT + NBT - 1;
-    constexpr int SA_COLS = GR_TC + NBT + 1;
-    constexpr int SA_ELEMS = (SA_COLS / 2) * (2 * NAT + 1);
-    constexpr int SB_ELEMS = (GR_TC / 2) * (2 * NBT + 1);
-    constexpr int SC_ELEMS = (GR_TC / 2) * (2 * NCT + 1);
-    return sizeof(T) * (size_t)((SA_ELEMS + SB_ELEMS) > SC_ELEMS ? (SA_ELEMS + SB_ELEMS) : SC_ELEMS);
+    if (tid == 0) gr_bulk_wait0();                                 // smem must outlive the last bulk store
 }
 
 template <typename T, int NAT, int NBT>
 int gr_launch(lbm_handle_t h, const GrArgs<T> &a) {
-    static_assert((GR_TC + NBT + 1) % 2 == 0, "slab column count must be even");
-    constexpr size_t smem = gr_smem_bytes<NAT, NBT, T>();
+    using G = GrGeom<T, NAT, NBT>;
+    static_assert((G::SA_ELEMS * sizeof(T)) % 16 == 0 && (G::SB_ELEMS * sizeof(T)) % 16 == 0 && (G::SC_ELEMS * sizeof(T)) % 16 == 0,
+                  "bulk copy sizes must be multiples of 16 bytes");
+    constexpr size_t smem = G::SMEM_BYTES;
     auto kern = gbmm_reg_kernel<T, NAT, NBT>;
     static int configured = 0;
     if (!(configured & (1 << h->device))) {
