@@ -28,12 +28,12 @@ namespace {
 using namespace lbm;
 
 constexpr int GR_NT = 128;          // threads per CTA
-constexpr int GR_TC = 2 * GR_NT;    // output columns per CTA
 
 template <typename T>
 struct GrArgs {
     int64_t m, n, k;
     int kla, kua, klb, kub, klc, kuc;
+    int pad;   // the slab starts `pad` columns before j0-kub so that its first byte is 16-byte aligned (bulk TMA)
     int64_t lda, ldb, ldc;
     T alpha, beta;
     const T *A;
@@ -85,24 +85,34 @@ __device__ __forceinline__ void load_run(T *dst, const T *p) {
 template <typename T, int NAT, int NBT>
 struct GrGeom {
     static constexpr int NCT = NAT + NBT - 1;
-    static constexpr int SA_COLS = (GR_TC + NBT + 3) & ~3;          // slab columns (multiple of 4: bulk sizes stay 16-byte multiples)
+    // a thread owns one column PAIR per sub-tile of 2*GR_NT columns; narrow instantiations take SUB sub-tiles per
+    // bulk copy so that a tile stays ~40 KB (per-tile latency, not bandwidth, bounds smaller tiles)
+    static constexpr int B256 = 2 * GR_NT * (NAT + NBT + NCT) * (int)sizeof(T);
+    static constexpr int SUB = B256 <= 12 * 1024 ? 4 : (B256 <= 24 * 1024 ? 2 : 1);
+    static constexpr int TC = 2 * GR_NT * SUB;                     // output columns per tile
+    static constexpr int SA_COLS = (TC + NBT + 3 + 3) & ~3;        // slab columns incl. <= 3 alignment columns (multiple of 4: bulk sizes stay 16-byte multiples)
     static constexpr int SA_ELEMS = SA_COLS * NAT;
-    static constexpr int SB_ELEMS = GR_TC * NBT;
-    static constexpr int SC_ELEMS = GR_TC * NCT;
-    static constexpr int SM_ELEMS = (SA_ELEMS + SB_ELEMS) > SC_ELEMS ? (SA_ELEMS + SB_ELEMS) : SC_ELEMS;
+    static constexpr int SB_ELEMS = TC * NBT;
+    static constexpr int SC_ELEMS = TC * NCT;
+    // small instantiations keep the C tile in its OWN region so the next tile's operands can be requested while the
+    // current tile is still being written out
+    static constexpr bool PIPE = (size_t)(SA_ELEMS + SB_ELEMS + SC_ELEMS) * sizeof(T) <= 76 * 1024;
+    static_assert(PIPE || SUB == 1, "aliased C tile needs a single sub-tile");
+    static constexpr int SM_ELEMS = PIPE ? (SA_ELEMS + SB_ELEMS + SC_ELEMS)
+                                         : ((SA_ELEMS + SB_ELEMS) > SC_ELEMS ? (SA_ELEMS + SB_ELEMS) : SC_ELEMS);
     static constexpr size_t SMEM_BYTES = (size_t)SM_ELEMS * sizeof(T) + 16;   // + the mbarrier
 };
 
-template <typename T, int NAT, int NBT>
+template <typename T, int NAT, int NBT, int PADODD>
 __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kernel(const GrArgs<T> a) {
     using G = GrGeom<T, NAT, NBT>;
     using V = typename vec2<T>::type;
-    constexpr int NCT = G::NCT, SA_COLS = G::SA_COLS;
+    constexpr int NCT = G::NCT, SA_COLS = G::SA_COLS, GR_TC = G::TC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     T *sA = reinterpret_cast<T *>(smem_raw + 16);
     T *sB = sA + G::SA_ELEMS;
-    T *sC = sA;                                                    // aliases sA/sB after the compute phase
+    T *sC = G::PIPE ? sB + G::SB_ELEMS : sA;                       // !PIPE: aliases sA/sB after the compute phase
 
     const int tid = threadIdx.x;
     const int NA = a.kla + a.kua + 1, NB = a.klb + a.kub + 1;
@@ -119,29 +129,42 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
     }
     __syncthreads();
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t j0 = tile * GR_TC;
-        const int cols = (int)((a.n - j0) < GR_TC ? (a.n - j0) : GR_TC);
-        const int64_t p0 = j0 - a.kub;                             // global column of slab column 0
+    // tile geometry / eligibility for the bulk-TMA path
+    auto tile_info = [&](int64_t tile, int64_t &j0, int &cols, bool &interior, bool &tma_in) {
+        j0 = tile * GR_TC;
+        cols = (int)((a.n - j0) < GR_TC ? (a.n - j0) : GR_TC);
+        const int64_t p0 = j0 - a.kub - a.pad;                     // global column of slab column 0
         // interior tile: every staged slot is inside the matrix, no index tests needed
-        const bool interior = cols == GR_TC && p0 - a.kua >= 0 && p0 + SA_COLS - 1 + a.kla < a.m && p0 + SA_COLS - 1 < a.k &&
-                              j0 + GR_TC - 1 + a.klb < a.k;
+        interior = cols == GR_TC && p0 - a.kua >= 0 && p0 + SA_COLS - 1 + a.kla < a.m && p0 + SA_COLS - 1 < a.k &&
+                   j0 + GR_TC - 1 + a.klb < a.k;
+        tma_in = interior && tight_in && ((p0 * NAT * (int64_t)sizeof(T)) & 15) == 0;
+    };
+    auto request = [&](int64_t j0) {                               // thread 0 only
+        gr_fence_proxy_async();                                    // earlier generic-proxy accesses of this smem are ordered first
+        mbar_expect_tx(bar, (uint32_t)((G::SA_ELEMS + G::SB_ELEMS) * sizeof(T)));
+        bulk_g2s(sA, a.A + (j0 - a.kub - a.pad) * a.lda, (uint32_t)(G::SA_ELEMS * sizeof(T)), bar);
+        bulk_g2s(sB, a.B + j0 * a.ldb, (uint32_t)(G::SB_ELEMS * sizeof(T)), bar);
+    };
+
+    bool requested = false;                                        // PIPE: this tile's operands were requested a tile ago
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t j0;
+        int cols;
+        bool interior, tma_in;
+        tile_info(tile, j0, cols, interior, tma_in);
+        const int64_t p0 = j0 - a.kub - a.pad;
         const T *Ag = a.A + p0 * a.lda;                            // may point before A for p0 < 0: never dereferenced there
         const T *Bg = a.B + j0 * a.ldb;
-        const bool tma_in = interior && tight_in && ((p0 * NAT * (int64_t)sizeof(T)) & 15) == 0;
 
-        // the previous tile's bulk store must have finished READING sC before anything overwrites it
-        if (tid == 0) gr_bulk_wait_read0();
-        __syncthreads();
+        if (!G::PIPE) {
+            // the previous tile's bulk store must have finished READING sC (= sA/sB) before anything overwrites it
+            if (tid == 0) gr_bulk_wait_read0();
+            __syncthreads();
+        }
 
         // ---- stage the A slab and the B tile, HBM layout kept ----
         if (tma_in) {
-            if (tid == 0) {
-                gr_fence_proxy_async();                            // earlier generic-proxy accesses of this smem are ordered first
-                mbar_expect_tx(bar, (uint32_t)((G::SA_ELEMS + G::SB_ELEMS) * sizeof(T)));
-                bulk_g2s(sA, Ag, (uint32_t)(G::SA_ELEMS * sizeof(T)), bar);
-                bulk_g2s(sB, Bg, (uint32_t)(G::SB_ELEMS * sizeof(T)), bar);
-            }
+            if (!requested && tid == 0) request(j0);
             mbar_wait(bar, parity);
             parity ^= 1u;
         } else {
@@ -168,75 +191,99 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
         }
+        requested = false;
 
-        // ---- compute: two columns, NCT accumulators each, everything in registers ----
-        T acc0[NCT], acc1[NCT];
+        const bool tma_out = tight_out && cols == GR_TC && j0 - a.kuc >= 0 && j0 + GR_TC - 1 + a.klc < a.m;
+        if (G::PIPE) {
+            // the previous tile's bulk store must have finished READING sC before it is rewritten
+            if (tid == 0) gr_bulk_wait_read0();
+            __syncthreads();
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < G::SUB; ++sub) {
+            // ---- compute: two columns, NCT accumulators each, everything in registers ----
+            T acc0[NCT], acc1[NCT];
 #pragma unroll
-        for (int t = 0; t < NCT; ++t) acc0[t] = acc1[t] = (T)0;
-        {
-            const T *pa = sA + 2 * tid * NAT;                      // column 2*tid + q starts q*NAT further on
-            const T *pb = sB + 2 * tid * NBT;                      // [B column 2*tid (NBT values) | B column 2*tid+1]
-            T b0n = (T)0, b1n = (T)0;                              // second halves of the B vectors, used at odd q
+            for (int t = 0; t < NCT; ++t) acc0[t] = acc1[t] = (T)0;
+            {
+                const int cp = 2 * (tid + sub * GR_NT);            // first column of this thread's pair
+                const T *pa = sA + (cp + a.pad) * NAT;             // slab column of (cp, s = 0); column cp + q starts q*NAT further on
+                const T *pb = sB + cp * NBT;                       // [B column cp (NBT values) | B column cp+1]
+                T b0n = (T)0, b1n = (T)0;                          // second halves of the B vectors, used at odd q
 #pragma unroll
-            for (int q = 0; q <= NBT; ++q) {
-                T av[NAT];
-                if ((q & 1) == 0) load_run<T, NAT, 0>(av, pa + q * NAT);   // index (2t+q)*NAT + r is even <=> q + r even
-                else load_run<T, NAT, 1>(av, pa + q * NAT);
-                T b0 = (T)0, b1 = (T)0;
-                if ((q & 1) == 0) {
-                    // elements q, q+1 of column 0 and NBT+q-1, NBT+q of the pair (NBT odd: both vectors are aligned)
-                    if (q + 1 < NBT) {
-                        const V v = *reinterpret_cast<const V *>(pb + q);
-                        b0 = v.x;
-                        b0n = v.y;
-                    } else if (q < NBT) b0 = pb[q];
+                for (int q = 0; q <= NBT; ++q) {
+                    T av[NAT];
+                    // index (cp+pad+q)*NAT + r is even <=> pad + q + r even
+                    if (((q + PADODD) & 1) == 0) load_run<T, NAT, 0>(av, pa + q * NAT);
+                    else load_run<T, NAT, 1>(av, pa + q * NAT);
+                    T b0 = (T)0, b1 = (T)0;
+                    if ((q & 1) == 0) {
+                        // elements q, q+1 of column 0 and NBT+q-1, NBT+q of the pair (NBT odd: both vectors are aligned)
+                        if (q + 1 < NBT) {
+                            const V v = *reinterpret_cast<const V *>(pb + q);
+                            b0 = v.x;
+                            b0n = v.y;
+                        } else if (q < NBT) b0 = pb[q];
+                        if (q >= 1) {
+                            const V w = *reinterpret_cast<const V *>(pb + NBT + q - 1);
+                            b1 = w.x;
+                            b1n = w.y;
+                        } else b1n = pb[NBT];
+                    } else {
+                        b0 = b0n;
+                        b1 = b1n;
+                    }
+                    if (q < NBT) {
+#pragma unroll
+                        for (int r = 0; r < NAT; ++r) acc0[r + q] = fma(av[r], b0, acc0[r + q]);
+                    }
                     if (q >= 1) {
-                        const V w = *reinterpret_cast<const V *>(pb + NBT + q - 1);
-                        b1 = w.x;
-                        b1n = w.y;
-                    } else b1n = pb[NBT];
-                } else {
-                    b0 = b0n;
-                    b1 = b1n;
-                }
-                if (q < NBT) {
 #pragma unroll
-                    for (int r = 0; r < NAT; ++r) acc0[r + q] = fma(av[r], b0, acc0[r + q]);
+                        for (int r = 0; r < NAT; ++r) acc1[r + q - 1] = fma(av[r], b1, acc1[r + q - 1]);
+                    }
                 }
-                if (q >= 1) {
+            }
+            if (!G::PIPE) __syncthreads();                         // all reads of sA / sB done: sC (aliased) may overwrite them
+
+            // ---- the C tile, HBM layout: [column cp (NCT values) | column cp+1], written as 2-element vectors ----
+            {
+                const T sc = tma_out ? a.alpha : (T)1;             // the bulk store cannot scale: do it here
+                T *pc = sC + 2 * (tid + sub * GR_NT) * NCT;
 #pragma unroll
-                    for (int r = 0; r < NAT; ++r) acc1[r + q - 1] = fma(av[r], b1, acc1[r + q - 1]);
+                for (int i = 0; i < NCT; ++i) {
+                    const int k0 = 2 * i, k1 = 2 * i + 1;
+                    const T lo = k0 < NCT ? acc0[k0 < NCT ? k0 : 0] : acc1[k0 >= NCT ? k0 - NCT : 0];
+                    const T hi = k1 < NCT ? acc0[k1 < NCT ? k1 : 0] : acc1[k1 >= NCT ? k1 - NCT : 0];
+                    V v;
+                    v.x = sc * lo;
+                    v.y = sc * hi;
+                    *reinterpret_cast<V *>(pc + 2 * i) = v;
                 }
             }
         }
-        __syncthreads();                                           // all reads of sA / sB done: sC may overwrite them
-
-        // ---- the C tile, HBM layout: [column 2*tid (NCT values) | column 2*tid+1], written as 2-element vectors ----
-        const bool tma_out = tight_out && cols == GR_TC && j0 - a.kuc >= 0 && j0 + GR_TC - 1 + a.klc < a.m;
-        {
-            const T sc = tma_out ? a.alpha : (T)1;                 // the bulk store cannot scale: do it here
-            T *pc = sC + 2 * tid * NCT;
-#pragma unroll
-            for (int i = 0; i < NCT; ++i) {
-                const int k0 = 2 * i, k1 = 2 * i + 1;
-                const T lo = k0 < NCT ? acc0[k0 < NCT ? k0 : 0] : acc1[k0 >= NCT ? k0 - NCT : 0];
-                const T hi = k1 < NCT ? acc0[k1 < NCT ? k1 : 0] : acc1[k1 >= NCT ? k1 - NCT : 0];
-                V v;
-                v.x = sc * lo;
-                v.y = sc * hi;
-                *reinterpret_cast<V *>(pc + 2 * i) = v;
+        if (tma_out) gr_fence_proxy_async();                       // generic-proxy writes of sC -> visible to the bulk store
+        __syncthreads();                                           // sC complete; every warp is done with sA / sB
+        if (G::PIPE) {
+            // request the next tile's operands now: they arrive while this tile drains
+            const int64_t nxt = tile + gridDim.x;
+            if (nxt < ntiles) {
+                int64_t nj0;
+                int ncols;
+                bool nint, ntma;
+                tile_info(nxt, nj0, ncols, nint, ntma);
+                if (ntma) {
+                    requested = true;
+                    if (tid == 0) request(nj0);
+                }
             }
         }
         T *Cg = a.C + j0 * a.ldc;
         if (tma_out) {
-            gr_fence_proxy_async();                                // generic-proxy writes -> visible to the bulk store
-            __syncthreads();
             if (tid == 0) {
                 gr_bulk_s2g(Cg, sC, (uint32_t)(G::SC_ELEMS * sizeof(T)));
                 gr_bulk_commit();
             }
         } else {
-            __syncthreads();
             const int NC = NA + NB - 1;
             const int total = cols * nbc;
             // flat element index e = c*nbc + row, advanced incrementally (no division in the loop)
@@ -266,16 +313,16 @@ int gr_launch(lbm_handle_t h, const GrArgs<T> &a) {
     static_assert((G::SA_ELEMS * sizeof(T)) % 16 == 0 && (G::SB_ELEMS * sizeof(T)) % 16 == 0 && (G::SC_ELEMS * sizeof(T)) % 16 == 0,
                   "bulk copy sizes must be multiples of 16 bytes");
     constexpr size_t smem = G::SMEM_BYTES;
-    auto kern = gbmm_reg_kernel<T, NAT, NBT>;
-    static int configured = 0;
-    if (!(configured & (1 << h->device))) {
+    auto kern = (a.pad & 1) ? gbmm_reg_kernel<T, NAT, NBT, 1> : gbmm_reg_kernel<T, NAT, NBT, 0>;
+    static int configured[2] = {0, 0};
+    if (!(configured[a.pad & 1] & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured |= (1 << h->device);
+        configured[a.pad & 1] |= (1 << h->device);
     }
     int per_sm = 1;
     LBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GR_NT, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t ntiles = (a.n + GR_TC - 1) / GR_TC;
+    const int64_t ntiles = (a.n + G::TC - 1) / G::TC;
     int64_t grid = (int64_t)h->sm_count * per_sm;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, GR_NT, smem, h->stream>>>(a);
@@ -308,6 +355,10 @@ int lbm_gbmm_reg(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64
     a.m = m; a.n = n; a.k = k;
     a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub; a.klc = (int)klc; a.kuc = (int)kuc;
     a.lda = lda; a.ldb = ldb; a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.A = A; a.B = B; a.C = C;
+    // tiles start at multiples of 256 columns, so (j0 - kub - pad) * NAT * sizeof(T) is a multiple of 16 for every tile
+    // once (kub + pad) is a multiple of 2 (f64) / 4 (f32): NAT is odd
+    const int al = 16 / (2 * (int)sizeof(T)) == 1 ? 2 : 4;
+    a.pad = (al - (int)(kub % al)) % al;
     if (NA <= 3) return gr_dispatch_b<T, 3>(h, a, (int)NB);
     if (NA <= 5) return gr_dispatch_b<T, 5>(h, a, (int)NB);
     if (NA <= 9) return gr_dispatch_b<T, 9>(h, a, (int)NB);
