@@ -105,6 +105,17 @@ def main():
         h.set_tuning(tri_force_shuffle=0)
         del d, e, e2, x, y
         torch.cuda.empty_cache()
+        # mat-mat: 8 right-hand sides share one read of the diagonals
+        n2, nrhs = 1 << (24 - sh), 8
+        d, e, e2 = vec(n2, 1), vec(n2 - 1, 2), vec(n2 - 1, 3)
+        X = torch.empty((nrhs, n2), dtype=torch.float64, device="cuda")
+        L.fill_uniform(X, 9)
+        Y = torch.empty_like(X)
+        for nm, A, arr in (("SymTridiagonal", L.SymTridiagonal(d, e), 2), ("Tridiagonal", L.Tridiagonal(e, d, e2), 3),
+                           ("Bidiagonal U", L.Bidiagonal(d, e, "U"), 2)):
+            emit(f"C2 {nm} * dense f64 n=2^{24 - sh} nrhs={nrhs}", timeit(lambda: L.mul_(Y.t(), A, X.t())), 8 * n2 * (arr + 2 * nrhs))
+        del d, e, e2, X, Y
+        torch.cuda.empty_cache()
 
     if "C3" in only:
         g = 8192 >> sh

@@ -78,6 +78,18 @@ elif which == "SP":
     for _ in range(2):
         R = T1 + T2
         P = T1 @ T2
+elif which == "MM1":
+    n, nrhs = 1 << 24, 8
+    A = L.brand(n, n, 1, 1, seed=1)
+    X = torch.empty((nrhs, n), dtype=torch.float64, device="cuda")
+    L.fill_uniform(X, 9)
+    Y = torch.empty_like(X)
+    d = torch.empty(n, dtype=torch.float64, device="cuda"); L.fill_uniform(d, 3)
+    e = torch.empty(n - 1, dtype=torch.float64, device="cuda"); L.fill_uniform(e, 4)
+    S = L.SymTridiagonal(d, e)
+    for _ in range(2):
+        L.mul_(Y.t(), A, X.t())
+        L.mul_(Y.t(), S, X.t())
 elif which == "MM":
     n, nrhs = 1 << 24, 8
     A = L.brand(n, n, 8, 8, seed=1)

@@ -459,9 +459,9 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_multi_kernel(const GbmvMultiArgs
         int64_t o0, o1, c0, c1, x0, x1;
         ranges(t, o0, o1, c0, c1, x0, x1);
         const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
-        const int64_t cntA = c1 * a.lda - e0a;
+        const int64_t cntA = stage_round<T>(c1 * a.lda - e0a, a.n * a.lda - e0a);
         const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
-        const int64_t cntx = x1 - x0a;
+        const int64_t cntx = stage_round<T>(x1 - x0a, nin - x0a);
         T *sA = sbase + (int64_t)s * stage_elems;
         T *sx = sA + a.sA_elems;
         mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + R * stage_bytes_bulk<T>(cntx));
@@ -582,11 +582,12 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv2_tile_kernel(const Gbmv2Args<T> 
         }
         cols(o0, o1, klm, kum, x0, x1);
         const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
-        bytes += stage_bytes_bulk<T>(x1 - x0a);
+        const int64_t cntx = x1 - x0a;
+        bytes += stage_bytes_bulk<T>(cntx);
         mbar_add_tx(&bars[s], bytes);
         stage_issue<T>(dst, a.A[0] + e0[0], cnt[0], &bars[s]);
         stage_issue<T>(dst + a.sA_elems[0], a.A[1] + e0[1], cnt[1], &bars[s]);
-        stage_issue<T>(dst + a.sA_elems[0] + a.sA_elems[1], a.x + x0a, x1 - x0a, &bars[s]);
+        stage_issue<T>(dst + a.sA_elems[0] + a.sA_elems[1], a.x + x0a, cntx, &bars[s]);
         mbar_arrive(&bars[s]);
     };
     if (tid == 0) {
@@ -927,8 +928,8 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
             a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda; a.nout = nout; a.alpha = alpha; a.beta = beta;
             a.A = A; a.X = X + c * ldx; a.Y = Y + c * ldy; a.ldx = ldx; a.ldy = ldy;
             auto stage_elems = [&](int64_t tl, int64_t &sa, int64_t &sx) {
-                sa = round_up((tl + kl + ku) * lda + EPV, EPV);
-                sx = round_up(tl + kl + ku + EPV, EPV);
+                sa = round_up((tl + kl + ku) * lda + 2 * EPV, EPV);   // + alignment offset + stage_round slack
+                sx = round_up(tl + kl + ku + 2 * EPV, EPV);
             };
             int64_t sa, sx, tile = GBMV_NT;
             for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {

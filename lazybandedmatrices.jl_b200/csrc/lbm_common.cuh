@@ -192,6 +192,18 @@ __device__ __forceinline__ uint32_t stage_bytes_bulk(int64_t count) {
     constexpr int EPV = 16 / (int)sizeof(T);
     return (uint32_t)((count / EPV) * EPV * (int64_t)sizeof(T));
 }
+// Round a copy length up to a whole number of 16-byte vectors when the source array extends that far (`avail` =
+// elements readable from src): the whole range then goes through the bulk copy and thread 0 never executes the scalar
+// tail, whose dependent global load (~1 us) would sit on the critical path of every tile.  The extra elements land in
+// the slack the stage buffer has and are never read.  Used by the multi-RHS kernel, where R+1 serialised tails per tile
+// were the bottleneck (3.8 -> 5.5 TB/s at l=u=1, 8 right-hand sides); measured A/B on the single-RHS, fused-sum and
+// tridiagonal ring kernels it is 5-8 % SLOWER than the tail (one tail per tile hides behind the ring depth), so they keep it.
+template <typename T>
+__device__ __forceinline__ int64_t stage_round(int64_t count, int64_t avail) {
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int64_t r = (count + EPV - 1) / EPV * EPV;
+    return r <= avail ? r : count;
+}
 template <typename T>
 __device__ __forceinline__ void stage_issue(T *dst, const T *src, int64_t count, uint64_t *bar) {
     constexpr int EPV = 16 / (int)sizeof(T);

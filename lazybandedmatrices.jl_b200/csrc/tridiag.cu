@@ -12,6 +12,8 @@
 //    global load.  A SymTridiagonal stages ev once and uses it for both off-diagonals.
 //  * tridiag_mv_kernel (mat-mat): 128-bit coalesced loads with the shifted operands taken from
 //    the neighbouring lane by warp shuffle; the diagonals stay in registers across the columns.
+#include <type_traits>
+
 #include "lbm_common.cuh"
 
 namespace {
@@ -38,7 +40,7 @@ template <> struct VecOps<float> {
 
 // HAS_DL / HAS_DU: off-diagonal present.  SYM: dl and du are the same array (read once).
 template <typename T, bool HAS_DL, bool HAS_DU, bool SYM>
-__global__ void __launch_bounds__(256) tridiag_mv_kernel(int64_t n, const T *__restrict__ dl, const T *__restrict__ d,
+__global__ void __launch_bounds__(256, 3) tridiag_mv_kernel(int64_t n, const T *__restrict__ dl, const T *__restrict__ d,
                                                         const T *__restrict__ du, T alpha, const T *__restrict__ X,
                                                         int64_t ldx, int64_t nrhs, T beta, T *__restrict__ Y,
                                                         int64_t ldy) {
@@ -72,41 +74,62 @@ __global__ void __launch_bounds__(256) tridiag_mv_kernel(int64_t n, const T *__r
                 dl_prev = __shfl_up_sync(0xffffffffu, VO::get(dlv, VN - 1), 1);
                 if (lane == 0) dl_prev = i0 > 0 ? dl[i0 - 1] : (T)0;
             }
-            for (int64_t c = 0; c < nrhs; ++c) {
-                const T *x = X + c * ldx;
-                T *y = Y + c * ldy;
-                const V xv = ld_stream(reinterpret_cast<const V *>(x + i0));
-                T x_prev = 0, x_next = 0;
-                if (HAS_DL) {
-                    x_prev = __shfl_up_sync(0xffffffffu, VO::get(xv, VN - 1), 1);
-                    if (lane == 0) x_prev = i0 > 0 ? x[i0 - 1] : (T)0;
-                }
-                if (HAS_DU) {
-                    x_next = __shfl_down_sync(0xffffffffu, VO::get(xv, 0), 1);
-                    if (lane == 31) x_next = x[i0 + VN];  // in bounds: i0+VN <= n-1 by vec_ok
-                }
-                V out;
+            // NB right-hand sides per step: all their loads (vector + the two lane-edge scalars) are issued before the
+            // first shuffle, so a thread keeps NB x 16 bytes in flight instead of one load per loop trip
+            auto cols = [&](auto nbtag, auto hbtag, int64_t c0) {
+                constexpr int NB = decltype(nbtag)::value;
+                constexpr bool HB = decltype(hbtag)::value;   // beta != 0: y is read as well
+                V xv[NB], yo[HB ? NB : 1];
+                T xe_prev[NB], xe_next[NB];
 #pragma unroll
-                for (int k = 0; k < VN; ++k) {
-                    T acc = 0;
+                for (int b = 0; b < NB; ++b) {
+                    const T *x = X + (c0 + b) * ldx;
+                    xv[b] = ld_stream(reinterpret_cast<const V *>(x + i0));
+                    xe_prev[b] = (HAS_DL && lane == 0 && i0 > 0) ? x[i0 - 1] : (T)0;
+                    xe_next[b] = (HAS_DU && lane == 31) ? x[i0 + VN] : (T)0;   // in bounds: i0+VN <= n-1 by vec_ok
+                    if (HB) yo[HB ? b : 0] = *reinterpret_cast<const V *>(Y + (c0 + b) * ldy + i0);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    T x_prev = 0, x_next = 0;
                     if (HAS_DL) {
-                        const T a_lo = k == 0 ? dl_prev : VO::get(dlv, k - 1);
-                        const T x_lo = k == 0 ? x_prev : VO::get(xv, k - 1);
-                        acc = a_lo * x_lo;
+                        x_prev = __shfl_up_sync(0xffffffffu, VO::get(xv[b], VN - 1), 1);
+                        if (lane == 0) x_prev = xe_prev[b];
                     }
-                    acc = fma(VO::get(dv, k), VO::get(xv, k), acc);
                     if (HAS_DU) {
-                        const T x_hi = k == VN - 1 ? x_next : VO::get(xv, k + 1);
-                        acc = fma(VO::get(duv, k), x_hi, acc);
+                        x_next = __shfl_down_sync(0xffffffffu, VO::get(xv[b], 0), 1);
+                        if (lane == 31) x_next = xe_next[b];
                     }
-                    VO::set(out, k, alpha * acc);
-                }
-                if (beta != (T)0) {
-                    const V yo = *reinterpret_cast<const V *>(y + i0);
+                    V out;
 #pragma unroll
-                    for (int k = 0; k < VN; ++k) VO::set(out, k, fma(beta, VO::get(yo, k), VO::get(out, k)));
+                    for (int k = 0; k < VN; ++k) {
+                        T acc = 0;
+                        if (HAS_DL) {
+                            const T a_lo = k == 0 ? dl_prev : VO::get(dlv, k - 1);
+                            const T x_lo = k == 0 ? x_prev : VO::get(xv[b], k - 1);
+                            acc = a_lo * x_lo;
+                        }
+                        acc = fma(VO::get(dv, k), VO::get(xv[b], k), acc);
+                        if (HAS_DU) {
+                            const T x_hi = k == VN - 1 ? x_next : VO::get(xv[b], k + 1);
+                            acc = fma(VO::get(duv, k), x_hi, acc);
+                        }
+                        VO::set(out, k, alpha * acc);
+                    }
+                    if (HB) {
+#pragma unroll
+                        for (int k = 0; k < VN; ++k) VO::set(out, k, fma(beta, VO::get(yo[HB ? b : 0], k), VO::get(out, k)));
+                    }
+                    st_stream(reinterpret_cast<V *>(Y + (c0 + b) * ldy + i0), out);
                 }
-                st_stream(reinterpret_cast<V *>(y + i0), out);
+            };
+            int64_t c = 0;
+            if (beta == (T)0) {
+                for (; c + 4 <= nrhs; c += 4) cols(std::integral_constant<int, 4>{}, std::false_type{}, c);
+                for (; c < nrhs; ++c) cols(std::integral_constant<int, 1>{}, std::false_type{}, c);
+            } else {
+                for (; c + 4 <= nrhs; c += 4) cols(std::integral_constant<int, 4>{}, std::true_type{}, c);
+                for (; c < nrhs; ++c) cols(std::integral_constant<int, 1>{}, std::true_type{}, c);
             }
         } else {
             // tail warp: scalar, fully bounds-checked

@@ -14,7 +14,8 @@ import threading
 from .errors import LbmArgumentError, LbmCudaError, LbmLibraryMissing
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblbm_b200.so")
+# LBM_B200_LIB: same override the Julia shim honours (benchmark A/B runs against another build of the library)
+SO_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "lbm_b200.h"))
 
 _lib = None
