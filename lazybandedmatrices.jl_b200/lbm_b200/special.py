@@ -9,7 +9,8 @@ result diagonals.  Like the reference, a result diagonal that is just one operan
 (`Bidiagonal(newdv, A.ev, A.uplo)`, special.jl:85-88) re-uses that operand's array.
 
 Products of two structured operands (test/test_special.jl:154-160, test/test_bidiag.jl:262-267) go
-through `BandedMatrix(A)` (lbm_?tridiag_pack) and lbm_?gbmm, giving the banded result the reference's
+through lbm_?tridiag_mm (the product band written in one pass; a BandedMatrix operand goes through `BandedMatrix(A)` =
+lbm_?tridiag_pack and lbm_?gbmm), giving the banded result the reference's
 ArrayLayouts route produces (bandwidths = sums).
 """
 from __future__ import annotations
