@@ -21,6 +21,10 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
 
 
 def main():
+    only = None
+    if "--only" in sys.argv:
+        only = sys.argv[sys.argv.index("--only") + 1].split(",")
+    want = lambda k: only is None or k in only  # noqa: E731
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -74,9 +78,24 @@ def main():
             L.fill_uniform(t, seed, offset=off)
         return t
 
+    # ---- GM: narrow banded x banded materialise n = 2^26, column-partitioned (static halo of A, no communication) ----
+    for l in ((1, 8) if want("GM") else ()):
+        n = 1 << 26
+        q = GbmmColumnShard.plan(n, l, l, l, l, rank, world)
+        nb = 2 * l + 1
+        A_slab = torch.empty((q.pb - q.pa, nb), dtype=torch.float64, device=dev)
+        L.fill_uniform(A_slab, 1, offset=nb * q.pa)
+        B_slab = torch.empty((q.c1 - q.c0, nb), dtype=torch.float64, device=dev)
+        L.fill_uniform(B_slab, 2, offset=nb * q.c0)
+        C_slab = torch.empty((q.c1 - q.c0, 4 * l + 1), dtype=torch.float64, device=dev)
+        emit(f"GM gbmm f64 n=2^26 ({l},{l})^2 -> ({2 * l},{2 * l}) register kernel", timeit(lambda: q.local_gbmm(A_slab, B_slab, C_slab), 5, 2),
+             8 * n * (2 * nb + 4 * l + 1), 2 * n * nb * nb)
+        del A_slab, B_slab, C_slab
+        torch.cuda.empty_cache()
+
     # ---- C2: SymTridiagonal / Bidiagonal mat-vec n = 2^28, row-sharded with ghost exchange ----
     n = 1 << 28
-    for nm, has_l, has_u, arrays in (("SymTridiagonal", True, True, 4), ("Bidiagonal U", False, True, 4)):
+    for nm, has_l, has_u, arrays in ((("SymTridiagonal", True, True, 4), ("Bidiagonal U", False, True, 4)) if want("C2") else ()):
         c0, c1 = ShardedTridiagonal.slices(n, int(has_l), int(has_u), rank, world)
         d = vec(c1 - c0, 1, c0)
         e = vec(c1 - c0 - 1, 2, c0)
@@ -89,6 +108,10 @@ def main():
         del d, e, sh, xb, y
         torch.cuda.empty_cache()
 
+    if world > 1 and only is not None and not (want("C3") or want("C4") or want("C5") or want("M")):
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # ---- C3: 2-D Laplacian on 8192^2, partitioned by grid columns ----
     g = 8192
     hh = 1.0 / g
