@@ -292,6 +292,9 @@ def main():
                 h.set_tuning(gbmm_variant=20, gbmm_tile=tpc)
                 emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA variant 20 (warp-specialised, 3-stage, 4 CTAs/SM), {tpc} row tiles per CTA",
                      timeit(lambda: L.gbmm(A, B, out=Cm), 2, 1), byts, flops)
+            for code, nm in ((205, "32 ns poll back-off"), (305, "128 ns poll back-off"), (5, "default")):
+                h.set_tuning(gbmm_variant=0, gbmm_tile=code)
+                emit(f"C4 gbmm f64 n=2^{20 - sh} (128,128)^2 DMMA default kernel, {nm}", timeit(lambda: L.gbmm(A, B, out=Cm), 3, 1), byts, flops)
             h.set_tuning(gbmm_variant=0, gbmm_tile=0)
 
 

@@ -60,6 +60,53 @@ __global__ void __launch_bounds__(128) tile_loop(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Does a DMMA in flight block the sub-core's issue port for OTHER warps?  CTA of 8 warps: warps 0-3 (one per sub-core)
+// run 16 independent DMMAs per iteration, warps 4-7 (the same four sub-cores) run NALU independent integer adds per
+// iteration.  If the two overlap, time = max(DMMA time, ALU time); if every DMMA holds the issue port, time = sum.
+template <int NALU>
+__global__ void __launch_bounds__(256) issue_contention(double *out, int iters, double a0, double b0) {
+    const int warp = threadIdx.x >> 5;
+    if (warp < 4) {
+        double c[16][2];
+        for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = threadIdx.x * 1e-9;
+        double a = a0 + threadIdx.x * 1e-12, b = b0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+        }
+        double s = 0;
+        for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else {
+        unsigned r[8];
+        for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < NALU; ++i) asm volatile("add.u32 %0, %0, %1;" : "+r"(r[i & 7]) : "r"(it));
+        }
+        unsigned s = 0;
+        for (int i = 0; i < 8; ++i) s += r[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = (double)s;
+    }
+}
+
+template <int NALU>
+void run_contention(int ctas_per_sm) {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    double *out; cudaMalloc(&out, sizeof(double) * sms * ctas_per_sm * 256);
+    const int iters = 20000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    issue_contention<NALU><<<sms * ctas_per_sm, 256>>>(out, 100, 1.0, 1e-9);
+    cudaEventRecord(e0);
+    issue_contention<NALU><<<sms * ctas_per_sm, 256>>>(out, iters, 1.0, 1e-9);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = (double)sms * ctas_per_sm * 4 * iters * 16 * 512.0;
+    printf("{\"test\": \"issue contention: 4 DMMA warps + 4 ALU warps, %d int adds per 16 DMMAs\", \"ctas_per_sm\": %d, \"ms\": %.3f, "
+           "\"dmma_tflops\": %.2f, \"clk_per_iter_at_1.92GHz\": %.0f}\n", NALU, ctas_per_sm, ms, fl / ms / 1e9, ms * 1e-3 * 1.92e9 / iters / ctas_per_sm);
+    cudaFree(out);
+}
+
 template <int XB, int YB>
 void run_tile(const char *name, int ctas_per_sm) {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -113,6 +160,16 @@ void run_tile_long(const char *name, int ctas_per_sm, int launches) {
 }
 
 int main(int argc, char **argv) {
+    if (argc > 1 && argv[1][0] == 'c') {   // "contention": do other warps' instructions steal DMMA issue time?
+        for (int c : {1, 2}) {
+            run_contention<0>(c);
+            run_contention<64>(c);
+            run_contention<128>(c);
+            run_contention<256>(c);
+            run_contention<512>(c);
+        }
+        return 0;
+    }
     if (argc > 1) {   // "long": sustained load (~2 s) vs a single launch
         run_tile_long<4, 4>("tile loop 32x32, 4 CTAs/SM", 4, 200);
         return 0;

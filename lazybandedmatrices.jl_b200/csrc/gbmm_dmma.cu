@@ -596,10 +596,14 @@ __device__ __forceinline__ void mbar_arrive_(uint64_t *bar) {
 __device__ __forceinline__ void mbar_cp_async_arrive_(uint64_t *bar) {   // arrives once this thread's prior cp.asyncs landed
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity, unsigned sleep_ns = 0) {
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t done = 0, spins = 0;
     while (!done) {
+        // experiment (gbmm_tile 2xx / 3xx): back off between polls so a waiting warp does not take issue slots from the
+        // DMMA-issuing warps of its sub-core (benchmarks/micro/fp64_pipes.cu "contention": a DMMA holds the issue port
+        // for ~5 of its 16 cycles, other warps' instructions fit in the remaining ~11)
+        if (sleep_ns && spins) __nanosleep(sleep_ns);
         if (++spins > (1u << 22)) __trap();   // a lost arrival must surface as a CUDA error, not a hang
         // suspend-time hint: the warp sleeps in hardware (up to ~4 us) instead of burning issue slots that the
         // DMMA-issuing warps of the same sub-core need (the plain spin loop was 31 % of all executed instructions)
@@ -621,6 +625,7 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
+    const unsigned sleep_ns = (a.flags & 8) ? 32u : ((a.flags & 16) ? 128u : 0u);
     // a CTA owns `tpc` consecutive row tiles of one 64-column block; the ring runs straight across tile boundaries
     // (the producer is already fetching the next tile while the consumers finish and store the current one)
     const int tpc = a.tpc;
@@ -673,7 +678,7 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
             const double *b_src = a.B + (a.kub + plo + 2 * (lane & 7)) + (a.ldb - 1) * (j0 + (lane >> 3));
             for (int it = 0; it < nch; ++it, ++gi) {
                 const int s = gi % NSTAGE;
-                if (gi >= NSTAGE) mbar_wait_(&bar_empty[s], (uint32_t)((gi / NSTAGE - 1) & 1));
+                if (gi >= NSTAGE) mbar_wait_(&bar_empty[s], (uint32_t)((gi / NSTAGE - 1) & 1), sleep_ns);
                 double *sA = smem + s * STAGE_DBL;
                 double *sB = sA + KC * PA;
                 const uint32_t dA = (uint32_t)__cvta_generic_to_shared(sA + 2 * lane);
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
             }
             // every warp observes every phase of full[s] in order (a parity wait only tells adjacent phases apart, so
             // a warp must not skip one), even when the chunk holds nothing for it
-            mbar_wait_(&bar_full[s], (uint32_t)((gi / NSTAGE) & 1));
+            mbar_wait_(&bar_full[s], (uint32_t)((gi / NSTAGE) & 1), sleep_ns);
             if (mA != 0 && mB != 0) {
                 const double *sA = smem + s * STAGE_DBL;
                 const double *sB = sA + KC * PA;
@@ -888,7 +893,9 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         // gbmm_tile doubles as "row tiles per CTA" here; default: 5 for the default variant, 1 for the explicit ones
         a.tpc = h->tune.gbmm_tile > 0 ? (int)(h->tune.gbmm_tile % 100) : (variant == 0 ? 5 : 1);
         if (a.tpc < 1) a.tpc = 1;
-        if (h->tune.gbmm_tile >= 100) a.flags |= 4;   // (+100: double-copy traffic experiment, results unchanged)
+        if (h->tune.gbmm_tile / 100 == 1) a.flags |= 4;   // (+100: double-copy traffic experiment, results unchanged)
+        if (h->tune.gbmm_tile / 100 == 2) a.flags |= 8;   // (+200: poll the ring barriers with a 32 ns back-off)
+        if (h->tune.gbmm_tile / 100 == 3) a.flags |= 16;  // (+300: 128 ns back-off)
         const int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
         const int64_t gws = total_ws < 1048576 ? total_ws : 1048576;
         dim3 grid_ws((unsigned)gws, (unsigned)((total_ws + gws - 1) / gws));
