@@ -617,8 +617,11 @@ __device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity, unsig
     }
 }
 
-template <int NSTAGE, int MINB>
-__global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArgs a) {
+template <int NSTAGE, int MINB, int NCONS>
+__global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(const DmmaArgs a) {
+    // NCONS consumer warps: 8 -> 32x16 blocks (8 accumulators per warp), 4 -> 32x32 blocks (16 accumulators, 8 fragment
+    // loads per 16 DMMAs instead of 6 per 8, half the per-chunk classification / barrier instructions per DMMA)
+    constexpr int WN = 128 / NCONS, YB = WN / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
     __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE];
@@ -658,14 +661,14 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init_(&bar_full[s], 32);             // the 32 producer lanes' cp.async arrivals
-            mbar_init_(&bar_empty[s], WS_CONSUMERS);  // one arrival per consumer warp
+            mbar_init_(&bar_empty[s], NCONS);  // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     int gi = 0;   // chunks issued / consumed so far by this CTA (ring position; identical in every warp)
-    if (warp == WS_CONSUMERS) {
+    if (warp == NCONS) {
         // ---------------- producer: raw dense windows, unpredicated 16-byte copies ----------------
         // A window 64 rows x 16 p: lane owns the row pair 2*lane, one copy per p.  B window 16 p x 64 j: lane owns
         // the p pair 2*(lane & 7) of columns (lane >> 3) + 4q.
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
     }
 
     // ---------------- consumers: warp (wa, wb) owns rows 32*wa.., columns 16*wb.. -------------------
-    const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+    const int wi = (warp & 1) * 32, wj = (warp >> 1) * WN;
     const int fr = lane >> 2, fc = lane & 3;
     const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
     const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + 8*x
@@ -717,23 +720,23 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
         int nch;
         if (!tile_params(t, i0, plo, nch)) continue;
         const int ia0 = (int)(i0 + wi - plo), jb0 = (int)(j0 + wj - plo);
-        double acc[4][2][2];
+        double acc[4][YB][2];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+            for (int y = 0; y < YB; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
 
         for (int it = 0; it < nch; ++it, ++gi) {
             const int s = gi % NSTAGE;
             const int pr = it * KC;
             // classify the chunk: a warp with nothing in band here only has to release the stage
             const bool full = (ia0 + 31 - pr <= kla) && (ia0 - (pr + KC - 1) >= -kua) && ((pr + KC - 1) - jb0 <= klb) &&
-                              (pr - (jb0 + 15) >= -kub);
+                              (pr - (jb0 + WN - 1) >= -kub);
             unsigned mA = 0xffffu, mB = 0xffffu;
             if (!full) {
                 const int da = ia0 - pr, db = jb0 - pr;
                 mA = band_mask(-kua - 7 - da, kla + 3 - da);
-                mB = band_mask(-klb - 7 - db, kub + 3 - db) & 0x3333u;   // two column blocks per warp
+                mB = band_mask(-klb - 7 - db, kub + 3 - db) & (YB == 2 ? 0x3333u : 0xffffu);   // YB column blocks per warp
             }
             // every warp observes every phase of full[s] in order (a parity wait only tells adjacent phases apart, so
             // a warp must not skip one), even when the chunk holds nothing for it
@@ -744,15 +747,15 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
                 if (full) {
 #pragma unroll
                     for (int ks = 0; ks < KC / 4; ++ks) {
-                        double ga[4], gb[2];
+                        double ga[4], gb[YB];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) ga[x] = sA[fa_off + 4 * ks * PA + 8 * x];
 #pragma unroll
-                        for (int y = 0; y < 2; ++y) gb[y] = sB[fb_off + 8 * y * PB + 4 * ks];
+                        for (int y = 0; y < YB; ++y) gb[y] = sB[fb_off + 8 * y * PB + 4 * ks];
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
+                            for (int y = 0; y < YB; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
                     }
                 } else {
                     const int da = ia0 - pr, db = jb0 - pr;
@@ -760,16 +763,16 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
                     const int vb = -db + fc - fr + kub, wb = klb + kub;
 #pragma unroll
                     for (int ks = 0; ks < KC / 4; ++ks) {
-                        const unsigned ma = (mA >> (4 * ks)) & 15u, mb = (mB >> (4 * ks)) & 3u;
+                        const unsigned ma = (mA >> (4 * ks)) & 15u, mb = (mB >> (4 * ks)) & (YB == 2 ? 3u : 15u);
                         if (ma == 0 || mb == 0) continue;
-                        double ga[4], gb[2];
+                        double ga[4], gb[YB];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
                             const double ra = sA[fa_off + 4 * ks * PA + 8 * x];
                             ga[x] = (unsigned)(va + 8 * x - 4 * ks) <= (unsigned)wa ? ra : 0.0;
                         }
 #pragma unroll
-                        for (int y = 0; y < 2; ++y) {
+                        for (int y = 0; y < YB; ++y) {
                             const double rb = sB[fb_off + 8 * y * PB + 4 * ks];
                             gb[y] = (unsigned)(vb - 8 * y + 4 * ks) <= (unsigned)wb ? rb : 0.0;
                         }
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
                         for (int x = 0; x < 4; ++x) {
                             if (!(ma >> x & 1u)) continue;
 #pragma unroll
-                            for (int y = 0; y < 2; ++y)
+                            for (int y = 0; y < YB; ++y)
                                 if (mb >> y & 1u) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
                         }
                     }
@@ -791,7 +794,7 @@ __global__ void __launch_bounds__(WS_NT, MINB) gbmm_dmma_ws_kernel(const DmmaArg
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int y = 0; y < 2; ++y)
+            for (int y = 0; y < YB; ++y)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int64_t i = i0 + wi + 8 * x + fr;
@@ -858,9 +861,9 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     const int64_t total = gx * gy;
     const int64_t gxx = total < 1048576 ? total : 1048576;
     dim3 grid((unsigned)gxx, (unsigned)((total + gxx - 1) / gxx));
-    // gbmm_variant: 0 = default = warp-specialised kernel (producer warp + 8 consumer warps, 3-stage ring, 4 CTAs/SM,
-    // 5 row tiles per CTA) for the interior tiles + the corner instantiation of the plain kernel; 20-23: the same
-    // with other ring depths / occupancies.  Plain kernel (lean interior + corner instantiations): 3: 2-stage / 5 CTAs,
+    // gbmm_variant: 0 = default = warp-specialised kernel (producer warp + 4 consumer warps of 32x32, 4-stage ring, 3 CTAs/SM,
+    // one CTA per 64-column block walking all its row tiles) for the interior tiles + the corner instantiation of the plain
+    // kernel; 20-23: 8 consumer warps of 32x16 with other ring depths / occupancies; 24-28: 4 consumer warps; 29: 8 / 5-stage.  Plain kernel (lean interior + corner instantiations): 3: 2-stage / 5 CTAs,
     // 1: 2-stage / 4 CTAs, 2: 3-stage / 3 CTAs, 4/5: column-persistent kernels, 6: 3-stage / 4 CTAs,
     // 7: 4-stage / 3 CTAs, 8-10: 6 + rotated quadrants / interleaved p-halves, 11: 6 as one launch, 12: 2-stage / 6 CTAs
     // (measured in profiles/configs_r01_*.jsonl; everything lands between 17 and 21 TFLOP/s)
@@ -886,12 +889,13 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
             gbmm_dmma_kernel<NS, MB, 2><<<grid, NT, smem, h->stream>>>(a);                                    \
         }                                                                                                     \
     } while (0)
-    if (variant == 0 || (variant >= 20 && variant <= 23)) {
+    if (variant == 0 || (variant >= 20 && variant <= 29)) {
         // warp-specialised interior kernel + the corner instantiation of the plain kernel
         // 20: 3-stage / 4 CTAs, 21: 3-stage / 3 CTAs, 22: 4-stage / 3 CTAs, 23: 2-stage / 4 CTAs
-        static int cfg_ws[4] = {0, 0, 0, 0};
+        static int cfg_ws[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         // gbmm_tile doubles as "row tiles per CTA" here; default: 5 for the default variant, 1 for the explicit ones
-        a.tpc = h->tune.gbmm_tile > 0 ? (int)(h->tune.gbmm_tile % 100) : (variant == 0 ? 5 : 1);
+        // default: one CTA walks ALL row tiles of its 64-column block (tpc = gy)
+        a.tpc = h->tune.gbmm_tile > 0 ? (int)(h->tune.gbmm_tile % 100) : (variant == 0 ? (int)(gy < 64 ? gy : 64) : 1);
         if (a.tpc < 1) a.tpc = 1;
         if (h->tune.gbmm_tile / 100 == 1) a.flags |= 4;   // (+100: double-copy traffic experiment, results unchanged)
         if (h->tune.gbmm_tile / 100 == 2) a.flags |= 8;   // (+200: poll the ring barriers with a 32 ns back-off)
@@ -899,19 +903,26 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         const int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
         const int64_t gws = total_ws < 1048576 ? total_ws : 1048576;
         dim3 grid_ws((unsigned)gws, (unsigned)((total_ws + gws - 1) / gws));
-#define LBM_WS_LAUNCH(IDX, NS, MB)                                                                                         \
+#define LBM_WS_LAUNCH(IDX, NS, MB, NC)                                                                                     \
     do {                                                                                                                   \
         const size_t smem = (size_t)(NS) * STAGE_DBL * sizeof(double);                                                     \
         if (!(cfg_ws[IDX] & (1 << h->device))) {                                                                           \
-            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_ws_kernel<NS, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_ws_kernel<NS, MB, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             cfg_ws[IDX] |= (1 << h->device);                                                                               \
         }                                                                                                                  \
-        gbmm_dmma_ws_kernel<NS, MB><<<grid_ws, WS_NT, smem, h->stream>>>(a);                                               \
+        gbmm_dmma_ws_kernel<NS, MB, NC><<<grid_ws, 32 * (NC + 1), smem, h->stream>>>(a);                                   \
     } while (0)
-        if (variant == 20 || variant == 0) LBM_WS_LAUNCH(0, 3, 4);
-        else if (variant == 21) LBM_WS_LAUNCH(1, 3, 3);
-        else if (variant == 22) LBM_WS_LAUNCH(2, 4, 3);
-        else LBM_WS_LAUNCH(3, 2, 4);
+        if (variant == 0) LBM_WS_LAUNCH(6, 4, 3, 4);         // default = variant 26 (measured 21.6 vs 19.9-21.2 for the others in one process)
+        else if (variant == 20) LBM_WS_LAUNCH(0, 3, 4, 8);
+        else if (variant == 21) LBM_WS_LAUNCH(1, 3, 3, 8);
+        else if (variant == 22) LBM_WS_LAUNCH(2, 4, 3, 8);
+        else if (variant == 24) LBM_WS_LAUNCH(4, 3, 4, 4);   // 4 consumer warps of 32x32
+        else if (variant == 25) LBM_WS_LAUNCH(5, 3, 3, 4);
+        else if (variant == 26) LBM_WS_LAUNCH(6, 4, 3, 4);
+        else if (variant == 27) LBM_WS_LAUNCH(7, 5, 2, 4);
+        else if (variant == 28) LBM_WS_LAUNCH(8, 6, 2, 4);
+        else if (variant == 29) LBM_WS_LAUNCH(9, 5, 2, 8);
+        else LBM_WS_LAUNCH(3, 2, 4, 8);
 #undef LBM_WS_LAUNCH
         LBM_LAUNCH_CHECK(h, "gbmm_dmma_ws_kernel");
         {

@@ -60,7 +60,7 @@ def test_gbmm_dmma_tensor_path(L, oracle):
         B_np, B = _band(L, oracle, k, n, klb, kub, 32 + s, torch.float64)
         want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
         tol = tol_rows(np.float64, min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
-        for f, variant in ((force, 0), (force, 1), (force, 2), (force, 3), (force, 4), (force, 5), (force, 3), (force, 6), (force, 7), (force, 10), (force, 11), (force, 21), (force, 22), (1, 0)):
+        for f, variant in ((force, 0), (force, 1), (force, 2), (force, 3), (force, 4), (force, 5), (force, 3), (force, 6), (force, 7), (force, 10), (force, 11), (force, 21), (force, 22), (force, 24), (force, 25), (force, 26), (1, 0)):
             h.set_tuning(gbmm_force=f, gbmm_variant=variant)
             try:
                 before = h.launch_count()
