@@ -38,6 +38,9 @@ struct DmmaArgs {
     int64_t gy;  // row tiles per column block
     int flags;   // 1: rotate the warp -> quadrant map per CTA, 2: interleave the two halves of the p-range
     int tpc;     // warp-specialised kernel: consecutive row tiles per CTA
+    // corner launch (MODE 2) of the plain kernel: it covers the column blocks [0, cb_lo) and [cb_hi0, gx) only -- every tile
+    // of the blocks in between is an interior tile the warp-specialised kernel has already done
+    int64_t cb_lo, cb_hi0;
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -114,7 +117,9 @@ __global__ void __launch_bounds__(NT, MINB) gbmm_dmma_kernel(const DmmaArgs a) {
     constexpr int WOFF = BSX == 1 ? 32 : 8, BST = 8 * BSX, SPAN = 24 * BSX + 7;  // first block, block stride, panel span - 1
     const int wi = (role & 1) * WOFF, wj = (role >> 1) * WOFF;
     const int64_t by = lin % a.gy;
-    const int64_t j0 = (lin / a.gy) * TN;
+    int64_t cb = lin / a.gy;
+    if (MODE == 2 && cb >= a.cb_lo) cb = a.cb_hi0 + (cb - a.cb_lo);
+    const int64_t j0 = cb * TN;
     if (j0 >= a.n) return;
     int64_t I0 = floordiv(j0 - a.kuc, TM);
     if (I0 < 0) I0 = 0;
@@ -858,6 +863,8 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     a.gy = gy;
     a.flags = 0;
     a.tpc = 1;
+    a.cb_lo = gx;      // corner launch covers every column block unless narrowed below
+    a.cb_hi0 = gx;
     const int64_t total = gx * gy;
     const int64_t gxx = total < 1048576 ? total : 1048576;
     dim3 grid((unsigned)gxx, (unsigned)((total + gxx - 1) / gxx));
@@ -926,13 +933,47 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
 #undef LBM_WS_LAUNCH
         LBM_LAUNCH_CHECK(h, "gbmm_dmma_ws_kernel");
         {
+            // Which column blocks still hold non-interior tiles?  The interior predicate (the device one, restated) fails only
+            // on a prefix and on a suffix of the column blocks, so scan inwards from both ends until a block is all-interior.
+            auto hfloordiv = [](int64_t x, int64_t y) { return x >= 0 ? x / y : -((-x + y - 1) / y); };
+            auto block_all_interior = [&](int64_t cbk) {
+                const int64_t j0 = cbk * TN;
+                int64_t I0 = hfloordiv(j0 - kuc, TM);
+                if (I0 < 0) I0 = 0;
+                for (int64_t by = 0; by < gy; ++by) {
+                    const int64_t i0 = (I0 + by) * TM;
+                    if (i0 >= m || i0 > j0 + TN - 1 + klc) continue;
+                    int64_t plo = i0 - kla > j0 - kub ? i0 - kla : j0 - kub;
+                    int64_t phi = i0 + TM - 1 + kua < j0 + TN - 1 + klb ? i0 + TM - 1 + kua : j0 + TN - 1 + klb;
+                    if (plo < 0) plo = 0;
+                    if (phi > k - 1) phi = k - 1;
+                    plo &= ~(int64_t)3;
+                    const int64_t nch = phi >= plo ? (phi - plo + KC) / KC : 0;
+                    const bool ok = nch > 0 && i0 + TM <= m && j0 >= 4 && j0 + TN + 4 <= n && plo >= 4 && plo + nch * KC + 4 <= k &&
+                                    lda >= 33 && ldb >= 33 && ((lda - 1) & 1) == 0 && ((ldb - 1) & 1) == 0 &&
+                                    ((reinterpret_cast<uintptr_t>(A + kua + i0 + (lda - 1) * plo) & 15u) == 0) &&
+                                    ((reinterpret_cast<uintptr_t>(B + kub + plo + (ldb - 1) * j0) & 15u) == 0);
+                    if (!ok) return false;
+                }
+                return true;
+            };
+            const int64_t scan = gx < 64 ? gx : 64;
+            int64_t lo = 0, hi = gx;                       // corner blocks: [0, lo) and [hi, gx)
+            while (lo < scan && !block_all_interior(lo)) ++lo;
+            if (lo < scan) {
+                while (hi > lo + 1 && gx - hi < scan && !block_all_interior(hi - 1)) --hi;
+                if (hi > lo && block_all_interior(hi - 1)) { a.cb_lo = lo; a.cb_hi0 = hi; }
+            }
+            const int64_t total_c = (a.cb_lo + (gx - a.cb_hi0)) * gy;
+            const int64_t gcx = total_c < 1048576 ? total_c : 1048576;
+            const dim3 grid_c((unsigned)(gcx > 0 ? gcx : 1), (unsigned)(total_c > 0 ? (total_c + gcx - 1) / gcx : 1));
             const size_t smem = (size_t)2 * STAGE_DBL * sizeof(double);
             static int cfg_corner = 0;
             if (!(cfg_corner & (1 << h->device))) {
                 LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<2, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 cfg_corner |= (1 << h->device);
             }
-            gbmm_dmma_kernel<2, 5, 2><<<grid, NT, smem, h->stream>>>(a);
+            if (total_c > 0) gbmm_dmma_kernel<2, 5, 2><<<grid_c, NT, smem, h->stream>>>(a);
         }
     } else if (variant == 4 || variant == 5) {
         // column-block persistent kernels: one CTA per 64-column block
