@@ -54,6 +54,38 @@ def main():
         got = np.asfortranarray(C.data.cpu().numpy().T)
         err = float(np.max(np.abs(O.band_to_dense(got, n, 2 * l, 2 * u) - O.band_to_dense(want, n, 2 * l, 2 * u))))
         rec(f"gbmm f64 n={n} (l=u={l})^2" + (" [DMMA]" if l >= 16 else ""), err, 4 * eps * (l + u + 1))
+    # narrow gbmm at a size that takes the register kernel (band arrays compared directly; n too large for dense)
+    for dt in (np.float64, np.float32):
+        e_ = np.finfo(dt).eps
+        for l in (1, 8):
+            n = 1 << 17
+            A_np, A = band(n, n, l, l, 1, dt)
+            B_np, B = band(n, n, l, l, 2, dt)
+            got = np.asfortranarray((A @ B).data.cpu().numpy().T)
+            want = O.gbmm(n, n, n, A_np, l, l, B_np, l, l)
+            r = np.arange(4 * l + 1)[:, None]
+            i = np.arange(n)[None, :] + r - 2 * l
+            inside = (i >= 0) & (i < n)
+            rec(f"gbmm {'f64' if dt == np.float64 else 'f32'} n=2^17 (l=u={l})^2 [register kernel]",
+                float(np.max(np.abs(np.where(inside, got - want, 0)))), 4 * e_ * (2 * l + 1))
+    # structured x structured product and mat-mat with 8 right-hand sides
+    n = 1 << 17
+    d, e1, e2 = O.fill_uniform(1, n), O.fill_uniform(2, n - 1), O.fill_uniform(3, n - 1)
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    P = L.Tridiagonal(t(e1), t(d), t(e2)) @ L.SymTridiagonal(t(d), t(e2))
+    gotP = np.asfortranarray(P.data.cpu().numpy().T)
+    TA = np.zeros((3, n)); TA[1] = d; TA[0, 1:] = e2; TA[2, :-1] = e1          # (1,1) band storage of Tridiagonal(e1,d,e2)
+    TS = np.zeros((3, n)); TS[1] = d; TS[0, 1:] = e2; TS[2, :-1] = e2
+    wantP = O.gbmm(n, n, n, np.asfortranarray(TA), 1, 1, np.asfortranarray(TS), 1, 1)
+    r = np.arange(5)[:, None]; i = np.arange(n)[None, :] + r - 2
+    rec("Tridiagonal * SymTridiagonal f64 n=2^17 [lbm_dtridiag_mm]", float(np.max(np.abs(np.where((i >= 0) & (i < n), gotP - wantP, 0)))), 4 * eps * 3)
+    X = O.fill_uniform(9, 8 * n).reshape(8, n)
+    Y = torch.empty((8, n), dtype=torch.float64, device="cuda")
+    L.mul_(Y.t(), L.SymTridiagonal(t(d), t(e1)), t(X).t())
+    rec("SymTridiagonal * dense (8 columns) f64 n=2^17", float(max(np.max(np.abs(Y[c].cpu().numpy() - O.tridiag_mv(n, e1, d, e1, X[c]))) for c in range(8))), 4 * eps * 3)
+    A_np, A = band(n, n, 1, 1, 1)
+    L.mul_(Y.t(), A, t(X).t())
+    rec("BandedMatrix (1,1) * dense (8 columns) f64 n=2^17", float(max(np.max(np.abs(Y[c].cpu().numpy() - O.gbmv("N", n, n, 1, 1, 1.0, A_np, X[c]))) for c in range(8))), 4 * eps * 3)
     # lazy chain apply (config 1): two stages
     n = 10_000
     A_np, A = band(n, n, 1, 1, 1)

@@ -638,12 +638,18 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     // (the producer is already fetching the next tile while the consumers finish and store the current one)
     const int tpc = a.tpc;
     const int64_t groups = (a.gy + tpc - 1) / tpc;
-    const int64_t lin = (int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y;
-    const int64_t j0 = (lin / groups) * TN;
-    if (j0 >= a.n) return;
-    const int64_t by0 = (lin % groups) * tpc;
-    int64_t I0 = floordiv(j0 - a.kuc, TM);
-    if (I0 < 0) I0 = 0;
+    // work items = (column block, group of tpc row tiles); a CTA takes every (gridDim)-th item, so a grid of SMs x MINB
+    // CTAs is persistent (the ring keeps running from one column block into the next) and a grid of `total` CTAs is not
+    const int64_t lin0 = (int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y;
+    const int64_t nct = (int64_t)gridDim.x * gridDim.y;
+    const int64_t total = ((a.n + TN - 1) / TN) * groups;
+    int64_t j0 = 0, by0 = 0, I0 = 0;
+    auto set_item = [&](int64_t lin) {
+        j0 = (lin / groups) * TN;
+        by0 = (lin % groups) * tpc;
+        I0 = floordiv(j0 - a.kuc, TM);
+        if (I0 < 0) I0 = 0;
+    };
 
     // per-tile parameters; valid = interior tile with work (the corner tiles are left to gbmm_dmma_kernel MODE 2)
     auto tile_params = [&](int t, int64_t &i0, int64_t &plo, int &nch) -> bool {
@@ -678,7 +684,9 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
         // A window 64 rows x 16 p: lane owns the row pair 2*lane, one copy per p.  B window 16 p x 64 j: lane owns
         // the p pair 2*(lane & 7) of columns (lane >> 3) + 4q.
         const int64_t a_step = a.lda - 1, b_step4 = 4 * (a.ldb - 1);
+        for (int64_t lin = lin0; lin < total; lin += nct)
         for (int t = 0; t < tpc; ++t) {
+            if (t == 0) set_item(lin);
             int64_t i0, plo;
             int nch;
             if (!tile_params(t, i0, plo, nch)) continue;
@@ -720,7 +728,9 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
     const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + 8*x
     const int fb_off = (wj + fr) * PB + fc;     // + 8*y*PB + 4*ks
+    for (int64_t lin = lin0; lin < total; lin += nct)
     for (int t = 0; t < tpc; ++t) {
+        if (t == 0) set_item(lin);
         int64_t i0, plo;
         int nch;
         if (!tile_params(t, i0, plo, nch)) continue;
@@ -907,7 +917,10 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         if (h->tune.gbmm_tile / 100 == 1) a.flags |= 4;   // (+100: double-copy traffic experiment, results unchanged)
         if (h->tune.gbmm_tile / 100 == 2) a.flags |= 8;   // (+200: poll the ring barriers with a 32 ns back-off)
         if (h->tune.gbmm_tile / 100 == 3) a.flags |= 16;  // (+300: 128 ns back-off)
-        const int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
+        int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
+        // gbmm_tile 4xx: persistent grid (SMs x resident CTAs, each walking every grid-th work item)
+        const bool persistent = h->tune.gbmm_tile / 100 == 4;
+        if (persistent && total_ws > (int64_t)h->sm_count * 3) total_ws = (int64_t)h->sm_count * 3;
         const int64_t gws = total_ws < 1048576 ? total_ws : 1048576;
         dim3 grid_ws((unsigned)gws, (unsigned)((total_ws + gws - 1) / gws));
 #define LBM_WS_LAUNCH(IDX, NS, MB, NC)                                                                                     \
