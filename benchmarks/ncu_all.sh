@@ -7,7 +7,7 @@ CFGS="${@:-C5 C4 C3 C2 M MM}"
 for cfg in $CFGS; do
   python benchmarks/prof_one.py $cfg > gpurun_out/plain_$cfg.log 2>&1 || { echo "plain $cfg failed"; tail -3 gpurun_out/plain_$cfg.log; continue; }
   timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'chain3|dmma_kernel|kron_ring|tridiag_ring|tridiag_dot|gbmv_tile|gbmv_multi|gbmv2|gbmm_reg|tridiag_axpby|tridiag_mm|tridiag_mv' \
+    -k regex:'chain3|dmma_kernel|dmma_ws_kernel|kron_ring|tridiag_ring|tridiag_dot|gbmv_tile|gbmv_multi|gbmv2|gbmm_reg|tridiag_axpby|tridiag_mm|tridiag_mv' \
     -o gpurun_out/prof_${cfg}_r01e -f python benchmarks/prof_one.py $cfg > gpurun_out/ncu_${cfg}_e.log 2>&1
   tail -1 gpurun_out/ncu_${cfg}_e.log
   python benchmarks/ncu_summary.py gpurun_out/prof_${cfg}_r01e.ncu-rep gpurun_out/ncu_${cfg}_r01.md --last-per-kernel
