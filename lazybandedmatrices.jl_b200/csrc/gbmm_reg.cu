@@ -170,23 +170,58 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
         } else {
             // element-wise cp.async (LDGSTS): nothing waits on a load inside the loop; src-size 0 zero-fills masked slots
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-            for (int e = tid; e < G::SA_ELEMS; e += GR_NT) {
-                const int c = e / NAT, r = e - c * NAT;
-                bool ok = r < NA;
-                if (ok && !interior) {
-                    const int64_t p = p0 + c, i = p + r - a.kua;
-                    ok = p >= 0 && p < a.k && i >= 0 && i < a.m;
+            const int lda32 = (int)a.lda, ldb32 = (int)a.ldb;     // <= 2^20 (checked by the host), c < 2^11: 32-bit offsets
+            // the NA (NB) stored rows of every column, walked with an incrementally updated (column, row) pair ...
+            {
+                const int dc = GR_NT / NA, dr = GR_NT - dc * NA;
+                int c = tid / NA, r = tid - c * NA;
+                for (int e = tid; e < SA_COLS * NA; e += GR_NT) {
+                    bool ok = true;
+                    if (!interior) {
+                        const int64_t p = p0 + c, i = p + r - a.kua;
+                        ok = p >= 0 && p < a.k && i >= 0 && i < a.m;
+                    }
+                    cp_async_elem<T>(sA_u + (uint32_t)((c * NAT + r) * (int)sizeof(T)), ok ? Ag + (r + lda32 * c) : a.A, ok);
+                    r += dr;
+                    c += dc;
+                    if (r >= NA) { r -= NA; ++c; }
                 }
-                cp_async_elem<T>(sA_u + (uint32_t)(e * (int)sizeof(T)), ok ? Ag + (r + a.lda * c) : a.A, ok);
             }
-            for (int e = tid; e < G::SB_ELEMS; e += GR_NT) {
-                const int c = e / NBT, s = e - c * NBT;
-                bool ok = s < NB && c < cols;
-                if (ok && !interior) {
-                    const int64_t p = j0 + c + s - a.kub;
-                    ok = p >= 0 && p < a.k;
+            {
+                const int dc = GR_NT / NB, dr = GR_NT - dc * NB;
+                int c = tid / NB, r = tid - c * NB;
+                for (int e = tid; e < GR_TC * NB; e += GR_NT) {
+                    bool ok = c < cols;
+                    if (ok && !interior) {
+                        const int64_t p = j0 + c + r - a.kub;
+                        ok = p >= 0 && p < a.k;
+                    }
+                    cp_async_elem<T>(sB_u + (uint32_t)((c * NBT + r) * (int)sizeof(T)), ok ? Bg + (r + ldb32 * c) : a.B, ok);
+                    r += dr;
+                    c += dc;
+                    if (r >= NB) { r -= NB; ++c; }
                 }
-                cp_async_elem<T>(sB_u + (uint32_t)(e * (int)sizeof(T)), ok ? Bg + (s + a.ldb * c) : a.B, ok);
+            }
+            // ... and zeros in the NAT-NA (NBT-NB) padding rows of the template
+            if (NA < NAT) {
+                const int np = NAT - NA, dc = GR_NT / np, dr = GR_NT - dc * np;
+                int c = tid / np, r = tid - c * np;
+                for (int e = tid; e < SA_COLS * np; e += GR_NT) {
+                    sA[c * NAT + NA + r] = (T)0;
+                    r += dr;
+                    c += dc;
+                    if (r >= np) { r -= np; ++c; }
+                }
+            }
+            if (NB < NBT) {
+                const int np = NBT - NB, dc = GR_NT / np, dr = GR_NT - dc * np;
+                int c = tid / np, r = tid - c * np;
+                for (int e = tid; e < GR_TC * np; e += GR_NT) {
+                    sB[c * NBT + NB + r] = (T)0;
+                    r += dr;
+                    c += dc;
+                    if (r >= np) { r -= np; ++c; }
+                }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
@@ -286,16 +321,21 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
         } else {
             const int NC = NA + NB - 1;
             const int total = cols * nbc;
+            const int ldc32 = (int)a.ldc;
+            const bool rows_inside = j0 - a.kuc >= 0 && j0 + GR_TC - 1 + a.klc < a.m;   // no out-of-matrix slot in this tile
             // flat element index e = c*nbc + row, advanced incrementally (no division in the loop)
             const int dc = GR_NT / nbc, dr = GR_NT - dc * nbc;
             int c = tid / nbc, row = tid - c * nbc;
             for (int e = tid; e < total; e += GR_NT) {
                 const int t = row - off;
-                const int64_t i = j0 + c + row - a.kuc;
-                const bool in = i >= 0 && i < a.m;
+                bool in = true;
+                if (!rows_inside) {
+                    const int64_t i = j0 + c + row - a.kuc;
+                    in = i >= 0 && i < a.m;
+                }
                 T v = (T)0;
-                if (t >= 0 && t < NC && in) v = sC[c * NCT + t];
-                T *dst = Cg + row + a.ldc * c;
+                if ((unsigned)t < (unsigned)NC && in) v = sC[c * NCT + t];
+                T *dst = Cg + (row + ldc32 * c);
                 if (a.beta == (T)0) *dst = a.alpha * v;
                 else if (in) *dst = fma(a.beta, *dst, a.alpha * v);
                 row += dr;
@@ -359,6 +399,12 @@ int lbm_gbmm_reg(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64
     // once (kub + pad) is a multiple of 2 (f64) / 4 (f32): NAT is odd
     const int al = 16 / (2 * (int)sizeof(T)) == 1 ? 2 : 4;
     a.pad = (al - (int)(kub % al)) % al;
+    // equal odd row counts (symmetric bands l = u = 3, 5, 6, 7 on both factors) have exact instantiations: no padding
+    // rows, and tight operands take the bulk-TMA path
+    if (NA == NB && NA == 7) return gr_launch<T, 7, 7>(h, a);
+    if (NA == NB && NA == 11) return gr_launch<T, 11, 11>(h, a);
+    if (NA == NB && NA == 13) return gr_launch<T, 13, 13>(h, a);
+    if (NA == NB && NA == 15) return gr_launch<T, 15, 15>(h, a);
     if (NA <= 3) return gr_dispatch_b<T, 3>(h, a, (int)NB);
     if (NA <= 5) return gr_dispatch_b<T, 5>(h, a, (int)NB);
     if (NA <= 9) return gr_dispatch_b<T, 9>(h, a, (int)NB);

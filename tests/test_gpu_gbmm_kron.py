@@ -113,7 +113,10 @@ def test_gbmm_register_kernel(L, oracle, dt):
     cases = [(6, 6, 6, 1, 1, 1, 1), (10, 8, 9, 2, 0, 1, 3), (5, 5, 5, 4, 4, 4, 4), (12, 12, 12, 0, 0, 2, 1), (1, 1, 1, 0, 0, 0, 0),
              (200, 170, 230, 3, 2, 1, 4), (700, 700, 700, 8, 8, 8, 8), (513, 515, 511, 8, 8, 1, 1), (600, 600, 600, 0, 16, 16, 0),
              (1000, 1030, 980, 10, 6, 5, 9), (300, 2000, 300, 2, 2, 2, 2), (2000, 300, 2000, 3, 1, 0, 7), (257, 256, 258, 4, 4, 2, 2),
-             (4000, 4000, 4000, 1, 1, 1, 1), (777, 777, 777, 0, 0, 0, 0)]
+             (4000, 4000, 4000, 1, 1, 1, 1), (777, 777, 777, 0, 0, 0, 0),
+             # exact instantiations for equal odd row counts 7, 11, 13, 15 (bulk-TMA path on the interior tiles)
+             (3000, 3000, 3000, 3, 3, 3, 3), (2900, 3100, 3000, 5, 5, 5, 5), (3000, 3000, 3000, 6, 6, 6, 6), (3000, 3000, 3000, 7, 7, 7, 7),
+             (3000, 3000, 3000, 2, 4, 5, 1), (3000, 3000, 3000, 10, 0, 3, 7)]
     for s, (m, n, k, kla, kua, klb, kub) in enumerate(cases):
         A_np, A = _band(L, oracle, m, k, kla, kua, 61 + s, dt)
         B_np, B = _band(L, oracle, k, n, klb, kub, 62 + s, dt)
