@@ -358,6 +358,40 @@ def run_b200(args):
         except Exception as e:  # never lose the headline line to the optional point
             breakdown["l128u128"] = {"error": str(e)[:200]}
 
+    # ---- banded x banded materialise, l=u=8 (the other half of the north-star target; not part of `value`):
+    #      n = 2^26 f64, columns of C partitioned over the ranks, static halo of A, no communication
+    if not args.no_wide:
+        try:
+            from lbm_b200.shard import GbmmColumnShard
+            nm_, lm = 1 << 26, 8
+            q = GbmmColumnShard.plan(nm_, lm, lm, lm, lm, rank, world)
+            nbm = 2 * lm + 1
+            A_slab = torch.empty((q.pb - q.pa, nbm), dtype=torch.float64, device=dev)
+            L.fill_uniform(A_slab, 0x1, offset=nbm * q.pa)
+            B_slab = torch.empty((q.c1 - q.c0, nbm), dtype=torch.float64, device=dev)
+            L.fill_uniform(B_slab, 0x2, offset=nbm * q.c0)
+            C_slab = torch.empty((q.c1 - q.c0, 4 * lm + 1), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                q.local_gbmm(A_slab, B_slab, C_slab)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record(stream)
+            for _ in range(reps):
+                q.local_gbmm(A_slab, B_slab, C_slab)
+            e1.record(stream)
+            barrier()
+            msm = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(msm, op=dist.ReduceOp.MAX)
+            gbs = 8 * nm_ * (2 * nbm + 4 * lm + 1) / (float(msm[0]) * 1e-3) / 1e9
+            breakdown["materialize_l8u8_x_l8u8"] = {"n": "2^26", "ms": float(msm[0]), "gbs": gbs, "frac_of_peak": gbs / (peak * world),
+                                                    "kernel": "gbmm_reg_kernel<double,17,17> (column-sharded, no communication)"}
+            del A_slab, B_slab, C_slab
+            torch.cuda.empty_cache()
+        except Exception as e:  # never lose the headline line to the optional point
+            breakdown["materialize_l8u8_x_l8u8"] = {"error": str(e)[:200]}
+
     # ---- e2e: the same metric through the C-ABI host-buffer call (H2D + kernel + D2H timed) ---
     e2e = None if args.no_e2e else run_e2e(args, L, h, n, rank, world, dev, barrier)
 
