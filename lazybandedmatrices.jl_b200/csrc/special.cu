@@ -80,16 +80,20 @@ __global__ void __launch_bounds__(SP_NT) tridiag_pack_kernel(int64_t n, const T 
         const int64_t j0 = t * SP_PACK_TC;
         const unsigned cols = (unsigned)((n - j0) < SP_PACK_TC ? (n - j0) : SP_PACK_TC);
         const unsigned total = rows * cols;
+        // flat index e = c*rows + r advanced incrementally (no division in the loop)
+        const unsigned dc = SP_NT / rows, dr = SP_NT - dc * rows;
+        unsigned c = threadIdx.x / rows, r = threadIdx.x - c * rows;
         for (unsigned e = threadIdx.x; e < total; e += SP_NT) {
-            const unsigned c = e / rows;
-            const int r = (int)(e - c * rows);
             const int64_t j = j0 + c;
-            const int k = ku - r;   // diagonal index j - i
+            const int k = ku - (int)r;   // diagonal index j - i
             T v = (T)0;
             if (k == 0) v = d[j];
             else if (k == 1) { if (du && j >= 1) v = du[j - 1]; }
             else if (k == -1) { if (dl && j + 1 < n) v = dl[j]; }
             AB[r + lda * j] = v;
+            r += dr;
+            c += dc;
+            if (r >= rows) { r -= rows; ++c; }
         }
     }
 }
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(SP_NT) tridiag_pack_kernel(int64_t n, const T 
 // (al/ad/au = A's sub/main/super diagonal indexed by COLUMN for al, ad and by ROW for au, as the reference stores them;
 //  sums run over k ascending like the banded oracle).  A thread owns a column; the tile is staged in shared memory
 // so the band array is written as one contiguous, fully coalesced range.
-constexpr int SP_MM_TC = 1024;
+constexpr int SP_MM_TC = 512;
 template <typename T, bool AL, bool AU, bool BL, bool BU>
 __global__ void __launch_bounds__(SP_NT) tridiag_mm_kernel(int64_t n, const T *__restrict__ al, const T *__restrict__ ad,
                                                            const T *__restrict__ au, const T *__restrict__ bl,
