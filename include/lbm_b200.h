@@ -187,6 +187,16 @@ int lbm_dkron3d_mv(lbm_handle_t h, int64_t n,
                    int64_t klc, int64_t kuc, const double *C, int64_t ldc,
                    double alpha, const double *x, double beta, double *y);
 
+/* ---- lazy product applied to a vector: y <- alpha*F_0*(F_1*(...F_{nf-1}*x)) + beta*y ------------------ */
+/* mul!(y, ApplyMatrix(*, F_0, ..., F_{nf-1}), x, alpha, beta): LazyArrays' right-to-left Mul flattening (the rule the
+ * reference relies on at /root/reference/src/blockkron.jl:208-214, pinned at test/test_blockkron.jl:345-348) as ONE call:
+ * factor f is m[f] x n[f] with bandwidths (kl[f], ku[f]), data A[f], leading dimension lda[f]; n[f] == m[f+1].
+ * nf launches on the handle's stream; the nf-1 temporaries live in the handle's scratch (no allocation per call). */
+int lbm_dgbmv_chain(lbm_handle_t h, int nf, const int64_t *m, const int64_t *n, const int64_t *kl, const int64_t *ku,
+                    const double *const *A, const int64_t *lda, double alpha, const double *x, double beta, double *y);
+int lbm_sgbmv_chain(lbm_handle_t h, int nf, const int64_t *m, const int64_t *n, const int64_t *kl, const int64_t *ku,
+                    const float *const *A, const int64_t *lda, float alpha, const float *x, float beta, float *y);
+
 /* ---- `+` / `-` among structured kinds, and their BandedMatrix storage ----------------------- */
 /* (odl, od, odu) <- alpha*(adl, ad, adu) + beta*(bdl, bd, bdu) + gamma*I on the three diagonals of an n x n
  * operand in ONE launch: every method of /root/reference/src/special.jl:75-222 (Diagonal / Bidiagonal /

@@ -1134,7 +1134,47 @@ int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl,
 
 }  // namespace
 
+
+// y <- alpha * F_0 (F_1 ( ... F_{nf-1} x)) + beta * y: the flattened right-to-left apply of a lazy product
+// (LazyArrays' Mul flattening, the rule the reference relies on at src/blockkron.jl:208-214) in ONE call: nf launches on
+// the handle's stream, the nf-1 temporaries ping-pong inside the handle's scratch buffer.
+template <typename T>
+int gbmv_chain_impl(lbm_handle_t h, int nf, const int64_t *m, const int64_t *n, const int64_t *kl, const int64_t *ku,
+                    const T *const *A, const int64_t *lda, T alpha, const T *x, T beta, T *y) {
+    if (!h) return -1;
+    if (nf < 1) return lbm_fail_arg(h, 2, "nf < 1");
+    if (!m || !n || !kl || !ku || !A || !lda) return lbm_fail_arg(h, 3, "NULL factor description");
+    int64_t tmax = 0;
+    for (int f = 0; f < nf; ++f) {
+        if (m[f] < 0 || n[f] < 0) return lbm_fail_arg(h, 3, "negative factor size");
+        if (f + 1 < nf && n[f] != m[f + 1]) return lbm_fail_arg(h, 4, "inner sizes of consecutive factors differ");
+        if (f > 0 && m[f] > tmax) tmax = m[f];
+    }
+    if (nf == 1) return gbmv_impl<T>(h, 'N', m[0], n[0], kl[0], ku[0], alpha, A[0], lda[0], x, beta, y);
+    const int64_t pitch = round_up(tmax > 0 ? tmax : 1, 32);
+    void *scr;
+    int rc = lbm_scratch(h, (size_t)(2 * pitch) * sizeof(T), &scr);
+    if (rc) return rc;
+    T *tmp[2] = {(T *)scr, (T *)scr + pitch};
+    const T *v = x;
+    for (int f = nf - 1; f >= 1; --f) {
+        T *t = tmp[f & 1];
+        rc = gbmv_impl<T>(h, 'N', m[f], n[f], kl[f], ku[f], (T)1, A[f], lda[f], v, (T)0, t);
+        if (rc) return rc;
+        v = t;
+    }
+    return gbmv_impl<T>(h, 'N', m[0], n[0], kl[0], ku[0], alpha, A[0], lda[0], v, beta, y);
+}
+
 extern "C" {
+int lbm_dgbmv_chain(lbm_handle_t h, int nf, const int64_t *m, const int64_t *n, const int64_t *kl, const int64_t *ku,
+                    const double *const *A, const int64_t *lda, double alpha, const double *x, double beta, double *y) {
+    return gbmv_chain_impl<double>(h, nf, m, n, kl, ku, A, lda, alpha, x, beta, y);
+}
+int lbm_sgbmv_chain(lbm_handle_t h, int nf, const int64_t *m, const int64_t *n, const int64_t *kl, const int64_t *ku,
+                    const float *const *A, const int64_t *lda, float alpha, const float *x, float beta, float *y) {
+    return gbmv_chain_impl<float>(h, nf, m, n, kl, ku, A, lda, alpha, x, beta, y);
+}
 int lbm_dgbmv(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha,
               const double *A, int64_t lda, const double *x, double beta, double *y) {
     return gbmv_impl<double>(h, trans, m, n, kl, ku, alpha, A, lda, x, beta, y);

@@ -66,6 +66,8 @@ def _sigs():
     }
     for p, ft in (("d", f64), ("s", f32)):
         s[f"lbm_{p}gbmv"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
+        s[f"lbm_{p}gbmv_chain"] = (C.c_int, [H, C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                                            C.POINTER(vp), C.POINTER(i64), ft, vp, ft, vp])
         s[f"lbm_{p}gbmv_multi"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, i64, ft, vp, i64, i64])
         s[f"lbm_{p}gbmv2"] = (C.c_int, [H, i64, i64, ft, i64, i64, vp, i64, ft, i64, i64, vp, i64, vp, ft, vp])
         s[f"lbm_{p}tridiag_dot"] = (C.c_int, [H, i64, vp, vp, vp, vp, vp, vp])

@@ -68,6 +68,27 @@ class ApplyMatrix:
                 f"second entry of size(A)={self.shape} and first entry of size(B) = {tuple(x.shape)} must match.")
         if y.shape[0] != self.shape[0]:
             raise DimensionMismatch(f"sizes size(A)={self.shape} and size(C) = {tuple(y.shape)} must match at first entry.")
+        # all-banded product applied to a vector: one C call (lbm_?gbmv_chain), temporaries in the handle's scratch
+        if (x.dim() == 1 and len(self.args) > 1 and all(isinstance(a, BandedMatrix) for a in self.args)
+                and all(a.dtype == x.dtype for a in self.args)):
+            nf = len(self.args)
+            key = tuple(a.data.data_ptr() for a in self.args)
+            desc = getattr(self, "_chain_desc", None)
+            if desc is None or desc[0] != key:      # factor description in C arrays, built once per set of buffers
+                arr = lambda vals: (C.c_int64 * nf)(*vals)  # noqa: E731
+                desc = (key, arr([a.m for a in self.args]), arr([a.n for a in self.args]), arr([a.l for a in self.args]),
+                        arr([a.u for a in self.args]), (C.c_void_p * nf)(*key), arr([a.lda for a in self.args]))
+                self._chain_desc = desc
+            h = _lib.handle_of(x)
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(x.dtype)}gbmv_chain")
+            ft = _lib.f64 if x.dtype == torch.float64 else _lib.f32
+            xc = x if x.is_contiguous() else x.contiguous()
+            yc = y if y.is_contiguous() else y.contiguous()
+            h.check(fn(h.ptr, nf, desc[1], desc[2], desc[3], desc[4], desc[5], desc[6], ft(alpha), _ptr(xc), ft(beta), _ptr(yc)),
+                    "lbm_gbmv_chain")
+            if yc is not y:
+                y.copy_(yc)
+            return y
         v = x
         for a in reversed(self.args[1:]):
             t = torch.empty((a.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)

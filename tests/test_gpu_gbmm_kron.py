@@ -224,6 +224,38 @@ def test_applymatrix_config1(L, oracle):
     assert torch.max(torch.abs(y3 - dense_y)).item() <= 1e-12
 
 
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_applymatrix_chain_apply_one_call(L, oracle, dt):
+    """mul!(y, ApplyMatrix(*, F0, F1, F2), x, alpha, beta) through lbm_?gbmv_chain: rectangular factors, different bands,
+    alpha/beta, temporaries in the handle's scratch (one C call, nf launches)."""
+    h = L.handle_for(0)
+    shapes = [(700, 900, 2, 1), (900, 650, 0, 3), (650, 800, 4, 4)]
+    nps, devs = [], []
+    for s_, (m, n, l, u) in enumerate(shapes):
+        a_np, a = _band(L, oracle, m, n, l, u, 21 + s_, dt)
+        nps.append(a_np)
+        devs.append(a)
+    x = oracle.fill_uniform(9, 800, NP[dt])
+    y0 = oracle.fill_uniform(10, 700, NP[dt])
+    v = x
+    for (m, n, l, u), a_np in zip(reversed(shapes[1:]), reversed(nps[1:])):
+        v = oracle.gbmv("N", m, n, l, u, 1.0, a_np, v)
+    m, n, l, u = shapes[0]
+    want = oracle.gbmv("N", m, n, l, u, -1.5, nps[0], v, 0.5, y0.copy())
+    M = L.ApplyMatrix("*", *devs)
+    y = torch.from_numpy(y0.copy()).cuda()
+    before = h.launch_count()
+    M.mul_(y, torch.from_numpy(x).cuda(), -1.5, 0.5)
+    assert h.launch_count() - before == 3
+    # stage bounds add: ||F2 x|| <= 9, ||F1 F2 x|| <= 36
+    tol = tol_rows(NP[dt], 9, 1.0, 1.0) + tol_rows(NP[dt], 4, 1.0, 9.0) + tol_rows(NP[dt], 4, 1.0, 36.0, 1.5, 0.5, 1.0)
+    assert np.max(np.abs(y.cpu().numpy() - want)) <= tol
+    with pytest.raises(L.LbmArgumentError):          # inner sizes must chain (C ABI: argument 4)
+        bad = L.ApplyMatrix.__new__(L.ApplyMatrix)
+        bad.f, bad.args = "*", (devs[0], devs[2])
+        bad.mul_(torch.empty(700, dtype=dt, device="cuda"), torch.from_numpy(x).cuda())
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 def test_chain3_batched(L, oracle, dt):
     npdt = NP[dt]
