@@ -208,6 +208,24 @@ for (T, p) in ((Float64, :d), (Float32, :s))
     end
 end
 
+# mul!(y, ApplyMatrix(*, F...), x, α, β) for all-banded device factors in ONE ccall (LazyArrays' flattening would issue k gbmv
+# ccalls and allocate k-1 temporaries; the library ping-pongs them inside the handle's scratch).  A package extension forwards
+# `materialize!(::MulAdd{<:ApplyLayout{typeof(*)}, DeviceColumnMajor, DeviceColumnMajor})` here.
+function chain_mul!(y::DevVector{Float64}, factors::NTuple{N,BandedMatrix}, x::DevVector{Float64}, α = 1.0, β = 0.0) where N
+    for f in 1:N-1
+        size(factors[f], 2) == size(factors[f+1], 1) || throw(DimensionMismatch("second entry of size(A)=$(size(factors[f])) and first entry of size(B) = $(size(factors[f+1])) must match."))
+    end
+    size(factors[1], 1) == length(y) || throw(DimensionMismatch("sizes size(A)=$(size(factors[1])) and size(C) = $(size(y)) must match at first entry."))
+    size(factors[N], 2) == length(x) || throw(DimensionMismatch("second entry of size(A)=$(size(factors[N])) and first entry of size(B) = $(size(x)) must match."))
+    m = Int64[size(F, 1) for F in factors]; n = Int64[size(F, 2) for F in factors]
+    kl = Int64[bandwidth(F, 1) for F in factors]; ku = Int64[bandwidth(F, 2) for F in factors]
+    ptrs = Ptr{Float64}[pointer(bandeddata(F)) for F in factors]; ld = Int64[size(bandeddata(F), 1) for F in factors]
+    check(ccall((:lbm_dgbmv_chain, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Float64}}, Ptr{Int64}, Float64, Ptr{Float64}, Float64, Ptr{Float64}),
+                handle().ptr, N, m, n, kl, ku, ptrs, ld, α, x, β, y), "lbm_dgbmv_chain")
+    y
+end
+
 # 2-D Laplacian: Δ = BroadcastArray(+, BlockKron(A, Eye(n2)), BlockKron(Eye(n1), B)) applied without
 # forming it (test/test_blockkron.jl:296-306): y = vec(X*A' + B*X).
 function kronsum_mul!(y::DevVector{Float64}, A::BandedMatrix, B::BandedMatrix, x::DevVector{Float64}, α = 1.0, β = 0.0)
