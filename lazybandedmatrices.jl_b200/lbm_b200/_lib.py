@@ -156,13 +156,17 @@ class Handle:
         """`cuda_stream_ptr` is a cudaStream_t as an integer; 0 = CUDA's legacy default stream
         (which is what torch's default stream is)."""
         self.check(lib().lbm_set_stream(self._h, vp(int(cuda_stream_ptr) or None)))
+        self._bound_stream = int(cuda_stream_ptr)
 
     def use_own_stream(self):
         self.check(lib().lbm_use_own_stream(self._h))
+        self._bound_stream = None
 
     def use_torch_stream(self):
         import torch
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        s = int(torch.cuda.current_stream(self.device).cuda_stream)
+        if getattr(self, "_bound_stream", None) != s:   # small-n calls are host-bound: skip the FFI call when nothing changed
+            self.set_stream(s)
 
     def sync(self):
         self.check(lib().lbm_sync(self._h), "lbm_sync")
