@@ -132,6 +132,7 @@ struct KronRingArgs {
     int stages;
     int64_t nchunks;
     int64_t n1_in, xoff, c_begin, c_end;  // see KronArgs
+    int prod;      // 0: X*A^T + B*X (Kronecker sum); 1: B*X*A^T (Kronecker product, one pass)
 };
 
 template <typename T, int NBA, int NBB, int RPT>
@@ -253,10 +254,22 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
                     const T *xa = xrow + cc * seg + 256 * k;                // X[r, c-kla+t] at xa[t*seg]
                     const T *xb = xa + a.kla * seg - a.klb;                 // X[r-klb+t, c] at xb[t]
                     T acc = 0;
+                    if (a.prod) {
+                        // (B*X)[r, c-kla+tA] for each of the NBA columns, combined with A's row: ((B X) A^T)[r, c]
 #pragma unroll
-                    for (int t = 0; t < NBA; ++t) acc = fma(cav[t], xa[t * seg], acc);
+                        for (int tA = 0; tA < NBA; ++tA) {
+                            const T *xc = xa + tA * seg - a.klb;
+                            T bx = 0;
 #pragma unroll
-                    for (int t = 0; t < NBB; ++t) acc = fma(cbv[k][t], xb[t], acc);
+                            for (int tB = 0; tB < NBB; ++tB) bx = fma(cbv[k][tB], xc[tB], bx);
+                            acc = fma(cav[tA], bx, acc);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < NBA; ++t) acc = fma(cav[t], xa[t * seg], acc);
+#pragma unroll
+                        for (int t = 0; t < NBB; ++t) acc = fma(cbv[k][t], xb[t], acc);
+                    }
                     T *yo = yp + 256 * k;
                     *yo = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *yo, a.alpha * acc);
                 }
@@ -275,6 +288,22 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
                         const T *xa = xrow + cc * seg + 256 * k;
                         const T *xb = xa + a.kla * seg - a.klb;
                         T acc = 0;
+                        if (a.prod) {
+#pragma unroll
+                            for (int tA = 0; tA < NBA; ++tA) {
+                                const int64_t qq = c + a.xoff - a.kla + tA;
+                                if (qq >= 0 && qq < a.n1_in) {
+                                    const T *xc = xa + tA * seg - a.klb;
+                                    T bx = 0;
+#pragma unroll
+                                    for (int tB = 0; tB < NBB; ++tB) {
+                                        const int64_t p = r - a.klb + tB;
+                                        if (p >= 0 && p < a.n2) bx = fma(cbv[k][tB], xc[tB], bx);
+                                    }
+                                    acc = fma(cav[tA], bx, acc);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int t = 0; t < NBA; ++t) {
                             const int64_t qq = c + a.xoff - a.kla + t;
@@ -284,6 +313,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
                         for (int t = 0; t < NBB; ++t) {
                             const int64_t p = r - a.klb + t;
                             if (p >= 0 && p < a.n2) acc = fma(cbv[k][t], xb[t], acc);
+                        }
                         }
                         T *yo = yp + 256 * k;
                         *yo = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *yo, a.alpha * acc);
@@ -324,7 +354,7 @@ int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_
 template <typename T>
 bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda,
                    int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc,
-                   int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0, int64_t c_end = -1) {
+                   int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0, int64_t c_end = -1, int prod = 0) {
     if (n1_in < 0) n1_in = n1;
     if (c_end < 0) c_end = n1;
     if (c_end <= c_begin) { *rc = 0; return true; }
@@ -336,7 +366,7 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     KronRingArgs<T> a;
     a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
     a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
-    a.n1_in = n1_in; a.xoff = xoff; a.c_begin = c_begin; a.c_end = c_end;
+    a.n1_in = n1_in; a.xoff = xoff; a.c_begin = c_begin; a.c_end = c_end; a.prod = prod;
     int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
     tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
     int64_t g = h->tune.kron_tc > 0 ? h->tune.kron_tc : 16;
@@ -524,12 +554,24 @@ int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     int rc = kron_check<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, x, y);
     if (rc || n1 == 0 || n2 == 0) return rc;
     lbm_device_guard g(h->device);
+    // one pass when the streaming ring kernel covers the band shapes: y[r,c] = sum_tA A[c,.] * (sum_tB B[r,.] * X[., .]),
+    // i.e. (B*X)*A^T entry by entry with X read once (2N doubles of traffic instead of 4N + a scratch matrix)
+    if (kron_ring_try<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y, &rc, -1, 0, 0, -1, 1)) return rc;
     void *z;
-    if ((rc = lbm_scratch(h, (size_t)(n1 * n2) * sizeof(double), &z))) return rc;
-    // Z = B*X, then Y = alpha*Z*A^T + beta*Y  (left to right, as src/blockkron.jl:440 evaluates B*X*A')
-    rc = kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, 1.0, x, 0.0, (double *)z, 0, 1);
+    const int64_t nz = n1 > n2 ? n1 : n2;
+    const int64_t zpad = (n1 * n2 + 1) & ~(int64_t)1;       // keeps the zero vector 16-byte aligned behind Z
+    if ((rc = lbm_scratch(h, (size_t)(zpad + nz) * sizeof(double), &z))) return rc;
+    double *Z = (double *)z, *zeros = Z + zpad;
+    // Z = B*X, then Y = alpha*Z*A^T + beta*Y  (left to right, as src/blockkron.jl:440 evaluates B*X*A').
+    // Each pass is a Kronecker SUM with a zero 1-band partner (X*0^T + B*X, then Z*A^T + 0*Z), which the streaming ring
+    // kernel covers for tridiagonal / pentadiagonal factors; other shapes take the halo'd tile kernel.
+    LBM_CUDA(h, cudaMemsetAsync(zeros, 0, (size_t)nz * sizeof(double), h->stream));
+    if (!kron_ring_try<double>(h, n1, n2, 0, 0, zeros, 1, klb, kub, B, ldb, 1.0, x, 0.0, Z, &rc))
+        rc = kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, 1.0, x, 0.0, Z, 0, 1);
     if (rc) return rc;
-    return kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, (const double *)z, beta, y, 1, 0);
+    if (!kron_ring_try<double>(h, n1, n2, kla, kua, A, lda, 0, 0, zeros, 1, alpha, Z, beta, y, &rc))
+        rc = kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, Z, beta, y, 1, 0);
+    return rc;
 }
 
 // Y = (A (x) B (x) C) applied to a full n x n x n tensor X (k fastest, then j, then l) as the three

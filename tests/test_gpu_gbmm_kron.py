@@ -427,7 +427,9 @@ def test_kronsum_ring_tunings_match_tile_kernel(L, oracle):
 
 def test_blockkron_apply(L, oracle):
     """BlockKron(A,B)*x = vec(B X A') without forming kron(A,B) (src/blockkron.jl:440 identity)."""
-    for (n1, n2, la, ua, lb, ub) in [(4, 4, 1, 1, 0, 0), (40, 30, 1, 1, 2, 1), (257, 300, 2, 2, 1, 1)]:
+    # the last three shapes are large enough for the streaming ring kernel (each pass = Kronecker sum with a zero partner)
+    for (n1, n2, la, ua, lb, ub) in [(4, 4, 1, 1, 0, 0), (40, 30, 1, 1, 2, 1), (257, 300, 2, 2, 1, 1), (300, 1024, 1, 1, 1, 1),
+                                     (129, 2050, 2, 2, 1, 1), (64, 512, 1, 1, 3, 0)]:
         A_np, A = _band(L, oracle, n1, n1, la, ua, 3, torch.float64)
         B_np, B = _band(L, oracle, n2, n2, lb, ub, 4, torch.float64)
         K = L.BlockKron(A, B)
