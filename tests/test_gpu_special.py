@@ -125,3 +125,22 @@ def test_sum_then_apply_matches_broadcast(L, oracle):
     L.mul_(y, R, _t(x))
     want = oracle.tridiag_mv(n, A[1], A[2], A[3], x) + oracle.tridiag_mv(n, B[1], B[2], None, x)
     assert np.max(np.abs(y.cpu().numpy() - want)) <= tol_rows(np.float64, 5, 1.0, 1.0)
+
+
+def test_special_abi_argument_errors(L):
+    """LAPACK-style negative returns from the C ABI (never a throw / abort across the boundary)."""
+    import ctypes as C
+    lib, h = L.lib(), L.handle_for(0)
+    d = torch.ones(8, dtype=torch.float64, device="cuda")
+    e = torch.ones(7, dtype=torch.float64, device="cuda")
+    out = torch.empty((8, 5), dtype=torch.float64, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    assert lib.lbm_dtridiag_axpby(h.ptr, -1, 1.0, None, p(d), None, 1.0, None, p(d), None, 0.0, None, p(d), None) == -2
+    assert lib.lbm_dtridiag_axpby(h.ptr, 8, 1.0, None, p(d), None, 1.0, None, p(d), None, 0.0, None, None, None) == -13
+    assert lib.lbm_dtridiag_mm(h.ptr, 8, p(e), p(d), p(e), p(e), p(d), p(e), p(out), 4) == -10      # ldc < 5
+    assert lib.lbm_dtridiag_mm(h.ptr, 8, p(e), None, p(e), p(e), p(d), p(e), p(out), 5) == -4
+    assert lib.lbm_dtridiag_pack(h.ptr, 8, p(e), p(d), None, 0, 1, p(out), 5) == -6                 # subdiagonal but kl == 0
+    assert lib.lbm_dtridiag_pack(h.ptr, 8, None, p(d), None, 1, 1, p(out), 2) == -9                 # lda < kl+ku+1
+    i64 = C.c_int64 * 1
+    assert lib.lbm_dgbmv_chain(h.ptr, 0, i64(8), i64(8), i64(0), i64(0), (C.c_void_p * 1)(d.data_ptr()), i64(1), 1.0, p(d), 0.0, p(d)) == -2
+    assert "nf < 1" in lib.lbm_last_error_string(h.ptr).decode()
