@@ -644,11 +644,14 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     const int64_t nct = (int64_t)gridDim.x * gridDim.y;
     const int64_t total = ((a.n + TN - 1) / TN) * groups;
     int64_t j0 = 0, by0 = 0, I0 = 0;
+    int rot = 0;   // flag 32: block c starts at row tile (-c mod tpc), so neighbouring column blocks -- which run at the same
+                   // time -- are on the SAME rows of A at the same step and share those tiles in L2 instead of re-reading them
     auto set_item = [&](int64_t lin) {
         j0 = (lin / groups) * TN;
         by0 = (lin % groups) * tpc;
         I0 = floordiv(j0 - a.kuc, TM);
         if (I0 < 0) I0 = 0;
+        rot = (a.flags & 32) ? (int)((tpc - (lin / groups) % tpc) % tpc) : 0;
     };
 
     // per-tile parameters; valid = interior tile with work (the corner tiles are left to gbmm_dmma_kernel MODE 2)
@@ -685,8 +688,9 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
         // the p pair 2*(lane & 7) of columns (lane >> 3) + 4q.
         const int64_t a_step = a.lda - 1, b_step4 = 4 * (a.ldb - 1);
         for (int64_t lin = lin0; lin < total; lin += nct)
-        for (int t = 0; t < tpc; ++t) {
-            if (t == 0) set_item(lin);
+        for (int tt = 0; tt < tpc; ++tt) {
+            if (tt == 0) set_item(lin);
+            const int t = tt + rot < tpc ? tt + rot : tt + rot - tpc;
             int64_t i0, plo;
             int nch;
             if (!tile_params(t, i0, plo, nch)) continue;
@@ -729,8 +733,9 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     const int fa_off = fc * PA + wi + fr;       // + 4*ks*PA + 8*x
     const int fb_off = (wj + fr) * PB + fc;     // + 8*y*PB + 4*ks
     for (int64_t lin = lin0; lin < total; lin += nct)
-    for (int t = 0; t < tpc; ++t) {
-        if (t == 0) set_item(lin);
+    for (int tt = 0; tt < tpc; ++tt) {
+        if (tt == 0) set_item(lin);
+        const int t = tt + rot < tpc ? tt + rot : tt + rot - tpc;
         int64_t i0, plo;
         int nch;
         if (!tile_params(t, i0, plo, nch)) continue;
@@ -917,6 +922,7 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         if (h->tune.gbmm_tile / 100 == 1) a.flags |= 4;   // (+100: double-copy traffic experiment, results unchanged)
         if (h->tune.gbmm_tile / 100 == 2) a.flags |= 8;   // (+200: poll the ring barriers with a 32 ns back-off)
         if (h->tune.gbmm_tile / 100 == 3) a.flags |= 16;  // (+300: 128 ns back-off)
+        if (h->tune.gbmm_tile / 100 == 5) a.flags |= 32;  // (+500: rotated row-tile order, see set_item)
         int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
         // gbmm_tile 4xx: persistent grid (SMs x resident CTAs, each walking every grid-th work item)
         const bool persistent = h->tune.gbmm_tile / 100 == 4;
