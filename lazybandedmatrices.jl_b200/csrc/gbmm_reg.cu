@@ -17,10 +17,12 @@
 //   * interior tiles with tight leading dimensions arrive as two 1-D bulk TMA copies (cp.async.bulk, SASS UBLKCP)
 //     and leave as one bulk TMA store -- zero staging instructions; edge tiles / padded lda use element-wise cp.async
 //     with zero-fill, which also masks BY INDEX every out-of-matrix slot (brand() fills them with random numbers);
-//   * the row counts NAT, NBT in {3,5,9,17} are odd, so with lanes one column PAIR apart (2*NAT elements) every
+//   * for odd row counts NAT, NBT (symmetric bands), with lanes one column PAIR apart (2*NAT elements), every
 //     2-element vector access (LDS.128 for f64, LDS.64 for f32) is bank-conflict-free, and an element (column 2t+q,
 //     row r) is vector-aligned exactly when q + r is even -- a compile-time fact, so each column is read as NAT/2
-//     vector loads plus one scalar.
+//     vector loads plus one scalar.  Even counts (2, 4, 6, 10, 12, 14; equal on both factors) are aligned when r is
+//     even and pay a 2- or 4-way bank conflict on a traffic that is small next to the HBM time; 8 and 16 rows (8-way)
+//     stay on the zero-padded 9 / 17 templates.
 #include "lbm_common.cuh"
 
 namespace {
@@ -248,25 +250,33 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
 #pragma unroll
                 for (int q = 0; q <= NBT; ++q) {
                     T av[NAT];
-                    // index (cp+pad+q)*NAT + r is even <=> pad + q + r even
-                    if (((q + PADODD) & 1) == 0) load_run<T, NAT, 0>(av, pa + q * NAT);
+                    // index (cp+pad+q)*NAT + r is even <=> (pad + q)*NAT + r even: odd NAT -> pad + q + r even, even NAT -> r even
+                    if ((NAT & 1) == 0 || ((q + PADODD) & 1) == 0) load_run<T, NAT, 0>(av, pa + q * NAT);
                     else load_run<T, NAT, 1>(av, pa + q * NAT);
                     T b0 = (T)0, b1 = (T)0;
+                    // B values of the pair sit at pb[0 .. 2*NBT): column 0 needs pb[q], column 1 needs pb[NBT + q - 1]; they
+                    // are fetched as aligned 2-element vectors one step ahead (which step depends on the parity of NBT)
                     if ((q & 1) == 0) {
-                        // elements q, q+1 of column 0 and NBT+q-1, NBT+q of the pair (NBT odd: both vectors are aligned)
                         if (q + 1 < NBT) {
                             const V v = *reinterpret_cast<const V *>(pb + q);
                             b0 = v.x;
                             b0n = v.y;
                         } else if (q < NBT) b0 = pb[q];
-                        if (q >= 1) {
-                            const V w = *reinterpret_cast<const V *>(pb + NBT + q - 1);
+                    } else b0 = b0n;
+                    if (NBT & 1) {
+                        if ((q & 1) == 0) {
+                            if (q >= 1) {
+                                const V w = *reinterpret_cast<const V *>(pb + NBT + q - 1);   // NBT + q - 1 even
+                                b1 = w.x;
+                                b1n = w.y;
+                            } else b1n = pb[NBT];
+                        } else b1 = b1n;
+                    } else {
+                        if (q & 1) {
+                            const V w = *reinterpret_cast<const V *>(pb + NBT + q - 1);       // NBT + q - 1 even
                             b1 = w.x;
                             b1n = w.y;
-                        } else b1n = pb[NBT];
-                    } else {
-                        b0 = b0n;
-                        b1 = b1n;
+                        } else b1 = b1n;                                                      // (unused at q = 0)
                     }
                     if (q < NBT) {
 #pragma unroll
@@ -405,6 +415,14 @@ int lbm_gbmm_reg(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64
     if (NA == NB && NA == 11) return gr_launch<T, 11, 11>(h, a);
     if (NA == NB && NA == 13) return gr_launch<T, 13, 13>(h, a);
     if (NA == NB && NA == 15) return gr_launch<T, 15, 15>(h, a);
+    // equal EVEN row counts (A*A', triangular bands, bidiagonal-like factors): exact too; their vector alignment depends on
+    // the row parity only.  (8 and 16 rows would put 8 lanes on the same banks: they stay on the padded 9 / 17 templates.)
+    if (NA == NB && NA == 2) return gr_launch<T, 2, 2>(h, a);
+    if (NA == NB && NA == 4) return gr_launch<T, 4, 4>(h, a);
+    if (NA == NB && NA == 6) return gr_launch<T, 6, 6>(h, a);
+    if (NA == NB && NA == 10) return gr_launch<T, 10, 10>(h, a);
+    if (NA == NB && NA == 12) return gr_launch<T, 12, 12>(h, a);
+    if (NA == NB && NA == 14) return gr_launch<T, 14, 14>(h, a);
     if (NA <= 3) return gr_dispatch_b<T, 3>(h, a, (int)NB);
     if (NA <= 5) return gr_dispatch_b<T, 5>(h, a, (int)NB);
     if (NA <= 9) return gr_dispatch_b<T, 9>(h, a, (int)NB);

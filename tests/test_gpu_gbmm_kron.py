@@ -116,7 +116,10 @@ def test_gbmm_register_kernel(L, oracle, dt):
              (4000, 4000, 4000, 1, 1, 1, 1), (777, 777, 777, 0, 0, 0, 0),
              # exact instantiations for equal odd row counts 7, 11, 13, 15 (bulk-TMA path on the interior tiles)
              (3000, 3000, 3000, 3, 3, 3, 3), (2900, 3100, 3000, 5, 5, 5, 5), (3000, 3000, 3000, 6, 6, 6, 6), (3000, 3000, 3000, 7, 7, 7, 7),
-             (3000, 3000, 3000, 2, 4, 5, 1), (3000, 3000, 3000, 10, 0, 3, 7)]
+             (3000, 3000, 3000, 2, 4, 5, 1), (3000, 3000, 3000, 10, 0, 3, 7),
+             # exact instantiations for equal EVEN row counts 2, 4, 6, 10, 12, 14 (A*A', triangular bands, bidiagonal-like)
+             (3000, 3000, 3000, 0, 1, 1, 0), (3000, 3100, 2900, 1, 0, 0, 1), (3000, 3000, 3000, 1, 2, 2, 1), (3000, 3000, 3000, 3, 2, 1, 4),
+             (3000, 3000, 3000, 5, 4, 4, 5), (2900, 3000, 3100, 6, 5, 5, 6), (3000, 3000, 3000, 0, 13, 13, 0), (3000, 3000, 3000, 4, 3, 3, 4)]
     for s, (m, n, k, kla, kua, klb, kub) in enumerate(cases):
         A_np, A = _band(L, oracle, m, k, kla, kua, 61 + s, dt)
         B_np, B = _band(L, oracle, k, n, klb, kub, 62 + s, dt)
