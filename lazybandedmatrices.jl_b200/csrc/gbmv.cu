@@ -261,6 +261,135 @@ __global__ void __launch_bounds__(1024) gbmv_wide_n_kernel(const GbmvWideArgs<T>
     for (; i < R1; i += NT) a.y[i] = (a.beta == (T)0) ? (T)0 : a.beta * a.y[i];
 }
 
+// Wide bands, op = N, R right-hand sides sharing ONE pass over A (mul!(C, A, B::Matrix) with l+u+1 > 33): the kernel
+// above with R accumulators per row and R x-windows per stage.  A is the whole traffic here (R*2/(l+u+1) of it is
+// x and y), so R columns cost about one gbmv instead of R.
+template <typename T> struct vec2w;
+template <> struct vec2w<double> { using type = double2; };
+template <> struct vec2w<float> { using type = float2; };
+
+template <typename T>
+struct GbmvWideMultiArgs {
+    GbmvWideArgs<T> w;   // x / y = first column of X / Y
+    int64_t ldx, ldy;
+};
+
+template <typename T, int R>
+__global__ void __launch_bounds__(1024) gbmv_wide_n_multi_kernel(const GbmvWideMultiArgs<T> am) {
+    const GbmvWideArgs<T> &a = am.w;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int NT = blockDim.x;
+    const int S = a.stages;
+    const int sxe = (int)a.sx_elems;
+    const int64_t stage_elems = a.sA_elems + R * a.sx_elems;
+    const int C = a.chunk;
+
+    const int64_t R0 = (int64_t)blockIdx.x * a.run;
+    const int64_t R1 = R0 + a.run < a.m ? R0 + a.run : a.m;
+    if (R0 >= R1) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int64_t cs = R0 - a.kl > 0 ? R0 - a.kl : 0;
+    cs &= ~(int64_t)(EPV - 1);
+    int64_t ce = R1 + a.ku < a.n ? R1 + a.ku : a.n;  // exclusive
+    if (cs > ce) cs = ce & ~(int64_t)(EPV - 1);
+    const int64_t nchunks = (ce - cs + C - 1) / C;
+
+    auto issue = [&](int64_t q, int s) {  // thread 0 only
+        const int64_t cb = cs + q * C;
+        const int64_t cq = cb + C < ce ? C : ce - cb;
+        T *sA = sbase + (int64_t)s * stage_elems;
+        T *sx = sA + a.sA_elems;
+        const int64_t cntA = stage_round<T>(cq * a.lda, (a.n - cb) * a.lda);
+        const int64_t cntx = stage_round<T>(cq, a.n - cb);
+        mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + R * stage_bytes_bulk<T>(cntx));
+        stage_issue<T>(sA, a.A + cb * a.lda, cntA, &bars[s]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) stage_issue<T>(sx + r * a.sx_elems, a.x + r * am.ldx + cb, cntx, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+
+    if (tid == 0) {
+        const int64_t pro = nchunks < S ? nchunks : S;
+        for (int64_t q = 0; q < pro; ++q) issue(q, (int)q);
+    }
+
+    int64_t i = R0 + tid;  // the row this thread currently accumulates
+    T acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = (T)0;
+    const int lda = (int)a.lda;
+
+    for (int64_t q = 0; q < nchunks; ++q) {
+        const int s = (int)(q % S);
+        const uint32_t parity = (uint32_t)((q / S) & 1);
+        const int64_t cb = cs + q * C;
+        const int cq = (int)(cb + C < ce ? C : ce - cb);
+        const T *sA = sbase + (int64_t)s * stage_elems;
+        const T *sx = sA + a.sA_elems;
+
+        mbar_wait(&bars[s], parity);
+
+        if (i < R1) {
+            int jlo = (int)(i - a.kl - cb);
+            int jhi = (int)(i + a.ku - cb);
+            if (jlo < 0) jlo = 0;
+            if (jhi > cq - 1) jhi = cq - 1;
+            const int base = (int)(a.ku + i - cb);
+            // two columns per step: their x values are one aligned 2-element broadcast load per right-hand side
+            using V2 = typename vec2w<T>::type;
+            int jj = jlo;
+            if ((jj & 1) && jj <= jhi) {
+                const T av = sA[base + jj * (lda - 1)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + jj], acc[r]);
+                ++jj;
+            }
+#pragma unroll 2
+            for (; jj + 1 <= jhi; jj += 2) {
+                const T av0 = sA[base + jj * (lda - 1)], av1 = sA[base + (jj + 1) * (lda - 1)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const V2 xv = *reinterpret_cast<const V2 *>(sx + r * sxe + jj);
+                    acc[r] = fma(av0, xv.x, acc[r]);
+                    acc[r] = fma(av1, xv.y, acc[r]);
+                }
+            }
+            if (jj <= jhi) {
+                const T av = sA[base + jj * (lda - 1)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + jj], acc[r]);
+            }
+            if (i + a.ku < cb + cq || q == nchunks - 1) {  // all columns of row i seen
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    T *yp = a.y + r * am.ldy + i;
+                    *yp = (a.beta == (T)0) ? a.alpha * acc[r] : fma(a.beta, *yp, a.alpha * acc[r]);
+                    acc[r] = (T)0;
+                }
+                i += NT;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && q + S < nchunks) issue(q + S, s);
+    }
+    for (; i < R1; i += NT)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            T *yp = a.y + r * am.ldy + i;
+            *yp = (a.beta == (T)0) ? (T)0 : a.beta * *yp;
+        }
+}
+
 // ------------------------------------------------------------------------------------------
 // wide bands, op = T, aligned: column chunks through the TMA ring, warp per column from smem
 // ------------------------------------------------------------------------------------------
@@ -961,6 +1090,65 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
             else rc = tr ? launch_multi<T, 2, true>(h, a, (int)grid, smem) : launch_multi<T, 2, false>(h, a, (int)grid, smem);
             if (rc) return rc;
             c += R;
+        }
+    }
+    // wide bands, op = N: groups of 8 / 4 / 2 columns share one pass over A (gbmv_wide_n_multi_kernel)
+    {
+        const bool wide_multi_ok = !tr && nb > 33 && nin > 0 && alpha != (T)0 && A && X && Y && lbm_aligned16(A) && lbm_aligned16(X) &&
+                                   lbm_aligned16(Y) && ldx % EPV == 0 && (nb + 32) <= 1024 && h->tune.gbmv_force != 1 &&
+                                   (32 * (lda + 8) + 64) * (int64_t)sizeof(T) <= smem_cap;
+        if (wide_multi_ok) {
+            lbm_device_guard g(h->device);
+            while (nrhs - c >= 2) {
+                const int R = nrhs - c >= 8 ? 8 : (nrhs - c >= 4 ? 4 : 2);
+                GbmvWideMultiArgs<T> am;
+                GbmvWideArgs<T> &a = am.w;
+                a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda;
+                a.alpha = alpha; a.beta = beta; a.A = A; a.x = X + c * ldx; a.y = Y + c * ldy;
+                am.ldx = ldx; am.ldy = ldy;
+                int64_t chunk = h->tune.gbmvw_chunk > 0 ? h->tune.gbmvw_chunk : (64 * 1024) / (lda * (int64_t)sizeof(T));
+                chunk = chunk / 16 * 16;
+                if (chunk < 16) chunk = 16;
+                while (chunk > 16 && (chunk + kl + ku > 1024 || (chunk * (lda + R) + (R + 1) * 2 * EPV) * (int64_t)sizeof(T) + 128 > smem_cap))
+                    chunk -= 16;
+                const int64_t nt = round_up(chunk + kl + ku, 32);
+                a.chunk = (int)chunk;
+                a.sA_elems = round_up(chunk * lda + 2 * EPV, EPV);
+                a.sx_elems = round_up(chunk + 2 * EPV, EPV);
+                const int64_t stage_bytes = (a.sA_elems + R * a.sx_elems) * (int64_t)sizeof(T);
+                int64_t stages = h->tune.gbmvw_stages > 0 ? h->tune.gbmvw_stages : 3;
+                if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+                while (stages > 1 && stages * stage_bytes + 128 > smem_cap) --stages;
+                a.stages = (int)stages;
+                const int64_t smem_cta = stages * stage_bytes + 128;
+                int64_t ctas = (227 * 1024) / (smem_cta + 1024);
+                if (ctas < 1) ctas = 1;
+                if (ctas * nt > 2048) ctas = 2048 / nt;
+                if (ctas < 1) ctas = 1;
+                int64_t grid = (int64_t)h->sm_count * ctas;
+                int64_t run = (m + grid - 1) / grid;
+                const int64_t min_run = 4 * (kl + ku) > 1024 ? 4 * (kl + ku) : 1024;
+                if (run < min_run) run = min_run;
+                run = round_up(run, EPV);
+                grid = (m + run - 1) / run;
+                a.run = run;
+#define LBM_WIDE_MULTI(RR)                                                                                              \
+    do {                                                                                                                \
+        static int cfg = 0;                                                                                             \
+        auto kern = gbmv_wide_n_multi_kernel<T, RR>;                                                                    \
+        if (!(cfg & (1 << h->device))) {                                                                                \
+            LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));    \
+            cfg |= (1 << h->device);                                                                                    \
+        }                                                                                                               \
+        kern<<<(unsigned)grid, (unsigned)nt, (size_t)smem_cta, h->stream>>>(am);                                        \
+    } while (0)
+                if (R == 8) LBM_WIDE_MULTI(8);
+                else if (R == 4) LBM_WIDE_MULTI(4);
+                else LBM_WIDE_MULTI(2);
+#undef LBM_WIDE_MULTI
+                LBM_LAUNCH_CHECK(h, "gbmv_wide_n_multi_kernel");
+                c += R;
+            }
         }
     }
     for (; c < nrhs; ++c) {
