@@ -274,8 +274,9 @@ struct GbmvWideMultiArgs {
     int64_t ldx, ldy;
 };
 
-template <typename T, int R>
-__global__ void __launch_bounds__(1024) gbmv_wide_n_multi_kernel(const GbmvWideMultiArgs<T> am) {
+// MAXT = 512 when the CTA has <= 512 threads: 128 registers per thread instead of 64, i.e. room for the unrolled loads
+template <typename T, int R, int MAXT>
+__global__ void __launch_bounds__(MAXT) gbmv_wide_n_multi_kernel(const GbmvWideMultiArgs<T> am) {
     const GbmvWideArgs<T> &a = am.w;
     constexpr int EPV = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(1024) gbmv_wide_n_multi_kernel(const GbmvWideM
                 for (int r = 0; r < R; ++r) acc[r] = fma(av, sx[r * sxe + jj], acc[r]);
                 ++jj;
             }
-#pragma unroll 2
+#pragma unroll 4
             for (; jj + 1 <= jhi; jj += 2) {
                 const T av0 = sA[base + jj * (lda - 1)], av1 = sA[base + (jj + 1) * (lda - 1)];
 #pragma unroll
@@ -1134,8 +1135,9 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
                 a.run = run;
 #define LBM_WIDE_MULTI(RR)                                                                                              \
     do {                                                                                                                \
-        static int cfg = 0;                                                                                             \
-        auto kern = gbmv_wide_n_multi_kernel<T, RR>;                                                                    \
+        static int cfg2[2] = {0, 0};                                                                                    \
+        int &cfg = cfg2[nt <= 512 ? 0 : 1];                                                                             \
+        auto kern = nt <= 512 ? gbmv_wide_n_multi_kernel<T, RR, 512> : gbmv_wide_n_multi_kernel<T, RR, 1024>;           \
         if (!(cfg & (1 << h->device))) {                                                                                \
             LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));    \
             cfg |= (1 << h->device);                                                                                    \
