@@ -361,6 +361,7 @@ def run_b200(args):
     # ---- banded x banded materialise, l=u=8 (the other half of the north-star target; not part of `value`):
     #      n = 2^26 f64, columns of C partitioned over the ranks, static halo of A, no communication
     if not args.no_wide:
+        ok, err = 1, ""
         try:
             from lbm_b200.shard import GbmmColumnShard
             nm_, lm = 1 << 26, 8
@@ -373,6 +374,13 @@ def run_b200(args):
             C_slab = torch.empty((q.c1 - q.c0, 4 * lm + 1), dtype=torch.float64, device=dev)
             for _ in range(2):
                 q.local_gbmm(A_slab, B_slab, C_slab)
+            torch.cuda.synchronize()
+        except Exception as e:  # never lose the headline line to the optional point
+            ok, err = 0, str(e)[:200]
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)   # every rank takes the same branch (no barrier mismatch)
+        if int(okt[0]):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 5
@@ -387,10 +395,10 @@ def run_b200(args):
             gbs = 8 * nm_ * (2 * nbm + 4 * lm + 1) / (float(msm[0]) * 1e-3) / 1e9
             breakdown["materialize_l8u8_x_l8u8"] = {"n": "2^26", "ms": float(msm[0]), "gbs": gbs, "frac_of_peak": gbs / (peak * world),
                                                     "kernel": "gbmm_reg_kernel<double,17,17> (column-sharded, no communication)"}
-            del A_slab, B_slab, C_slab
-            torch.cuda.empty_cache()
-        except Exception as e:  # never lose the headline line to the optional point
-            breakdown["materialize_l8u8_x_l8u8"] = {"error": str(e)[:200]}
+        else:
+            breakdown["materialize_l8u8_x_l8u8"] = {"error": err or "failed on another rank"}
+        A_slab = B_slab = C_slab = None
+        torch.cuda.empty_cache()
 
     # ---- e2e: the same metric through the C-ABI host-buffer call (H2D + kernel + D2H timed) ---
     e2e = None if args.no_e2e else run_e2e(args, L, h, n, rank, world, dev, barrier)
