@@ -28,17 +28,90 @@ def main():
     init_comm(local)                                    # library communicator + peer-memory mailboxes
     assert h.comm_world == world
     peer = bool(L._lib.lib().lbm_peer_active(h.ptr))
-    for mode in ((0, 1) if peer else (1,)):             # peer mailboxes, then in-library ncclSend/ncclRecv
-        h.set_tuning(exchange_mode=mode)
+    # peer mailboxes with the exchange FUSED into the compute launch (default), the same mailboxes through the two-kernel
+    # exchange (exchange_fuse = 2), then in-library ncclSend/ncclRecv
+    for mode, fuse in (((0, 0), (0, 2), (1, 0)) if peer else ((1, 0),)):
+        h.set_tuning(exchange_mode=mode, exchange_fuse=fuse)
         _check(rank, world, dev, eps)
         _check_kron_gbmm(rank, world, dev, eps)
         _check_epochs(rank, world, dev, eps)
-    h.set_tuning(exchange_mode=0)
+        _check_short_shards(rank, world, dev, eps)
+        _check_tridiag(rank, world, dev, eps)
+    h.set_tuning(exchange_mode=0, exchange_fuse=0)
+    if peer:
+        _check_launch_counts(rank, world, dev, h)
     dist.barrier()
     if rank == 0:
         print(f"OK sharded mul!/chain/kron/tridiag on {world} GPUs match the oracle (torch P2P, "
               f"{'peer-memory mailboxes, ' if peer else 'NO peer access: '}in-library NCCL)")
     dist.destroy_process_group()
+
+
+def _check_launch_counts(rank, world, dev, h):
+    """with the fused exchange a sharded apply is ONE launch per rank (was 4.75)."""
+    for (n, l, u) in ((1 << 22, 1, 1), (1 << 22, 8, 8)):
+        f = ShardedBanded.brand(n, l, u, rank, world, device=dev, seed=3)
+        xb = f.plan.new_vector(torch.float64, dev)
+        y = torch.empty(f.plan.m_loc, dtype=torch.float64, device=dev)
+        f.mul_(y, xb)
+        l0 = h.launch_count()
+        for _ in range(10):
+            f.mul_(y, xb)
+        assert h.launch_count() - l0 == 10, ("launches per apply", (h.launch_count() - l0) / 10)
+    g = 2048
+    D = L.banded_from_diagonals(g, {0: -2.0, 1: 1.0, -1: 1.0}, device=dev)
+    p = RowShard.plan(g, 1, 1, rank, world)
+    sh = ShardedKronSum(g, g, 1, 1, D.data[p.c0:p.c1].contiguous(), D, rank, world)
+    xb = sh.new_buffer(torch.float64, dev)
+    y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
+    sh.mul_(y, xb)
+    l0 = h.launch_count()
+    for _ in range(10):
+        sh.mul_(y, xb)
+    assert h.launch_count() - l0 == 10, ("kronsum launches per apply", (h.launch_count() - l0) / 10)
+    torch.cuda.synchronize()
+
+
+def _check_short_shards(rank, world, dev, eps):
+    """trailing shards empty or shorter than the halo (n < 4*world, ...) must neither hang nor fault: the
+    effective world shrinks, empty ranks return at once, everyone agrees."""
+    for (n, l, u) in ((100, 8, 5), (4 * world - 2, 1, 1), (16 * world - 13, 2, 3)):
+        try:
+            f = ShardedBanded.brand(n, l, u, rank, world, device=dev, seed=0x33)
+        except L.LbmArgumentError:
+            continue        # shards narrower than the halo: every rank raises alike (pure function of n, l, u, world)
+        M = np.asfortranarray(O.fill_uniform(0x33, (l + u + 1) * n).reshape((l + u + 1, n), order="F"))
+        x_full = O.fill_uniform(0x9, n)
+        want = O.gbmv("N", n, n, l, u, 1.0, M, x_full)[f.plan.r0:f.plan.r1]
+        xbuf = f.plan.new_vector(torch.float64, dev)
+        f.plan.owned(xbuf).copy_(torch.from_numpy(x_full[f.plan.r0:f.plan.r1]).to(dev))
+        for k in range(6):
+            y = torch.full((f.plan.m_loc,), float("nan"), dtype=torch.float64, device=dev)
+            f.mul_(y, xbuf, overlap=bool(k % 2 == 0))
+            if f.plan.m_loc:
+                err = np.max(np.abs(y.cpu().numpy() - want))
+                assert err <= 4 * eps * (l + u + 1), ("short shards", n, l, u, k, err)
+    torch.cuda.synchronize()
+
+
+def _check_tridiag(rank, world, dev, eps):
+    """C2 path: one C call per apply (lbm_?tridiag_mv_sharded), all three kinds, x changing between applies."""
+    n = 1 << 20
+    d_full, e_full, x_full = O.fill_uniform(1, n), O.fill_uniform(2, n - 1), O.fill_uniform(4, n)
+    for has_l, has_u in ((1, 1), (0, 1), (1, 0)):
+        c0, c1 = ShardedTridiagonal.slices(n, has_l, has_u, rank, world)
+        d = torch.from_numpy(d_full[c0:c1]).to(dev)
+        e = torch.from_numpy(e_full[c0:c1 - 1]).to(dev)
+        sh = ShardedTridiagonal(n, e if has_l else None, d, e if has_u else None, rank, world)
+        p = sh.plan
+        want = O.tridiag_mv(n, e_full if has_l else None, d_full, e_full if has_u else None, x_full)[p.r0:p.r1]
+        xb = p.new_vector(torch.float64, dev)
+        for k in range(8):
+            p.owned(xb).copy_(torch.from_numpy(x_full[p.r0:p.r1] * float(2 ** (k % 3))).to(dev))
+            y = torch.full((p.m_loc,), float("nan"), dtype=torch.float64, device=dev)
+            sh.mul_(y, xb, overlap=bool(k % 2 == 0))
+            err = np.max(np.abs(y.cpu().numpy() / float(2 ** (k % 3)) - want))
+            assert err <= 4 * eps * 3, ("tridiag", has_l, has_u, k, err)
 
 
 def _check_epochs(rank, world, dev, eps):

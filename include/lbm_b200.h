@@ -235,9 +235,17 @@ int lbm_stridiag_mm(lbm_handle_t h, int64_t n, const float *adl, const float *ad
  * ghost-cell vector [left | owned | right] of length c1-c0.  lbm_shard_plan writes
  * {r0, r1, c0, c1, left, right, kl_loc, ku_loc} (pure integers, no GPU).  The communicator is
  * NCCL (dlopen'ed): rank 0 calls lbm_comm_unique_id, the host broadcasts the 128 bytes, every
- * rank calls lbm_comm_init.  lbm_?gbmv_sharded = ghost exchange (ncclSend/ncclRecv over
- * NVLink on a private stream) overlapped with the interior rows, then the <= kl+ku boundary
- * rows: y_own <- alpha*A[r0:r1,:]*x + beta*y_own.  No all-reduce/all-gather on the path. */
+ * rank calls lbm_comm_init.  lbm_?gbmv_sharded: y_own <- alpha*A[r0:r1,:]*x + beta*y_own.  With the peer mailboxes
+ * connected (below) and overlap = 1 the ghost exchange is FUSED into the compute launch (csrc/halo.cuh): one kernel per
+ * apply pushes this rank's boundary values over NVLink at its start and patches the ghost part of its last tiles' x
+ * windows in shared memory -- the ghost CELLS of xbuf are then scratch (unspecified after the call).  Otherwise: ghost
+ * exchange (two small kernels, or ncclSend/ncclRecv) on a private stream overlapped with the interior rows, then the
+ * <= kl+ku boundary rows.  No all-reduce/all-gather on the path.
+ * Shards: rows are split in blocks of per = roundup4(ceil(n/world)); trailing ranks may own NOTHING (they have no
+ * neighbours and every sharded call returns 0 on them) and the last non-empty shard may be short.  A partition whose
+ * full shards are narrower than the halo (per < max(kl,ku) with more than one non-empty rank) is rejected with -2 on
+ * EVERY rank alike.  A device-side ghost wait that times out (lbm_set_tuning "halo_timeout_ms", default 30000) never
+ * traps: it sets a fault word that the next sharded call / lbm_sync returns as 2001. */
 int lbm_shard_plan(int64_t n, int64_t kl, int64_t ku, int rank, int world, int64_t *out8);
 int lbm_comm_unique_id(void *id128);
 int lbm_comm_init(lbm_handle_t h, const void *id128, int rank, int world);
@@ -258,6 +266,27 @@ int lbm_dgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, double 
 int lbm_sgbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, float alpha, const float *A_slab,
                       int64_t lda, float *xbuf, float beta, float *y_own, int overlap);
 
+/* mul!(y, ApplyMatrix(*, F_0, ..., F_{nf-1}), x) row-sharded in ONE call: right to left, the output of stage f is written
+ * into the owned block of a ghost-cell vector laid out for the factor that consumes it, whose apply exchanges that
+ * intermediate's halo (north_star: "halos of the intermediate in product chains"; flattening rule of
+ * /root/reference/src/blockkron.jl:208-214).  Factor f is n x n with bandwidths (kl[f],ku[f]); A_slab[f] is this rank's
+ * column slice of its band array (lbm_shard_plan(n,kl[f],ku[f],...)), xbuf the ghost-cell vector of factor nf-1, y_own
+ * the owned rows.  Temporaries live in the handle's scratch. */
+int lbm_dgbmv_chain_sharded(lbm_handle_t h, int nf, int64_t n, const int64_t *kl, const int64_t *ku,
+                            const double *const *A_slab, const int64_t *lda, double alpha, double *xbuf, double beta,
+                            double *y_own);
+int lbm_sgbmv_chain_sharded(lbm_handle_t h, int nf, int64_t n, const int64_t *kl, const int64_t *ku,
+                            const float *const *A_slab, const int64_t *lda, float alpha, float *xbuf, float beta,
+                            float *y_own);
+/* Tridiagonal / SymTridiagonal / Bidiagonal mat-vec row-sharded in ONE call (BASELINE config 2): plan =
+ * lbm_shard_plan(n, dl_ext != NULL, du_ext != NULL, ...); d_ext = d[c0:c1], dl_ext = dl[c0:c1-1], du_ext = du[c0:c1-1]
+ * (the diagonals over the ghost-extended index range; SymTridiagonal passes dl_ext == du_ext); xbuf = ghost-cell vector
+ * of length c1-c0; y_own = rows [r0,r1).  overlap = 1: the one-element ghost exchange is fused into the launch. */
+int lbm_dtridiag_mv_sharded(lbm_handle_t h, int64_t n, const double *dl_ext, const double *d_ext, const double *du_ext,
+                            double alpha, double *xbuf, double beta, double *y_own, int overlap);
+int lbm_stridiag_mv_sharded(lbm_handle_t h, int64_t n, const float *dl_ext, const float *d_ext, const float *du_ext,
+                            float alpha, float *xbuf, float beta, float *y_own, int overlap);
+
 /* kron(A,I)+kron(I,B) partitioned by grid columns: plan = lbm_shard_plan(n1, kla, kua, ...) over COLUMNS
  * of X; A_slab = columns [c0,c1) of A's band array; xbuf = n2 x (c1-c0) ghost-cell buffer
  * [left ghost columns | owned | right ghost columns]; y_own = n2 x (r1-r0).  Ghost columns travel by
@@ -268,6 +297,47 @@ int lbm_dkronsum2d_mv_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kl
 int lbm_skronsum2d_mv_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua,
                               const float *A_slab, int64_t lda, int64_t klb, int64_t kub, const float *B,
                               int64_t ldb, float alpha, float *xbuf, float beta, float *y_own, int overlap);
+
+/* ---- single-process multi-device mode ("one host thread driving every GPU") -------------------------- */
+/* For a host that is ONE process (a Julia session): no MPI.jl / Distributed.jl, no rendezvous, no NCCL.
+ * lbm_create_multi creates one handle + stream per device, enables peer access between row-neighbours and cross-links
+ * their mailbox blocks by plain peer pointers; every call below ENQUEUES on all devices from the calling thread and
+ * returns (lbm_multi_sync waits).  The per-device handles (lbm_multi_handle) carry rank / world, so every `*_sharded`
+ * entry point above also works on them (buffers from lbm_malloc on that handle) -- e.g. lbm_?tridiag_mv_sharded and
+ * lbm_?kronsum2d_mv_sharded; call them device by device (for a multi-stage operation: all devices of one stage before
+ * the next stage).  This is the object behind a sharded device layout in the Julia shim: `materialize!(::MulAdd{...})`
+ * (hooks of /root/reference/src/tridiag.jl:685-688, src/bidiag.jl:438-440) forwards to lbm_?gbmv_sharded_all. */
+typedef struct lbm_multi_s *lbm_multi_t;
+typedef struct lbm_shard_s *lbm_shard_t;   /* row partition of an n x n banded operator + its per-device slabs */
+typedef struct lbm_svec_s *lbm_svec_t;     /* a length-n vector in the ghost-cell layout of a shard */
+int lbm_create_multi(lbm_multi_t *out, int ndev, const int *devices);   /* devices == NULL: 0 .. ndev-1 */
+int lbm_destroy_multi(lbm_multi_t m);
+int lbm_multi_ndev(lbm_multi_t m);
+lbm_handle_t lbm_multi_handle(lbm_multi_t m, int r);
+int lbm_multi_sync(lbm_multi_t m);                       /* waits for every device; reports device-side faults */
+const char *lbm_multi_last_error_string(lbm_multi_t m);
+/* elem_bytes: 8 = Float64, 4 = Float32.  The shard OWNS its device memory (the library allocates the slabs). */
+int lbm_shard_create(lbm_multi_t m, int elem_bytes, int64_t n, int64_t kl, int64_t ku, lbm_shard_t *out);
+int lbm_shard_destroy(lbm_shard_t s);
+/* A_host: the (kl+ku+1) x n diagonal-major array as BandedMatrices stores it (leading dimension lda_host); device r
+ * receives the column slice [c0,c1) of lbm_shard_plan. */
+int lbm_shard_distribute(lbm_shard_t s, const void *A_host, int64_t lda_host);
+int lbm_shard_fill_uniform(lbm_shard_t s, uint64_t seed);          /* brand(n,n,kl,ku) from the counter-based stream */
+int lbm_shard_slab(lbm_shard_t s, int r, void **dptr, int64_t *plan8);
+int lbm_svec_create(lbm_shard_t s, lbm_svec_t *out);
+int lbm_svec_destroy(lbm_svec_t v);
+int lbm_svec_distribute(lbm_svec_t v, const void *x_host);         /* n host elements -> owned blocks */
+int lbm_svec_gather(lbm_svec_t v, void *y_host);                   /* owned blocks -> n host elements */
+int lbm_svec_fill_uniform(lbm_svec_t v, uint64_t seed);
+int lbm_svec_buffer(lbm_svec_t v, int r, void **ghost_buf, void **owned);
+/* y <- alpha*A*x + beta*y on all devices: one launch per device, ghost exchange fused into it.  x must be a vector of A's
+ * own layout (lbm_svec_create(A, ...)); y any vector of the same n; -3 / -5 = DimensionMismatch. */
+int lbm_dgbmv_sharded_all(lbm_shard_t A, double alpha, lbm_svec_t x, double beta, lbm_svec_t y);
+int lbm_sgbmv_sharded_all(lbm_shard_t A, float alpha, lbm_svec_t x, float beta, lbm_svec_t y);
+/* y <- alpha*F_0*(F_1*(...F_{nf-1}*x)) + beta*y, every factor sharded over the same devices; x in F_{nf-1}'s layout;
+ * the halos of each intermediate are exchanged by the stage that consumes it. */
+int lbm_dgbmv_chain_sharded_all(int nf, const lbm_shard_t *F, double alpha, lbm_svec_t x, double beta, lbm_svec_t y);
+int lbm_sgbmv_chain_sharded_all(int nf, const lbm_shard_t *F, float alpha, lbm_svec_t x, float beta, lbm_svec_t y);
 
 /* ---- structure helpers (pure integer, host side, no GPU needed) ------------------------ */
 /* bandwidths(ApplyMatrix(*, F1..Fnf)) = min.(size-1, (sum kl, sum ku))  ([up] LazyArrays;

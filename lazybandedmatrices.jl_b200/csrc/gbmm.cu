@@ -142,7 +142,7 @@ int gbmm_impl(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64_t 
     a.sA_elems = (tile + klb + kub) * lda;
     const int64_t grid = (n + tile - 1) / tile;
     if (smem_need(tile) <= smem_cap) {
-        static int configured_dev_mask = 0;
+        static std::atomic<int> configured_dev_mask{0};
         auto kern = gbmm_diag_kernel<T, true>;
         if (!(configured_dev_mask & (1 << h->device))) {
             LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
@@ -692,7 +692,7 @@ int chain3_t_launch2(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int64
                      int64_t sC, T *D, int64_t sD) {
     using G = ChainGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
     constexpr size_t smem = (size_t)(G::LDA * (G::NP + 4) + G::LD01 * G::NQ) * sizeof(T);
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     auto kern = gbmm_chain3_t_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC, MINB>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -717,7 +717,7 @@ int chain3_reg_launch(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int6
                       const T *C, int64_t sC, T *D, int64_t sD) {
     using G = ChainGeom<T, KLA, KUA, KLB, KUB, KLC, KUC>;
     constexpr size_t smem = (size_t)G::SMEM_ELEMS * sizeof(T);
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     auto kern = gbmm_chain3_reg_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -791,7 +791,7 @@ int chain3_impl(lbm_handle_t h, int64_t batch, int64_t n, const int64_t *kl, con
     const int64_t smem = layout(tile, oB, oC, oAB);
     if (smem > smem_cap) return lbm_fail_arg(h, 4, "bands too wide for the fused chain kernel (use lbm_?gbmm twice)");
     a.tile = (int)tile; a.offB = (int)oB; a.offC = (int)oC; a.offAB = (int)oAB;
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     auto kern = gbmm_chain3_kernel<T>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));

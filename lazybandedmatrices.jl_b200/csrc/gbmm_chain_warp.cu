@@ -310,7 +310,7 @@ int chain3_warp_launch(lbm_handle_t h, int64_t batch, int64_t n, const T *A, int
     static_assert(NWMAX >= 1, "tile slab exceeds shared memory");
     constexpr size_t smem = (size_t)NW * G::BYTES_WARP;
     auto kern = gbmm_chain3_warp_kernel<T, KLA, KUA, KLB, KUB, KLC, KUC, NW, ABBUF>;
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_dev_mask |= (1 << h->device);

@@ -890,7 +890,7 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     // 7: 4-stage / 3 CTAs, 8-10: 6 + rotated quadrants / interleaved p-halves, 11: 6 as one launch, 12: 2-stage / 6 CTAs
     // (measured in profiles/configs_r01_*.jsonl; everything lands between 17 and 21 TFLOP/s)
     const int variant = (int)h->tune.gbmm_variant;
-    static int configured_dev_mask[6] = {0, 0, 0, 0, 0, 0};
+    static std::atomic<int> configured_dev_mask[6] = {};
 #define LBM_DMMA_LAUNCH(IDX, NS, MB)                                                                         \
     do {                                                                                                      \
         const size_t smem = (size_t)(NS) * STAGE_DBL * sizeof(double);                                        \
@@ -914,7 +914,7 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
     if (variant == 0 || (variant >= 20 && variant <= 29)) {
         // warp-specialised interior kernel + the corner instantiation of the plain kernel
         // 20: 3-stage / 4 CTAs, 21: 3-stage / 3 CTAs, 22: 4-stage / 3 CTAs, 23: 2-stage / 4 CTAs
-        static int cfg_ws[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        static std::atomic<int> cfg_ws[10] = {};
         // gbmm_tile doubles as "row tiles per CTA" here; default: 5 for the default variant, 1 for the explicit ones
         // default: one CTA walks ALL row tiles of its 64-column block (tpc = gy)
         a.tpc = h->tune.gbmm_tile > 0 ? (int)(h->tune.gbmm_tile % 100) : (variant == 0 ? (int)(gy < 64 ? gy : 64) : 1);
@@ -987,7 +987,7 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
             const int64_t gcx = total_c < 1048576 ? total_c : 1048576;
             const dim3 grid_c((unsigned)(gcx > 0 ? gcx : 1), (unsigned)(total_c > 0 ? (total_c + gcx - 1) / gcx : 1));
             const size_t smem = (size_t)2 * STAGE_DBL * sizeof(double);
-            static int cfg_corner = 0;
+            static std::atomic<int> cfg_corner{0};
             if (!(cfg_corner & (1 << h->device))) {
                 LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<2, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 cfg_corner |= (1 << h->device);
@@ -998,7 +998,7 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         // column-block persistent kernels: one CTA per 64-column block
         const int64_t gcol = gx < 1048576 ? gx : 1048576;
         dim3 gridc((unsigned)gcol, (unsigned)((gx + gcol - 1) / gcol));
-        static int cfg_col[2] = {0, 0};
+        static std::atomic<int> cfg_col[2] = {};
         if (variant == 4) {
             const size_t smem = (size_t)2 * STAGE_DBL * sizeof(double);
             if (!(cfg_col[0] & (1 << h->device))) {

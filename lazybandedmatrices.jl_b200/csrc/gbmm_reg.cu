@@ -364,7 +364,7 @@ int gr_launch(lbm_handle_t h, const GrArgs<T> &a) {
                   "bulk copy sizes must be multiples of 16 bytes");
     constexpr size_t smem = G::SMEM_BYTES;
     auto kern = (a.pad & 1) ? gbmm_reg_kernel<T, NAT, NBT, 1> : gbmm_reg_kernel<T, NAT, NBT, 0>;
-    static int configured[2] = {0, 0};
+    static std::atomic<int> configured[2] = {};
     if (!(configured[a.pad & 1] & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[a.pad & 1] |= (1 << h->device);

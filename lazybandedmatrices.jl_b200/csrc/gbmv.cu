@@ -20,7 +20,7 @@
 //    the same TMA ring; one warp reduces a whole column from smem with a shuffle tree.
 //  * gbmv_wide_t_kernel: unaligned fallback of the above, reading global memory directly.
 //  * gbmv_direct_kernel: any alignment / any lda fallback, thread per output, L1/L2 served.
-#include "lbm_common.cuh"
+#include "halo.cuh"
 
 namespace {
 
@@ -46,8 +46,11 @@ struct GbmvArgs {
 // ------------------------------------------------------------------------------------------
 // narrow bands: streamed tiles
 // ------------------------------------------------------------------------------------------
-template <typename T, int NB, bool TRANS>
-__global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a) {
+// HALO: the row-sharded apply in ONE launch (halo.cuh) -- CTA 0 pushes this rank's boundary values of x to the
+// neighbours' mailboxes first; tiles are walked rotated by one so that the tiles whose x window overlaps ghost cells
+// (the first and the last) come last, and those tiles patch their window in shared memory from the local mailbox.
+template <typename T, int NB, bool TRANS, bool HALO>
+__global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a, const HaloFuse hf) {
     constexpr int EPV = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a)
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    if (HALO && blockIdx.x == 0) halo_push(hf, tid, GBMV_NT);   // before anything else: the neighbours are waiting for it
     __syncthreads();
 
     // tiles of this CTA: t = blockIdx.x + k*gridDim.x
@@ -69,6 +73,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a)
     const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
 
     auto ranges = [&](int64_t t, int64_t &o0, int64_t &o1, int64_t &c0, int64_t &c1, int64_t &x0, int64_t &x1) {
+        if (HALO) t = t + 1 < a.ntiles ? t + 1 : 0;   // rotate: tile 0 (left ghosts) last, tile ntiles-1 second to last
         o0 = t * a.tile;
         o1 = o0 + a.tile < a.nout ? o0 + a.tile : a.nout;
         if (!TRANS) {
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a)
         const T *sx = sA + a.sA_elems;
 
         mbar_wait(&bars[s], parity);
+        if (HALO) halo_patch_1d<T>(hf, const_cast<T *>(sx), x0a, x1, tid, GBMV_NT);
 
         // interior tiles need no index masks
         const bool interior = TRANS ? (o0 - a.ku >= 0 && o1 - 1 + a.kl < a.m)
@@ -161,6 +167,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a)
         __syncthreads();  // every thread is done reading stage s
         if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
     }
+    if (HALO && blockIdx.x == 0) halo_final_wait(hf, tid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -774,37 +781,39 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv2_tile_kernel(const Gbmv2Args<T> 
 // ------------------------------------------------------------------------------------------
 static inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 
-template <typename T, int NB, bool TRANS>
-int launch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem) {
-    static int configured_dev_mask = 0;
-    auto kern = gbmv_tile_kernel<T, NB, TRANS>;
-    if (!(configured_dev_mask & (1 << h->device))) {
+template <typename T, int NB, bool TRANS, bool HALO>
+int launch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem, const HaloFuse &hf) {
+    static std::atomic<int> configured_dev_mask{0};
+    auto kern = gbmv_tile_kernel<T, NB, TRANS, HALO>;
+    if (!(configured_dev_mask.load(std::memory_order_acquire) & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-        configured_dev_mask |= (1 << h->device);
+        configured_dev_mask.fetch_or(1 << h->device, std::memory_order_release);
     }
-    kern<<<grid, GBMV_NT, smem, h->stream>>>(a);
+    kern<<<grid, GBMV_NT, smem, h->stream>>>(a, hf);
     LBM_LAUNCH_CHECK(h, "gbmv_tile_kernel");
     return 0;
 }
 
-template <typename T, bool TRANS>
-int dispatch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem) {
+template <typename T, bool TRANS, bool HALO>
+int dispatch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem, const HaloFuse &hf) {
     switch ((int)(a.kl + a.ku + 1)) {
-        case 1: return launch_tile<T, 1, TRANS>(h, a, grid, smem);
-        case 2: return launch_tile<T, 2, TRANS>(h, a, grid, smem);
-        case 3: return launch_tile<T, 3, TRANS>(h, a, grid, smem);
-        case 5: return launch_tile<T, 5, TRANS>(h, a, grid, smem);
-        case 7: return launch_tile<T, 7, TRANS>(h, a, grid, smem);
-        case 9: return launch_tile<T, 9, TRANS>(h, a, grid, smem);
-        case 17: return launch_tile<T, 17, TRANS>(h, a, grid, smem);
-        case 33: return launch_tile<T, 33, TRANS>(h, a, grid, smem);
-        default: return launch_tile<T, 0, TRANS>(h, a, grid, smem);
+        case 1: return launch_tile<T, 1, TRANS, HALO>(h, a, grid, smem, hf);
+        case 2: return launch_tile<T, 2, TRANS, HALO>(h, a, grid, smem, hf);
+        case 3: return launch_tile<T, 3, TRANS, HALO>(h, a, grid, smem, hf);
+        case 5: return launch_tile<T, 5, TRANS, HALO>(h, a, grid, smem, hf);
+        case 7: return launch_tile<T, 7, TRANS, HALO>(h, a, grid, smem, hf);
+        case 9: return launch_tile<T, 9, TRANS, HALO>(h, a, grid, smem, hf);
+        case 17: return launch_tile<T, 17, TRANS, HALO>(h, a, grid, smem, hf);
+        case 33: return launch_tile<T, 33, TRANS, HALO>(h, a, grid, smem, hf);
+        default: return launch_tile<T, 0, TRANS, HALO>(h, a, grid, smem, hf);
     }
 }
 
+// `hf` != NULL: the caller (dist.cu) wants the ghost exchange fused into this launch; only the streamed-tile kernel can
+// do that, so any other route returns LBM_NOT_FUSED WITHOUT launching and the caller takes the unfused path.
 template <typename T>
 int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha, const T *A,
-              int64_t lda, const T *x, T beta, T *y) {
+              int64_t lda, const T *x, T beta, T *y, const HaloFuse *hf = nullptr) {
     if (!h) return -1;
     const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
     if (!tr && !(trans == 'N' || trans == 'n')) return lbm_fail_arg(h, 2, "trans must be N, T or C");
@@ -820,6 +829,7 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
     lbm_device_guard g(h->device);
     constexpr int EPV = 16 / (int)sizeof(T);
 
+    if (hf && (nin == 0 || alpha == (T)0 || tr)) return LBM_NOT_FUSED;
     if (nin == 0 || alpha == (T)0) {  // y <- beta*y
         int64_t blocks = (nout + 255) / 256;
         if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
@@ -849,6 +859,7 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
     else if (tr && nb >= 32 && aligned && force != 4 && (32 * lda + 64 + 32 + nb) * (int64_t)sizeof(T) <= smem_cap) path = 5;
     else if (tr && nb >= 32) path = 4;
     else path = 1;
+    if (hf && path != 2) return LBM_NOT_FUSED;
 
     if (path == 2) {
         GbmvArgs<T> a;
@@ -894,7 +905,10 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         int64_t grid = (int64_t)h->sm_count * ctas;
         if (grid > a.ntiles) grid = a.ntiles;
         const size_t smem = (size_t)(128 + stages * stage_bytes);
-        return tr ? dispatch_tile<T, true>(h, a, (int)grid, smem) : dispatch_tile<T, false>(h, a, (int)grid, smem);
+        HaloFuse none;
+        none.on = 0;
+        if (hf) return dispatch_tile<T, false, true>(h, a, (int)grid, smem, *hf);
+        return tr ? dispatch_tile<T, true, false>(h, a, (int)grid, smem, none) : dispatch_tile<T, false, false>(h, a, (int)grid, smem, none);
     }
 
     if (path == 3) {
@@ -931,7 +945,7 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         run = round_up(run, EPV);
         grid = (m + run - 1) / run;
         a.run = run;
-        static int configured_dev_mask = 0;
+        static std::atomic<int> configured_dev_mask{0};
         auto kern = gbmv_wide_n_kernel<T>;
         if (!(configured_dev_mask & (1 << h->device))) {
             LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -973,7 +987,7 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         run = round_up(run, 32);
         grid = (n + run - 1) / run;
         a.run = run;
-        static int configured_dev_mask = 0;
+        static std::atomic<int> configured_dev_mask{0};
         auto kern = gbmv_wide_t_ring_kernel<T>;
         if (!(configured_dev_mask & (1 << h->device))) {
             LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -1006,7 +1020,7 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
 
 template <typename T, int R, bool TRANS, int NBU>
 int launch_multi2(lbm_handle_t h, const GbmvMultiArgs<T> &a, int grid, size_t smem) {
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     auto kern = gbmv_multi_kernel<T, R, TRANS, NBU>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -1135,8 +1149,8 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
                 a.run = run;
 #define LBM_WIDE_MULTI(RR)                                                                                              \
     do {                                                                                                                \
-        static int cfg2[2] = {0, 0};                                                                                    \
-        int &cfg = cfg2[nt <= 512 ? 0 : 1];                                                                             \
+        static std::atomic<int> cfg2[2] = {};                                                                                  \
+        std::atomic<int> &cfg = cfg2[nt <= 512 ? 0 : 1];                                                                          \
         auto kern = nt <= 512 ? gbmv_wide_n_multi_kernel<T, RR, 512> : gbmv_wide_n_multi_kernel<T, RR, 1024>;           \
         if (!(cfg & (1 << h->device))) {                                                                                \
             LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));    \
@@ -1162,7 +1176,7 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
 
 template <typename T, int NBU>
 int launch_gbmv2(lbm_handle_t h, const Gbmv2Args<T> &a, int grid, size_t smem) {
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     auto kern = gbmv2_tile_kernel<T, NBU>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -1252,6 +1266,7 @@ int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl,
                    int64_t lda, const T *x, T beta, T *y) {
     if (!h) return -1;
     const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');
+    if (!tr && !(trans == 'N' || trans == 'n')) return lbm_fail_arg(h, 2, "trans must be N, T or C");
     if (m < 0) return lbm_fail_arg(h, 3, "m < 0");
     if (n < 0) return lbm_fail_arg(h, 4, "n < 0");
     if (kl < 0) return lbm_fail_arg(h, 5, "kl < 0");
@@ -1259,6 +1274,9 @@ int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl,
     if (lda < kl + ku + 1) return lbm_fail_arg(h, 9, "lda < kl+ku+1");
     const int64_t nout = tr ? n : m, nin = tr ? m : n;
     if (nout == 0) return 0;
+    if (!y) return lbm_fail_arg(h, 12, "y == NULL");
+    if (nin > 0 && !A) return lbm_fail_arg(h, 8, "A == NULL");
+    if (nin > 0 && !x) return lbm_fail_arg(h, 10, "x == NULL");
     lbm_device_guard g(h->device);
     void *dAv, *dxv, *dyv;
     int rc;
@@ -1273,7 +1291,10 @@ int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl,
         if (nin) LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, h->stream));
         if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, h->stream));
         rc = gbmv_impl<T>(h, trans, m, n, kl, ku, alpha, dA, lda, dx, beta, dy);
-        if (rc) return rc;
+        if (rc) {  // the header's promise: `_host` calls return with no DMA left in flight on the caller's buffers
+            cudaStreamSynchronize(h->stream);
+            return rc;
+        }
         LBM_CUDA(h, cudaMemcpyAsync(y, dy, (size_t)nout * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
         LBM_CUDA(h, cudaStreamSynchronize(h->stream));
         return 0;
@@ -1285,40 +1306,48 @@ int gbmv_host_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl,
         LBM_CUDA(h, cudaEventCreateWithFlags(&h->ev_kern, cudaEventDisableTiming));
     }
     cudaStream_t sc = h->h2d_stream, sk = h->stream, so = h->d2h_stream;
-    // order the pipeline after whatever is already queued on the handle's stream
-    LBM_CUDA(h, cudaEventRecord(h->ev_kern, sk));
-    LBM_CUDA(h, cudaStreamWaitEvent(sc, h->ev_kern, 0));
-    LBM_CUDA(h, cudaStreamWaitEvent(so, h->ev_kern, 0));
-    LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, sc));
-    if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, sc));
-    int64_t r_done = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += chunk_cols) {
-        const int64_t c1 = c0 + chunk_cols < n ? c0 + chunk_cols : n;
-        LBM_CUDA(h, cudaMemcpyAsync(dA + c0 * lda, A + c0 * lda, (size_t)((c1 - c0) * lda) * sizeof(T),
-                                    cudaMemcpyHostToDevice, sc));
-        LBM_CUDA(h, cudaEventRecord(h->ev_copy, sc));
-        // rows whose columns [i-kl, i+ku] all lie in [0, c1): i < c1 - ku (all remaining rows once c1 == n)
-        int64_t r_hi = c1 == n ? m : c1 - ku;
-        r_hi &= ~(int64_t)3;                   // keep sub-slabs 16-byte aligned
-        if (c1 == n) r_hi = m;
-        if (r_hi > m) r_hi = m;
-        if (r_hi <= r_done) continue;
-        LBM_CUDA(h, cudaStreamWaitEvent(sk, h->ev_copy, 0));
-        const int64_t a0 = r_done, b0 = r_hi;
-        const int64_t cc0 = a0 - kl > 0 ? a0 - kl : 0;
-        const int64_t cc1 = b0 + ku < n ? b0 + ku : n;
-        const int64_t shift = a0 - cc0;
-        rc = gbmv_impl<T>(h, 'N', b0 - a0, cc1 - cc0, kl - shift, ku + shift, alpha, dA + cc0 * lda, lda, dx + cc0, beta,
-                          dy + a0);
-        if (rc) return rc;
+    // the pipeline proper; ANY failure inside still drains the three streams before returning, so the caller may free or
+    // reuse A, x and y (the header's promise for `_host` entry points)
+    auto pipeline = [&]() -> int {
+        // order the pipeline after whatever is already queued on the handle's stream
         LBM_CUDA(h, cudaEventRecord(h->ev_kern, sk));
+        LBM_CUDA(h, cudaStreamWaitEvent(sc, h->ev_kern, 0));
         LBM_CUDA(h, cudaStreamWaitEvent(so, h->ev_kern, 0));
-        LBM_CUDA(h, cudaMemcpyAsync(y + a0, dy + a0, (size_t)(b0 - a0) * sizeof(T), cudaMemcpyDeviceToHost, so));
-        r_done = r_hi;
-    }
-    LBM_CUDA(h, cudaStreamSynchronize(so));
-    LBM_CUDA(h, cudaStreamSynchronize(sk));
-    LBM_CUDA(h, cudaStreamSynchronize(sc));
+        LBM_CUDA(h, cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(T), cudaMemcpyHostToDevice, sc));
+        if (beta != (T)0) LBM_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)nout * sizeof(T), cudaMemcpyHostToDevice, sc));
+        int64_t r_done = 0;
+        for (int64_t c0 = 0; c0 < n; c0 += chunk_cols) {
+            const int64_t c1 = c0 + chunk_cols < n ? c0 + chunk_cols : n;
+            LBM_CUDA(h, cudaMemcpyAsync(dA + c0 * lda, A + c0 * lda, (size_t)((c1 - c0) * lda) * sizeof(T),
+                                        cudaMemcpyHostToDevice, sc));
+            LBM_CUDA(h, cudaEventRecord(h->ev_copy, sc));
+            // rows whose columns [i-kl, i+ku] all lie in [0, c1): i < c1 - ku (all remaining rows once c1 == n)
+            int64_t r_hi = c1 == n ? m : c1 - ku;
+            r_hi &= ~(int64_t)3;                   // keep sub-slabs 16-byte aligned
+            if (c1 == n) r_hi = m;
+            if (r_hi > m) r_hi = m;
+            if (r_hi <= r_done) continue;
+            LBM_CUDA(h, cudaStreamWaitEvent(sk, h->ev_copy, 0));
+            const int64_t a0 = r_done, b0 = r_hi;
+            const int64_t cc0 = a0 - kl > 0 ? a0 - kl : 0;
+            const int64_t cc1 = b0 + ku < n ? b0 + ku : n;
+            const int64_t shift = a0 - cc0;
+            int rc2 = gbmv_impl<T>(h, 'N', b0 - a0, cc1 - cc0, kl - shift, ku + shift, alpha, dA + cc0 * lda, lda, dx + cc0,
+                                   beta, dy + a0);
+            if (rc2) return rc2;
+            LBM_CUDA(h, cudaEventRecord(h->ev_kern, sk));
+            LBM_CUDA(h, cudaStreamWaitEvent(so, h->ev_kern, 0));
+            LBM_CUDA(h, cudaMemcpyAsync(y + a0, dy + a0, (size_t)(b0 - a0) * sizeof(T), cudaMemcpyDeviceToHost, so));
+            r_done = r_hi;
+        }
+        return 0;
+    };
+    rc = pipeline();
+    const cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sk), e3 = cudaStreamSynchronize(so);
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return lbm_fail_cuda(h, e1, "cudaStreamSynchronize(h2d)");
+    if (e2 != cudaSuccess) return lbm_fail_cuda(h, e2, "cudaStreamSynchronize(compute)");
+    if (e3 != cudaSuccess) return lbm_fail_cuda(h, e3, "cudaStreamSynchronize(d2h)");
     return 0;
 }
 
@@ -1354,6 +1383,17 @@ int gbmv_chain_impl(lbm_handle_t h, int nf, const int64_t *m, const int64_t *n, 
         v = t;
     }
     return gbmv_impl<T>(h, 'N', m[0], n[0], kl[0], ku[0], alpha, A[0], lda[0], v, beta, y);
+}
+
+// dist.cu: the row-sharded apply with the ghost exchange fused into the launch (returns LBM_NOT_FUSED when the
+// streamed-tile kernel does not cover the shape; nothing has been launched then)
+int lbm_internal_dgbmv_fused(lbm_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, double alpha, const double *A,
+                             int64_t lda, const double *x, double beta, double *y, const lbm::HaloFuse *hf) {
+    return gbmv_impl<double>(h, 'N', m, n, kl, ku, alpha, A, lda, x, beta, y, hf);
+}
+int lbm_internal_sgbmv_fused(lbm_handle_t h, int64_t m, int64_t n, int64_t kl, int64_t ku, float alpha, const float *A,
+                             int64_t lda, const float *x, float beta, float *y, const lbm::HaloFuse *hf) {
+    return gbmv_impl<float>(h, 'N', m, n, kl, ku, alpha, A, lda, x, beta, y, hf);
 }
 
 extern "C" {

@@ -19,7 +19,20 @@ int lbm_fail_arg(lbm_handle_t h, int argno, const char *what) {
     return -argno;
 }
 
+// One scratch buffer per handle (chain temporaries, Kronecker Z buffers, reduction partials).  The handle's stream can be
+// re-bound between calls (the Python layer follows torch's current stream), so two calls issued from different streams
+// could overlap on the device and overwrite each other's scratch: when the bound stream differs from the one the
+// previous user ran on, the new stream first waits for everything queued on the old one.
 int lbm_scratch(lbm_handle_t h, size_t bytes, void **out) {
+    if (h->scratch_used && h->scratch_stream != h->stream) {
+        if (!h->ev_scratch) LBM_CUDA(h, cudaEventCreateWithFlags(&h->ev_scratch, cudaEventDisableTiming));
+        if (cudaEventRecord(h->ev_scratch, h->scratch_stream) == cudaSuccess)
+            LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_scratch, 0));
+        else
+            cudaGetLastError();   // the old stream no longer exists: its work has drained
+    }
+    h->scratch_stream = h->stream;
+    h->scratch_used = 1;
     if (bytes > h->scratch_bytes) {
         if (h->scratch) LBM_CUDA(h, cudaFree(h->scratch));
         h->scratch = nullptr;
@@ -41,6 +54,18 @@ int lbm_stage(lbm_handle_t h, int slot, size_t bytes, void **out) {
     }
     *out = h->stage[slot];
     return 0;
+}
+
+int lbm_check_fault(lbm_handle_t h) {
+    if (!h || !h->status_host) return 0;
+    const int code = *reinterpret_cast<volatile int *>(h->status_host);
+    if (!code) return 0;
+    *reinterpret_cast<volatile int *>(h->status_host) = 0;
+    snprintf(h->err, 512,
+             "device fault %d: a ghost-exchange wait timed out (the neighbour rank did not publish its epoch within %lld ms); "
+             "the boundary rows of the last sharded result are unspecified",
+             code, (long long)(h->tune.halo_timeout_ms > 0 ? h->tune.halo_timeout_ms : 30000));
+    return 2000 + code;
 }
 
 extern "C" {
@@ -77,6 +102,13 @@ int lbm_create(lbm_handle_t *out, int device) {
     h->err[0] = 0;
     h->rank = 0;
     h->world = 1;
+    if (cudaHostAlloc((void **)&h->status_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+        memset(h->status_host, 0, 64);
+        if (cudaHostGetDevicePointer((void **)&h->status_dev, h->status_host, 0) != cudaSuccess) h->status_dev = nullptr;
+    } else {
+        h->status_host = nullptr;
+    }
+    cudaGetLastError();
     *out = h;
     return 0;
 }
@@ -93,6 +125,8 @@ int lbm_destroy(lbm_handle_t h) {
         cudaEventDestroy(h->ev_kern);
     }
     if (h->scratch) cudaFree(h->scratch);
+    if (h->ev_scratch) cudaEventDestroy(h->ev_scratch);
+    if (h->status_host) cudaFreeHost(h->status_host);
     for (int i = 0; i < 4; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     cudaStreamDestroy(h->own_stream);
@@ -116,7 +150,7 @@ int lbm_sync(lbm_handle_t h) {
     if (!h) return -1;
     lbm_device_guard g(h->device);
     LBM_CUDA(h, cudaStreamSynchronize(h->stream));
-    return 0;
+    return lbm_check_fault(h);
 }
 
 const char *lbm_last_error_string(lbm_handle_t h) { return h ? h->err : g_create_err; }
@@ -126,7 +160,7 @@ int64_t lbm_launch_count(lbm_handle_t h) { return h ? h->launches : -1; }
 #define LBM_TUNE_KEYS(X)                                                                                       \
     X(gbmv_tile) X(gbmv_stages) X(gbmv_ctas_per_sm) X(gbmv_force) X(gbmvw_chunk) X(gbmvw_stages)               \
     X(gbmvw_ctas_per_sm) X(tri_ctas_per_sm) X(tri_force_scalar) X(tri_force_shuffle) X(tri_tile) X(tri_stages) X(kron_tr) X(kron_tc) X(kron_stages) X(kron_ctas_per_sm) X(kron_force_tile) X(gbmm_force) X(gbmm_tile) X(gbmm_variant) \
-    X(chain_tile) X(chain_force_generic) X(chain_variant) X(exchange_mode)
+    X(chain_tile) X(chain_force_generic) X(chain_variant) X(exchange_mode) X(exchange_fuse) X(halo_timeout_ms)
 
 int lbm_set_tuning(lbm_handle_t h, const char *key, int64_t value) {
     if (!h) return -1;

@@ -16,9 +16,8 @@
 //  * kron_tile_kernel (any bands / any alignment): a CTA owns a TR x TC tile of Y, stages the
 //    (TR+klb+kub) x (TC+kla+kua) halo'd tile of X in shared memory (zero outside the grid) and
 //    the tile's coefficient rows of A and B with out-of-matrix slots masked to zero BY INDEX.
-#include "lbm_common.cuh"
+#include "halo.cuh"
 
-int lbm_internal_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int64_t *plan8);
 
 namespace {
 
@@ -135,8 +134,12 @@ struct KronRingArgs {
     int prod;      // 0: X*A^T + B*X (Kronecker sum); 1: B*X*A^T (Kronecker product, one pass)
 };
 
-template <typename T, int NBA, int NBB, int RPT>
-__global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a) {
+// HALO: grid-column-sharded apply in ONE launch (halo.cuh).  CTA (0,0) pushes this rank's boundary grid columns to the
+// neighbours' mailboxes; column chunks are walked rotated by one so the first / last chunk (the only ones whose stage
+// holds ghost columns) come last, and those chunks overwrite the ghost columns of their stage -- rows [rs,re) of this
+// CTA's strip only -- in shared memory from the local mailbox.
+template <typename T, int NBA, int NBB, int RPT, bool HALO>
+__global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a, const HaloFuse hf) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     T *sbase = reinterpret_cast<T *>(smem_raw + 128);
@@ -150,10 +153,17 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    if (HALO && blockIdx.x == 0 && blockIdx.y == 0) halo_push(hf, tid, 256);
     __syncthreads();
 
-    const int64_t first = blockIdx.y, step = gridDim.y;
-    const int64_t mine = first < a.nchunks ? (a.nchunks - first + step - 1) / step : 0;
+    const int64_t step = gridDim.y;
+    const int64_t mine = (int64_t)blockIdx.y < a.nchunks ? (a.nchunks - blockIdx.y + step - 1) / step : 0;
+    // logical chunk L = blockIdx.y + kk*step; physical chunk = L+1 (mod nchunks) when HALO.  All code below works on
+    // physical chunk numbers: chunk_of(kk).
+    auto chunk_of = [&](int64_t kk) -> int64_t {
+        const int64_t L = blockIdx.y + kk * step;
+        return HALO ? (L + 1 < a.nchunks ? L + 1 : 0) : L;
+    };
     // rows staged per grid column: [rs, re) (both 16-byte aligned: n2 % EPV == 0)
     const int64_t rs = r0 - a.hp > 0 ? r0 - a.hp : 0;
     const int64_t re = r0 + a.tr + a.hp < a.n2 ? r0 + a.tr + a.hp : a.n2;
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
     };
     if (tid < 32) {
         const int64_t pro = mine < S ? mine : S;
-        for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
+        for (int64_t k = 0; k < pro; ++k) issue(chunk_of(k), (int)k);
     }
 
     // A coefficients of a chunk's columns, ca[cc][t] = A[c, c-kla+t] (zero outside the matrix):
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
         const int64_t qq = c + a.xoff - a.kla + t;  // input column
         return (c < a.c_end && qq >= 0 && qq < a.n1_in) ? a.A[(a.kua + a.kla - t) + a.lda * qq] : (T)0;
     };
-    if (mine > 0 && tid < ncoef) sCA[tid] = load_coef(first);
+    if (mine > 0 && tid < ncoef) sCA[tid] = load_coef(chunk_of(0));
 
     // B coefficients of this thread's rows: cb[k][t] = B[r, r-klb+t], zero outside the matrix
     T cbv[RPT][NBB];
@@ -230,15 +240,45 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
     for (int64_t kk = 0; kk < mine; ++kk) {
         const int s = (int)(kk % S);
         const uint32_t parity = (uint32_t)((kk / S) & 1);
-        const int64_t q = first + kk * step;
+        const int64_t q = chunk_of(kk);
         const int64_t c0 = a.c_begin + q * a.g;
         const int gq = (int)(c0 + a.g < a.c_end ? a.g : a.c_end - c0);
         const T *st = sbase + (int64_t)s * stage_elems;
         const T *ca = sCA + (kk & 1) * ncoef;
         const bool edge = row_edge || (c0 + a.xoff - a.kla < 0) || (c0 + a.xoff + gq + a.kua > a.n1_in);
         T cnext = (T)0;
-        if (kk + 1 < mine) cnext = load_coef(q + step);  // in flight during this chunk's compute
+        if (kk + 1 < mine) cnext = load_coef(chunk_of(kk + 1));  // in flight during this chunk's compute
         mbar_wait(&bars[s], parity);
+        if (HALO) {
+            // input columns staged for this chunk: [ci0, ci0 + g + kla + kua) clipped to [0, n1_in)
+            const int64_t ci0 = c0 + a.xoff - a.kla;
+            const int64_t sa = ci0 > 0 ? ci0 : 0;
+            const int64_t sb = ci0 + a.g + a.kla + a.kua < a.n1_in ? ci0 + a.g + a.kla + a.kua : a.n1_in;
+            bool need[2];
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd)
+                need[sd] = hf.ghost_end[sd] > hf.ghost_begin[sd] && sa < hf.ghost_end[sd] && sb > hf.ghost_begin[sd];
+            if (need[0] || need[1]) {   // CTA-uniform
+                if (tid == 0 && need[0]) halo_wait_flag(hf.pull_flag[0], hf.epoch, hf.timeout_ns, hf.status);
+                if (tid == 1 && need[1]) halo_wait_flag(hf.pull_flag[1], hf.epoch, hf.timeout_ns, hf.status);
+                __syncthreads();
+                const int rows_in = (int)(re - rs);
+#pragma unroll
+                for (int sd = 0; sd < 2; ++sd) {
+                    if (!need[sd]) continue;
+                    const int64_t ga = sa > hf.ghost_begin[sd] ? sa : hf.ghost_begin[sd];
+                    const int64_t gb = sb < hf.ghost_end[sd] ? sb : hf.ghost_end[sd];
+                    const T *mb = reinterpret_cast<const T *>(hf.pull_src[sd]);
+                    for (int64_t c = ga; c < gb; ++c) {
+                        T *dstc = const_cast<T *>(st) + (c - ci0) * a.seg + roff;
+                        const T *srcc = mb + (c - hf.ghost_begin[sd]) * a.n2 + rs;
+                        for (int r = tid; r < rows_in; r += 256) dstc[r] = __ldcg(srcc + r);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+            }
+        }
         const int seg = a.seg;
         const T *xrow = st + tid + a.hp;                 // X[r0+tid, c0-kla] of this stage
         T *yp = a.y + (r0 + tid) + a.n2 * c0;             // Y[r0+tid, c0]; += n2 per column
@@ -324,29 +364,38 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a)
         }
         if (kk + 1 < mine && tid < ncoef) sCA[((kk + 1) & 1) * ncoef + tid] = cnext;
         __syncthreads();
-        if (tid < 32 && kk + S < mine) issue(first + (kk + S) * step, s);
+        if (tid < 32 && kk + S < mine) issue(chunk_of(kk + S), s);
     }
+    if (HALO && blockIdx.x == 0 && blockIdx.y == 0) halo_final_wait(hf, tid);
 }
 
-template <typename T, int NBA, int NBB, int RPT>
-int kron_ring_launch3(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem) {
-    static int configured_dev_mask = 0;
-    auto kern = kron_ring_kernel<T, NBA, NBB, RPT>;
+template <typename T, int NBA, int NBB, int RPT, bool HALO>
+int kron_ring_launch4(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem, const HaloFuse &hf) {
+    static std::atomic<int> configured_dev_mask{0};
+    auto kern = kron_ring_kernel<T, NBA, NBB, RPT, HALO>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         configured_dev_mask |= (1 << h->device);
     }
-    kern<<<grid, 256, smem, h->stream>>>(a);
+    kern<<<grid, 256, smem, h->stream>>>(a, hf);
     LBM_LAUNCH_CHECK(h, "kron_ring_kernel");
     return 0;
 }
 
+template <typename T, int NBA, int NBB, int RPT>
+int kron_ring_launch3(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem, const HaloFuse *hf) {
+    if (hf) return kron_ring_launch4<T, NBA, NBB, RPT, true>(h, a, grid, smem, *hf);
+    HaloFuse none;
+    none.on = 0;
+    return kron_ring_launch4<T, NBA, NBB, RPT, false>(h, a, grid, smem, none);
+}
+
 template <typename T, int NBA, int NBB>
-int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem) {
+int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem, const HaloFuse *hf) {
     switch (a.tr / 256) {
-        case 1: return kron_ring_launch3<T, NBA, NBB, 1>(h, a, grid, smem);
-        case 2: return kron_ring_launch3<T, NBA, NBB, 2>(h, a, grid, smem);
-        default: return kron_ring_launch3<T, NBA, NBB, 4>(h, a, grid, smem);
+        case 1: return kron_ring_launch3<T, NBA, NBB, 1>(h, a, grid, smem, hf);
+        case 2: return kron_ring_launch3<T, NBA, NBB, 2>(h, a, grid, smem, hf);
+        default: return kron_ring_launch3<T, NBA, NBB, 4>(h, a, grid, smem, hf);
     }
 }
 
@@ -354,7 +403,8 @@ int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_
 template <typename T>
 bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda,
                    int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc,
-                   int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0, int64_t c_end = -1, int prod = 0) {
+                   int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0, int64_t c_end = -1, int prod = 0,
+                   const HaloFuse *hf = nullptr) {
     if (n1_in < 0) n1_in = n1;
     if (c_end < 0) c_end = n1;
     if (c_end <= c_begin) { *rc = 0; return true; }
@@ -395,12 +445,12 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     if (phases < 1) phases = 1;
     dim3 grid((unsigned)nstrips, (unsigned)phases);
     const size_t smem = (size_t)(128 + stages * stage_bytes(g) + 2 * g * nba * (int64_t)sizeof(T));
-    if (nba == 3 && nbb == 3) *rc = kron_ring_launch2<T, 3, 3>(h, a, grid, smem);
-    else if (nba == 1 && nbb == 3) *rc = kron_ring_launch2<T, 1, 3>(h, a, grid, smem);
-    else if (nba == 3 && nbb == 1) *rc = kron_ring_launch2<T, 3, 1>(h, a, grid, smem);
-    else if (nba == 5 && nbb == 5) *rc = kron_ring_launch2<T, 5, 5>(h, a, grid, smem);
-    else if (nba == 3 && nbb == 5) *rc = kron_ring_launch2<T, 3, 5>(h, a, grid, smem);
-    else *rc = kron_ring_launch2<T, 5, 3>(h, a, grid, smem);
+    if (nba == 3 && nbb == 3) *rc = kron_ring_launch2<T, 3, 3>(h, a, grid, smem, hf);
+    else if (nba == 1 && nbb == 3) *rc = kron_ring_launch2<T, 1, 3>(h, a, grid, smem, hf);
+    else if (nba == 3 && nbb == 1) *rc = kron_ring_launch2<T, 3, 1>(h, a, grid, smem, hf);
+    else if (nba == 5 && nbb == 5) *rc = kron_ring_launch2<T, 5, 5>(h, a, grid, smem, hf);
+    else if (nba == 3 && nbb == 5) *rc = kron_ring_launch2<T, 3, 5>(h, a, grid, smem, hf);
+    else *rc = kron_ring_launch2<T, 5, 3>(h, a, grid, smem, hf);
     return true;
 }
 
@@ -441,7 +491,7 @@ int kron_launch(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua
     a.tr = (int)tr; a.tc = (int)tc; a.pitch = pitch; a.offCA = oCA; a.offCB = oCB;
     const int64_t gx = (n2 + tr - 1) / tr, gy = (a.c_end - a.c_begin + tc - 1) / tc;
     if (gy > 65535) return lbm_fail_arg(h, 2, "n1 too large for the tile grid");
-    static int configured_dev_mask = 0;
+    static std::atomic<int> configured_dev_mask{0};
     auto kern = kron_tile_kernel<T>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
@@ -491,11 +541,12 @@ int kronsum_impl(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t ku
 template <typename T>
 int kronsum_range(lbm_handle_t h, int64_t m_loc, int64_t n_loc, int64_t left, int64_t n2, int64_t kla, int64_t kua,
                   const T *A, int64_t lda, int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *xbuf, T beta,
-                  T *y, int64_t cb, int64_t ce) {
-    if (ce <= cb) return 0;
+                  T *y, int64_t cb, int64_t ce, const HaloFuse *hf = nullptr) {
+    if (ce <= cb) return hf ? LBM_NOT_FUSED : 0;
     int rc = 0;
-    if (kron_ring_try<T>(h, m_loc, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, xbuf, beta, y, &rc, n_loc, left, cb, ce))
+    if (kron_ring_try<T>(h, m_loc, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, xbuf, beta, y, &rc, n_loc, left, cb, ce, 0, hf))
         return rc;
+    if (hf) return LBM_NOT_FUSED;   // only the ring kernel carries the fused exchange; nothing was launched
     return kron_launch<T>(h, m_loc, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, xbuf, beta, y, 1, 1, 1, 0, n_loc, left,
                           cb, ce);
 }
@@ -506,12 +557,20 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
     int rc = kron_check<T>(h, n1, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, xbuf, y_own);
     if (rc || n1 == 0 || n2 == 0) return rc;
     lbm_device_guard g(h->device);
-    int64_t pl[8];
-    if ((rc = lbm_internal_exchange(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T), pl))) return rc;
-    const int64_t m_loc = pl[1] - pl[0], n_loc = pl[3] - pl[2], left = pl[4], right = pl[5];
+    int64_t pl[10];
+    HaloFuse hf;
+    int fused = 0;
+    // plan + uniform validation + either a fused-exchange descriptor or the two-kernel / NCCL exchange already in flight
+    if ((rc = lbm_internal_exchange(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T), pl, overlap, &hf, &fused))) return rc;
+    const int64_t m_loc = pl[9], n_loc = pl[3] - pl[2], left = pl[4], right = pl[5];
     if (m_loc == 0) return 0;
-    if (h->world == 1)
+    if (h->world == 1 || pl[8] <= 1)
         return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc);
+    if (fused) {   // ONE launch: push at kernel start, ghost columns patched into the last chunks' stages
+        rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc, &hf);
+        if (rc != LBM_NOT_FUSED) return rc;
+        if ((rc = lbm_internal_exchange_unfuse(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T)))) return rc;
+    }
     if (!overlap) {
         LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
         return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc);

@@ -5,13 +5,17 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "../../include/lbm_b200.h"
 
-#define LBM_VERSION 10100
+#define LBM_VERSION 10200
+
+// internal status: "this shape cannot take the fused-exchange launch" (nothing was launched)
+#define LBM_NOT_FUSED (-100000)
 
 struct lbm_tuning {
     // gbmv narrow (streamed tile) kernel
@@ -38,6 +42,8 @@ struct lbm_tuning {
     int64_t chain_tile;
     int64_t chain_force_generic;
     int64_t exchange_mode;    // multi-GPU ghost exchange: 0 auto (peer mailboxes when connected), 1 force NCCL send/recv
+    int64_t exchange_fuse;    // 0 auto (exchange fused into the compute launch when the kernel supports it), 2 never fuse
+    int64_t halo_timeout_ms;  // wall-clock bound of a ghost-flag wait on the device (0 = default 30 s)
     int64_t chain_variant;    // 0 auto (= 4 when covered), 1 split-column register kernel, 2/3 transposed-smem kernel, 4 warp-autonomous TMA kernel
 };
 
@@ -52,6 +58,12 @@ struct lbm_handle_s {
     lbm_tuning tune;
     void *scratch;
     size_t scratch_bytes;
+    cudaStream_t scratch_stream;  // stream of the last call that used the scratch buffer (see lbm_scratch)
+    int scratch_used;
+    cudaEvent_t ev_scratch;
+    // device-side fault word (mapped pinned host memory): a ghost-flag wait that timed out sets it; reported -- as a
+    // normal return code, never a trap -- by the next sharded call or lbm_sync (dist.cu: lbm_check_fault)
+    int *status_host, *status_dev;
     void *stage[4];           // device staging for *_host entry points
     size_t stage_bytes[4];
     // *_host pipeline: copy-in / copy-out streams and their events (created on first use)
@@ -69,11 +81,14 @@ struct lbm_handle_s {
     size_t peer_slot_bytes;      // capacity of one mailbox slot
     uint64_t peer_epoch;         // exchanges done so far (identical on all ranks: SPMD)
     int peer_on;                 // 1 once lbm_peer_connect succeeded
+    int peer_direct;             // 1: single-process multi-device mode (multi.cu) -- peer_remote are plain peer pointers, no IPC
+    int has_comm;                // a row partition exists (NCCL communicator and/or direct peers): rank/world are meaningful
 };
 
 int lbm_fail_cuda(lbm_handle_t h, cudaError_t e, const char *what);
 int lbm_fail_arg(lbm_handle_t h, int argno, const char *what);
 int lbm_scratch(lbm_handle_t h, size_t bytes, void **out);
+int lbm_check_fault(lbm_handle_t h);   // 0, or 2001 after a device-side ghost wait timed out (clears the word)
 int lbm_stage(lbm_handle_t h, int slot, size_t bytes, void **out);
 
 #define LBM_CUDA(h, call)                                          \
@@ -134,9 +149,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
     const uint32_t a = smem_u32(bar);
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!done) {
-        // a lost transaction must surface as a CUDA error, never as a hung GPU
-        if (++spins > (1u << 24)) __trap();
+        // A lost bulk-copy transaction is a programming error on a par with an illegal address: it must surface as a CUDA
+        // error, never as a hung GPU.  The bound is WALL-CLOCK (20 s, read every 64 Ki polls), not a spin count that
+        // varies with clocks and contention.
+        if ((++spins & 0xFFFFu) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) __trap();
+        }
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

@@ -14,7 +14,7 @@
 //    the neighbouring lane by warp shuffle; the diagonals stay in registers across the columns.
 #include <type_traits>
 
-#include "lbm_common.cuh"
+#include "halo.cuh"
 
 namespace {
 
@@ -176,8 +176,10 @@ struct TriRingArgs {
 
 // smem stage layout: [ d | x | lo | hi ], each `seg` elements, all windows starting at the
 // 16-byte aligned element w0 = max(0, i0 - EPV) so that index (i - w0) works for i0-1 .. i1.
-template <typename T, bool HAS_DL, bool HAS_DU, bool SYM>
-__global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<T> a) {
+// HALO: row-sharded apply in one launch (halo.cuh): the one-element ghosts of x are pushed by CTA 0 and patched into the
+// first / last tile's x window in shared memory; tiles are walked rotated by one so those two tiles come last.
+template <typename T, bool HAS_DL, bool HAS_DU, bool SYM, bool HALO>
+__global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<T> a, const HaloFuse hf) {
     constexpr int EPV = 16 / (int)sizeof(T);
     constexpr int NARR = 2 + ((HAS_DL || HAS_DU) ? 1 : 0) + ((HAS_DL && HAS_DU && !SYM) ? 1 : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -190,13 +192,15 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    if (HALO && blockIdx.x == 0) halo_push(hf, tid, TRI_NT);
     __syncthreads();
     const int64_t first = blockIdx.x, step = gridDim.x;
     const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
     const int64_t noff = a.n - 1;  // length of the off-diagonals actually read
+    auto rot = [&](int64_t tt) -> int64_t { return HALO ? (tt + 1 < a.ntiles ? tt + 1 : 0) : tt; };
 
     auto issue = [&](int64_t tt, int s) {  // thread 0 only
-        const int64_t t = a.tile0 + tt;
+        const int64_t t = a.tile0 + rot(tt);
         const int64_t i0 = t * a.tile;
         const int64_t i1 = i0 + a.tile < a.n ? i0 + a.tile : a.n;
         const int64_t w0 = i0 >= EPV ? i0 - EPV : 0;
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
     for (int64_t k = 0; k < mine; ++k) {
         const int s = (int)(k % S);
         const uint32_t parity = (uint32_t)((k / S) & 1);
-        const int64_t t = a.tile0 + first + k * step;
+        const int64_t t = a.tile0 + rot(first + k * step);
         const int64_t i0 = t * a.tile;
         const int64_t i1 = i0 + a.tile < a.n ? i0 + a.tile : a.n;
         const int64_t w0 = i0 >= EPV ? i0 - EPV : 0;
@@ -234,6 +238,7 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         const T *slo = sx + a.seg;                                  // dl window (HAS_DL)
         const T *shi = (HAS_DL && HAS_DU && !SYM) ? slo + a.seg : slo;  // du window
         mbar_wait(&bars[s], parity);
+        if (HALO) halo_patch_1d<T>(hf, const_cast<T *>(sx), w0, i1 + 1 < a.n ? i1 + 1 : a.n, tid, TRI_NT);
         const int64_t ie = i1 < a.row_end ? i1 : a.row_end;
         for (int64_t i = i0 + tid; i < ie; i += TRI_NT) {
             if (i < a.row_begin) continue;
@@ -248,19 +253,27 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         __syncthreads();
         if (tid == 0 && k + S < mine) issue(first + (k + S) * step, s);
     }
+    if (HALO && blockIdx.x == 0) halo_final_wait(hf, tid);
 }
 
-template <typename T, bool HL, bool HU, bool SY>
-int launch_tri_ring(lbm_handle_t h, const TriRingArgs<T> &a, int grid, size_t smem) {
-    static int configured_dev_mask = 0;
-    auto kern = tridiag_ring_kernel<T, HL, HU, SY>;
+template <typename T, bool HL, bool HU, bool SY, bool HALO>
+int launch_tri_ring2(lbm_handle_t h, const TriRingArgs<T> &a, int grid, size_t smem, const HaloFuse &hf) {
+    static std::atomic<int> configured_dev_mask{0};
+    auto kern = tridiag_ring_kernel<T, HL, HU, SY, HALO>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         configured_dev_mask |= (1 << h->device);
     }
-    kern<<<grid, TRI_NT, smem, h->stream>>>(a);
+    kern<<<grid, TRI_NT, smem, h->stream>>>(a, hf);
     LBM_LAUNCH_CHECK(h, "tridiag_ring_kernel");
     return 0;
+}
+template <typename T, bool HL, bool HU, bool SY>
+int launch_tri_ring(lbm_handle_t h, const TriRingArgs<T> &a, int grid, size_t smem, const HaloFuse *hf) {
+    if (hf) return launch_tri_ring2<T, HL, HU, SY, true>(h, a, grid, smem, *hf);
+    HaloFuse none;
+    none.on = 0;
+    return launch_tri_ring2<T, HL, HU, SY, false>(h, a, grid, smem, none);
 }
 
 // any-alignment fallback
@@ -288,7 +301,8 @@ __global__ void __launch_bounds__(256) tridiag_mv_scalar_kernel(int64_t n, const
 
 template <typename T>
 int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du, T alpha, const T *X, int64_t ldx,
-                 int64_t nrhs, T beta, T *Y, int64_t ldy, int64_t row_begin = 0, int64_t row_end = -1) {
+                 int64_t nrhs, T beta, T *Y, int64_t ldy, int64_t row_begin = 0, int64_t row_end = -1,
+                 const HaloFuse *hf = nullptr) {
     if (!h) return -1;
     if (n < 0) return lbm_fail_arg(h, 2, "n < 0");
     if (row_end < 0) row_end = n;
@@ -308,6 +322,7 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
     const bool aligned = lbm_aligned16(d) && lbm_aligned16(X) && lbm_aligned16(Y) && (!dl || lbm_aligned16(dl)) &&
                          (!du || lbm_aligned16(du)) && (nrhs == 1 || (ldx % VN == 0 && ldy % VN == 0));
     const int64_t ctas = h->tune.tri_ctas_per_sm > 0 ? h->tune.tri_ctas_per_sm : 16;
+    if (hf && (!aligned || h->tune.tri_force_scalar || nrhs != 1)) return LBM_NOT_FUSED;
     if ((!aligned || h->tune.tri_force_scalar) && ranged)
         return lbm_fail_arg(h, 13, "row-ranged tridiagonal apply needs 16-byte aligned operands");
     if (!aligned || h->tune.tri_force_scalar) {
@@ -343,11 +358,11 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
         int64_t grid = (int64_t)h->sm_count * cps;
         if (grid > a.ntiles) grid = a.ntiles;
         const size_t smem = (size_t)(128 + stages * stage_bytes);
-        if (sym) return launch_tri_ring<T, true, true, true>(h, a, (int)grid, smem);
-        if (dl && du) return launch_tri_ring<T, true, true, false>(h, a, (int)grid, smem);
-        if (dl) return launch_tri_ring<T, true, false, false>(h, a, (int)grid, smem);
-        if (du) return launch_tri_ring<T, false, true, false>(h, a, (int)grid, smem);
-        return launch_tri_ring<T, false, false, false>(h, a, (int)grid, smem);
+        if (sym) return launch_tri_ring<T, true, true, true>(h, a, (int)grid, smem, hf);
+        if (dl && du) return launch_tri_ring<T, true, true, false>(h, a, (int)grid, smem, hf);
+        if (dl) return launch_tri_ring<T, true, false, false>(h, a, (int)grid, smem, hf);
+        if (du) return launch_tri_ring<T, false, true, false>(h, a, (int)grid, smem, hf);
+        return launch_tri_ring<T, false, false, false>(h, a, (int)grid, smem, hf);
     }
     const int64_t ngroups = (n + VN - 1) / VN;
     int64_t blocks = (ngroups + 255) / 256;
@@ -366,6 +381,18 @@ int tridiag_impl(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du
 }
 
 }  // namespace
+
+// dist.cu: rows [row_begin,row_end) of the ghost-extended system with the ghost exchange fused into the launch
+int lbm_internal_dtridiag_rows_fused(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du, double alpha,
+                                     const double *x, double beta, double *y, int64_t row_begin, int64_t row_end,
+                                     const lbm::HaloFuse *hf) {
+    return tridiag_impl<double>(h, n, dl, d, du, alpha, x, n, 1, beta, y, n, row_begin, row_end, hf);
+}
+int lbm_internal_stridiag_rows_fused(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du, float alpha,
+                                     const float *x, float beta, float *y, int64_t row_begin, int64_t row_end,
+                                     const lbm::HaloFuse *hf) {
+    return tridiag_impl<float>(h, n, dl, d, du, alpha, x, n, 1, beta, y, n, row_begin, row_end, hf);
+}
 
 extern "C" {
 int lbm_dtridiag_mv(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du, double alpha,

@@ -64,7 +64,29 @@ def _sigs():
         "lbm_peer_active": (C.c_int, [H]),
         "lbm_halo_exchange": (C.c_int, [H, i64, i64, i64, vp, C.c_int]),
     }
+    M, S, V = vp, vp, vp      # lbm_multi_t, lbm_shard_t, lbm_svec_t
+    s.update({
+        "lbm_create_multi": (C.c_int, [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]),
+        "lbm_destroy_multi": (C.c_int, [M]),
+        "lbm_multi_ndev": (C.c_int, [M]),
+        "lbm_multi_handle": (vp, [M, C.c_int]),
+        "lbm_multi_sync": (C.c_int, [M]),
+        "lbm_multi_last_error_string": (C.c_char_p, [M]),
+        "lbm_shard_create": (C.c_int, [M, C.c_int, i64, i64, i64, C.POINTER(vp)]),
+        "lbm_shard_destroy": (C.c_int, [S]),
+        "lbm_shard_distribute": (C.c_int, [S, vp, i64]),
+        "lbm_shard_fill_uniform": (C.c_int, [S, u64]),
+        "lbm_shard_slab": (C.c_int, [S, C.c_int, C.POINTER(vp), C.POINTER(i64)]),
+        "lbm_svec_create": (C.c_int, [S, C.POINTER(vp)]),
+        "lbm_svec_destroy": (C.c_int, [V]),
+        "lbm_svec_distribute": (C.c_int, [V, vp]),
+        "lbm_svec_gather": (C.c_int, [V, vp]),
+        "lbm_svec_fill_uniform": (C.c_int, [V, u64]),
+        "lbm_svec_buffer": (C.c_int, [V, C.c_int, C.POINTER(vp), C.POINTER(vp)]),
+    })
     for p, ft in (("d", f64), ("s", f32)):
+        s[f"lbm_{p}gbmv_sharded_all"] = (C.c_int, [S, ft, V, ft, V])
+        s[f"lbm_{p}gbmv_chain_sharded_all"] = (C.c_int, [C.c_int, C.POINTER(vp), ft, V, ft, V])
         s[f"lbm_{p}gbmv"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
         s[f"lbm_{p}gbmv_chain"] = (C.c_int, [H, C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                                             C.POINTER(vp), C.POINTER(i64), ft, vp, ft, vp])
@@ -77,6 +99,9 @@ def _sigs():
         s[f"lbm_{p}tridiag_pack"] = (C.c_int, [H, i64, vp, vp, vp, i64, i64, vp, i64])
         s[f"lbm_{p}gbmv_host"] = (C.c_int, [H, ch, i64, i64, i64, i64, ft, vp, i64, vp, ft, vp])
         s[f"lbm_{p}gbmv_sharded"] = (C.c_int, [H, i64, i64, i64, ft, vp, i64, vp, ft, vp, C.c_int])
+        s[f"lbm_{p}gbmv_chain_sharded"] = (C.c_int, [H, C.c_int, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64),
+                                                    ft, vp, ft, vp])
+        s[f"lbm_{p}tridiag_mv_sharded"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, ft, vp, C.c_int])
         s[f"lbm_{p}tridiag_mv"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}bidiag_mv"] = (C.c_int, [H, ch, i64, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}tridiag_mv_rows"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, ft, vp, i64, i64])

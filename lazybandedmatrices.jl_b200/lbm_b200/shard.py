@@ -90,11 +90,21 @@ def connect_peers(h, device: int, group=None, slot_bytes: int = 1 << 20) -> bool
 def split_rows(n: int, world: int, rank: int, align: int = 4):
     """Contiguous near-equal row blocks whose starts are multiples of `align` (keeps every
     shard's slab and vectors 16-byte aligned for the bulk-TMA path)."""
-    per = -(-n // world)
-    per = -(-per // align) * align
+    per = rows_per_shard(n, world, align)
     r0 = min(n, rank * per)
     r1 = min(n, r0 + per)
     return r0, r1
+
+
+def rows_per_shard(n: int, world: int, align: int = 4) -> int:
+    per = -(-n // world)
+    return max(align, -(-per // align) * align)
+
+
+def effective_world(n: int, world: int, align: int = 4) -> int:
+    """Ranks that own rows.  Rounding the shard size up can leave trailing ranks EMPTY (n=100, world=8: rank 6 has four
+    rows, rank 7 none); those ranks have no neighbours and take no part in the exchange (csrc/dist.cu:make_plan)."""
+    return max(1, -(-n // rows_per_shard(n, world, align)))
 
 
 @dataclass
@@ -112,9 +122,13 @@ class RowShard:
     @classmethod
     def plan(cls, n: int, l: int, u: int, rank: int, world: int) -> "RowShard":
         r0, r1 = split_rows(n, world, rank)
-        if world > 1 and (r1 - r0) < max(l, u, 1):
+        # validated against EVERY rank's shard (a pure function of n, l, u, world), so all ranks fail alike and none
+        # returns while a neighbour still waits for it; a short LAST shard is fine (the ghosts it serves are clipped at n)
+        if effective_world(n, world) > 1 and rows_per_shard(n, world) < max(l, u):
             raise LbmArgumentError(
-                f"shard of {r1 - r0} rows is narrower than the halo max(l,u)={max(l, u)}: use fewer ranks")
+                f"shards of {rows_per_shard(n, world)} rows are narrower than the halo max(l,u)={max(l, u)}: use fewer ranks")
+        if r1 == r0:      # beyond the effective world: owns nothing, stores nothing, has no neighbours
+            return cls(n, l, u, rank, world, r0, r1, r0, r0)
         return cls(n, l, u, rank, world, r0, r1, max(0, r0 - l), min(n, r1 + u))
 
     # geometry ------------------------------------------------------------------------
@@ -133,6 +147,18 @@ class RowShard:
     @property
     def right(self):    # ghost entries after it
         return self.c1 - self.r1
+
+    @property
+    def world_eff(self):
+        return effective_world(self.n, self.world)
+
+    @property
+    def has_left(self):
+        return 0 < self.rank < self.world_eff
+
+    @property
+    def has_right(self):
+        return self.rank < self.world_eff - 1
 
     @property
     def kl_loc(self):
@@ -154,14 +180,14 @@ class RowShard:
         """P2P ops that fill this rank's ghosts and serve the neighbours' ghosts."""
         ops = []
         own = self.owned(xbuf)
-        if self.rank > 0:
+        if self.has_left:
             # previous rank's right ghost = my first u owned entries (clipped at n by construction)
             cnt = min(self.u, self.m_loc)
             if cnt:
                 ops.append(dist.P2POp(dist.isend, own[:cnt], self.rank - 1, group))
             if self.left:
                 ops.append(dist.P2POp(dist.irecv, xbuf[: self.left], self.rank - 1, group))
-        if self.rank < self.world - 1:
+        if self.has_right:
             cnt = min(self.l, self.m_loc)
             if cnt:
                 ops.append(dist.P2POp(dist.isend, own[self.m_loc - cnt:], self.rank + 1, group))
@@ -279,6 +305,23 @@ def sharded_chain_mul_(y_own, factors, xbuf, tmp_bufs, group=None, local_gbmv=No
     """`mul!(y, ApplyMatrix(*, F1, ..., Fk), x)` row-sharded: right-to-left; stage output i is
     written into the owned block of a ghost-cell vector laid out for the factor that consumes
     it, whose `mul_` then exchanges that intermediate's halo (width max(l,u) of the consumer)."""
+    if local_gbmv is None and group is None and xbuf.is_cuda and len(factors) >= 1:
+        # product path: ONE C call (lbm_?gbmv_chain_sharded) -- stages, intermediate halos and temporaries inside the library
+        import ctypes as C
+
+        from . import _lib
+        from .banded import _ft, _pfx, _ptr
+        h = _lib.handle_of(xbuf)
+        p0 = factors[0].plan
+        if p0.world == 1 or h.comm_world == p0.world:
+            nf = len(factors)
+            I64, VP = C.c_int64 * nf, C.c_void_p * nf
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}gbmv_chain_sharded")
+            ft = _ft(xbuf.dtype)
+            h.check(fn(h.ptr, nf, p0.n, I64(*[f.plan.l for f in factors]), I64(*[f.plan.u for f in factors]),
+                       VP(*[f.data.data_ptr() for f in factors]), I64(*[f.plan.l + f.plan.u + 1 for f in factors]),
+                       ft(1.0), _ptr(xbuf), ft(0.0), _ptr(y_own)), "lbm_gbmv_chain_sharded")
+            return y_own
     order = list(reversed(factors))          # F_k ... F_1
     v = xbuf                                 # ghost layout of F_k
     for idx, f in enumerate(order[:-1]):
@@ -399,13 +442,13 @@ class ShardedKronSum:
         flat = xbuf.view(-1)
         ops, n2 = [], self.n2
         own0 = p.left * n2
-        if p.rank > 0:
+        if p.has_left:
             cnt = min(p.u, p.m_loc) * n2
             if cnt:
                 ops.append(dist.P2POp(dist.isend, flat[own0: own0 + cnt], p.rank - 1, group))
             if p.left:
                 ops.append(dist.P2POp(dist.irecv, flat[: own0], p.rank - 1, group))
-        if p.rank < p.world - 1:
+        if p.has_right:
             cnt = min(p.l, p.m_loc) * n2
             end = own0 + p.m_loc * n2
             if cnt:
@@ -465,22 +508,20 @@ class ShardedTridiagonal:
         p = RowShard.plan(n, l, u, rank, world)
         return p.c0, p.c1
 
-    def mul_(self, y_own, xbuf, alpha=1.0, beta=0.0, group=None, local_apply=None):
+    def mul_(self, y_own, xbuf, alpha=1.0, beta=0.0, group=None, local_apply=None, overlap=True):
         p = self.plan
         if local_apply is None and group is None and xbuf.is_cuda:
             from . import _lib
             from .banded import _ft, _pfx, _ptr
             h = _lib.handle_of(xbuf)
-            if p.world > 1:
-                if h.comm_world != p.world:
-                    raise LbmArgumentError("call lbm_b200.shard.init_comm() first")
-                h.check(_lib.lib().lbm_halo_exchange(h.ptr, p.n, p.l, p.u, C_void(xbuf), xbuf.element_size()),
-                        "lbm_halo_exchange")
-            # the extended square system, restricted to the owned rows: written straight into y_own
-            fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}tridiag_mv_rows")
+            if p.world > 1 and h.comm_world != p.world:
+                raise LbmArgumentError("call lbm_b200.shard.init_comm() first")
+            # ONE call: the one-element ghost exchange (fused into the launch when the peer mailboxes are up) + the
+            # ghost-extended square system restricted to the owned rows, written straight into y_own
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}tridiag_mv_sharded")
             ft = _ft(xbuf.dtype)
-            h.check(fn(h.ptr, p.n_loc, _ptr(self.dl), _ptr(self.d), _ptr(self.du), ft(alpha), _ptr(xbuf), ft(beta),
-                       _ptr(y_own), p.left, p.left + p.m_loc), "lbm_tridiag_mv_rows")
+            h.check(fn(h.ptr, p.n, _ptr(self.dl), _ptr(self.d), _ptr(self.du), ft(alpha), _ptr(xbuf), ft(beta),
+                       _ptr(y_own), 1 if overlap else 0), "lbm_tridiag_mv_sharded")
             return y_own
         if self._ybuf is None or self._ybuf.shape[0] != p.n_loc or self._ybuf.device != xbuf.device:
             self._ybuf = torch.empty(p.n_loc, dtype=xbuf.dtype, device=xbuf.device)

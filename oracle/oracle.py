@@ -94,6 +94,71 @@ def fill_uniform_numpy(seed: int, count: int, dtype=np.float64, offset: int = 0)
     return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0**-24)).astype(np.float32)
 
 
+def stream_at(seed: int, idx, dtype=np.float64) -> np.ndarray:
+    """The same counter-based stream evaluated at arbitrary (array of) 64-bit indices: what lets a full-size
+    result (n = 2^27 ... 2^28) be checked row by row without regenerating the operands."""
+    with np.errstate(over="ignore"):
+        idx = np.asarray(idx).astype(np.uint64)
+        z = np.uint64(seed & (2**64 - 1)) + (idx + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    if np.dtype(dtype) == np.float64:
+        return (z >> np.uint64(11)).astype(np.float64) * 2.0**-53
+    return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0**-24)).astype(np.float32)
+
+
+def gbmv_rows_stream(n: int, kl: int, ku: int, seed_a: int, seed_x: int, rows, x_scale: float = 1.0) -> np.ndarray:
+    """(A x)[rows] for A = brand(n,n,kl,ku) (stream `seed_a`, tight lda) and x = x_scale * stream(`seed_x`): each row
+    summed in ascending column order, as oracle_?gbmv does (lbm_oracle_impl.h), from regenerated entries only."""
+    rows = np.asarray(rows, dtype=np.int64)
+    nb = kl + ku + 1
+    acc = np.zeros(rows.shape, dtype=np.float64)
+    for q in range(nb):
+        j = rows - kl + q
+        ok = (j >= 0) & (j < n)
+        jj = np.where(ok, j, 0)
+        a = stream_at(seed_a, (kl + ku - q) + nb * jj)          # band row ku + i - j = kl + ku - q
+        xv = stream_at(seed_x, jj) * x_scale
+        acc = np.where(ok, acc + a * xv, acc)
+    return acc
+
+
+def tridiag_rows_stream(n: int, seed_dl, seed_d: int, seed_du, seed_x: int, rows, x_scale: float = 1.0) -> np.ndarray:
+    """(A x)[rows] for Tridiagonal(dl, d, du) built from streams (None = that diagonal absent; SymTridiagonal passes
+    the same seed twice): dl[i-1] x[i-1] + d[i] x[i] + du[i] x[i+1] in that order (src/tridiag.jl:471-484)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    acc = np.zeros(rows.shape, dtype=np.float64)
+    x = lambda i: stream_at(seed_x, i) * x_scale  # noqa: E731
+    if seed_dl is not None:
+        ok = rows > 0
+        im = np.where(ok, rows - 1, 0)
+        acc = np.where(ok, acc + stream_at(seed_dl, im) * x(im), acc)
+    acc = acc + stream_at(seed_d, rows) * x(rows)
+    if seed_du is not None:
+        ok = rows < n - 1
+        ip = np.where(ok, rows + 1, 0)
+        acc = np.where(ok, acc + stream_at(seed_du, np.where(ok, rows, 0)) * x(ip), acc)
+    return acc
+
+
+def laplacian_points_stream(g: int, c2: float, seed_x: int, r, c, x_scale: float = 1.0) -> np.ndarray:
+    """((kron(D,I)+kron(I,D)) x)[r + g*c] for D = c2*tridiag(1,-2,1), x = vec(X) from the stream: A-term columns
+    c-1, c, c+1 then B-term rows r-1, r, r+1 (the order of oracle_?kronsum2d_mv)."""
+    r = np.asarray(r, dtype=np.int64)
+    c = np.asarray(c, dtype=np.int64)
+    acc = np.zeros(r.shape, dtype=np.float64)
+
+    def X(rr, cc):
+        ok = (rr >= 0) & (rr < g) & (cc >= 0) & (cc < g)
+        return np.where(ok, stream_at(seed_x, np.where(ok, rr + g * cc, 0)) * x_scale, 0.0), ok
+
+    for (dr, dc, co) in ((0, -1, c2), (0, 0, -2 * c2), (0, 1, c2), (-1, 0, c2), (0, 0, -2 * c2), (1, 0, c2)):
+        v, ok = X(r + dr, c + dc)
+        acc = np.where(ok, acc + co * v, acc)
+    return acc
+
+
 def brand(m: int, n: int, l: int, u: int, seed: int, dtype=np.float64) -> np.ndarray:
     """`brand(m,n,l,u)` analogue: ALL (l+u+1)*n storage slots are U[0,1) ([up]
     BandedMatrices).  Returns the (l+u+1) x n column-major data

@@ -58,7 +58,8 @@ def _worker(rank, world, port, n, bands, q):
         f.mul_(y_no, xbuf, local_gbmv=_oracle_local_gbmv, overlap=False)
         assert torch.equal(y_no, y)
         a, b = f.interior_rows()
-        assert 0 <= a <= b <= f.plan.m_loc and (f.plan.left == 0 or a >= f.plan.l) and a % 4 == 0
+        assert 0 <= a <= b <= f.plan.m_loc and (f.plan.left == 0 or a >= min(f.plan.l, f.plan.m_loc))
+        assert a % 4 == 0 or a == f.plan.m_loc        # a short last shard has no interior at all
         # ghosts really were filled from the neighbours
         assert np.array_equal(xbuf.numpy(), x_full[f.plan.c0:f.plan.c1])
         # lazy chain: y = F1 (F2 (... x))
@@ -67,8 +68,12 @@ def _worker(rank, world, port, n, bands, q):
         sharded_chain_mul_(y2, factors, xbuf, tmp, local_gbmv=_oracle_local_gbmv)
         out["chain"] = (factors[0].plan.r0, y2.numpy().copy())
         q.put((rank, out))
-    finally:
         dist.barrier()
+    except BaseException as e:      # report instead of leaving the other ranks (and the test) hanging in a collective
+        import traceback
+        q.put((rank, {"error": traceback.format_exc() or repr(e)}))
+        raise
+    finally:
         dist.destroy_process_group()
 
 
@@ -77,6 +82,11 @@ def _worker(rank, world, port, n, bands, q):
     (2, 4099, [(8, 8), (2, 5), (1, 1)]),
     (3, 2000, [(128, 128), (3, 0)]),
     (2, 64, [(0, 1), (1, 0)]),
+    # trailing shards EMPTY or SHORT (n < 4*world / the last shard narrower than the halo): the effective world shrinks,
+    # empty ranks have no neighbours, nobody posts an unmatched send (csrc/dist.cu:make_plan, shard.py:effective_world)
+    (4, 10, [(1, 1), (2, 1)]),
+    (8, 100, [(8, 5), (1, 1)]),
+    (3, 5, [(1, 1)]),
 ])
 def test_row_sharded_mul_matches_single_process(world, n, bands, oracle):
     ctx = mp.get_context("spawn")
@@ -86,12 +96,18 @@ def test_row_sharded_mul_matches_single_process(world, n, bands, oracle):
     for p in procs:
         p.start()
     res = {}
-    for _ in range(world):
-        rank, out = q.get(timeout=120)
-        res[rank] = out
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        for _ in range(world):
+            rank, out = q.get(timeout=120)
+            assert "error" not in out, f"rank {rank}: {out['error']}"
+            res[rank] = out
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     # single-process oracle on the full operator
     x = oracle.fill_uniform(0x9, n)
     mats = [np.asfortranarray(oracle.fill_uniform(0x1 + i, (l + u + 1) * n).reshape((l + u + 1, n), order="F"))
@@ -132,12 +148,24 @@ def test_plan_geometry():
     from lbm_b200.errors import LbmArgumentError
     with pytest.raises(LbmArgumentError):
         RowShard.plan(64, 128, 128, 0, 4)
+    # the verdict is a function of (n, l, u, world) only: EVERY rank fails alike, including the empty / short ones
+    for r in range(8):
+        with pytest.raises(LbmArgumentError):
+            RowShard.plan(100, 20, 0, r, 8)
+    # n=100, world=8: shards of 16 rows -> 7 ranks own rows (the last one 4 rows), rank 7 owns nothing and has no neighbours
+    ps = [RowShard.plan(100, 8, 5, r, 8) for r in range(8)]
+    assert [p.m_loc for p in ps] == [16] * 6 + [4, 0] and ps[0].world_eff == 7
+    assert [p.has_right for p in ps] == [True] * 6 + [False, False] and [p.has_left for p in ps] == [False] + [True] * 6 + [False]
+    assert ps[7].n_loc == 0 and ps[5].right == 4 and ps[6].left == 8 and ps[6].right == 0
     # the C library's plan (used by lbm_?gbmv_sharded) is the same function, bit for bit
     import ctypes as C
     import lbm_b200
     lib = lbm_b200.lib()
     out = (C.c_int64 * 8)()
-    for (nn, ll, uu, ww) in [(1 << 27, 8, 8, 8), (1003, 1, 1, 3), (4099, 128, 128, 2), (64, 0, 1, 2), (10, 2, 3, 1)]:
+    for r in range(8):
+        assert lib.lbm_shard_plan(100, 20, 0, r, 8, out) == -2
+    for (nn, ll, uu, ww) in [(1 << 27, 8, 8, 8), (1003, 1, 1, 3), (4099, 128, 128, 2), (64, 0, 1, 2), (10, 2, 3, 1), (100, 8, 5, 8),
+                             (10, 1, 1, 4), (5, 1, 1, 3), (0, 1, 1, 2)]:
         for r in range(ww):
             pl = RowShard.plan(nn, ll, uu, r, ww)
             assert lib.lbm_shard_plan(nn, ll, uu, r, ww, out) == 0
