@@ -34,13 +34,16 @@ def main():
     h = L.handle_for(local)
     peer = world > 1 and bool(L._lib.lib().lbm_peer_active(h.ptr))
     # ghost transports to report for the configs that exchange: peer-memory mailboxes (default) and NCCL send/recv
-    modes = ((0, "peer mailboxes"), (1, "ncclSend/Recv")) if peer else ((1, "ncclSend/Recv" if world > 1 else "1 GPU"),)
+    modes = (((0, 0, "peer mailboxes, exchange fused into the launch"), (0, 2, "peer mailboxes, two-kernel exchange"), (1, 0, "ncclSend/Recv"))
+             if peer else ((1, 0, "ncclSend/Recv" if world > 1 else "1 GPU"),))
 
     def both(name, fn, byts, reps=10, warm=3):
-        for mode, label in modes:
-            h.set_tuning(exchange_mode=mode)
-            emit(f"{name} [{label}]", timeit(fn, reps, warm), byts)
-        h.set_tuning(exchange_mode=0)
+        for mode, fuse, label in modes:
+            h.set_tuning(exchange_mode=mode, exchange_fuse=fuse)
+            l0 = h.launch_count()
+            ms = timeit(fn, reps, warm)
+            emit(f"{name} [{label}]", ms, byts, launches_per_apply=(h.launch_count() - l0) / (reps + warm))
+        h.set_tuning(exchange_mode=0, exchange_fuse=0)
 
     def timeit(fn, reps=10, warm=3):
         for _ in range(warm):
@@ -108,47 +111,61 @@ def main():
         del d, e, sh, xb, y
         torch.cuda.empty_cache()
 
-    if world > 1 and only is not None and not (want("C3") or want("C4") or want("C5") or want("M")):
-        dist.barrier()
-        dist.destroy_process_group()
-        return
     # ---- C3: 2-D Laplacian on 8192^2, partitioned by grid columns ----
-    g = 8192
-    hh = 1.0 / g
-    D = L.banded_from_diagonals(g, {0: -2.0 / hh**2, 1: 1.0 / hh**2, -1: 1.0 / hh**2}, device=dev)
-    p = RowShard.plan(g, 1, 1, rank, world)
-    sh = ShardedKronSum(g, g, 1, 1, D.data[p.c0:p.c1].contiguous(), D, rank, world)
-    xb = sh.new_buffer(torch.float64, dev)
-    L.fill_uniform(sh.owned(xb).view(-1), 5, offset=p.r0 * g)
-    y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
-    both("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192", lambda: sh.mul_(y, xb), 16 * g * g, 20, 5)
-    del sh, xb, y
-    torch.cuda.empty_cache()
+    if want("C3"):
+        g = 8192
+        hh = 1.0 / g
+        D = L.banded_from_diagonals(g, {0: -2.0 / hh**2, 1: 1.0 / hh**2, -1: 1.0 / hh**2}, device=dev)
+        p = RowShard.plan(g, 1, 1, rank, world)
+        sh = ShardedKronSum(g, g, 1, 1, D.data[p.c0:p.c1].contiguous(), D, rank, world)
+        xb = sh.new_buffer(torch.float64, dev)
+        L.fill_uniform(sh.owned(xb).view(-1), 5, offset=p.r0 * g)
+        y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
+        both("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192", lambda: sh.mul_(y, xb), 16 * g * g, 20, 5)
+        del sh, xb, y
+        torch.cuda.empty_cache()
 
     # ---- C4: gbmm l=u=128, n = 2^20, column-partitioned (static halo of A, no communication) ----
-    n = 1 << 20
-    q = GbmmColumnShard.plan(n, 128, 128, 128, 128, rank, world)
-    A_slab = torch.empty((q.pb - q.pa, 257), dtype=torch.float64, device=dev)
-    L.fill_uniform(A_slab, 1, offset=257 * q.pa)
-    B_slab = torch.empty((q.c1 - q.c0, 257), dtype=torch.float64, device=dev)
-    L.fill_uniform(B_slab, 2, offset=257 * q.c0)
-    C_slab = torch.empty((q.c1 - q.c0, 513), dtype=torch.float64, device=dev)
-    emit("C4 gbmm f64 n=2^20 (128,128)^2 -> (256,256)", timeit(lambda: q.local_gbmm(A_slab, B_slab, C_slab), 3, 1),
-         8 * n * (257 + 257 + 513), 2 * n * 257 * 257)
-    del A_slab, B_slab, C_slab
-    torch.cuda.empty_cache()
+    if want("C4"):
+        n = 1 << 20
+        q = GbmmColumnShard.plan(n, 128, 128, 128, 128, rank, world)
+        A_slab = torch.empty((q.pb - q.pa, 257), dtype=torch.float64, device=dev)
+        L.fill_uniform(A_slab, 1, offset=257 * q.pa)
+        B_slab = torch.empty((q.c1 - q.c0, 257), dtype=torch.float64, device=dev)
+        L.fill_uniform(B_slab, 2, offset=257 * q.c0)
+        C_slab = torch.empty((q.c1 - q.c0, 513), dtype=torch.float64, device=dev)
+        emit("C4 gbmm f64 n=2^20 (128,128)^2 -> (256,256)", timeit(lambda: q.local_gbmm(A_slab, B_slab, C_slab), 3, 1),
+             8 * n * (257 + 257 + 513), 2 * n * 257 * 257)
+        del A_slab, B_slab, C_slab
+        torch.cuda.empty_cache()
 
     # ---- C5: 4096 fused chains A*B*C, brand(4096,4096,4,4) f32, batch split ----
-    batch, nn = 4096, 4096
-    b0, b1 = split_batch(batch, world, rank)
-    fs = [torch.empty((b1 - b0, nn, 9), dtype=torch.float32, device=dev) for _ in range(3)]
-    for i, f in enumerate(fs):
-        L.fill_uniform(f, 1 + i, offset=b0 * nn * 9)
-    emit("C5 fused chain A*B*C f32 batch=4096 n=4096 (4,4)^3", timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2),
-         batch * 4 * nn * (9 + 9 + 9 + 25), batch * 2 * nn * (9 * 9 + 17 * 9))
-    del fs
-    torch.cuda.empty_cache()
+    if want("C5"):
+        batch, nn = 4096, 4096
+        b0, b1 = split_batch(batch, world, rank)
+        fs = [torch.empty((b1 - b0, nn, 9), dtype=torch.float32, device=dev) for _ in range(3)]
+        for i, f in enumerate(fs):
+            L.fill_uniform(f, 1 + i, offset=b0 * nn * 9)
+        emit("C5 fused chain A*B*C f32 batch=4096 n=4096 (4,4)^3", timeit(lambda: L.chain3_batched(*fs, [4, 4, 4], [4, 4, 4]), 5, 2),
+             batch * 4 * nn * (9 + 9 + 9 + 25), batch * 2 * nn * (9 * 9 + 17 * 9))
+        del fs
+        torch.cuda.empty_cache()
 
+    # ---- M: gbmv n = 2^27, l=u=1 / 8 (the metric's timed region), every transport ----
+    for l in ((1, 8) if want("M") else ()):
+        n = 1 << 27
+        sh = ShardedBanded.brand(n, l, l, rank, world, device=dev, seed=1)
+        xb = sh.plan.new_vector(torch.float64, dev)
+        L.fill_uniform(xb, 9, offset=sh.plan.c0)
+        y = torch.empty(sh.plan.m_loc, dtype=torch.float64, device=dev)
+        both(f"M gbmv f64 n=2^27 l=u={l}", lambda: sh.mul_(y, xb), 8 * n * (2 * l + 3), 20, 5)
+        del sh, xb, y
+        torch.cuda.empty_cache()
+    if only is not None and not want("M128"):
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     # ---- M: gbmv n = 2^27, l=u=128 (needs >= 2 GPUs) ----
     if world >= 2:
         n = 1 << 27

@@ -229,6 +229,23 @@ int lbm_dtridiag_mm(lbm_handle_t h, int64_t n, const double *adl, const double *
 int lbm_stridiag_mm(lbm_handle_t h, int64_t n, const float *adl, const float *ad, const float *adu,
                     const float *bdl, const float *bd, const float *bdu, float *C, int64_t ldc);
 
+/* ---- solves with the structured kinds:  X <- A \ B ---------------------------------------------------------------- */
+/* `A \ b` for Tridiagonal / SymTridiagonal (pass dl == du == ev) / Bidiagonal (a triangular solve: the missing
+ * diagonal is NULL, or lbm_?bidiag_solve with uplo) -- SURVEY.md 8(f) rank 4; exercised by the reference at
+ * /root/reference/test/test_tridiag.jl:345-363 (`A90\b90`), where `\` falls through ArrayLayouts to LinearAlgebra's
+ * sequential tridiagonal LU.  Here: the partition method, recursively (csrc/solve.cu), 9n elements of HBM traffic.
+ * B, X are n x nrhs column-major (ldb, ldx); X may alias B (in place).  NO PIVOTING (Thomas): exact for diagonally
+ * dominant and symmetric positive definite operators.  info_dev (DEVICE int, may be NULL) is set to 1 when a zero pivot
+ * was met (the result then holds Inf/NaN), 0 otherwise -- LAPACK's info > 0. */
+int lbm_dtridiag_solve(lbm_handle_t h, int64_t n, const double *dl, const double *d, const double *du,
+                       const double *B, int64_t ldb, int64_t nrhs, double *X, int64_t ldx, int *info_dev);
+int lbm_stridiag_solve(lbm_handle_t h, int64_t n, const float *dl, const float *d, const float *du,
+                       const float *B, int64_t ldb, int64_t nrhs, float *X, int64_t ldx, int *info_dev);
+int lbm_dbidiag_solve(lbm_handle_t h, char uplo, int64_t n, const double *dv, const double *ev,
+                      const double *B, int64_t ldb, int64_t nrhs, double *X, int64_t ldx, int *info_dev);
+int lbm_sbidiag_solve(lbm_handle_t h, char uplo, int64_t n, const float *dv, const float *ev,
+                      const float *B, int64_t ldb, int64_t nrhs, float *X, int64_t ldx, int *info_dev);
+
 /* ---- row-sharded mul! across the GPUs of one box (one process per GPU) ------------------- */
 /* Rank r of `world` owns rows [r0,r1) of a square n x n operator and stores the COLUMN slice
  * [c0,c1) = [max(0,r0-kl), min(n,r1+ku)) of the diagonal-major array (same lda); x lives in a

@@ -127,7 +127,10 @@ Plan make_plan(int64_t n, int64_t kl, int64_t ku, int rank, int world) {
 bool plan_valid(const Plan &p, int64_t kl, int64_t ku) { return p.world_eff <= 1 || p.per >= (kl > ku ? kl : ku); }
 
 // ---- peer-mailbox transport -----------------------------------------------------------------------------------------
-constexpr size_t PEER_FLAG_BYTES = 256;   // flags[0] = epoch published by the LEFT neighbour, flags[1] = by the RIGHT one
+// flag words: [0, NF) = epochs published by the LEFT neighbour, [NF, 2NF) = by the RIGHT one.  The 1-D exchanges use word 0
+// of each side; the grid-column exchange of the Kronecker-sum kernel uses one word per 256-row strip (kron.cu).
+constexpr int PEER_NFLAGS = 4096;
+constexpr size_t PEER_FLAG_BYTES = (size_t)2 * PEER_NFLAGS * sizeof(unsigned long long);
 
 inline char *peer_slot(void *block, size_t slot_bytes, int from_side, int parity) {
     return reinterpret_cast<char *>(block) + PEER_FLAG_BYTES + (size_t)(2 * from_side + parity) * slot_bytes;
@@ -140,11 +143,12 @@ inline unsigned long long halo_timeout_ns(lbm_handle_t h) {
 
 // Everything one epoch of the mailbox protocol needs, for the fused kernels and for the two-kernel exchange alike.
 // Advances the epoch.  `unit` = bytes per ghost unit (an element, or a grid column of n2 elements).
-lbm::HaloFuse make_fuse(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t unit) {
+lbm::HaloFuse make_fuse(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t unit, int nflags = 1) {
     lbm::HaloFuse f;
     memset(&f, 0, sizeof(f));
     f.on = 1;
     f.elem_bytes = (int)unit;
+    f.nflags = nflags >= 1 && nflags <= PEER_NFLAGS ? nflags : 1;
     const unsigned long long epoch = ++h->peer_epoch;
     const int par = (int)(epoch & 1);
     f.epoch = epoch;
@@ -156,7 +160,7 @@ lbm::HaloFuse make_fuse(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, c
         const int64_t cnt = ku < p.m_loc ? ku : p.m_loc;
         f.push_src[0] = own;
         f.push_dst[0] = peer_slot(h->peer_remote[0], h->peer_slot_bytes, /*from its RIGHT*/ 1, par);
-        f.push_flag[0] = reinterpret_cast<unsigned long long *>(h->peer_remote[0]) + 1;
+        f.push_flag[0] = reinterpret_cast<unsigned long long *>(h->peer_remote[0]) + PEER_NFLAGS;
         f.push_bytes[0] = cnt * unit;
         f.pull_src[0] = peer_slot(h->peer_local, h->peer_slot_bytes, 0, par);
         f.pull_flag[0] = lflags + 0;
@@ -171,7 +175,7 @@ lbm::HaloFuse make_fuse(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, c
         f.push_flag[1] = reinterpret_cast<unsigned long long *>(h->peer_remote[1]) + 0;
         f.push_bytes[1] = cnt * unit;
         f.pull_src[1] = peer_slot(h->peer_local, h->peer_slot_bytes, 1, par);
-        f.pull_flag[1] = lflags + 1;
+        f.pull_flag[1] = lflags + PEER_NFLAGS;
         f.ghost_begin[1] = p.left + p.m_loc;
         f.ghost_end[1] = p.left + p.m_loc + p.right;
         f.wait_only[1] = p.right == 0;
@@ -195,7 +199,10 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const lbm::HaloFuse f, c
     const int s = blockIdx.x;
     if (!f.pull_flag[s]) return;
     __shared__ int ok;
-    if (threadIdx.x == 0) ok = lbm::halo_wait_flag(f.pull_flag[s], f.epoch, f.timeout_ns, f.status) ? 1 : 0;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < f.nflags; i += blockDim.x)   // a strip-wise pusher publishes one word per strip
+        if (!lbm::halo_wait_flag(f.pull_flag[s] + i, f.epoch, f.timeout_ns, f.status)) ok = 0;
     __syncthreads();
     const int64_t nb = (f.ghost_end[s] - f.ghost_begin[s]) * f.elem_bytes;
     if (!ok || nb <= 0) return;
@@ -211,10 +218,10 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const lbm::HaloFuse f, c
 }
 
 // same contract as exchange_nccl(): ghosts of xbuf valid once h->ev_halo has fired
-int exchange_peer(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb) {
+int exchange_peer(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb, int nflags) {
     LBM_CUDA(h, cudaEventRecord(h->ev_ready, h->stream));
     LBM_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
-    const lbm::HaloFuse f = make_fuse(h, p, kl, ku, xbuf, eb);
+    const lbm::HaloFuse f = make_fuse(h, p, kl, ku, xbuf, eb, nflags);
     halo_push_kernel<<<1, 256, 0, h->comm_stream>>>(f);
     LBM_LAUNCH_CHECK(h, "halo_push_kernel");
     halo_pull_kernel<<<2, 256, 0, h->comm_stream>>>(f, xbuf);
@@ -247,9 +254,16 @@ int exchange_nccl(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *x
     return 0;
 }
 
+// A rank beyond the effective world owns nothing and takes no part in an exchange -- but the epoch counter is the
+// protocol's clock and must tick on EVERY rank for every exchange the others perform, or a rank that is empty for one
+// operator and owns rows of the next (a different n) would rejoin its neighbours out of step.
+void skip_exchange(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, int64_t unit) {
+    if (h->world > 1 && p.world_eff > 1 && peer_usable(h, kl, ku, unit)) ++h->peer_epoch;
+}
+
 // transport choice; the halo each way is at most max(kl,ku) units.  Only called on ranks that own rows.
-int exchange(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb) {
-    if (peer_usable(h, kl, ku, eb)) return exchange_peer(h, p, kl, ku, xbuf, eb);
+int exchange(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, char *xbuf, int64_t eb, int nflags = 1) {
+    if (peer_usable(h, kl, ku, eb)) return exchange_peer(h, p, kl, ku, xbuf, eb, nflags);
     return exchange_nccl(h, p, kl, ku, xbuf, eb);
 }
 
@@ -346,7 +360,10 @@ int gbmv_sharded(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, T alpha, con
     const Plan p = make_plan(n, kl, ku, h->rank, h->world);
     int rc = sharded_enter(h, p, kl, ku);
     if (rc) return rc;
-    if (p.m_loc == 0) return 0;   // beyond the effective world: owns nothing, has no neighbours
+    if (p.m_loc == 0) {   // beyond the effective world: owns nothing, has no neighbours
+        skip_exchange(h, p, kl, ku, sizeof(T));
+        return 0;
+    }
     return gbmv_sharded_plan<T>(h, p, kl, ku, alpha, A, lda, xbuf, beta, y, overlap);
 }
 
@@ -374,7 +391,10 @@ int gbmv_chain_sharded(lbm_handle_t h, int nf, int64_t n, const int64_t *kl, con
         if (p.n_loc > pitch) pitch = p.n_loc;
     }
     const Plan p0 = make_plan(n, kl[0], ku[0], h->rank, h->world);
-    if (p0.m_loc == 0) return 0;
+    if (p0.m_loc == 0) {   // one exchange per factor on the ranks that own rows
+        for (int f = 0; f < nf; ++f) skip_exchange(h, make_plan(n, kl[f], ku[f], h->rank, h->world), kl[f], ku[f], sizeof(T));
+        return 0;
+    }
     if (nf == 1) return gbmv_sharded_plan<T>(h, p0, kl[0], ku[0], alpha, A[0], lda[0], xbuf, beta, y, 1);
     pitch = (pitch + 31) / 32 * 32;
     void *scr;
@@ -402,7 +422,10 @@ int tridiag_sharded(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T 
     const Plan p = make_plan(n, kl, ku, h->rank, h->world);
     int rc = sharded_enter(h, p, kl, ku);
     if (rc) return rc;
-    if (p.m_loc == 0) return 0;
+    if (p.m_loc == 0) {
+        skip_exchange(h, p, kl, ku, sizeof(T));
+        return 0;
+    }
     if (!d) return lbm_fail_arg(h, 4, "d == NULL");
     if (!xbuf) return lbm_fail_arg(h, 7, "xbuf == NULL");
     if (!y) return lbm_fail_arg(h, 9, "y_own == NULL");
@@ -426,7 +449,7 @@ int tridiag_sharded(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T 
 // main stream does NOT wait -- the caller overlaps interior work and then waits on h->ev_halo).  < 0 / > 1: error code.
 // plan10 = {r0, r1, c0, c1, left, right, kl_loc, ku_loc, world_eff, m_loc}.
 int lbm_internal_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int64_t *plan10,
-                          int overlap, lbm::HaloFuse *hf, int *fused) {
+                          int overlap, lbm::HaloFuse *hf, int *fused, int nflags) {
     const Plan p = make_plan(n, kl, ku, h->rank, h->world);
     plan10[0] = p.r0; plan10[1] = p.r1; plan10[2] = p.c0; plan10[3] = p.c1;
     plan10[4] = p.left; plan10[5] = p.right; plan10[6] = p.kl_loc; plan10[7] = p.ku_loc;
@@ -434,13 +457,14 @@ int lbm_internal_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, voi
     *fused = 0;
     int rc = sharded_enter(h, p, kl, ku);
     if (rc) return rc;
+    if (p.m_loc == 0) skip_exchange(h, p, kl, ku, unit_bytes);
     if (h->world == 1 || p.world_eff <= 1 || p.m_loc == 0) return 0;
     if (hf && want_fused(h, kl, ku, unit_bytes, overlap)) {
-        *hf = make_fuse(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes);
+        *hf = make_fuse(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes, nflags);
         *fused = 1;
         return 0;
     }
-    return exchange(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes);
+    return exchange(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes, nflags);
 }
 // comm stream + events of a handle that takes part in a row partition (created once)
 int lbm_internal_comm_resources(lbm_handle_t h) {
@@ -461,10 +485,10 @@ int lbm_internal_peer_alloc_local(lbm_handle_t h, size_t slot_bytes) {
     return 0;
 }
 // the kernel turned the fused launch down (LBM_NOT_FUSED): give the epoch back and run the unfused exchange
-int lbm_internal_exchange_unfuse(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes) {
+int lbm_internal_exchange_unfuse(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int nflags) {
     --h->peer_epoch;
     const Plan p = make_plan(n, kl, ku, h->rank, h->world);
-    return exchange(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes);
+    return exchange(h, p, kl, ku, reinterpret_cast<char *>(buf), unit_bytes, nflags);
 }
 
 extern "C" {
@@ -601,6 +625,7 @@ int lbm_halo_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *x
     const Plan p = make_plan(n, kl, ku, h->rank, h->world);
     int rc = sharded_enter(h, p, kl, ku);   // same verdict on every rank
     if (rc) return rc;
+    if (p.m_loc == 0) skip_exchange(h, p, kl, ku, elem_bytes);
     if (p.m_loc == 0 || p.world_eff <= 1) return 0;   // owns nothing / is alone: no neighbours, nothing to exchange
     if ((rc = exchange(h, p, kl, ku, reinterpret_cast<char *>(xbuf), elem_bytes))) return rc;
     LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));

@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
-    if (HALO && blockIdx.x == 0) halo_push(hf, tid, GBMV_NT);   // before anything else: the neighbours are waiting for it
     __syncthreads();
 
     // tiles of this CTA: t = blockIdx.x + k*gridDim.x
@@ -112,6 +111,8 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         const int64_t pro = mine < S ? mine : S;
         for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
     }
+    // the push rides on the latency of the prologue copies already in flight (the neighbours need it only for their LAST tiles)
+    if (HALO && blockIdx.x == 0) halo_push(hf, tid, GBMV_NT);
 
     const int lda = (int)a.lda;
     for (int64_t k = 0; k < mine; ++k) {

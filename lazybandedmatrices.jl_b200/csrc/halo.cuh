@@ -32,6 +32,7 @@ struct HaloFuse {
     const char *pull_src[2];         // local mailbox slot
     const unsigned long long *pull_flag[2];
     int64_t ghost_begin[2], ghost_end[2];   // ghost range in x-index space (units); empty when there is no neighbour
+    int nflags;                      // flag words in use per side: 1 for the 1-D kernels, one per row strip for the grid-column exchange
     int wait_only[2];                // a neighbour exists on that side but sends no ghosts (kl or ku == 0): its flag must still
                                      // be awaited once per epoch, or this rank could lap it and overwrite a slot it is reading
     unsigned long long epoch;
@@ -72,37 +73,41 @@ __device__ __forceinline__ bool halo_wait_flag(const unsigned long long *flag, u
     }
 }
 
-// Called by every thread of the pushing CTA at kernel start.
+// Copy `nb` bytes to peer memory (all threads of the CTA).
+__device__ __forceinline__ void halo_copy(const char *src, char *dst, int64_t nb, int tid, int nthreads) {
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nb) & 15u) == 0) {
+        const int4 *s4 = reinterpret_cast<const int4 *>(src);
+        int4 *d4 = reinterpret_cast<int4 *>(dst);
+        for (int64_t i = tid; i < nb / 16; i += nthreads) d4[i] = s4[i];
+    } else if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nb) & 3u) == 0) {
+        const int *s1 = reinterpret_cast<const int *>(src);
+        int *d1 = reinterpret_cast<int *>(dst);
+        for (int64_t i = tid; i < nb / 4; i += nthreads) d1[i] = s1[i];
+    } else {
+        for (int64_t i = tid; i < nb; i += nthreads) dst[i] = src[i];
+    }
+}
+
+// Called by every thread of the pushing CTA (1-D kernels: the whole payload, flag word 0).  Payload first, then a
+// system-scope fence and a CTA barrier, then the flags.
 __device__ __forceinline__ void halo_push(const HaloFuse &hf, int tid, int nthreads) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (!hf.push_flag[s]) continue;
-        const int64_t nb = hf.push_bytes[s];
-        const char *src = hf.push_src[s];
-        char *dst = hf.push_dst[s];
-        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nb) & 15u) == 0) {
-            const int4 *s4 = reinterpret_cast<const int4 *>(src);
-            int4 *d4 = reinterpret_cast<int4 *>(dst);
-            for (int64_t i = tid; i < nb / 16; i += nthreads) d4[i] = s4[i];
-        } else if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nb) & 3u) == 0) {
-            const int *s1 = reinterpret_cast<const int *>(src);
-            int *d1 = reinterpret_cast<int *>(dst);
-            for (int64_t i = tid; i < nb / 4; i += nthreads) d1[i] = s1[i];
-        } else {
-            for (int64_t i = tid; i < nb; i += nthreads) dst[i] = src[i];
-        }
-    }
+    for (int s = 0; s < 2; ++s)
+        if (hf.push_flag[s]) halo_copy(hf.push_src[s], hf.push_dst[s], hf.push_bytes[s], tid, nthreads);
     __threadfence_system();
     __syncthreads();
-    if (tid == 0 && hf.push_flag[0]) st_release_sys(hf.push_flag[0], hf.epoch);
-    if (tid == 1 && hf.push_flag[1]) st_release_sys(hf.push_flag[1], hf.epoch);
+    // every flag word of the side (nflags > 1 only when this is the unfused push kernel serving a strip-wise waiter)
+    for (int i = tid; i < 2 * hf.nflags; i += nthreads) {
+        const int s = i / hf.nflags;
+        if (hf.push_flag[s]) st_release_sys(hf.push_flag[s] + (i - s * hf.nflags), hf.epoch);
+    }
 }
 
 // Called by every thread of the pushing CTA after its last tile: keeps the epochs of a neighbour pair in lock-step on the
 // sides this rank receives nothing from (see wait_only).
-__device__ __forceinline__ void halo_final_wait(const HaloFuse &hf, int tid) {
-    if (tid == 0 && hf.wait_only[0]) halo_wait_flag(hf.pull_flag[0], hf.epoch, hf.timeout_ns, hf.status);
-    if (tid == 1 && hf.wait_only[1]) halo_wait_flag(hf.pull_flag[1], hf.epoch, hf.timeout_ns, hf.status);
+__device__ __forceinline__ void halo_final_wait(const HaloFuse &hf, int tid, int flag_idx = 0) {
+    if (tid == 0 && hf.wait_only[0]) halo_wait_flag(hf.pull_flag[0] + flag_idx, hf.epoch, hf.timeout_ns, hf.status);
+    if (tid == 1 && hf.wait_only[1]) halo_wait_flag(hf.pull_flag[1] + flag_idx, hf.epoch, hf.timeout_ns, hf.status);
 }
 
 // 1-D windows (gbmv / tridiagonal kernels): the stage's x window holds x[w0 .. w1) at sx[0 ..].  If it overlaps ghost
@@ -145,7 +150,7 @@ int lbm_internal_stridiag_rows_fused(lbm_handle_t h, int64_t n, const float *dl,
                                      const float *x, float beta, float *y, int64_t row_begin, int64_t row_end,
                                      const lbm::HaloFuse *hf);
 int lbm_internal_exchange(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int64_t *plan10,
-                          int overlap, lbm::HaloFuse *hf, int *fused);
-int lbm_internal_exchange_unfuse(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes);
+                          int overlap, lbm::HaloFuse *hf, int *fused, int nflags);
+int lbm_internal_exchange_unfuse(lbm_handle_t h, int64_t n, int64_t kl, int64_t ku, void *buf, int64_t unit_bytes, int nflags);
 int lbm_internal_comm_resources(lbm_handle_t h);
 int lbm_internal_peer_alloc_local(lbm_handle_t h, size_t slot_bytes);

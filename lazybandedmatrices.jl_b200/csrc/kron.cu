@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
-    if (HALO && blockIdx.x == 0 && blockIdx.y == 0) halo_push(hf, tid, 256);
     __syncthreads();
 
     const int64_t step = gridDim.y;
@@ -194,6 +193,25 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
     if (tid < 32) {
         const int64_t pro = mine < S ? mine : S;
         for (int64_t k = 0; k < pro; ++k) issue(chunk_of(k), (int)k);
+    }
+    // STRIP-WISE push (rides on the latency of the prologue copies): the CTA (strip, 0) sends rows [r0, r0+tr) of this
+    // rank's boundary grid columns -- all the neighbour's CTAs of the same strip need -- and publishes the epoch in the
+    // strip's own flag word, so no CTA ever moves more than a few KB and nobody waits for rows it does not use.
+    if (HALO && blockIdx.y == 0) {
+        const int64_t rows = (r0 + a.tr < a.n2 ? r0 + a.tr : a.n2) - r0;
+#pragma unroll
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!hf.push_flag[sd]) continue;
+            const int64_t colbytes = a.n2 * (int64_t)sizeof(T);
+            const int64_t ncols = hf.push_bytes[sd] / colbytes;
+            for (int64_t c = 0; c < ncols; ++c)
+                halo_copy(hf.push_src[sd] + c * colbytes + r0 * (int64_t)sizeof(T), hf.push_dst[sd] + c * colbytes + r0 * (int64_t)sizeof(T),
+                          rows * (int64_t)sizeof(T), tid, 256);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0 && hf.push_flag[0]) st_release_sys(hf.push_flag[0] + blockIdx.x, hf.epoch);
+        if (tid == 1 && hf.push_flag[1]) st_release_sys(hf.push_flag[1] + blockIdx.x, hf.epoch);
     }
 
     // A coefficients of a chunk's columns, ca[cc][t] = A[c, c-kla+t] (zero outside the matrix):
@@ -259,10 +277,12 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
             for (int sd = 0; sd < 2; ++sd)
                 need[sd] = hf.ghost_end[sd] > hf.ghost_begin[sd] && sa < hf.ghost_end[sd] && sb > hf.ghost_begin[sd];
             if (need[0] || need[1]) {   // CTA-uniform
-                if (tid == 0 && need[0]) halo_wait_flag(hf.pull_flag[0], hf.epoch, hf.timeout_ns, hf.status);
-                if (tid == 1 && need[1]) halo_wait_flag(hf.pull_flag[1], hf.epoch, hf.timeout_ns, hf.status);
+                if (tid == 0 && need[0]) halo_wait_flag(hf.pull_flag[0] + blockIdx.x, hf.epoch, hf.timeout_ns, hf.status);
+                if (tid == 1 && need[1]) halo_wait_flag(hf.pull_flag[1] + blockIdx.x, hf.epoch, hf.timeout_ns, hf.status);
                 __syncthreads();
-                const int rows_in = (int)(re - rs);
+                // only rows [r0, r0+tr) of a ghost column are ever read (the A-term X[r, c+-t]; the B-term reads owned columns)
+                const int rows_in = (int)((r0 + a.tr < a.n2 ? r0 + a.tr : a.n2) - r0);
+                const int rskip = (int)(r0 - rs);
 #pragma unroll
                 for (int sd = 0; sd < 2; ++sd) {
                     if (!need[sd]) continue;
@@ -270,8 +290,8 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
                     const int64_t gb = sb < hf.ghost_end[sd] ? sb : hf.ghost_end[sd];
                     const T *mb = reinterpret_cast<const T *>(hf.pull_src[sd]);
                     for (int64_t c = ga; c < gb; ++c) {
-                        T *dstc = const_cast<T *>(st) + (c - ci0) * a.seg + roff;
-                        const T *srcc = mb + (c - hf.ghost_begin[sd]) * a.n2 + rs;
+                        T *dstc = const_cast<T *>(st) + (c - ci0) * a.seg + roff + rskip;
+                        const T *srcc = mb + (c - hf.ghost_begin[sd]) * a.n2 + r0;
                         for (int r = tid; r < rows_in; r += 256) dstc[r] = __ldcg(srcc + r);
                     }
                 }
@@ -366,7 +386,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         __syncthreads();
         if (tid < 32 && kk + S < mine) issue(chunk_of(kk + S), s);
     }
-    if (HALO && blockIdx.x == 0 && blockIdx.y == 0) halo_final_wait(hf, tid);
+    if (HALO && blockIdx.y == 0) halo_final_wait(hf, tid, blockIdx.x);
 }
 
 template <typename T, int NBA, int NBB, int RPT, bool HALO>
@@ -560,8 +580,16 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
     int64_t pl[10];
     HaloFuse hf;
     int fused = 0;
+    // one flag word per row strip of the ring kernel (same `tr` rule as kron_ring_try; uniform across ranks); when the
+    // strips do not fit the flag block everybody uses ONE word and the unfused exchange
+    int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
+    tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
+    const int64_t nstrips = (n2 + tr - 1) / tr;
+    const int nflags = nstrips <= 4096 ? (int)nstrips : 1;
+    if (nflags == 1 && nstrips > 1) overlap = overlap ? 2 : 0;   // 2: overlapped but never fused
     // plan + uniform validation + either a fused-exchange descriptor or the two-kernel / NCCL exchange already in flight
-    if ((rc = lbm_internal_exchange(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T), pl, overlap, &hf, &fused))) return rc;
+    if ((rc = lbm_internal_exchange(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T), pl, overlap == 1, overlap == 1 ? &hf : nullptr, &fused, nflags)))
+        return rc;
     const int64_t m_loc = pl[9], n_loc = pl[3] - pl[2], left = pl[4], right = pl[5];
     if (m_loc == 0) return 0;
     if (h->world == 1 || pl[8] <= 1)
@@ -569,7 +597,7 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
     if (fused) {   // ONE launch: push at kernel start, ghost columns patched into the last chunks' stages
         rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc, &hf);
         if (rc != LBM_NOT_FUSED) return rc;
-        if ((rc = lbm_internal_exchange_unfuse(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T)))) return rc;
+        if ((rc = lbm_internal_exchange_unfuse(h, n1, kla, kua, xbuf, n2 * (int64_t)sizeof(T), nflags))) return rc;
     }
     if (!overlap) {
         LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));

@@ -192,7 +192,6 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
-    if (HALO && blockIdx.x == 0) halo_push(hf, tid, TRI_NT);
     __syncthreads();
     const int64_t first = blockIdx.x, step = gridDim.x;
     const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
@@ -226,6 +225,7 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         const int64_t pro = mine < S ? mine : S;
         for (int64_t k = 0; k < pro; ++k) issue(first + k * step, (int)k);
     }
+    if (HALO && blockIdx.x == 0) halo_push(hf, tid, TRI_NT);   // rides on the latency of the prologue copies
     for (int64_t k = 0; k < mine; ++k) {
         const int s = (int)(k % S);
         const uint32_t parity = (uint32_t)((k / S) & 1);

@@ -102,6 +102,8 @@ def _sigs():
         s[f"lbm_{p}gbmv_chain_sharded"] = (C.c_int, [H, C.c_int, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64),
                                                     ft, vp, ft, vp])
         s[f"lbm_{p}tridiag_mv_sharded"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, ft, vp, C.c_int])
+        s[f"lbm_{p}tridiag_solve"] = (C.c_int, [H, i64, vp, vp, vp, vp, i64, i64, vp, i64, vp])
+        s[f"lbm_{p}bidiag_solve"] = (C.c_int, [H, ch, i64, vp, vp, vp, i64, i64, vp, i64, vp])
         s[f"lbm_{p}tridiag_mv"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}bidiag_mv"] = (C.c_int, [H, ch, i64, vp, vp, ft, vp, i64, i64, ft, vp, i64])
         s[f"lbm_{p}tridiag_mv_rows"] = (C.c_int, [H, i64, vp, vp, vp, ft, vp, ft, vp, i64, i64])

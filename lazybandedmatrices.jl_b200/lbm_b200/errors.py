@@ -10,6 +10,10 @@ class LbmArgumentError(ValueError):
     """Julia's `ArgumentError` / a negative LAPACK-style `info` from the C ABI."""
 
 
+class SingularException(ArithmeticError):
+    """Julia's `SingularException`: a zero pivot in a factorisation / solve."""
+
+
 class LbmCudaError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"[cuda {code}] {msg}")

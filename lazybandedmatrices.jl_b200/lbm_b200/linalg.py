@@ -38,6 +38,13 @@ def matmul(A, other):
     raise LbmArgumentError(f"* is not defined for {type(A).__name__} and {type(other).__name__}")
 
 
+def ldiv(A, b, out=None):
+    """`A \\ b` for the structured kinds (Tridiagonal / SymTridiagonal / Bidiagonal): lbm_?tridiag_solve."""
+    if hasattr(A, "solve"):
+        return A.solve(b, out)
+    raise LbmArgumentError(f"\\ is not defined for {type(A).__name__} on the B200 path")
+
+
 def bandwidths(A):
     return tuple(A.bandwidths())
 

@@ -95,6 +95,33 @@ class _Structured:
             return out
         return out.reshape(1, self.n) if dims == 1 else out.reshape(self.n, 1)
 
+    def solve(self, b: torch.Tensor, out: torch.Tensor = None, check: bool = True) -> torch.Tensor:
+        """`A \\ b` (vector or n x nrhs matrix): lbm_?tridiag_solve -- the recursive partition method, no pivoting (exact
+        for diagonally dominant / SPD operators).  In the reference `\\` reaches LinearAlgebra's tridiagonal LU through
+        ArrayLayouts (exercised at test/test_tridiag.jl:345-363).  `check`: raise on a zero pivot (costs one device sync)."""
+        if b.shape[0] != self.n or b.dim() not in (1, 2):
+            raise DimensionMismatch(f"A has size {self.shape}, b has size {tuple(b.shape)}")
+        dl, d, du = self._diagonals()
+        if b.dtype != d.dtype:
+            raise LbmArgumentError(f"element types differ: {d.dtype} vs {b.dtype}")
+        if out is None:
+            out = torch.empty_like(b)
+        if self.n == 0 or b.numel() == 0:
+            return out
+        Bc, ldb = _colmajor(b)
+        Xc, ldx = _colmajor(out)
+        nrhs = b.shape[1] if b.dim() == 2 else 1
+        info = torch.zeros(1, dtype=torch.int32, device=d.device)
+        h = _lib.handle_of(d)
+        fn = getattr(_lib.lib(), f"lbm_{_pfx(d.dtype)}tridiag_solve")
+        h.check(fn(h.ptr, self.n, _ptr(dl), _ptr(d), _ptr(du), _ptr(Bc), ldb, nrhs, _ptr(Xc), ldx, _ptr(info)), "lbm_tridiag_solve")
+        if Xc is not out:
+            out.copy_(Xc)
+        if check and int(info.item()) != 0:
+            from .errors import SingularException
+            raise SingularException("zero pivot in the (unpivoted) tridiagonal elimination")
+        return out
+
     @property
     def shape(self):
         return (self.n, self.n)

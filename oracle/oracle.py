@@ -299,6 +299,26 @@ def kron2d_mv(n1, n2, A, kla, kua, B, klb, kub, x, alpha=1.0, beta=0.0, y=None):
     return _kron_call("kron2d_mv", n1, n2, A, kla, kua, B, klb, kub, x, alpha, beta, y)
 
 
+def tridiag_solve(dl, d, du, B):
+    """`Tridiagonal(dl,d,du) \\ B`.  The reference has no solve code of its own: `\\` goes through ArrayLayouts to
+    LinearAlgebra's `lu(::Tridiagonal)` = LAPACK ?gttrf/?gttrs (partial pivoting; exercised at
+    /root/reference/test/test_tridiag.jl:345-363).  The oracle is therefore LAPACK ?gtsv itself (scipy), the same
+    pivoted elimination; a missing diagonal (Bidiagonal) is zeros."""
+    from scipy.linalg import lapack
+    d = np.asarray(d)
+    n = len(d)
+    z = np.zeros(max(n - 1, 0), dtype=d.dtype)
+    dl = z if dl is None else np.asarray(dl)[: max(n - 1, 0)]
+    du = z if du is None else np.asarray(du)[: max(n - 1, 0)]
+    B2 = np.asarray(B, dtype=d.dtype).reshape(n, -1)
+    if n == 0:
+        return np.asarray(B).copy()
+    fn = lapack.dgtsv if d.dtype == np.float64 else lapack.sgtsv
+    _, _, _, X, info = fn(dl.copy(), d.copy(), du.copy(), np.asfortranarray(B2.copy()))
+    assert info == 0, info
+    return X.reshape(np.asarray(B).shape)
+
+
 def tridiag_dot(x, dl, d, du, y):
     dt = d.dtype
     fn = getattr(lib(), f"oracle_{_pfx(dt)}tridiag_dot")
