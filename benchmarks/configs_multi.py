@@ -60,13 +60,20 @@ def main():
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
         if world > 1:
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank[:] = [round(float(v[0]), 4) for v in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        else:
+            per_rank[:] = [round(float(t[0]), 4)]
         return float(t[0])
+
+    per_rank = []
 
     def emit(name, ms, byts=None, flops=None, **kw):
         if rank:
             return
-        r = {"config": name, "n_gpus": world, "ms": ms}
+        r = {"config": name, "n_gpus": world, "ms": ms, "ms_per_rank": list(per_rank)}
         if byts is not None:
             r["GBs"] = byts / ms / 1e6
             r["frac_of_aggregate_hbm"] = r["GBs"] / (PEAK * world)
@@ -159,6 +166,8 @@ def main():
         L.fill_uniform(xb, 9, offset=sh.plan.c0)
         y = torch.empty(sh.plan.m_loc, dtype=torch.float64, device=dev)
         both(f"M gbmv f64 n=2^27 l=u={l}", lambda: sh.mul_(y, xb), 8 * n * (2 * l + 3), 20, 5)
+        # the same slab kernels with NO exchange at all (stale ghosts: timing only) -- what the ranks cost uncoupled
+        emit(f"M gbmv f64 n=2^27 l=u={l} [no exchange: timing only]", timeit(lambda: sh.mul_(y, xb, exchange=False), 20, 5), 8 * n * (2 * l + 3))
         del sh, xb, y
         torch.cuda.empty_cache()
     if only is not None and not want("M128"):

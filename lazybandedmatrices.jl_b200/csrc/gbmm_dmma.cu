@@ -703,12 +703,14 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
                 double *sB = sA + KC * PA;
                 const uint32_t dA = (uint32_t)__cvta_generic_to_shared(sA + 2 * lane);
                 const uint32_t dB = (uint32_t)__cvta_generic_to_shared(sB + (lane >> 3) * PB + 2 * (lane & 7));
+                if (!(a.flags & 64)) {   // flag 64 (ablation, wrong results): no copies at all -- what the consumers cost when data never has to arrive
 #pragma unroll
                 for (int q = 0; q < KC; ++q)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dA + (uint32_t)(q * PA * 8)), "l"(a_src + a_step * q) : "memory");
 #pragma unroll
                 for (int q = 0; q < 16; ++q)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dB + (uint32_t)(q * 4 * PB * 8)), "l"(b_src + b_step4 * q) : "memory");
+                }
                 if (a.flags & 4) {   // experiment: issue every copy twice (2x L2 -> smem traffic, same arithmetic)
 #pragma unroll
                     for (int q = 0; q < KC; ++q)
@@ -811,6 +813,7 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
         }
 
         // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1}) -> band storage; interior tiles need no bounds tests
+        if ((a.flags & 128) && acc[0][0][0] != 12345.678) continue;   // flag 128 (ablation, wrong results): no C stores
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -923,6 +926,9 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         if (h->tune.gbmm_tile / 100 == 2) a.flags |= 8;   // (+200: poll the ring barriers with a 32 ns back-off)
         if (h->tune.gbmm_tile / 100 == 3) a.flags |= 16;  // (+300: 128 ns back-off)
         if (h->tune.gbmm_tile / 100 == 5) a.flags |= 32;  // (+500: rotated row-tile order, see set_item)
+        if (h->tune.gbmm_tile / 100 == 6) a.flags |= 64;  // (+600: ablation, no operand copies)
+        if (h->tune.gbmm_tile / 100 == 7) a.flags |= 128; // (+700: ablation, no C stores)
+        if (h->tune.gbmm_tile / 100 == 8) a.flags |= 64 | 128; // (+800: both)
         int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
         // gbmm_tile 4xx: persistent grid (SMs x resident CTAs, each walking every grid-th work item)
         const bool persistent = h->tune.gbmm_tile / 100 == 4;

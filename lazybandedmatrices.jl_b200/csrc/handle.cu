@@ -24,6 +24,7 @@ int lbm_fail_arg(lbm_handle_t h, int argno, const char *what) {
 // could overlap on the device and overwrite each other's scratch: when the bound stream differs from the one the
 // previous user ran on, the new stream first waits for everything queued on the old one.
 int lbm_scratch(lbm_handle_t h, size_t bytes, void **out) {
+    lbm_device_guard g(h->device);   // callers driving several devices from one thread (multi.cu) may sit on another device
     if (h->scratch_used && h->scratch_stream != h->stream) {
         if (!h->ev_scratch) LBM_CUDA(h, cudaEventCreateWithFlags(&h->ev_scratch, cudaEventDisableTiming));
         if (cudaEventRecord(h->ev_scratch, h->scratch_stream) == cudaSuccess)
@@ -45,6 +46,7 @@ int lbm_scratch(lbm_handle_t h, size_t bytes, void **out) {
 }
 
 int lbm_stage(lbm_handle_t h, int slot, size_t bytes, void **out) {
+    lbm_device_guard g(h->device);
     if (bytes > h->stage_bytes[slot]) {
         if (h->stage[slot]) LBM_CUDA(h, cudaFree(h->stage[slot]));
         h->stage[slot] = nullptr;

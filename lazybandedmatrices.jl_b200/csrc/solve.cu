@@ -5,26 +5,30 @@
 //
 // HBM-bound like everything else on this path, but with a loop-carried dependence, so the algorithm is the partition
 // method (Wang 1981) applied recursively:
-//   pass 1  every THREAD owns R = 32 consecutive rows (a tile of 128 x 32 rows is staged in shared memory with
-//           coalesced loads, chunk pitch R+1 -> conflict-free).  Forward elimination inside the chunk expresses each
-//           row through u_{c-1} (= x of the previous chunk's last row) and its own unknowns; a register-only backward
-//           sweep expresses the chunk's FIRST row through u_{c-1} and u_c.  Only 8 numbers per chunk leave the SM.
+//   pass 1  every THREAD owns R = 8 consecutive rows IN REGISTERS (a tile of 256 x 8 rows is staged through shared memory
+//           with coalesced loads, chunk pitch R+1 -> conflict-free; 16 warps per SM hide the dependent-division latency,
+//           one reciprocal per row).  Forward elimination inside the chunk expresses each row through u_{c-1} (= x of the
+//           previous chunk's last row) and its own unknowns; a backward sweep expresses the chunk's FIRST row through
+//           u_{c-1} and u_c.  Only 8 numbers per chunk leave the SM.
 //   reduce  combining the last row of chunk c with the first row of chunk c+1 gives a scalar tridiagonal system of
-//           size P = ceil(n/R) in the u_c -- solved by the same three kernels (levels shrink 32x: n = 2^28 needs 5).
-//   pass 2  with u_{c-1}, u_c known every chunk is an independent (R-1)-row system: plain Thomas in shared memory,
-//           coalesced store of x.
-// Traffic: 2 reads of (dl, d, du, b) + 1 write of x = 9n elements against the 5n of a single pass: the ceiling of this
-// formulation is 55 % of the copy roofline.  NO PIVOTING (as gtsv2_nopivot / Thomas): exact for diagonally dominant
-// and symmetric positive definite operators -- the discretisation matrices this package exists for; a zero pivot is
-// reported through *info (LAPACK style, > 0) instead of being hidden.
+//           size P = ceil(n/R) in the u_c -- solved by the same three kernels (levels shrink 8x).
+//   pass 2  with u_{c-1}, u_c known every chunk is an independent (R-1)-row system: plain Thomas in registers,
+//           coalesced store of x through shared memory.
+// Traffic: 2 reads of (dl, d, du, b) + 1 write of x = 9n elements, + ~3.3 per row for the reduced levels, against the 5n of
+// a single pass: the ceiling of this formulation is ~40 % of the copy roofline.  NO PIVOTING (as gtsv2_nopivot / Thomas):
+// exact for diagonally dominant and symmetric positive definite operators -- the discretisation matrices this package
+// exists for; a zero pivot is reported through *info (LAPACK style, > 0) instead of being hidden.
 #include "lbm_common.cuh"
 
 namespace {
 
-constexpr int SV_R = 32;     // rows per thread chunk
-constexpr int SV_NT = 128;   // threads per CTA
+constexpr int SV_R = 8;      // rows per thread chunk
+constexpr int SV_NT = 256;   // threads per CTA
 constexpr int SV_TILE = SV_R * SV_NT;
 constexpr int SV_PITCH = SV_R + 1;
+
+__device__ __forceinline__ double rcp_(double x) { return __drcp_rn(x); }
+__device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
 
 template <typename T>
 struct SolveArgs {
@@ -41,7 +45,9 @@ struct SolveArgs {
 // stage rows [t0, t0 + SV_TILE) as (a, b, c, g); rows >= n are identity rows (decoupled, solution 0)
 template <typename T>
 __device__ __forceinline__ void stage_tile(const SolveArgs<T> &a, int64_t t0, T *sa, T *sb, T *sc, T *sg) {
-    for (int idx = threadIdx.x; idx < SV_TILE; idx += SV_NT) {
+#pragma unroll
+    for (int q = 0; q < SV_R; ++q) {
+        const int idx = threadIdx.x + q * SV_NT;
         const int64_t i = t0 + idx;
         const int s = (idx / SV_R) * SV_PITCH + (idx % SV_R);
         const bool in = i < a.n;
@@ -53,7 +59,7 @@ __device__ __forceinline__ void stage_tile(const SolveArgs<T> &a, int64_t t0, T 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SV_NT) tridiag_solve_pass1_kernel(const SolveArgs<T> a) {
+__global__ void __launch_bounds__(SV_NT, 2) tridiag_solve_pass1_kernel(const SolveArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sa = reinterpret_cast<T *>(smem_raw);
     T *sb = sa + SV_NT * SV_PITCH, *sc = sb + SV_NT * SV_PITCH, *sg = sc + SV_NT * SV_PITCH;
@@ -65,35 +71,34 @@ __global__ void __launch_bounds__(SV_NT) tridiag_solve_pass1_kernel(const SolveA
         __syncthreads();
         const int64_t c = tile * SV_NT + threadIdx.x;   // global chunk
         if (c < a.P) {
-            T *pa = sa + threadIdx.x * SV_PITCH, *pb = sb + threadIdx.x * SV_PITCH, *pc = sc + threadIdx.x * SV_PITCH,
-              *pg = sg + threadIdx.x * SV_PITCH;
-            // forward: row k becomes  f_k u_{c-1} + d'_k x_k + c_k x_{k+1} = g_k   (f, d', g overwrite a, b, g)
-            T f = pa[0], dp = pb[0], gp = pg[0], cp = pc[0];
-            bool bad = dp == (T)0;
-#pragma unroll 4
+            const int o = threadIdx.x * SV_PITCH;
+            T f[SV_R], d[SV_R], cc[SV_R], g[SV_R], ri[SV_R];
+#pragma unroll
+            for (int k = 0; k < SV_R; ++k) { f[k] = sa[o + k]; d[k] = sb[o + k]; cc[k] = sc[o + k]; g[k] = sg[o + k]; }
+            // forward: row k becomes  f_k u_{c-1} + d_k x_k + c_k x_{k+1} = g_k
+            bool bad = d[0] == (T)0;
+            ri[0] = rcp_(d[0]);
+#pragma unroll
             for (int k = 1; k < SV_R; ++k) {
-                const T m = pa[k] / dp;
-                f = -m * f;
-                dp = pb[k] - m * cp;
-                gp = pg[k] - m * gp;
-                cp = pc[k];
-                pa[k] = f; pb[k] = dp; pg[k] = gp;
-                bad |= dp == (T)0;
+                const T m = f[k] * ri[k - 1];
+                f[k] = -m * f[k - 1];
+                d[k] = d[k] - m * cc[k - 1];
+                g[k] = g[k] - m * g[k - 1];
+                bad |= d[k] == (T)0;
+                ri[k] = rcp_(d[k]);
             }
-            const T fL = f, dL = dp, cL = cp, gL = gp;
-            // backward (registers only): the FIRST row becomes  fF u_{c-1} + dF x_first + rF u_c = gF
-            T f2 = pa[SV_R - 2], d2 = pb[SV_R - 2], r = pc[SV_R - 2], g2 = pg[SV_R - 2];
-#pragma unroll 4
+            // backward: the FIRST row becomes  fF u_{c-1} + dF x_first + rF u_c = gF
+            T f2 = f[SV_R - 2], r = cc[SV_R - 2], g2 = g[SV_R - 2];
+#pragma unroll
             for (int k = SV_R - 3; k >= 0; --k) {
-                const T m = pc[k] / d2;
-                f2 = pa[k] - m * f2;
+                const T m = cc[k] * ri[k + 1];
+                f2 = f[k] - m * f2;
                 r = -m * r;
-                g2 = pg[k] - m * g2;
-                d2 = pb[k];
+                g2 = g[k] - m * g2;
             }
-            T *o = a.red + c;
-            o[0] = fL; o[a.P] = dL; o[2 * a.P] = cL; o[3 * a.P] = gL;
-            o[4 * a.P] = f2; o[5 * a.P] = d2; o[6 * a.P] = r; o[7 * a.P] = g2;
+            T *out = a.red + c;
+            out[0] = f[SV_R - 1]; out[a.P] = d[SV_R - 1]; out[2 * a.P] = cc[SV_R - 1]; out[3 * a.P] = g[SV_R - 1];
+            out[4 * a.P] = f2; out[5 * a.P] = d[0]; out[6 * a.P] = r; out[7 * a.P] = g2;
             if (bad && a.info) *a.info = 1;
         }
     }
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(256) tridiag_solve_reduce_kernel(int64_t P, co
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SV_NT) tridiag_solve_pass2_kernel(const SolveArgs<T> a) {
+__global__ void __launch_bounds__(SV_NT, 2) tridiag_solve_pass2_kernel(const SolveArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sa = reinterpret_cast<T *>(smem_raw);
     T *sb = sa + SV_NT * SV_PITCH, *sc = sb + SV_NT * SV_PITCH, *sg = sc + SV_NT * SV_PITCH;
@@ -135,32 +140,34 @@ __global__ void __launch_bounds__(SV_NT) tridiag_solve_pass2_kernel(const SolveA
         __syncthreads();
         const int64_t c = tile * SV_NT + threadIdx.x;
         if (c < a.P) {
-            T *pa = sa + threadIdx.x * SV_PITCH, *pb = sb + threadIdx.x * SV_PITCH, *pc = sc + threadIdx.x * SV_PITCH,
-              *pg = sg + threadIdx.x * SV_PITCH;
+            const int o = threadIdx.x * SV_PITCH;
+            T av[SV_R], bv[SV_R], cp[SV_R], gp[SV_R];
+#pragma unroll
+            for (int k = 0; k < SV_R; ++k) { av[k] = sa[o + k]; bv[k] = sb[o + k]; cp[k] = sc[o + k]; gp[k] = sg[o + k]; }
             const T uprev = c > 0 ? a.u[c - 1] : (T)0;
             const T uc = a.u[c];
-            // rows 0 .. R-2 with x_{-1} = uprev and x_{R-1} = uc known: Thomas (c', g' overwrite c, g)
-            T den = pb[0];
-            T cp = pc[0] / den;
-            T gp = (pg[0] - pa[0] * uprev) / den;
-            pc[0] = cp; pg[0] = gp;
-#pragma unroll 4
+            // rows 0 .. R-2 with x_{-1} = uprev and x_{R-1} = uc known: Thomas
+            T r = rcp_(bv[0]);
+            cp[0] = cp[0] * r;
+            gp[0] = (gp[0] - av[0] * uprev) * r;
+#pragma unroll
             for (int k = 1; k < SV_R - 1; ++k) {
-                den = pb[k] - pa[k] * cp;
-                cp = pc[k] / den;
-                gp = (pg[k] - pa[k] * gp) / den;
-                pc[k] = cp; pg[k] = gp;
+                r = rcp_(bv[k] - av[k] * cp[k - 1]);
+                cp[k] = cp[k] * r;
+                gp[k] = (gp[k] - av[k] * gp[k - 1]) * r;
             }
             T xk = uc;
-            pg[SV_R - 1] = xk;
-#pragma unroll 4
+            sg[o + SV_R - 1] = xk;
+#pragma unroll
             for (int k = SV_R - 2; k >= 0; --k) {
-                xk = pg[k] - pc[k] * xk;
-                pg[k] = xk;
+                xk = gp[k] - cp[k] * xk;
+                sg[o + k] = xk;
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < SV_TILE; idx += SV_NT) {
+#pragma unroll
+        for (int q = 0; q < SV_R; ++q) {
+            const int idx = threadIdx.x + q * SV_NT;
             const int64_t i = t0 + idx;
             if (i < a.n) a.x[i] = sg[(idx / SV_R) * SV_PITCH + (idx % SV_R)];
         }
@@ -190,7 +197,7 @@ __global__ void tridiag_solve_seq_kernel(int64_t n, const T *dl, const T *d, con
     if (bad && info) *info = 1;
 }
 
-constexpr int64_t SV_BASE = 512;
+constexpr int64_t SV_BASE = 32;
 
 // scratch elements one right-hand side needs below a system of size n (all levels)
 int64_t solve_scratch_elems(int64_t n) {
@@ -223,8 +230,7 @@ int solve_level(lbm_handle_t h, int64_t n, const T *dl, const T *d, const T *du,
         configured_dev_mask |= (1 << h->device);
     }
     const int64_t ntiles = (n + SV_TILE - 1) / SV_TILE;
-    const int64_t cps = (int64_t)(200 * 1024) / (int64_t)(smem + 1024) > 0 ? (int64_t)(200 * 1024) / (int64_t)(smem + 1024) : 1;
-    int64_t grid = (int64_t)h->sm_count * cps;
+    int64_t grid = (int64_t)h->sm_count * 2;
     if (grid > ntiles) grid = ntiles;
     tridiag_solve_pass1_kernel<T><<<(unsigned)grid, SV_NT, smem, h->stream>>>(a);
     LBM_LAUNCH_CHECK(h, "tridiag_solve_pass1_kernel");

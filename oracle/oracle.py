@@ -313,6 +313,8 @@ def tridiag_solve(dl, d, du, B):
     B2 = np.asarray(B, dtype=d.dtype).reshape(n, -1)
     if n == 0:
         return np.asarray(B).copy()
+    if n == 1:
+        return (B2 / d[0]).reshape(np.asarray(B).shape)
     fn = lapack.dgtsv if d.dtype == np.float64 else lapack.sgtsv
     _, _, _, X, info = fn(dl.copy(), d.copy(), du.copy(), np.asfortranarray(B2.copy()))
     assert info == 0, info
