@@ -630,6 +630,12 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
     __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE];
+    // Per stage and consumer warp: the chunk's class, computed ONCE by the producer (lane w classifies for consumer warp w,
+    // all warps in one SIMT pass) instead of ~95 instructions in every consumer's chunk loop.  0 = nothing in band for that
+    // warp, 0xffffffff = wholly in band (unmasked path), else mA | mB << 16 (block masks of the ramp chunks).  Round 2
+    // ablations (profiles/dmma_r02_notes.md): with NO operand copies and NO C stores the kernel still took 5.97 of
+    // 6.48 ms -- the time is the consumers' own per-chunk instruction stream, not memory.
+    __shared__ unsigned chunk_desc[NSTAGE][8];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
@@ -674,7 +680,7 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init_(&bar_full[s], 32);             // the 32 producer lanes' cp.async arrivals
+            mbar_init_(&bar_full[s], 33);             // the 32 producer lanes' cp.async arrivals + lane 0's release of the descriptors
             mbar_init_(&bar_empty[s], NCONS);  // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -696,9 +702,27 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
             if (!tile_params(t, i0, plo, nch)) continue;
             const double *a_src = a.A + (a.kua + i0 + 2 * lane) + (a.lda - 1) * plo;
             const double *b_src = a.B + (a.kub + plo + 2 * (lane & 7)) + (a.ldb - 1) * (j0 + (lane >> 3));
+            // lane w < NCONS classifies for consumer warp w: rows 32*(w&1).., columns WN*(w>>1)..
+            const int c_ia0 = (int)(i0 + (lane & 1) * 32 - plo), c_jb0 = (int)(j0 + (lane >> 1) * WN - plo);
+            const int p_kla = (int)a.kla, p_kua = (int)a.kua, p_klb = (int)a.klb, p_kub = (int)a.kub;
             for (int it = 0; it < nch; ++it, ++gi) {
                 const int s = gi % NSTAGE;
                 if (gi >= NSTAGE) mbar_wait_(&bar_empty[s], (uint32_t)((gi / NSTAGE - 1) & 1), sleep_ns);
+                if (lane < NCONS) {
+                    const int pr = it * KC;
+                    const bool full = (c_ia0 + 31 - pr <= p_kla) && (c_ia0 - (pr + KC - 1) >= -p_kua) && ((pr + KC - 1) - c_jb0 <= p_klb) &&
+                                      (pr - (c_jb0 + WN - 1) >= -p_kub);
+                    unsigned d = 0xffffffffu;
+                    if (!full) {
+                        const int da = c_ia0 - pr, db = c_jb0 - pr;
+                        const unsigned mA = band_mask(-p_kua - 7 - da, p_kla + 3 - da);
+                        const unsigned mB = band_mask(-p_klb - 7 - db, p_kub + 3 - db) & (YB == 2 ? 0x3333u : 0xffffu);
+                        d = (mA == 0 || mB == 0) ? 0u : (mA | (mB << 16));
+                    }
+                    chunk_desc[s][lane] = d;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_(&bar_full[s]);   // release: publishes the descriptors with the stage
                 double *sA = smem + s * STAGE_DBL;
                 double *sB = sA + KC * PA;
                 const uint32_t dA = (uint32_t)__cvta_generic_to_shared(sA + 2 * lane);
@@ -751,19 +775,13 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
         for (int it = 0; it < nch; ++it, ++gi) {
             const int s = gi % NSTAGE;
             const int pr = it * KC;
-            // classify the chunk: a warp with nothing in band here only has to release the stage
-            const bool full = (ia0 + 31 - pr <= kla) && (ia0 - (pr + KC - 1) >= -kua) && ((pr + KC - 1) - jb0 <= klb) &&
-                              (pr - (jb0 + WN - 1) >= -kub);
-            unsigned mA = 0xffffu, mB = 0xffffu;
-            if (!full) {
-                const int da = ia0 - pr, db = jb0 - pr;
-                mA = band_mask(-kua - 7 - da, kla + 3 - da);
-                mB = band_mask(-klb - 7 - db, kub + 3 - db) & (YB == 2 ? 0x3333u : 0xffffu);   // YB column blocks per warp
-            }
             // every warp observes every phase of full[s] in order (a parity wait only tells adjacent phases apart, so
             // a warp must not skip one), even when the chunk holds nothing for it
             mbar_wait_(&bar_full[s], (uint32_t)((gi / NSTAGE) & 1), sleep_ns);
-            if (mA != 0 && mB != 0) {
+            const unsigned desc = chunk_desc[s][warp];      // the producer's classification of this chunk for this warp
+            const bool full = desc == 0xffffffffu;
+            const unsigned mA = desc & 0xffffu, mB = desc >> 16;
+            if (desc != 0u) {
                 const double *sA = smem + s * STAGE_DBL;
                 const double *sB = sA + KC * PA;
                 if (full) {
