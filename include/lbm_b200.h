@@ -58,6 +58,7 @@ int lbm_host_alloc(lbm_handle_t h, void **hptr, size_t bytes);   /* pinned */
 int lbm_host_free(lbm_handle_t h, void *hptr);
 int lbm_memcpy_h2d(lbm_handle_t h, void *dst, const void *src, size_t bytes);  /* async on stream */
 int lbm_memcpy_d2h(lbm_handle_t h, void *dst, const void *src, size_t bytes);
+int lbm_memcpy_d2d(lbm_handle_t h, void *dst, const void *src, size_t bytes);
 int lbm_memset0(lbm_handle_t h, void *dst, size_t bytes);
 
 /* ---- synthetic data: counter-based U[0,1) (same stream as oracle/) ---- */
@@ -177,6 +178,10 @@ int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
                    int64_t kla, int64_t kua, const double *A, int64_t lda,
                    int64_t klb, int64_t kub, const double *B, int64_t ldb,
                    double alpha, const double *x, double beta, double *y);
+int lbm_skron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2,
+                   int64_t kla, int64_t kua, const float *A, int64_t lda,
+                   int64_t klb, int64_t kub, const float *B, int64_t ldb,
+                   float alpha, const float *x, float beta, float *y);
 
 /* y <- alpha*(A (x) B (x) C)*x + beta*y on a full n x n x n tensor (k fastest): the three mode
  * products of /root/reference/src/blockkron.jl:441-450 (A on dim 3, B on dim 2, C on dim 1), i.e.
@@ -186,6 +191,23 @@ int lbm_dkron3d_mv(lbm_handle_t h, int64_t n,
                    int64_t klb, int64_t kub, const double *B, int64_t ldb,
                    int64_t klc, int64_t kuc, const double *C, int64_t ldc,
                    double alpha, const double *x, double beta, double *y);
+int lbm_skron3d_mv(lbm_handle_t h, int64_t n,
+                   int64_t kla, int64_t kua, const float *A, int64_t lda,
+                   int64_t klb, int64_t kub, const float *B, int64_t ldb,
+                   int64_t klc, int64_t kuc, const float *C, int64_t ldc,
+                   float alpha, const float *x, float beta, float *y);
+
+/* DiagTrav ordering on the device (/root/reference/src/blockkron.jl:14-24, :101-133; zero_bottomright :27-64; InvDiagTrav
+ * :226-256): X is the m x n matrix (ndim = 2) or n x n x n tensor (ndim = 3, m == n) in column-major order, v the block
+ * vector of its anti-diagonals; entries below the last anti-diagonal block (the "bottom right") do not belong to v and
+ * are written as zeros by lbm_?invdiagtrav / lbm_?zero_bottomright (in place).  lbm_diagtrav_length = length(v). */
+int lbm_ddiagtrav(lbm_handle_t h, int ndim, int64_t m, int64_t n, const double *X, double *v);
+int lbm_sdiagtrav(lbm_handle_t h, int ndim, int64_t m, int64_t n, const float *X, float *v);
+int lbm_dinvdiagtrav(lbm_handle_t h, int ndim, int64_t m, int64_t n, const double *v, double *X);
+int lbm_sinvdiagtrav(lbm_handle_t h, int ndim, int64_t m, int64_t n, const float *v, float *X);
+int lbm_dzero_bottomright(lbm_handle_t h, int ndim, int64_t m, int64_t n, double *X);
+int lbm_szero_bottomright(lbm_handle_t h, int ndim, int64_t m, int64_t n, float *X);
+int64_t lbm_diagtrav_length(int ndim, int64_t m, int64_t n);
 
 /* ---- lazy product applied to a vector: y <- alpha*F_0*(F_1*(...F_{nf-1}*x)) + beta*y ------------------ */
 /* mul!(y, ApplyMatrix(*, F_0, ..., F_{nf-1}), x, alpha, beta): LazyArrays' right-to-left Mul flattening (the rule the

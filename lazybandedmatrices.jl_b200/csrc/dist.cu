@@ -325,8 +325,18 @@ bool want_fused(lbm_handle_t h, int64_t kl, int64_t ku, int64_t unit, int overla
 template <typename T>
 int gbmv_sharded_plan(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, T alpha, const T *A, int64_t lda, T *xbuf, T beta,
                       T *y, int overlap) {
-    if (p.world_eff <= 1 || h->world == 1) return apply_rows<T>(h, p, 0, p.m_loc, alpha, A, lda, xbuf, beta, y);
     int rc;
+    if (p.world_eff <= 1 || h->world == 1) {
+        if (h->tune.exchange_fuse == 3) {   // self-test knob: the HALO instantiation with no neighbours (what the variant itself costs)
+            lbm::HaloFuse none;
+            memset(&none, 0, sizeof(none));
+            none.on = 1;
+            none.nflags = 1;
+            rc = gbmv_fused_call<T>(h, p.m_loc, p.n_loc, p.kl_loc, p.ku_loc, alpha, A, lda, xbuf, beta, y, &none);
+            if (rc != LBM_NOT_FUSED) return rc;
+        }
+        return apply_rows<T>(h, p, 0, p.m_loc, alpha, A, lda, xbuf, beta, y);
+    }
     if (want_fused(h, kl, ku, sizeof(T), overlap)) {
         const lbm::HaloFuse f = make_fuse(h, p, kl, ku, reinterpret_cast<char *>(xbuf), sizeof(T));
         rc = gbmv_fused_call<T>(h, p.m_loc, p.n_loc, p.kl_loc, p.ku_loc, alpha, A, lda, xbuf, beta, y, &f);

@@ -636,6 +636,7 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     // ablations (profiles/dmma_r02_notes.md): with NO operand copies and NO C stores the kernel still took 5.97 of
     // 6.48 ms -- the time is the consumers' own per-chunk instruction stream, not memory.
     __shared__ unsigned chunk_desc[NSTAGE][8];
+    __shared__ unsigned chunk_kind[NSTAGE][8];   // 0 empty, 1 ramp (masked path), 2 wholly in band; a ramp chunk may have ALL block bits set
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
@@ -712,14 +713,16 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
                     const int pr = it * KC;
                     const bool full = (c_ia0 + 31 - pr <= p_kla) && (c_ia0 - (pr + KC - 1) >= -p_kua) && ((pr + KC - 1) - c_jb0 <= p_klb) &&
                                       (pr - (c_jb0 + WN - 1) >= -p_kub);
-                    unsigned d = 0xffffffffu;
+                    unsigned d = 0xffffffffu, kind = 2u;
                     if (!full) {
                         const int da = c_ia0 - pr, db = c_jb0 - pr;
                         const unsigned mA = band_mask(-p_kua - 7 - da, p_kla + 3 - da);
                         const unsigned mB = band_mask(-p_klb - 7 - db, p_kub + 3 - db) & (YB == 2 ? 0x3333u : 0xffffu);
-                        d = (mA == 0 || mB == 0) ? 0u : (mA | (mB << 16));
+                        d = mA | (mB << 16);
+                        kind = (mA == 0 || mB == 0) ? 0u : 1u;
                     }
                     chunk_desc[s][lane] = d;
+                    chunk_kind[s][lane] = kind;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_(&bar_full[s]);   // release: publishes the descriptors with the stage
@@ -779,9 +782,10 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
             // a warp must not skip one), even when the chunk holds nothing for it
             mbar_wait_(&bar_full[s], (uint32_t)((gi / NSTAGE) & 1), sleep_ns);
             const unsigned desc = chunk_desc[s][warp];      // the producer's classification of this chunk for this warp
-            const bool full = desc == 0xffffffffu;
+            const unsigned kind = chunk_kind[s][warp];
+            const bool full = kind == 2u;
             const unsigned mA = desc & 0xffffu, mB = desc >> 16;
-            if (desc != 0u) {
+            if (kind != 0u) {
                 const double *sA = smem + s * STAGE_DBL;
                 const double *sB = sA + KC * PA;
                 if (full) {

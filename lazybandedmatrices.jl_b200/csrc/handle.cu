@@ -225,6 +225,12 @@ int lbm_memcpy_d2h(lbm_handle_t h, void *dst, const void *src, size_t bytes) {
     if (bytes) LBM_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
+int lbm_memcpy_d2d(lbm_handle_t h, void *dst, const void *src, size_t bytes) {
+    if (!h) return -1;
+    lbm_device_guard g(h->device);
+    if (bytes) LBM_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
 int lbm_memset0(lbm_handle_t h, void *dst, size_t bytes) {
     if (!h) return -1;
     lbm_device_guard g(h->device);

@@ -132,6 +132,7 @@ struct KronRingArgs {
     int64_t nchunks;
     int64_t n1_in, xoff, c_begin, c_end;  // see KronArgs
     int prod;      // 0: X*A^T + B*X (Kronecker sum); 1: B*X*A^T (Kronecker product, one pass)
+    int64_t batch_stride;   // blockIdx.z walks independent slices (x, y advance by this many elements): 3-D mode products
 };
 
 // HALO: grid-column-sharded apply in ONE launch (halo.cuh).  CTA (0,0) pushes this rank's boundary grid columns to the
@@ -148,6 +149,8 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
     const int scols = a.g + a.kla + a.kua;
     const int64_t stage_elems = (int64_t)scols * a.seg;
     const int64_t r0 = (int64_t)blockIdx.x * a.tr;
+    const T *const xz = a.x + (int64_t)blockIdx.z * a.batch_stride;
+    T *const yz = a.y + (int64_t)blockIdx.z * a.batch_stride;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         if (lane == 0) mbar_add_tx(&bars[s], (uint32_t)(cb - ca) * col_bytes);
         __syncwarp();
         for (int64_t c = ca + lane; c < cb; c += 32)
-            bulk_g2s(st + (c - ci0) * a.seg + roff, a.x + c * a.n2 + rs, col_bytes, &bars[s]);
+            bulk_g2s(st + (c - ci0) * a.seg + roff, xz + c * a.n2 + rs, col_bytes, &bars[s]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[s]);
     };
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         }
         const int seg = a.seg;
         const T *xrow = st + tid + a.hp;                 // X[r0+tid, c0-kla] of this stage
-        T *yp = a.y + (r0 + tid) + a.n2 * c0;             // Y[r0+tid, c0]; += n2 per column
+        T *yp = yz + (r0 + tid) + a.n2 * c0;              // Y[r0+tid, c0]; += n2 per column
         if (!edge) {
             // interior chunk: no index tests, 32-bit smem offsets, one pointer bump per column
 #pragma unroll 4
@@ -424,19 +427,23 @@ template <typename T>
 bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda,
                    int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc,
                    int64_t n1_in = -1, int64_t xoff = 0, int64_t c_begin = 0, int64_t c_end = -1, int prod = 0,
-                   const HaloFuse *hf = nullptr) {
+                   const HaloFuse *hf = nullptr, int64_t batch = 1, int64_t batch_stride = 0) {
     if (n1_in < 0) n1_in = n1;
     if (c_end < 0) c_end = n1;
     if (c_end <= c_begin) { *rc = 0; return true; }
     constexpr int EPV = 16 / (int)sizeof(T);
     const int64_t nba = kla + kua + 1, nbb = klb + kub + 1;
-    const bool shape_ok = (nba == 3 || nba == 1 || nba == 5) && (nbb == 3 || nbb == 1 || nbb == 5) &&
-                          !(nba == 5 && nbb == 1) && !(nba == 1 && nbb == 5) && !(nba == 1 && nbb == 1);
+    // instantiated band-count pairs: {1,3,5} x {1,3,5} (tri / pentadiagonal factors and their one-sided mode products) and
+    // the 9-diagonal ((4,4)) family {9,9}, {9,1}, {1,9}
+    const bool small = (nba == 3 || nba == 1 || nba == 5) && (nbb == 3 || nbb == 1 || nbb == 5);
+    const bool nine = (nba == 9 && (nbb == 9 || nbb == 1)) || (nba == 1 && nbb == 9);
+    const bool shape_ok = (small || nine) && !(nba == 1 && nbb == 1);
+    if (batch > 65535 || (batch > 1 && (batch_stride % EPV != 0 || hf))) return false;
     if (!shape_ok || n2 % EPV != 0 || !lbm_aligned16(x) || n2 < 512 || (c_end < 0 ? n1 : c_end) - c_begin < 1 || h->tune.kron_force_tile) return false;
     KronRingArgs<T> a;
     a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
     a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
-    a.n1_in = n1_in; a.xoff = xoff; a.c_begin = c_begin; a.c_end = c_end; a.prod = prod;
+    a.n1_in = n1_in; a.xoff = xoff; a.c_begin = c_begin; a.c_end = c_end; a.prod = prod; a.batch_stride = batch_stride;
     int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
     tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
     // columns per chunk: 16 for full-size grids; a per-rank slice of <= 2048 grid columns (what one rank of an 8-GPU job
@@ -462,18 +469,23 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     while (cps > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --cps;
     a.stages = (int)stages;
     const int64_t nstrips = (n2 + tr - 1) / tr;
-    int64_t phases = ((int64_t)h->sm_count * cps) / nstrips;  // floor: every CTA resident, one wave
+    int64_t phases = ((int64_t)h->sm_count * cps) / (nstrips * batch);  // floor: every CTA resident, one wave
     if (phases > a.nchunks) phases = a.nchunks;
     if (phases > 65535) phases = 65535;
-    if (phases < 1) phases = 1;
-    dim3 grid((unsigned)nstrips, (unsigned)phases);
+    if (phases < 1) phases = 1;   // batched slices: one CTA per (strip, slice) walks all its chunks, several waves
+    dim3 grid((unsigned)nstrips, (unsigned)phases, (unsigned)batch);
     const size_t smem = (size_t)(128 + stages * stage_bytes(g) + 2 * g * nba * (int64_t)sizeof(T));
     if (nba == 3 && nbb == 3) *rc = kron_ring_launch2<T, 3, 3>(h, a, grid, smem, hf);
     else if (nba == 1 && nbb == 3) *rc = kron_ring_launch2<T, 1, 3>(h, a, grid, smem, hf);
     else if (nba == 3 && nbb == 1) *rc = kron_ring_launch2<T, 3, 1>(h, a, grid, smem, hf);
     else if (nba == 5 && nbb == 5) *rc = kron_ring_launch2<T, 5, 5>(h, a, grid, smem, hf);
     else if (nba == 3 && nbb == 5) *rc = kron_ring_launch2<T, 3, 5>(h, a, grid, smem, hf);
-    else *rc = kron_ring_launch2<T, 5, 3>(h, a, grid, smem, hf);
+    else if (nba == 5 && nbb == 3) *rc = kron_ring_launch2<T, 5, 3>(h, a, grid, smem, hf);
+    else if (nba == 5 && nbb == 1) *rc = kron_ring_launch2<T, 5, 1>(h, a, grid, smem, hf);
+    else if (nba == 1 && nbb == 5) *rc = kron_ring_launch2<T, 1, 5>(h, a, grid, smem, hf);
+    else if (nba == 9 && nbb == 9) *rc = kron_ring_launch2<T, 9, 9>(h, a, grid, smem, hf);
+    else if (nba == 9 && nbb == 1) *rc = kron_ring_launch2<T, 9, 1>(h, a, grid, smem, hf);
+    else *rc = kron_ring_launch2<T, 1, 9>(h, a, grid, smem, hf);
     return true;
 }
 
@@ -595,8 +607,17 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
         return rc;
     const int64_t m_loc = pl[9], n_loc = pl[3] - pl[2], left = pl[4], right = pl[5];
     if (m_loc == 0) return 0;
-    if (h->world == 1 || pl[8] <= 1)
+    if (h->world == 1 || pl[8] <= 1) {
+        if (h->tune.exchange_fuse == 3) {   // self-test knob: the HALO instantiation with no neighbours (what the variant itself costs)
+            HaloFuse none;
+            memset(&none, 0, sizeof(none));
+            none.on = 1;
+            none.nflags = 1;
+            rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc, &none);
+            if (rc != LBM_NOT_FUSED) return rc;
+        }
         return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc);
+    }
     if (fused) {   // ONE launch: push at kernel start, ghost columns patched into the last chunks' stages
         rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc, &hf);
         if (rc != LBM_NOT_FUSED) return rc;
@@ -613,6 +634,75 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
     LBM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
     if ((rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, a))) return rc;
     return kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, b, m_loc);
+}
+
+// y <- alpha*kron(A,B)*x + beta*y = alpha*vec(B*X*A^T) + beta*y  (BlockKron(A,B)*x; KronTrav(A,B)*DiagTrav(X) before the
+// DiagTrav re-ordering, /root/reference/src/blockkron.jl:433-440)
+template <typename T>
+int kron2d_impl(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda, int64_t klb,
+                int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y) {
+    int rc = kron_check<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, x, y);
+    if (rc || n1 == 0 || n2 == 0) return rc;
+    lbm_device_guard g(h->device);
+    // one pass when the streaming ring kernel covers the band shapes: y[r,c] = sum_tA A[c,.] * (sum_tB B[r,.] * X[., .]),
+    // i.e. (B*X)*A^T entry by entry with X read once (2N elements of traffic instead of 4N + a scratch matrix)
+    if (kron_ring_try<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y, &rc, -1, 0, 0, -1, 1)) return rc;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    void *z;
+    const int64_t nz = n1 > n2 ? n1 : n2;
+    const int64_t zpad = (n1 * n2 + EPV - 1) / EPV * EPV;   // keeps the zero vector 16-byte aligned behind Z
+    if ((rc = lbm_scratch(h, (size_t)(zpad + nz) * sizeof(T), &z))) return rc;
+    T *Z = (T *)z, *zeros = Z + zpad;
+    // Z = B*X, then Y = alpha*Z*A^T + beta*Y  (left to right, as src/blockkron.jl:440 evaluates B*X*A').
+    // Each pass is a Kronecker SUM with a zero 1-band partner (X*0^T + B*X, then Z*A^T + 0*Z), which the streaming ring
+    // kernel covers for tridiagonal / pentadiagonal factors; other shapes take the halo'd tile kernel.
+    LBM_CUDA(h, cudaMemsetAsync(zeros, 0, (size_t)nz * sizeof(T), h->stream));
+    if (!kron_ring_try<T>(h, n1, n2, 0, 0, zeros, 1, klb, kub, B, ldb, (T)1, x, (T)0, Z, &rc))
+        rc = kron_launch<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, (T)1, x, (T)0, Z, 0, 1);
+    if (rc) return rc;
+    if (!kron_ring_try<T>(h, n1, n2, kla, kua, A, lda, 0, 0, zeros, 1, alpha, Z, beta, y, &rc))
+        rc = kron_launch<T>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, Z, beta, y, 1, 0);
+    return rc;
+}
+
+// Y = (A (x) B (x) C) applied to a full n x n x n tensor X (k fastest, then j, then l) as the three
+// mode products of /root/reference/src/blockkron.jl:441-450: A along dim 3, B along dim 2, C along
+// dim 1 -- the arithmetic of KronTrav(A,B,C)*DiagTrav(X) before the DiagTrav re-ordering.
+template <typename T>
+int kron3d_impl(lbm_handle_t h, int64_t n, int64_t kla, int64_t kua, const T *A, int64_t lda, int64_t klb, int64_t kub,
+                const T *B, int64_t ldb, int64_t klc, int64_t kuc, const T *C, int64_t ldc, T alpha, const T *x, T beta, T *y) {
+    if (!h) return -1;
+    if (n < 0) return lbm_fail_arg(h, 2, "n < 0");
+    if (kla < 0 || kua < 0 || lda < kla + kua + 1) return lbm_fail_arg(h, 6, "bad band of A");
+    if (klb < 0 || kub < 0 || ldb < klb + kub + 1) return lbm_fail_arg(h, 10, "bad band of B");
+    if (klc < 0 || kuc < 0 || ldc < klc + kuc + 1) return lbm_fail_arg(h, 14, "bad band of C");
+    if (n == 0) return 0;
+    if (!A) return lbm_fail_arg(h, 5, "A == NULL");
+    if (!B) return lbm_fail_arg(h, 9, "B == NULL");
+    if (!C) return lbm_fail_arg(h, 13, "C == NULL");
+    if (!x) return lbm_fail_arg(h, 16, "x == NULL");
+    if (!y) return lbm_fail_arg(h, 18, "y == NULL");
+    lbm_device_guard g(h->device);
+    constexpr int EPV = 16 / (int)sizeof(T);
+    void *z1v;
+    int rc;
+    const int64_t n3 = n * n * n, n3p = (n3 + EPV - 1) / EPV * EPV, nz = n * n;
+    if ((rc = lbm_scratch(h, (size_t)(2 * n3p + nz + EPV) * sizeof(T), &z1v))) return rc;
+    T *z1 = (T *)z1v, *z2 = z1 + n3p, *zeros = z2 + n3p;
+    LBM_CUDA(h, cudaMemsetAsync(zeros, 0, (size_t)nz * sizeof(T), h->stream));
+    // mode 3: X as an (n^2 x n) matrix, Z1 = X * A^T -- a Kronecker sum with a zero 1-band partner on the long side, which
+    // the streaming ring kernel takes in ONE launch when A is tri/pentadiagonal (n^2 rows per grid column)
+    if (!kron_ring_try<T>(h, n, n * n, kla, kua, A, lda, 0, 0, zeros, 1, (T)1, x, (T)0, z1, &rc))
+        rc = kron_launch<T>(h, n, n * n, kla, kua, A, lda, 0, 0, A, lda, (T)1, x, (T)0, z1, 1, 0);
+    if (rc) return rc;
+    // mode 2: each l-slice (n x n): Z2[:,:,l] = Z1[:,:,l] * B^T   (batched over l: blockIdx.z of the ring kernel)
+    if (!kron_ring_try<T>(h, n, n, klb, kub, B, ldb, 0, 0, zeros, 1, (T)1, z1, (T)0, z2, &rc, -1, 0, 0, -1, 0, nullptr, n, n * n))
+        rc = kron_launch<T>(h, n, n, klb, kub, B, ldb, 0, 0, B, ldb, (T)1, z1, (T)0, z2, 1, 0, n, n * n);
+    if (rc) return rc;
+    // mode 1: Z2 as an (n x n^2) matrix, Y = alpha * C * Z2 + beta * Y: the ring kernel again (X*0^T + C*X over n^2 columns)
+    if (!kron_ring_try<T>(h, n * n, n, 0, 0, zeros, 1, klc, kuc, C, ldc, alpha, z2, beta, y, &rc))
+        rc = kron_launch<T>(h, n * n, n, 0, 0, C, ldc, klc, kuc, C, ldc, alpha, z2, beta, y, 0, 1);
+    return rc;
 }
 
 }  // namespace
@@ -641,58 +731,20 @@ int lbm_skronsum2d_mv(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64
 int lbm_dkron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const double *A, int64_t lda,
                    int64_t klb, int64_t kub, const double *B, int64_t ldb, double alpha, const double *x, double beta,
                    double *y) {
-    int rc = kron_check<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, x, y);
-    if (rc || n1 == 0 || n2 == 0) return rc;
-    lbm_device_guard g(h->device);
-    // one pass when the streaming ring kernel covers the band shapes: y[r,c] = sum_tA A[c,.] * (sum_tB B[r,.] * X[., .]),
-    // i.e. (B*X)*A^T entry by entry with X read once (2N doubles of traffic instead of 4N + a scratch matrix)
-    if (kron_ring_try<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y, &rc, -1, 0, 0, -1, 1)) return rc;
-    void *z;
-    const int64_t nz = n1 > n2 ? n1 : n2;
-    const int64_t zpad = (n1 * n2 + 1) & ~(int64_t)1;       // keeps the zero vector 16-byte aligned behind Z
-    if ((rc = lbm_scratch(h, (size_t)(zpad + nz) * sizeof(double), &z))) return rc;
-    double *Z = (double *)z, *zeros = Z + zpad;
-    // Z = B*X, then Y = alpha*Z*A^T + beta*Y  (left to right, as src/blockkron.jl:440 evaluates B*X*A').
-    // Each pass is a Kronecker SUM with a zero 1-band partner (X*0^T + B*X, then Z*A^T + 0*Z), which the streaming ring
-    // kernel covers for tridiagonal / pentadiagonal factors; other shapes take the halo'd tile kernel.
-    LBM_CUDA(h, cudaMemsetAsync(zeros, 0, (size_t)nz * sizeof(double), h->stream));
-    if (!kron_ring_try<double>(h, n1, n2, 0, 0, zeros, 1, klb, kub, B, ldb, 1.0, x, 0.0, Z, &rc))
-        rc = kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, 1.0, x, 0.0, Z, 0, 1);
-    if (rc) return rc;
-    if (!kron_ring_try<double>(h, n1, n2, kla, kua, A, lda, 0, 0, zeros, 1, alpha, Z, beta, y, &rc))
-        rc = kron_launch<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, Z, beta, y, 1, 0);
-    return rc;
+    return kron2d_impl<double>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y);
 }
-
-// Y = (A (x) B (x) C) applied to a full n x n x n tensor X (k fastest, then j, then l) as the three
-// mode products of /root/reference/src/blockkron.jl:441-450: A along dim 3, B along dim 2, C along
-// dim 1 -- the arithmetic of KronTrav(A,B,C)*DiagTrav(X) before the DiagTrav re-ordering.
+int lbm_skron2d_mv(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const float *A, int64_t lda,
+                   int64_t klb, int64_t kub, const float *B, int64_t ldb, float alpha, const float *x, float beta, float *y) {
+    return kron2d_impl<float>(h, n1, n2, kla, kua, A, lda, klb, kub, B, ldb, alpha, x, beta, y);
+}
 int lbm_dkron3d_mv(lbm_handle_t h, int64_t n, int64_t kla, int64_t kua, const double *A, int64_t lda, int64_t klb,
                    int64_t kub, const double *B, int64_t ldb, int64_t klc, int64_t kuc, const double *C, int64_t ldc,
                    double alpha, const double *x, double beta, double *y) {
-    if (!h) return -1;
-    if (n < 0) return lbm_fail_arg(h, 2, "n < 0");
-    if (kla < 0 || kua < 0 || lda < kla + kua + 1) return lbm_fail_arg(h, 6, "bad band of A");
-    if (klb < 0 || kub < 0 || ldb < klb + kub + 1) return lbm_fail_arg(h, 10, "bad band of B");
-    if (klc < 0 || kuc < 0 || ldc < klc + kuc + 1) return lbm_fail_arg(h, 14, "bad band of C");
-    if (n == 0) return 0;
-    if (!A) return lbm_fail_arg(h, 5, "A == NULL");
-    if (!B) return lbm_fail_arg(h, 9, "B == NULL");
-    if (!C) return lbm_fail_arg(h, 13, "C == NULL");
-    if (!x) return lbm_fail_arg(h, 16, "x == NULL");
-    if (!y) return lbm_fail_arg(h, 18, "y == NULL");
-    lbm_device_guard g(h->device);
-    void *z1v, *z2v;
-    int rc;
-    const size_t bytes = (size_t)(n * n * n) * sizeof(double);
-    if ((rc = lbm_scratch(h, 2 * bytes, &z1v))) return rc;
-    double *z1 = (double *)z1v, *z2 = z1 + n * n * n;
-    (void)z2v;
-    // mode 3: X as (n^2 x n) matrix, Z1 = X * A^T
-    if ((rc = kron_launch<double>(h, n, n * n, kla, kua, A, lda, 0, 0, A, lda, 1.0, x, 0.0, z1, 1, 0))) return rc;
-    // mode 2: each l-slice (n x n): Z2[:,:,l] = Z1[:,:,l] * B^T   (batched over l)
-    if ((rc = kron_launch<double>(h, n, n, klb, kub, B, ldb, 0, 0, B, ldb, 1.0, z1, 0.0, z2, 1, 0, n, n * n))) return rc;
-    // mode 1: Z2 as (n x n^2) matrix, Y = alpha * C * Z2 + beta * Y
-    return kron_launch<double>(h, n * n, n, 0, 0, C, ldc, klc, kuc, C, ldc, alpha, z2, beta, y, 0, 1);
+    return kron3d_impl<double>(h, n, kla, kua, A, lda, klb, kub, B, ldb, klc, kuc, C, ldc, alpha, x, beta, y);
+}
+int lbm_skron3d_mv(lbm_handle_t h, int64_t n, int64_t kla, int64_t kua, const float *A, int64_t lda, int64_t klb,
+                   int64_t kub, const float *B, int64_t ldb, int64_t klc, int64_t kuc, const float *C, int64_t ldc,
+                   float alpha, const float *x, float beta, float *y) {
+    return kron3d_impl<float>(h, n, kla, kua, A, lda, klb, kub, B, ldb, klc, kuc, C, ldc, alpha, x, beta, y);
 }
 }

@@ -70,5 +70,16 @@ def sig_lines():
     return lines
 
 
+def rewrite_shim(path=os.path.join(HERE, "LBMB200.jl")):
+    """Replace the table between the BEGIN / END SIGNATURES markers of the shim with the current one."""
+    src = open(path, encoding="utf-8").read()
+    a = src.index("#= BEGIN SIGNATURES =#") + len("#= BEGIN SIGNATURES =#\n")
+    b = src.index("#= END SIGNATURES =#")
+    open(path, "w", encoding="utf-8").write(src[:a] + "\n".join(sig_lines()) + "\n" + src[b:])
+
+
 if __name__ == "__main__":
-    sys.stdout.write("\n".join(sig_lines()) + "\n")
+    if "--write" in sys.argv:
+        rewrite_shim()
+    else:
+        sys.stdout.write("\n".join(sig_lines()) + "\n")

@@ -49,6 +49,7 @@ def _sigs():
         "lbm_host_free": (C.c_int, [H, vp]),
         "lbm_memcpy_h2d": (C.c_int, [H, vp, vp, sz]),
         "lbm_memcpy_d2h": (C.c_int, [H, vp, vp, sz]),
+        "lbm_memcpy_d2d": (C.c_int, [H, vp, vp, sz]),
         "lbm_memset0": (C.c_int, [H, vp, sz]),
         "lbm_dfill_uniform": (C.c_int, [H, u64, i64, i64, vp]),
         "lbm_sfill_uniform": (C.c_int, [H, u64, i64, i64, vp]),
@@ -115,8 +116,13 @@ def _sigs():
                                                vp, ft, vp])
         s[f"lbm_{p}kronsum2d_mv_sharded"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, ft,
                                                        vp, ft, vp, C.c_int])
-    s["lbm_dkron2d_mv"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, f64, vp, f64, vp])
-    s["lbm_dkron3d_mv"] = (C.c_int, [H, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, f64, vp, f64, vp])
+    s["lbm_diagtrav_length"] = (i64, [C.c_int, i64, i64])
+    for p, ft in (("d", f64), ("s", f32)):
+        s[f"lbm_{p}diagtrav"] = (C.c_int, [H, C.c_int, i64, i64, vp, vp])
+        s[f"lbm_{p}invdiagtrav"] = (C.c_int, [H, C.c_int, i64, i64, vp, vp])
+        s[f"lbm_{p}zero_bottomright"] = (C.c_int, [H, C.c_int, i64, i64, vp])
+        s[f"lbm_{p}kron2d_mv"] = (C.c_int, [H, i64, i64, i64, i64, vp, i64, i64, i64, vp, i64, ft, vp, ft, vp])
+        s[f"lbm_{p}kron3d_mv"] = (C.c_int, [H, i64, i64, i64, vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, ft, vp, ft, vp])
     return s
 
 

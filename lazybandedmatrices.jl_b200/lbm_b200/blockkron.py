@@ -86,14 +86,13 @@ class BlockKron:
                 f"second entry of size(A)={self.shape} and first entry of size(B) = {tuple(x.shape)} must match.")
         if y.shape[0] != n1 * n2:
             raise DimensionMismatch(f"sizes size(A)={self.shape} and size(C) = {tuple(y.shape)} must match at first entry.")
-        if x.dtype != torch.float64:
-            raise LbmArgumentError("lbm_dkron2d_mv is Float64")
         Ab = A.as_banded(x.dtype, x.device) if isinstance(A, Eye) else A
         Bb = B.as_banded(x.dtype, x.device) if isinstance(B, Eye) else B
         h = _lib.handle_of(x)
-        h.check(_lib.lib().lbm_dkron2d_mv(h.ptr, n1, n2, Ab.l, Ab.u, _ptr(Ab.data), Ab.lda, Bb.l, Bb.u,
-                                          _ptr(Bb.data), Bb.lda, float(alpha), _ptr(x), float(beta), _ptr(y)),
-                "lbm_dkron2d_mv")
+        fn = getattr(_lib.lib(), f"lbm_{_pfx(x.dtype)}kron2d_mv")
+        ft = _ft(x.dtype)
+        h.check(fn(h.ptr, n1, n2, Ab.l, Ab.u, _ptr(Ab.data), Ab.lda, Bb.l, Bb.u,
+                   _ptr(Bb.data), Bb.lda, ft(alpha), _ptr(x), ft(beta), _ptr(y)), "lbm_kron2d_mv")
         return y
 
     def __matmul__(self, x):
@@ -189,38 +188,72 @@ def _diagtrav_index(shape):
 class DiagTrav:
     """`DiagTrav(X)`: a matrix / cubic tensor viewed as a block vector by anti-diagonal traversal.
     The constructor zeroes the bottom-right part (zero_bottomright, src/blockkron.jl:27-64).
-    `array` is a device tensor indexed [k, j(, l)]; storage is column-major (k fastest)."""
 
-    def __init__(self, array: torch.Tensor):
-        if array.dim() == 2:
-            m, n = array.shape
-            k = torch.arange(m, device=array.device).view(m, 1)
-            j = torch.arange(n, device=array.device).view(1, n)
-            keep = (k + j) <= (max(m, n) - 1)
-        elif array.dim() == 3:
-            n = array.shape[0]
-            r = torch.arange(n, device=array.device)
-            keep = (r.view(n, 1, 1) + r.view(1, n, 1) + r.view(1, 1, n)) <= (n - 1)
-        else:
-            raise LbmArgumentError("DiagTrav supports 2-D and 3-D arrays")
-        self.array = torch.where(keep, array, torch.zeros((), dtype=array.dtype, device=array.device))
-        self._idx = None
+    Storage is the column-major vec of the array (k fastest) -- what the Julia side holds natively and what the Kronecker
+    kernels take -- so `KronTrav.mul_diagtrav` runs kernel to kernel with no re-layout in between; the DiagTrav ordering,
+    its inverse and zero_bottomright are device kernels (lbm_?diagtrav / lbm_?invdiagtrav / lbm_?zero_bottomright)."""
+
+    def __init__(self, array: torch.Tensor = None, *, _flat: torch.Tensor = None, _shape=None):
+        if _flat is None:
+            if array.dim() not in (2, 3):
+                raise LbmArgumentError("DiagTrav supports 2-D and 3-D arrays")
+            if array.dim() == 3 and not (array.shape[0] == array.shape[1] == array.shape[2]):
+                raise LbmArgumentError("3-D DiagTrav needs a cubic array")
+            _shape = tuple(int(v) for v in array.shape)
+            # torch indexes [k, j(, l)] row-major; the one-time conversion to the column-major vec happens HERE, outside the apply
+            _flat = array.permute(*reversed(range(array.dim()))).contiguous().view(-1).clone()
+        self.shape = tuple(_shape)
+        self._flat = _flat
+        if _flat.numel():
+            h = _lib.handle_of(_flat)
+            m = self.shape[0]
+            n = self.shape[1]
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(_flat.dtype)}zero_bottomright")
+            h.check(fn(h.ptr, len(self.shape), m, n, _ptr(_flat)), "lbm_zero_bottomright")
+
+    @property
+    def array(self) -> torch.Tensor:
+        """The array indexed [k, j(, l)] (a VIEW of the column-major storage)."""
+        return self._flat.view(*reversed(self.shape)).permute(*reversed(range(len(self.shape))))
 
     def colmajor(self) -> torch.Tensor:
         """vec(array) with k fastest (the layout the Kronecker kernels take)."""
-        return self.array.permute(*reversed(range(self.array.dim()))).contiguous().view(-1)
+        return self._flat
+
+    def __len__(self):
+        return int(_lib.lib().lbm_diagtrav_length(len(self.shape), self.shape[0], self.shape[1]))
 
     def vector(self) -> torch.Tensor:
-        """The block vector (what `Vector(DiagTrav(X))` returns in the reference)."""
-        if self._idx is None:
-            self._idx = torch.tensor(_diagtrav_index(tuple(self.array.shape)), dtype=torch.int64,
-                                     device=self.array.device)
-        return self.colmajor().index_select(0, self._idx)
+        """The block vector (what `Vector(DiagTrav(X))` returns in the reference): lbm_?diagtrav."""
+        out = torch.empty(len(self), dtype=self._flat.dtype, device=self._flat.device)
+        if out.numel():
+            h = _lib.handle_of(self._flat)
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(self._flat.dtype)}diagtrav")
+            h.check(fn(h.ptr, len(self.shape), self.shape[0], self.shape[1], _ptr(self._flat), _ptr(out)), "lbm_diagtrav")
+        return out
+
+    @classmethod
+    def from_vector(cls, v: torch.Tensor, shape):
+        """`InvDiagTrav`: the array whose DiagTrav is the block vector `v` (bottom-right zero): lbm_?invdiagtrav."""
+        shape = tuple(int(s) for s in shape)
+        want = int(_lib.lib().lbm_diagtrav_length(len(shape), shape[0], shape[1]))
+        if v.numel() != want:
+            raise DimensionMismatch(f"block vector has {v.numel()} entries, DiagTrav of a {shape} array has {want}")
+        total = 1
+        for d in shape:
+            total *= d
+        flat = torch.empty(total, dtype=v.dtype, device=v.device)
+        if total:
+            h = _lib.handle_of(v)
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(v.dtype)}invdiagtrav")
+            h.check(fn(h.ptr, len(shape), shape[0], shape[1], _ptr(v.contiguous()), _ptr(flat)), "lbm_invdiagtrav")
+        obj = cls.__new__(cls)
+        obj.shape, obj._flat = shape, flat
+        return obj
 
     @classmethod
     def from_colmajor(cls, v: torch.Tensor, shape):
-        arr = v.view(*reversed(shape)).permute(*reversed(range(len(shape))))
-        return cls(arr)
+        return cls(_flat=v, _shape=shape)
 
 
 class KronTrav:
@@ -232,29 +265,30 @@ class KronTrav:
         self.args = args
 
     def mul_diagtrav(self, X: "DiagTrav") -> "DiagTrav":
-        arr = X.array
-        if arr.dtype != torch.float64:
-            raise LbmArgumentError("the device KronTrav apply is Float64")
-        h = _lib.handle_of(arr)
+        """Kernel to kernel: lbm_?kron2d_mv / lbm_?kron3d_mv on the column-major storage, then the DiagTrav constructor's
+        zero_bottomright kernel -- no eager tensor ops in between."""
         x = X.colmajor()
+        h = _lib.handle_of(x)
         y = torch.empty_like(x)
-        bm = [a.as_banded(arr.dtype, arr.device) if isinstance(a, Eye) else a for a in self.args]
-        if len(bm) == 2 and arr.dim() == 2:
+        ft = _ft(x.dtype)
+        bm = [a.as_banded(x.dtype, x.device) if isinstance(a, Eye) else a for a in self.args]
+        if len(bm) == 2 and len(X.shape) == 2:
             A, B = bm
-            n2, n1 = arr.shape                      # X is size(B,2) x size(A,2)
+            n2, n1 = X.shape                        # X is size(B,2) x size(A,2)
             if (A.shape[1], B.shape[1]) != (n1, n2):
-                raise DimensionMismatch(f"KronTrav factors {A.shape}, {B.shape} do not match DiagTrav array {tuple(arr.shape)}")
-            h.check(_lib.lib().lbm_dkron2d_mv(h.ptr, n1, n2, A.l, A.u, _ptr(A.data), A.lda, B.l, B.u, _ptr(B.data),
-                                              B.lda, 1.0, _ptr(x), 0.0, _ptr(y)), "lbm_dkron2d_mv")
+                raise DimensionMismatch(f"KronTrav factors {A.shape}, {B.shape} do not match DiagTrav array {tuple(X.shape)}")
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(x.dtype)}kron2d_mv")
+            h.check(fn(h.ptr, n1, n2, A.l, A.u, _ptr(A.data), A.lda, B.l, B.u, _ptr(B.data), B.lda, ft(1.0), _ptr(x), ft(0.0),
+                       _ptr(y)), "lbm_kron2d_mv")
             return DiagTrav.from_colmajor(y, (n2, n1))
-        if len(bm) == 3 and arr.dim() == 3:
+        if len(bm) == 3 and len(X.shape) == 3:
             A, B, Cm = bm
-            n = arr.shape[0]
+            n = X.shape[0]
             if not all(f.shape == (n, n) for f in bm):
                 raise DimensionMismatch("3-factor KronTrav apply needs n x n factors and an n^3 tensor")
-            h.check(_lib.lib().lbm_dkron3d_mv(h.ptr, n, A.l, A.u, _ptr(A.data), A.lda, B.l, B.u, _ptr(B.data), B.lda,
-                                              Cm.l, Cm.u, _ptr(Cm.data), Cm.lda, 1.0, _ptr(x), 0.0, _ptr(y)),
-                    "lbm_dkron3d_mv")
+            fn = getattr(_lib.lib(), f"lbm_{_pfx(x.dtype)}kron3d_mv")
+            h.check(fn(h.ptr, n, A.l, A.u, _ptr(A.data), A.lda, B.l, B.u, _ptr(B.data), B.lda,
+                       Cm.l, Cm.u, _ptr(Cm.data), Cm.lda, ft(1.0), _ptr(x), ft(0.0), _ptr(y)), "lbm_kron3d_mv")
             return DiagTrav.from_colmajor(y, (n, n, n))
         raise LbmArgumentError("KronTrav apply is defined for 2 factors x matrix or 3 factors x cubic tensor")
 

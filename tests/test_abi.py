@@ -51,3 +51,101 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 src = open(os.path.join(dp, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|liblbm_oracle|oracle/", src, flags=re.M), f
+
+
+# ---- the Julia shim (julia/LBMB200.jl) cannot run here: check it mechanically against the header ----------------------
+def _shim():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return open(os.path.join(root, "lazybandedmatrices.jl_b200", "julia", "LBMB200.jl"), encoding="utf-8").read()
+
+
+def _gen_sigs():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_sigs", os.path.join(root, "lazybandedmatrices.jl_b200", "julia", "gen_sigs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _split_args(src, i):
+    """src[i] == '(' : return (list of top-level argument strings, index after the matching ')')."""
+    depth, j, args, cur, instr = 0, i, [], "", False
+    while j < len(src):
+        ch = src[j]
+        if instr:
+            cur += ch
+            if ch == '"' and src[j - 1] != "\\":
+                instr = False
+        elif ch == '"':
+            instr = True
+            cur += ch
+        elif ch in "([{":
+            depth += 1
+            if depth > 1:
+                cur += ch
+        elif ch in ")]}":
+            depth -= 1
+            if depth == 0:
+                if cur.strip():
+                    args.append(cur.strip())
+                return args, j + 1
+            cur += ch
+        elif ch == "," and depth == 1:
+            args.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+        j += 1
+    raise AssertionError("unbalanced parentheses in the shim")
+
+
+def test_julia_shim_signature_table_matches_header():
+    """Every entry point of include/lbm_b200.h is bound in the shim with the argument count and types the header declares."""
+    import re
+    gen = _gen_sigs()
+    want = gen.sig_lines()
+    src = _shim()
+    block = src[src.index("#= BEGIN SIGNATURES =#"):src.index("#= END SIGNATURES =#")]
+    have = [ln.strip() for ln in block.splitlines() if ln.strip().startswith("@sig ")]
+    assert have == want, "julia/LBMB200.jl's @sig table is out of date: regenerate it with julia/gen_sigs.py"
+    assert len(have) == len(gen.header_signatures()) >= 90
+    # and the python binding agrees on the argument COUNT of every entry point
+    from lbm_b200._lib import SIGNATURES
+    for name, (_, args) in gen.header_signatures().items():
+        assert len(SIGNATURES[name][1]) == len(args), name
+    assert re.search(r"struct DeviceColumnMajor <: MemoryLayout end", src)      # not an AbstractColumnMajor (ADVICE r1)
+
+
+def test_julia_shim_calls_have_the_declared_argument_counts():
+    """Every `c_lbm_*(...)` call in the shim (direct, or through the `$var(...)` interpolations of the @eval loops) passes as
+    many arguments as the header declares for that entry point."""
+    import re
+    gen = _gen_sigs()
+    sigs = gen.header_signatures()
+    src = _shim()
+    body = src[src.index("#= END SIGNATURES =#"):]
+    checked = set()
+    for m in re.finditer(r"\bc_(lbm_[a-z0-9_]+)\(", body):
+        name = m.group(1)
+        assert name in sigs, f"shim calls c_{name}, which the header does not declare"
+        args, _ = _split_args(body, m.end() - 1)
+        assert len(args) == len(sigs[name][1]), (name, len(args), len(sigs[name][1]), args)
+        checked.add(name)
+    # interpolated: var = Symbol(:c_lbm_, p, :suffix)  ...  $var(args...)
+    var2suffix = dict(re.findall(r"(\w+) = Symbol\(:c_lbm_, p, :([a-z0-9_]+)\)", body))
+    assert len(var2suffix) >= 25
+    for var, suffix in var2suffix.items():
+        calls = list(re.finditer(r"\$" + var + r"\(", body))
+        assert calls, f"{var} (lbm_?{suffix}) is bound but never called"
+        for m in calls:
+            args, _ = _split_args(body, m.end() - 1)
+            for pfx in ("d", "s"):
+                name = f"lbm_{pfx}{suffix}"
+                if name in sigs:
+                    assert len(args) == len(sigs[name][1]), (name, len(args), len(sigs[name][1]))
+                    checked.add(name)
+    missing = sorted(set(sigs) - checked)
+    assert not missing, f"entry points bound in the @sig table but never used by a method of the shim: {missing}"
