@@ -39,10 +39,11 @@ for n1 in (1024, 4096, 8192):
     xb.uniform_()
     y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
     res = {}
-    for fuse in (0, 3, 0, 3):
-        h.set_tuning(exchange_fuse=fuse)
-        res.setdefault(fuse, []).append(round(timeit(lambda: sh.mul_(y, xb)), 2))
-    print(json.dumps({"kronsum n1": n1, "plain_us": res[0], "halo_variant_us": res[3]}), flush=True)
+    for fuse, sub in ((0, 0), (3, 0), (3, 2), (3, 4), (3, 6), (0, 0), (3, 0)):
+        h.set_tuning(exchange_fuse=fuse, halo_timeout_ms=sub)
+        res.setdefault((fuse, sub), []).append(round(timeit(lambda: sh.mul_(y, xb)), 2))
+    print(json.dumps({"kronsum n1": n1, "plain_us": res[(0, 0)], "halo_variant_us": res[(3, 0)], "no_rotation": res[(3, 2)], "no_patch_test": res[(3, 4)],
+                      "neither": res[(3, 6)]}), flush=True)
 for (n, l) in ((1 << 24, 1), (1 << 24, 8), (1 << 26, 1)):
     sh = ShardedBanded.brand(n, l, l, 0, 1, device=dev)
     xb = sh.plan.new_vector(torch.float64, dev)
@@ -53,9 +54,10 @@ for (n, l) in ((1 << 24, 1), (1 << 24, 8), (1 << 26, 1)):
     args = (h.ptr, n, l, l, C.c_double(1.0), C.c_void_p(sh.data.data_ptr()), 2 * l + 1, C.c_void_p(xb.data_ptr()), C.c_double(0.0),
             C.c_void_p(y.data_ptr()), 1)
     res = {}
-    for fuse in (0, 3, 0, 3):
-        h.set_tuning(exchange_fuse=fuse)
+    for fuse, sub in ((0, 0), (3, 0), (3, 2), (3, 4), (3, 6), (0, 0), (3, 0)):
+        h.set_tuning(exchange_fuse=fuse, halo_timeout_ms=sub)
         h.use_torch_stream()
-        res.setdefault(fuse, []).append(round(timeit(lambda: fn(*args)), 2))
-    print(json.dumps({"gbmv n": n, "l": l, "plain_us": res[0], "halo_variant_us": res[3]}), flush=True)
-h.set_tuning(exchange_fuse=0)
+        res.setdefault((fuse, sub), []).append(round(timeit(lambda: fn(*args)), 2))
+    print(json.dumps({"gbmv n": n, "l": l, "plain_us": res[(0, 0)], "halo_variant_us": res[(3, 0)], "no_rotation": res[(3, 2)],
+                      "no_patch_test": res[(3, 4)], "neither": res[(3, 6)]}), flush=True)
+h.set_tuning(exchange_fuse=0, halo_timeout_ms=0)

@@ -330,7 +330,7 @@ int gbmv_sharded_plan(lbm_handle_t h, const Plan &p, int64_t kl, int64_t ku, T a
         if (h->tune.exchange_fuse == 3) {   // self-test knob: the HALO instantiation with no neighbours (what the variant itself costs)
             lbm::HaloFuse none;
             memset(&none, 0, sizeof(none));
-            none.on = 1;
+            none.on = 1 | (int)(h->tune.halo_timeout_ms & 6);   // self-test sub-knobs ride in halo_timeout_ms: 2 = no rotation, 4 = no patch test
             none.nflags = 1;
             rc = gbmv_fused_call<T>(h, p.m_loc, p.n_loc, p.kl_loc, p.ku_loc, alpha, A, lda, xbuf, beta, y, &none);
             if (rc != LBM_NOT_FUSED) return rc;

@@ -782,7 +782,9 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
             // a warp must not skip one), even when the chunk holds nothing for it
             mbar_wait_(&bar_full[s], (uint32_t)((gi / NSTAGE) & 1), sleep_ns);
             const unsigned desc = chunk_desc[s][warp];      // the producer's classification of this chunk for this warp
-            const unsigned kind = chunk_kind[s][warp];
+            unsigned kind = chunk_kind[s][warp];
+            if ((a.flags & 256) && kind == 1u) kind = 0u;   // ablation (wrong results): ramp chunks skipped
+            if ((a.flags & 512) && kind == 1u) kind = 2u;   // ablation (wrong results): ramp chunks through the unmasked path
             const bool full = kind == 2u;
             const unsigned mA = desc & 0xffffu, mB = desc >> 16;
             if (kind != 0u) {
@@ -951,6 +953,8 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
         if (h->tune.gbmm_tile / 100 == 6) a.flags |= 64;  // (+600: ablation, no operand copies)
         if (h->tune.gbmm_tile / 100 == 7) a.flags |= 128; // (+700: ablation, no C stores)
         if (h->tune.gbmm_tile / 100 == 8) a.flags |= 64 | 128; // (+800: both)
+        if (h->tune.gbmm_tile / 100 == 9) a.flags |= 64 | 128 | 256;   // (+900: no memory, ramp chunks skipped)
+        if (h->tune.gbmm_tile / 100 == 10) a.flags |= 64 | 128 | 512;  // (+1000: no memory, ramp chunks unmasked)
         int64_t total_ws = gx * ((gy + a.tpc - 1) / a.tpc);
         // gbmm_tile 4xx: persistent grid (SMs x resident CTAs, each walking every grid-th work item)
         const bool persistent = h->tune.gbmm_tile / 100 == 4;

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
     const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
 
     auto ranges = [&](int64_t t, int64_t &o0, int64_t &o1, int64_t &c0, int64_t &c1, int64_t &x0, int64_t &x1) {
-        if (HALO) t = t + 1 < a.ntiles ? t + 1 : 0;   // rotate: tile 0 (left ghosts) last, tile ntiles-1 second to last
+        if (HALO && !(hf.on & 2)) t = t + 1 < a.ntiles ? t + 1 : 0;   // rotate: tile 0 (left ghosts) last, tile ntiles-1 second to last
         o0 = t * a.tile;
         o1 = o0 + a.tile < a.nout ? o0 + a.tile : a.nout;
         if (!TRANS) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         const T *sx = sA + a.sA_elems;
 
         mbar_wait(&bars[s], parity);
-        if (HALO) halo_patch_1d<T>(hf, const_cast<T *>(sx), x0a, x1, tid, GBMV_NT);
+        if (HALO && !(hf.on & 4)) halo_patch_1d<T>(hf, const_cast<T *>(sx), x0a, x1, tid, GBMV_NT);
 
         // interior tiles need no index masks
         const bool interior = TRANS ? (o0 - a.ku >= 0 && o1 - 1 + a.kl < a.m)

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
     // physical chunk numbers: chunk_of(kk).
     auto chunk_of = [&](int64_t kk) -> int64_t {
         const int64_t L = blockIdx.y + kk * step;
-        return HALO ? (L + 1 < a.nchunks ? L + 1 : 0) : L;
+        return (HALO && !(hf.on & 2)) ? (L + 1 < a.nchunks ? L + 1 : 0) : L;
     };
     // rows staged per grid column: [rs, re) (both 16-byte aligned: n2 % EPV == 0)
     const int64_t rs = r0 - a.hp > 0 ? r0 - a.hp : 0;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         T cnext = (T)0;
         if (kk + 1 < mine) cnext = load_coef(chunk_of(kk + 1));  // in flight during this chunk's compute
         mbar_wait(&bars[s], parity);
-        if (HALO) {
+        if (HALO && !(hf.on & 4)) {
             // input columns staged for this chunk: [ci0, ci0 + g + kla + kua) clipped to [0, n1_in)
             const int64_t ci0 = c0 + a.xoff - a.kla;
             const int64_t sa = ci0 > 0 ? ci0 : 0;
@@ -611,7 +611,7 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
         if (h->tune.exchange_fuse == 3) {   // self-test knob: the HALO instantiation with no neighbours (what the variant itself costs)
             HaloFuse none;
             memset(&none, 0, sizeof(none));
-            none.on = 1;
+            none.on = 1 | (int)(h->tune.halo_timeout_ms & 6);   // self-test sub-knobs ride in halo_timeout_ms: 2 = no rotation, 4 = no patch test
             none.nflags = 1;
             rc = kronsum_range<T>(h, m_loc, n_loc, left, n2, kla, kua, A_slab, lda, klb, kub, B, ldb, alpha, xbuf, beta, y_own, 0, m_loc, &none);
             if (rc != LBM_NOT_FUSED) return rc;

@@ -445,7 +445,16 @@ def krontrav_mul_diagtrav(A: np.ndarray, B: np.ndarray, X: np.ndarray) -> np.nda
 
 
 def zero_bottomright(X: np.ndarray) -> np.ndarray:
-    """src/blockkron.jl:38-47: zero entries with k + j > max(m,n) + 1 (1-based)."""
+    """src/blockkron.jl:38-47: zero entries with k + j > max(m,n) + 1 (1-based); 3-D cubic arrays (:57-64): zero
+    X[k+1, j+1, l+1] for k >= n - (l + j) (0-based k, j, l).  In place, like `zero_bottomright!`."""
+    if X.ndim == 3:
+        n = X.shape[0]
+        assert X.shape == (n, n, n)
+        for ell in range(n):
+            for j in range(n):
+                for k in range(max(0, n - (ell + j)), n):
+                    X[k, j, ell] = 0
+        return X
     m, n = X.shape
     mu = max(m, n)
     for j in range(1, n + 1):
