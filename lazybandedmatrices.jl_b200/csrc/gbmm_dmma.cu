@@ -804,6 +804,12 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
                             for (int y = 0; y < YB; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
                     }
                 } else {
+                    // Ramp chunk (a band edge of A and / or B crosses it).  Round-2 ablations (profiles/dmma_r02_notes.md): the
+                    // former path -- 16 individually predicated DMMAs per k-step, each behind its own bit test and warp
+                    // reconvergence -- cost MORE sub-core time with its 24 useful DMMAs per chunk (1.78 ms of the 6.27) than
+                    // running all 64 unmasked (1.61 ms).  Now: out-of-band entries are zeroed IN THE FRAGMENTS (per-lane select,
+                    // so the column blocks of B need no skipping at all), whole k-steps with nothing in band are skipped, and
+                    // the row blocks of A are skipped four DMMAs at a time (one warp-uniform branch per block).
                     const int da = ia0 - pr, db = jb0 - pr;
                     const int va = da + fr - fc + kua, wa = kla + kua;
                     const int vb = -db + fc - fr + kub, wb = klb + kub;
@@ -811,12 +817,7 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
                     for (int ks = 0; ks < KC / 4; ++ks) {
                         const unsigned ma = (mA >> (4 * ks)) & 15u, mb = (mB >> (4 * ks)) & (YB == 2 ? 3u : 15u);
                         if (ma == 0 || mb == 0) continue;
-                        double ga[4], gb[YB];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const double ra = sA[fa_off + 4 * ks * PA + 8 * x];
-                            ga[x] = (unsigned)(va + 8 * x - 4 * ks) <= (unsigned)wa ? ra : 0.0;
-                        }
+                        double gb[YB];
 #pragma unroll
                         for (int y = 0; y < YB; ++y) {
                             const double rb = sB[fb_off + 8 * y * PB + 4 * ks];
@@ -825,9 +826,10 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
                             if (!(ma >> x & 1u)) continue;
+                            const double ra = sA[fa_off + 4 * ks * PA + 8 * x];
+                            const double ga = (unsigned)(va + 8 * x - 4 * ks) <= (unsigned)wa ? ra : 0.0;
 #pragma unroll
-                            for (int y = 0; y < YB; ++y)
-                                if (mb >> y & 1u) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
+                            for (int y = 0; y < YB; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga, gb[y]);
                         }
                     }
                 }

@@ -50,7 +50,7 @@ struct GbmvArgs {
 // neighbours' mailboxes first; tiles are walked rotated by one so that the tiles whose x window overlaps ghost cells
 // (the first and the last) come last, and those tiles patch their window in shared memory from the local mailbox.
 template <typename T, int NB, bool TRANS, bool HALO>
-__global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a, const HaloFuse hf) {
+__global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a, const __grid_constant__ HaloFuse hf) {
     constexpr int EPV = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         const T *sx = sA + a.sA_elems;
 
         mbar_wait(&bars[s], parity);
-        if (HALO && !(hf.on & 4)) halo_patch_1d<T>(hf, const_cast<T *>(sx), x0a, x1, tid, GBMV_NT);
+        // ghost cells can only sit in the x windows of the first and of the last two tiles (halo <= 128 < tile)
+        if (HALO && !(hf.on & 4) && (o0 == 0 || o1 + 2 * a.tile > a.nout)) halo_patch_1d<T>(hf, const_cast<T *>(sx), x0a, x1, tid, GBMV_NT);
 
         // interior tiles need no index masks
         const bool interior = TRANS ? (o0 - a.ku >= 0 && o1 - 1 + a.kl < a.m)

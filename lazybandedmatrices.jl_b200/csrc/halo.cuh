@@ -96,11 +96,12 @@ __device__ __forceinline__ void halo_push(const HaloFuse &hf, int tid, int nthre
         if (hf.push_flag[s]) halo_copy(hf.push_src[s], hf.push_dst[s], hf.push_bytes[s], tid, nthreads);
     __threadfence_system();
     __syncthreads();
-    // every flag word of the side (nflags > 1 only when this is the unfused push kernel serving a strip-wise waiter)
-    for (int i = tid; i < 2 * hf.nflags; i += nthreads) {
-        const int s = i / hf.nflags;
-        if (hf.push_flag[s]) st_release_sys(hf.push_flag[s] + (i - s * hf.nflags), hf.epoch);
-    }
+    // every flag word of the side (nflags > 1 only when this is the unfused push kernel serving a strip-wise waiter);
+    // static indexing of the parameter struct (a dynamic index would copy it to local memory)
+    if (hf.push_flag[0])
+        for (int i = tid; i < hf.nflags; i += nthreads) st_release_sys(hf.push_flag[0] + i, hf.epoch);
+    if (hf.push_flag[1])
+        for (int i = tid; i < hf.nflags; i += nthreads) st_release_sys(hf.push_flag[1] + i, hf.epoch);
 }
 
 // Called by every thread of the pushing CTA after its last tile: keeps the epochs of a neighbour pair in lock-step on the
@@ -113,22 +114,27 @@ __device__ __forceinline__ void halo_final_wait(const HaloFuse &hf, int tid, int
 // 1-D windows (gbmv / tridiagonal kernels): the stage's x window holds x[w0 .. w1) at sx[0 ..].  If it overlaps ghost
 // cells, wait for the owning neighbour and overwrite them in shared memory from the mailbox.  Must be reached by ALL
 // threads of the CTA (it synchronises); the overlap test is CTA-uniform.
+// Out of line on purpose: it runs for at most three tiles per launch, and inlining it cost the streaming loop 2-4 % (one GPU,
+// benchmarks/halo_selftest.py); the callers guard it with a cheap uniform test on the tile number.
 template <typename T>
-__device__ __forceinline__ void halo_patch_1d(const HaloFuse &hf, T *sx, int64_t w0, int64_t w1, int tid, int nthreads) {
-    bool need[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) need[s] = hf.ghost_end[s] > hf.ghost_begin[s] && w0 < hf.ghost_end[s] && w1 > hf.ghost_begin[s];
-    if (!(need[0] || need[1])) return;
-    if (tid == 0 && need[0]) halo_wait_flag(hf.pull_flag[0], hf.epoch, hf.timeout_ns, hf.status);
-    if (tid == 1 && need[1]) halo_wait_flag(hf.pull_flag[1], hf.epoch, hf.timeout_ns, hf.status);
+__device__ __noinline__ void halo_patch_1d(const HaloFuse &hf, T *sx, int64_t w0, int64_t w1, int tid, int nthreads) {
+    const bool need0 = hf.ghost_end[0] > hf.ghost_begin[0] && w0 < hf.ghost_end[0] && w1 > hf.ghost_begin[0];
+    const bool need1 = hf.ghost_end[1] > hf.ghost_begin[1] && w0 < hf.ghost_end[1] && w1 > hf.ghost_begin[1];
+    if (!(need0 || need1)) return;
+    if (tid == 0 && need0) halo_wait_flag(hf.pull_flag[0], hf.epoch, hf.timeout_ns, hf.status);
+    if (tid == 1 && need1) halo_wait_flag(hf.pull_flag[1], hf.epoch, hf.timeout_ns, hf.status);
     __syncthreads();
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (!need[s]) continue;
-        const int64_t a = w0 > hf.ghost_begin[s] ? w0 : hf.ghost_begin[s];
-        const int64_t b = w1 < hf.ghost_end[s] ? w1 : hf.ghost_end[s];
-        const T *mb = reinterpret_cast<const T *>(hf.pull_src[s]);
-        for (int64_t i = a + tid; i < b; i += nthreads) sx[i - w0] = __ldcg(mb + (i - hf.ghost_begin[s]));
+    if (need0) {
+        const int64_t a = w0 > hf.ghost_begin[0] ? w0 : hf.ghost_begin[0];
+        const int64_t b = w1 < hf.ghost_end[0] ? w1 : hf.ghost_end[0];
+        const T *mb = reinterpret_cast<const T *>(hf.pull_src[0]);
+        for (int64_t i = a + tid; i < b; i += nthreads) sx[i - w0] = __ldcg(mb + (i - hf.ghost_begin[0]));
+    }
+    if (need1) {
+        const int64_t a = w0 > hf.ghost_begin[1] ? w0 : hf.ghost_begin[1];
+        const int64_t b = w1 < hf.ghost_end[1] ? w1 : hf.ghost_end[1];
+        const T *mb = reinterpret_cast<const T *>(hf.pull_src[1]);
+        for (int64_t i = a + tid; i < b; i += nthreads) sx[i - w0] = __ldcg(mb + (i - hf.ghost_begin[1]));
     }
     // the patched words are generic-proxy stores into a buffer the async proxy (bulk TMA) overwrites when the stage is
     // re-issued: order the two proxies before the CTA-wide barrier that precedes that re-issue

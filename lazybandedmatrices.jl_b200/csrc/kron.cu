@@ -135,12 +135,42 @@ struct KronRingArgs {
     int64_t batch_stride;   // blockIdx.z walks independent slices (x, y advance by this many elements): 3-D mode products
 };
 
+// Ghost columns of one stage: wait for the strip's flag, then overwrite rows [r0, r0+rows) of every ghost column the stage
+// holds from the local mailbox (only those rows are ever read: the A-term X[r, c+-t]; the B-term reads owned columns).
+template <typename T>
+__device__ __noinline__ void kron_halo_patch(const HaloFuse &hf, T *st, int64_t ci0, int scols, int64_t n1_in, int seg, int rowoff,
+                                             int64_t r0, int rows, int64_t n2, int strip) {
+    const int tid = threadIdx.x;
+    const int64_t sa = ci0 > 0 ? ci0 : 0;
+    const int64_t sb = ci0 + scols < n1_in ? ci0 + scols : n1_in;
+    const bool need0 = hf.ghost_end[0] > hf.ghost_begin[0] && sa < hf.ghost_end[0] && sb > hf.ghost_begin[0];
+    const bool need1 = hf.ghost_end[1] > hf.ghost_begin[1] && sa < hf.ghost_end[1] && sb > hf.ghost_begin[1];
+    if (!(need0 || need1)) return;   // CTA-uniform
+    if (tid == 0 && need0) halo_wait_flag(hf.pull_flag[0] + strip, hf.epoch, hf.timeout_ns, hf.status);
+    if (tid == 1 && need1) halo_wait_flag(hf.pull_flag[1] + strip, hf.epoch, hf.timeout_ns, hf.status);
+    __syncthreads();
+    if (need0) {
+        const int64_t ga = sa > hf.ghost_begin[0] ? sa : hf.ghost_begin[0], gb = sb < hf.ghost_end[0] ? sb : hf.ghost_end[0];
+        const T *mb = reinterpret_cast<const T *>(hf.pull_src[0]);
+        for (int64_t c = ga; c < gb; ++c)
+            for (int r = tid; r < rows; r += 256) st[(c - ci0) * seg + rowoff + r] = __ldcg(mb + (c - hf.ghost_begin[0]) * n2 + r0 + r);
+    }
+    if (need1) {
+        const int64_t ga = sa > hf.ghost_begin[1] ? sa : hf.ghost_begin[1], gb = sb < hf.ghost_end[1] ? sb : hf.ghost_end[1];
+        const T *mb = reinterpret_cast<const T *>(hf.pull_src[1]);
+        for (int64_t c = ga; c < gb; ++c)
+            for (int r = tid; r < rows; r += 256) st[(c - ci0) * seg + rowoff + r] = __ldcg(mb + (c - hf.ghost_begin[1]) * n2 + r0 + r);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+}
+
 // HALO: grid-column-sharded apply in ONE launch (halo.cuh).  CTA (0,0) pushes this rank's boundary grid columns to the
 // neighbours' mailboxes; column chunks are walked rotated by one so the first / last chunk (the only ones whose stage
 // holds ghost columns) come last, and those chunks overwrite the ghost columns of their stage -- rows [rs,re) of this
 // CTA's strip only -- in shared memory from the local mailbox.
 template <typename T, int NBA, int NBB, int RPT, bool HALO>
-__global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a, const HaloFuse hf) {
+__global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a, const __grid_constant__ HaloFuse hf) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     T *sbase = reinterpret_cast<T *>(smem_raw + 128);
@@ -270,38 +300,11 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         T cnext = (T)0;
         if (kk + 1 < mine) cnext = load_coef(chunk_of(kk + 1));  // in flight during this chunk's compute
         mbar_wait(&bars[s], parity);
-        if (HALO && !(hf.on & 4)) {
-            // input columns staged for this chunk: [ci0, ci0 + g + kla + kua) clipped to [0, n1_in)
-            const int64_t ci0 = c0 + a.xoff - a.kla;
-            const int64_t sa = ci0 > 0 ? ci0 : 0;
-            const int64_t sb = ci0 + a.g + a.kla + a.kua < a.n1_in ? ci0 + a.g + a.kla + a.kua : a.n1_in;
-            bool need[2];
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd)
-                need[sd] = hf.ghost_end[sd] > hf.ghost_begin[sd] && sa < hf.ghost_end[sd] && sb > hf.ghost_begin[sd];
-            if (need[0] || need[1]) {   // CTA-uniform
-                if (tid == 0 && need[0]) halo_wait_flag(hf.pull_flag[0] + blockIdx.x, hf.epoch, hf.timeout_ns, hf.status);
-                if (tid == 1 && need[1]) halo_wait_flag(hf.pull_flag[1] + blockIdx.x, hf.epoch, hf.timeout_ns, hf.status);
-                __syncthreads();
-                // only rows [r0, r0+tr) of a ghost column are ever read (the A-term X[r, c+-t]; the B-term reads owned columns)
-                const int rows_in = (int)((r0 + a.tr < a.n2 ? r0 + a.tr : a.n2) - r0);
-                const int rskip = (int)(r0 - rs);
-#pragma unroll
-                for (int sd = 0; sd < 2; ++sd) {
-                    if (!need[sd]) continue;
-                    const int64_t ga = sa > hf.ghost_begin[sd] ? sa : hf.ghost_begin[sd];
-                    const int64_t gb = sb < hf.ghost_end[sd] ? sb : hf.ghost_end[sd];
-                    const T *mb = reinterpret_cast<const T *>(hf.pull_src[sd]);
-                    for (int64_t c = ga; c < gb; ++c) {
-                        T *dstc = const_cast<T *>(st) + (c - ci0) * a.seg + roff + rskip;
-                        const T *srcc = mb + (c - hf.ghost_begin[sd]) * a.n2 + r0;
-                        for (int r = tid; r < rows_in; r += 256) dstc[r] = __ldcg(srcc + r);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-            }
-        }
+        // only the first / last chunk of the rank's column range can hold ghost columns: one cheap uniform test here, the
+        // wait + patch itself out of line so that it does not touch the register allocation of the streaming loop
+        if (HALO && !(hf.on & 4) && (q == 0 || q + 1 == a.nchunks))
+            kron_halo_patch<T>(hf, const_cast<T *>(st), c0 + a.xoff - a.kla, a.g + a.kla + a.kua, a.n1_in, a.seg, roff + (int)(r0 - rs), r0,
+                               (int)((r0 + a.tr < a.n2 ? r0 + a.tr : a.n2) - r0), a.n2, (int)blockIdx.x);
         const int seg = a.seg;
         const T *xrow = st + tid + a.hp;                 // X[r0+tid, c0-kla] of this stage
         T *yp = yz + (r0 + tid) + a.n2 * c0;              // Y[r0+tid, c0]; += n2 per column

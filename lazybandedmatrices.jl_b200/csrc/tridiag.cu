@@ -179,7 +179,7 @@ struct TriRingArgs {
 // HALO: row-sharded apply in one launch (halo.cuh): the one-element ghosts of x are pushed by CTA 0 and patched into the
 // first / last tile's x window in shared memory; tiles are walked rotated by one so those two tiles come last.
 template <typename T, bool HAS_DL, bool HAS_DU, bool SYM, bool HALO>
-__global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<T> a, const HaloFuse hf) {
+__global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<T> a, const __grid_constant__ HaloFuse hf) {
     constexpr int EPV = 16 / (int)sizeof(T);
     constexpr int NARR = 2 + ((HAS_DL || HAS_DU) ? 1 : 0) + ((HAS_DL && HAS_DU && !SYM) ? 1 : 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         const T *slo = sx + a.seg;                                  // dl window (HAS_DL)
         const T *shi = (HAS_DL && HAS_DU && !SYM) ? slo + a.seg : slo;  // du window
         mbar_wait(&bars[s], parity);
-        if (HALO) halo_patch_1d<T>(hf, const_cast<T *>(sx), w0, i1 + 1 < a.n ? i1 + 1 : a.n, tid, TRI_NT);
+        if (HALO && (i0 < a.tile || i1 + a.tile >= a.n))   // only the first / last tile's window can hold a ghost
+            halo_patch_1d<T>(hf, const_cast<T *>(sx), w0, i1 + 1 < a.n ? i1 + 1 : a.n, tid, TRI_NT);
         const int64_t ie = i1 < a.row_end ? i1 : a.row_end;
         for (int64_t i = i0 + tid; i < ie; i += TRI_NT) {
             if (i < a.row_begin) continue;
