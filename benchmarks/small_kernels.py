@@ -73,6 +73,18 @@ def main():
                 h.set_tuning(gbmv_tile=0, gbmv_stages=0, gbmv_ctas_per_sm=0)
             del A, x, y
             torch.cuda.empty_cache()
+    if "B" in only:
+        # the per-rank slab of a row shard is a RECTANGULAR banded matrix with bandwidths (l - left, u + left): (1,1) on rank 0,
+        # (0,2) on the others -- same 3 stored diagonals, different alignment of the slab / x window inside a tile
+        n = 1 << 25
+        for (kl, ku) in ((1, 1), (0, 2), (2, 0)):
+            data = torch.rand((n + 2, 3), dtype=torch.float64, device="cuda")
+            A = L.BandedMatrix(data, n, kl, ku)          # n x (n+2)
+            x = torch.rand(n + 2, dtype=torch.float64, device="cuda")
+            y = torch.empty(n, dtype=torch.float64, device="cuda")
+            emit(f"gbmv rectangular n=2^25 x (n+2), bandwidths ({kl},{ku})", timeit(lambda: L.mul_(y, A, x)), 8 * n * 5)
+            del data, A, x, y
+            torch.cuda.empty_cache()
     if "T" in only:
         for log2n in (25, 28):
             n = 1 << log2n

@@ -197,7 +197,10 @@ class Handle:
 
     def use_torch_stream(self):
         import torch
-        s = int(torch.cuda.current_stream(self.device).cuda_stream)
+        try:    # raw handle of torch's current stream without building a Stream object (small applies are host-bound)
+            s = int(torch._C._cuda_getCurrentRawStream(self.device))
+        except Exception:
+            s = int(torch.cuda.current_stream(self.device).cuda_stream)
         if getattr(self, "_bound_stream", None) != s:   # small-n calls are host-bound: skip the FFI call when nothing changed
             self.set_stream(s)
 

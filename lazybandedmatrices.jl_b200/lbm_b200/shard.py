@@ -278,13 +278,26 @@ class ShardedBanded:
             # product fast path: exchange + kernels inside the library (needs init_comm())
             from . import _lib
             from .banded import _ft, _pfx, _ptr
+            # the prepared call (bound function + converted arguments) is cached per operand set: at 8 GPUs an apply is
+            # ~0.1 ms and the host side of the call must stay in the noise
+            key = (y_own.data_ptr(), xbuf.data_ptr(), float(alpha), float(beta), bool(overlap))
+            cached = getattr(self, "_prepared", None)
+            if cached is not None and cached[0] == key:
+                h, fn, args = cached[1]
+                h.use_torch_stream()
+                rc = fn(*args)
+                if rc:
+                    h.check(rc, "lbm_gbmv_sharded")
+                return y_own
             h = _lib.handle_of(self.data)
             if h.comm_world == p.world:
                 fn = getattr(_lib.lib(), f"lbm_{_pfx(self.data.dtype)}gbmv_sharded")
                 ft = _ft(self.data.dtype)
                 assert xbuf.is_contiguous() and y_own.is_contiguous() and xbuf.shape[0] == p.n_loc
-                h.check(fn(h.ptr, p.n, p.l, p.u, ft(alpha), _ptr(self.data), p.l + p.u + 1, _ptr(xbuf), ft(beta),
-                           _ptr(y_own), 1 if overlap else 0), "lbm_gbmv_sharded")
+                args = (h.ptr, p.n, p.l, p.u, ft(alpha), _ptr(self.data), p.l + p.u + 1, _ptr(xbuf), ft(beta), _ptr(y_own),
+                        1 if overlap else 0)
+                self._prepared = (key, (h, fn, args))
+                h.check(fn(*args), "lbm_gbmv_sharded")
                 return y_own
         if not overlap:
             p.exchange(xbuf, group)
@@ -465,14 +478,24 @@ class ShardedKronSum:
         if local_apply is None and group is None and xbuf.is_cuda:
             from . import _lib
             from .banded import _ft, _pfx, _ptr
+            key = (y_own.data_ptr(), xbuf.data_ptr(), float(alpha), float(beta), bool(overlap))
+            cached = getattr(self, "_prepared", None)
+            if cached is not None and cached[0] == key:      # prepared call (see ShardedBanded.mul_)
+                h, fn, args = cached[1]
+                h.use_torch_stream()
+                rc = fn(*args)
+                if rc:
+                    h.check(rc, "lbm_kronsum2d_mv_sharded")
+                return y_own
             h = _lib.handle_of(xbuf)
             if p.world == 1 or h.comm_world == p.world:
                 fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}kronsum2d_mv_sharded")
                 ft = _ft(xbuf.dtype)
                 B = self.B
-                h.check(fn(h.ptr, self.n1, self.n2, self.kla, self.kua, _ptr(self.a_slab), self.kla + self.kua + 1,
-                           B.l, B.u, _ptr(B.data), B.lda, ft(alpha), _ptr(xbuf), ft(beta), _ptr(y_own),
-                           1 if overlap else 0), "lbm_kronsum2d_mv_sharded")
+                args = (h.ptr, self.n1, self.n2, self.kla, self.kua, _ptr(self.a_slab), self.kla + self.kua + 1,
+                        B.l, B.u, _ptr(B.data), B.lda, ft(alpha), _ptr(xbuf), ft(beta), _ptr(y_own), 1 if overlap else 0)
+                self._prepared = (key, (h, fn, args))
+                h.check(fn(*args), "lbm_kronsum2d_mv_sharded")
                 return y_own
             raise LbmArgumentError("call lbm_b200.shard.init_comm() first (or pass a local_apply for host-logic tests)")
         if p.world > 1:
@@ -513,6 +536,15 @@ class ShardedTridiagonal:
         if local_apply is None and group is None and xbuf.is_cuda:
             from . import _lib
             from .banded import _ft, _pfx, _ptr
+            key = (y_own.data_ptr(), xbuf.data_ptr(), float(alpha), float(beta), bool(overlap))
+            cached = getattr(self, "_prepared", None)
+            if cached is not None and cached[0] == key:      # prepared call (see ShardedBanded.mul_)
+                h, fn, args = cached[1]
+                h.use_torch_stream()
+                rc = fn(*args)
+                if rc:
+                    h.check(rc, "lbm_tridiag_mv_sharded")
+                return y_own
             h = _lib.handle_of(xbuf)
             if p.world > 1 and h.comm_world != p.world:
                 raise LbmArgumentError("call lbm_b200.shard.init_comm() first")
@@ -520,8 +552,10 @@ class ShardedTridiagonal:
             # ghost-extended square system restricted to the owned rows, written straight into y_own
             fn = getattr(_lib.lib(), f"lbm_{_pfx(xbuf.dtype)}tridiag_mv_sharded")
             ft = _ft(xbuf.dtype)
-            h.check(fn(h.ptr, p.n, _ptr(self.dl), _ptr(self.d), _ptr(self.du), ft(alpha), _ptr(xbuf), ft(beta),
-                       _ptr(y_own), 1 if overlap else 0), "lbm_tridiag_mv_sharded")
+            args = (h.ptr, p.n, _ptr(self.dl), _ptr(self.d), _ptr(self.du), ft(alpha), _ptr(xbuf), ft(beta), _ptr(y_own),
+                    1 if overlap else 0)
+            self._prepared = (key, (h, fn, args))
+            h.check(fn(*args), "lbm_tridiag_mv_sharded")
             return y_own
         if self._ybuf is None or self._ybuf.shape[0] != p.n_loc or self._ybuf.device != xbuf.device:
             self._ybuf = torch.empty(p.n_loc, dtype=xbuf.dtype, device=xbuf.device)
