@@ -83,6 +83,17 @@ def main():
             x = torch.rand(n + 2, dtype=torch.float64, device="cuda")
             y = torch.empty(n, dtype=torch.float64, device="cuda")
             emit(f"gbmv rectangular n=2^25 x (n+2), bandwidths ({kl},{ku})", timeit(lambda: L.mul_(y, A, x)), 8 * n * 5)
+            if (kl, ku) != (2, 0):
+                for tile in (512, 768, 1024, 1280, 1536, 2048):
+                    for st in (2, 3):
+                        for cps in (0, 2, 4):
+                            h.set_tuning(gbmv_tile=tile, gbmv_stages=st, gbmv_ctas_per_sm=cps)
+                            emit(f"gbmv rectangular ({kl},{ku}) tile={tile} stages={st} cps={cps}", timeit(lambda: L.mul_(y, A, x), 50, 5), 8 * n * 5)
+                h.set_tuning(gbmv_tile=0, gbmv_stages=0, gbmv_ctas_per_sm=0)
+                for skew in (2, 4, 6, 16):
+                    h.set_tuning(gbmv_skew=skew)
+                    emit(f"gbmv rectangular ({kl},{ku}) skew={skew}", timeit(lambda: L.mul_(y, A, x), 50, 5), 8 * n * 5)
+                h.set_tuning(gbmv_skew=0)
             del data, A, x, y
             torch.cuda.empty_cache()
     if "T" in only:

@@ -858,6 +858,168 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), MINB) gbmm_dmma_ws_kernel(co
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// warp-autonomous variant for interior tiles (round 2)
+// ------------------------------------------------------------------------------------------
+// What round 2's ablations showed (profiles/dmma_r02_notes.md): with NO operand copies and NO C stores the warp-specialised
+// kernel still needs 5.8 of its 6.2 ms, it runs at 82 % of the DMMA pipe when every chunk is forced through the unmasked
+// path and at 62-70 % otherwise -- the loss is the LOCK-STEP of a CTA's four quadrant warps through a shared ring: near both
+// ends of a tile's p-range the quadrants sit on different sides of the band edges (full / ramp / nothing), the ring advances
+// at the pace of the busiest one, and 19 % of all warp-chunks are pure hand-shakes.
+// Here every WARP is its own pipeline, as in gbmm_chain_warp.cu: it owns one 32x32 block of C (block-diagonal order), stages
+// ITS OWN dense 32x8 (A) and 8x32 (B) windows with 16-byte cp.async into a private 3-stage ring (no mbarrier, no producer
+// warp, __syncwarp only), walks exactly the p-range of its block (no empty chunks), and knows the range of wholly-in-band
+// chunks up front (no per-chunk classification on the unmasked path).  A warp's bubbles -- cp.async latency, ramp chunks,
+// the epilogue -- are covered by the other eleven warps of the SM, none of which ever waits for it.  The price is twice the
+// L2 -> shared-memory traffic per DMMA (windows are not shared between warps), which the "every copy issued twice"
+// experiment of round 1 priced at 3 %.
+constexpr int WA_KC = 8;                    // p per chunk: two k-steps, 32 DMMAs
+constexpr int WA_PA = 36, WA_PB = 12;       // sA[p][i] / sB[j][p] pitches: 2*PA = 8, 2*PB = 24 (mod 32) -> conflict-free fragment loads
+constexpr int WA_STAGE = WA_KC * WA_PA + 32 * WA_PB;   // 672 doubles = 5376 B per warp and stage
+constexpr int WA_WARPS = 4;
+
+template <int NS>
+__global__ void __launch_bounds__(32 * WA_WARPS, 3) gbmm_dmma_wa_kernel(const DmmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NS * WA_STAGE;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int kla = (int)a.kla, kua = (int)a.kua, klb = (int)a.klb, kub = (int)a.kub;
+    // block-diagonal range of C: blocks (bi, bj = bi - d) with 32 d - 31 <= klc and 32 d + 31 >= -kuc
+    const int64_t dlo = -((a.kuc + 31) / 32), dhi = (a.klc + 31) / 32, nd = dhi - dlo + 1;
+    const int64_t nbi = a.m / 32, nbj = a.n / 32;
+    const int64_t items = nbi * nd;
+    const int64_t wid = ((int64_t)blockIdx.x + (int64_t)gridDim.x * blockIdx.y) * WA_WARPS + warp;
+    const int64_t nw = (int64_t)gridDim.x * gridDim.y * WA_WARPS;
+    // cp.async lane roles: A window 8 p x 32 rows = 8 columns of 256 B; B window 32 columns of 64 B
+    const int a_p = lane >> 4, a_r = 2 * (lane & 15);   // + 2q in p
+    const int b_j = lane >> 2, b_p = 2 * (lane & 3);    // + 8q in j
+    const int fa_off = fc * WA_PA + fr;                 // + 4*ks*PA + 8*x
+    const int fb_off = fr * WA_PB + fc;                 // + 8*y*PB + 4*ks
+
+    for (int64_t item = wid; item < items; item += nw) {
+        const int64_t bi = item / nd, d = dlo + (item - bi * nd);
+        const int64_t bj = bi - d;
+        if (bj < 0 || bj >= nbj) continue;
+        const int64_t i0 = bi * 32, j0 = bj * 32;
+        const int64_t cb = j0 / TN;                      // 64-column block: the corner launch owns some of them entirely
+        if (cb < a.cb_lo || cb >= a.cb_hi0) continue;
+        int64_t plo = i0 - a.kla > j0 - a.kub ? i0 - a.kla : j0 - a.kub;
+        int64_t phi = i0 + 31 + a.kua < j0 + 31 + a.klb ? i0 + 31 + a.kua : j0 + 31 + a.klb;
+        if (plo < 0) plo = 0;
+        if (phi > a.k - 1) phi = a.k - 1;
+        plo &= ~(int64_t)3;
+        const int nch = phi >= plo ? (int)((phi - plo + WA_KC) / WA_KC) : 0;
+        if (nch == 0) continue;
+        const int ia0 = (int)(i0 - plo), jb0 = (int)(j0 - plo);
+        // chunks [it_lo, it_hi] are wholly inside both bands (pr = it*KC): the linear inequalities of the chunk classification
+        int lo1 = ia0 + 31 - kla, lo2 = jb0 + 31 - kub;
+        int hi1 = ia0 + kua - (WA_KC - 1), hi2 = jb0 + klb - (WA_KC - 1);
+        int lo = lo1 > lo2 ? lo1 : lo2;
+        if (lo < 0) lo = 0;
+        const int hi = hi1 < hi2 ? hi1 : hi2;
+        const int it_lo = (lo + WA_KC - 1) / WA_KC;
+        const int it_hi = hi >= 0 ? hi / WA_KC : -1;
+
+        const double *a_src = a.A + (a.kua + i0 + a_r) + (a.lda - 1) * (plo + a_p);
+        const double *b_src = a.B + (a.kub + plo + b_p) + (a.ldb - 1) * (j0 + b_j);
+        const int64_t a_step2 = 2 * (a.lda - 1), b_step8 = 8 * (a.ldb - 1);
+        auto issue = [&](int it) {
+            double *sA = ring + (it % NS) * WA_STAGE;
+            double *sB = sA + WA_KC * WA_PA;
+            const uint32_t dA = (uint32_t)__cvta_generic_to_shared(sA + a_p * WA_PA + a_r);
+            const uint32_t dB = (uint32_t)__cvta_generic_to_shared(sB + b_j * WA_PB + b_p);
+            const double *as = a_src + (a.lda - 1) * (int64_t)(it * WA_KC);
+            const double *bs = b_src + it * WA_KC;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dA + (uint32_t)(2 * q * WA_PA * 8)), "l"(as + a_step2 * q) : "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dB + (uint32_t)(8 * q * WA_PB * 8)), "l"(bs + b_step8 * q) : "memory");
+        };
+
+        double acc[4][4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+
+#pragma unroll
+        for (int q = 0; q < NS - 1; ++q) {
+            if (q < nch) issue(q);
+            cp_async_commit();
+        }
+        for (int it = 0; it < nch; ++it) {
+            if (it + NS - 1 < nch) issue(it + NS - 1);
+            cp_async_commit();
+            cp_async_wait<NS - 1>();
+            __syncwarp();
+            const double *sA = ring + (it % NS) * WA_STAGE;
+            const double *sB = sA + WA_KC * WA_PA;
+            if (it >= it_lo && it <= it_hi) {
+#pragma unroll
+                for (int ks = 0; ks < WA_KC / 4; ++ks) {
+                    double ga[4], gb[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) ga[x] = sA[fa_off + 4 * ks * WA_PA + 8 * x];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) gb[y] = sB[fb_off + 8 * y * WA_PB + 4 * ks];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga[x], gb[y]);
+                }
+            } else {
+                // ramp chunk: out-of-band entries zeroed in the fragments, empty k-steps and empty row blocks of A skipped
+                const int pr = it * WA_KC;
+                const int da = ia0 - pr, db = jb0 - pr;
+                const unsigned mA = band_mask(-kua - 7 - da, kla + 3 - da);
+                const unsigned mB = band_mask(-klb - 7 - db, kub + 3 - db);
+                const int va = da + fr - fc + kua, wa = kla + kua;
+                const int vb = -db + fc - fr + kub, wb = klb + kub;
+#pragma unroll
+                for (int ks = 0; ks < WA_KC / 4; ++ks) {
+                    const unsigned ma = (mA >> (4 * ks)) & 15u, mb = (mB >> (4 * ks)) & 15u;
+                    if (ma == 0 || mb == 0) continue;
+                    double gb[4];
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const double rb = sB[fb_off + 8 * y * WA_PB + 4 * ks];
+                        gb[y] = (unsigned)(vb - 8 * y + 4 * ks) <= (unsigned)wb ? rb : 0.0;
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        if (!(ma >> x & 1u)) continue;
+                        const double ra = sA[fa_off + 4 * ks * WA_PA + 8 * x];
+                        const double ga = (unsigned)(va + 8 * x - 4 * ks) <= (unsigned)wa ? ra : 0.0;
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], ga, gb[y]);
+                    }
+                }
+            }
+            __syncwarp();   // every lane is done with this stage before the next iteration refills it
+        }
+        cp_async_wait<0>();
+        // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1}) -> band storage
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t i = i0 + 8 * x + fr;
+                    const int64_t j = j0 + 8 * y + 2 * fc + e;
+                    const int64_t f = a.kuc + i - j;
+                    if (f >= 0 && f <= a.klc + a.kuc) {
+                        double *c = a.C + f + a.ldc * j;
+                        const double v = a.alpha * acc[x][y][e];
+                        *c = (a.beta == 0.0) ? v : fma(a.beta, *c, v);
+                    }
+                }
+    }
+}
+
 // out-of-matrix slots of C's band (first kuc / last klc columns) are written 0 when beta == 0
 __global__ void __launch_bounds__(256) gbmm_zero_corners_kernel(int64_t m, int64_t n, int64_t klc, int64_t kuc,
                                                                double *C, int64_t ldc) {
@@ -940,7 +1102,90 @@ int lbm_gbmm_dmma_f64(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double al
             gbmm_dmma_kernel<NS, MB, 2><<<grid, NT, smem, h->stream>>>(a);                                    \
         }                                                                                                     \
     } while (0)
-    if (variant == 0 || (variant >= 20 && variant <= 29)) {
+    if (variant == 30 || variant == 31 || variant == 32) {
+        // warp-autonomous interior kernel + the corner instantiation of the plain kernel (same corner scan as below)
+        auto hfloordiv = [](int64_t x, int64_t y) { return x >= 0 ? x / y : -((-x + y - 1) / y); };
+        auto block_all_interior = [&](int64_t cbk) {
+            const int64_t j0 = cbk * TN;
+            int64_t I0 = hfloordiv(j0 - kuc, TM);
+            if (I0 < 0) I0 = 0;
+            for (int64_t by = 0; by < gy; ++by) {
+                const int64_t i0 = (I0 + by) * TM;
+                if (i0 >= m || i0 > j0 + TN - 1 + klc) continue;
+                int64_t plo = i0 - kla > j0 - kub ? i0 - kla : j0 - kub;
+                int64_t phi = i0 + TM - 1 + kua < j0 + TN - 1 + klb ? i0 + TM - 1 + kua : j0 + TN - 1 + klb;
+                if (plo < 0) plo = 0;
+                if (phi > k - 1) phi = k - 1;
+                plo &= ~(int64_t)3;
+                const int64_t nch = phi >= plo ? (phi - plo + KC) / KC : 0;
+                const bool ok = nch > 0 && i0 + TM <= m && j0 >= 4 && j0 + TN + 4 <= n && plo >= 4 && plo + nch * KC + 4 <= k &&
+                                lda >= 33 && ldb >= 33 && ((lda - 1) & 1) == 0 && ((ldb - 1) & 1) == 0 &&
+                                ((reinterpret_cast<uintptr_t>(A + kua + i0 + (lda - 1) * plo) & 15u) == 0) &&
+                                ((reinterpret_cast<uintptr_t>(B + kub + plo + (ldb - 1) * j0) & 15u) == 0);
+                if (!ok) return false;
+            }
+            return true;
+        };
+        const int64_t scan = gx < 64 ? gx : 64;
+        int64_t lo = 0, hi = gx;
+        while (lo < scan && !block_all_interior(lo)) ++lo;
+        bool have_interior = false;
+        if (lo < scan) {
+            while (hi > lo + 1 && gx - hi < scan && !block_all_interior(hi - 1)) --hi;
+            // one more column block goes to the corner kernel at the far end: a 32x32 block's last 8-wide chunk may reach up
+            // to 7 columns of p beyond the end of its 64x64 tile's 16-wide chunks
+            if (hi > lo + 1 && block_all_interior(hi - 1) && m % 32 == 0 && n % 32 == 0 && (kua & 1) == 0 && (kub & 1) == 0) {
+                a.cb_lo = lo;
+                a.cb_hi0 = hi - 1;
+                have_interior = true;
+            }
+        }
+        if (have_interior) {
+            const int64_t saved_lo = a.cb_lo, saved_hi = a.cb_hi0;
+            const int64_t dlo = -((kuc + 31) / 32), dhi = (klc + 31) / 32;
+            const int64_t items = (m / 32) * (dhi - dlo + 1);
+            int64_t ctas = (items + WA_WARPS - 1) / WA_WARPS;
+            if (variant == 31 && ctas > (int64_t)h->sm_count * 3) ctas = (int64_t)h->sm_count * 3;   // persistent
+            const int64_t gxw = ctas < 1048576 ? ctas : 1048576;
+            dim3 grid_wa((unsigned)gxw, (unsigned)((ctas + gxw - 1) / gxw));
+            static std::atomic<int> cfg_wa[2] = {};
+            if (variant == 32) {
+                const size_t smem = (size_t)WA_WARPS * 4 * WA_STAGE * sizeof(double);
+                if (!(cfg_wa[1] & (1 << h->device))) {
+                    LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_wa_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    cfg_wa[1] |= (1 << h->device);
+                }
+                // interior blocks only: the kernel skips the corner column blocks [0, cb_lo) and [cb_hi0, gx)
+                gbmm_dmma_wa_kernel<4><<<grid_wa, 32 * WA_WARPS, smem, h->stream>>>(a);
+            } else {
+                const size_t smem = (size_t)WA_WARPS * 3 * WA_STAGE * sizeof(double);
+                if (!(cfg_wa[0] & (1 << h->device))) {
+                    LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_wa_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    cfg_wa[0] |= (1 << h->device);
+                }
+                gbmm_dmma_wa_kernel<3><<<grid_wa, 32 * WA_WARPS, smem, h->stream>>>(a);
+            }
+            LBM_LAUNCH_CHECK(h, "gbmm_dmma_wa_kernel");
+            a.cb_lo = saved_lo;
+            a.cb_hi0 = saved_hi;
+        }
+        // corner column blocks (all of them when no interior range was found): the plain zero-filling kernel
+        const int64_t total_c = (a.cb_lo + (gx - a.cb_hi0)) * gy;
+        const int64_t gcx = total_c < 1048576 ? total_c : 1048576;
+        const dim3 grid_c((unsigned)(gcx > 0 ? gcx : 1), (unsigned)(total_c > 0 ? (total_c + gcx - 1) / gcx : 1));
+        const size_t smemc = (size_t)2 * STAGE_DBL * sizeof(double);
+        static std::atomic<int> cfg_corner2{0};
+        if (!(cfg_corner2 & (1 << h->device))) {
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<2, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
+            LBM_CUDA(h, cudaFuncSetAttribute(gbmm_dmma_kernel<2, 5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc));
+            cfg_corner2 |= (1 << h->device);
+        }
+        if (have_interior) {
+            if (total_c > 0) gbmm_dmma_kernel<2, 5, 2><<<grid_c, NT, smemc, h->stream>>>(a);
+        } else {
+            gbmm_dmma_kernel<2, 5, 0><<<grid, NT, smemc, h->stream>>>(a);   // every tile through the general kernel
+        }
+    } else if (variant == 0 || (variant >= 20 && variant <= 29)) {
         // warp-specialised interior kernel + the corner instantiation of the plain kernel
         // 20: 3-stage / 4 CTAs, 21: 3-stage / 3 CTAs, 22: 4-stage / 3 CTAs, 23: 2-stage / 4 CTAs
         static std::atomic<int> cfg_ws[10] = {};

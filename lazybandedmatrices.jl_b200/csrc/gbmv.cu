@@ -41,6 +41,7 @@ struct GbmvArgs {
     int64_t ntiles;
     int stages;
     int64_t sA_elems, sx_elems;  // per-stage smem capacity in elements (multiples of 16B)
+    int64_t skew;    // experiment: start every bulk copy this many elements (a multiple of 16 B) before its natural aligned start
 };
 
 // ------------------------------------------------------------------------------------------
@@ -95,9 +96,11 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
     auto issue = [&](int64_t t, int s) {  // thread 0 only
         int64_t o0, o1, c0, c1, x0, x1;
         ranges(t, o0, o1, c0, c1, x0, x1);
-        const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        if (e0a >= a.skew) e0a -= a.skew;
+        if (x0a >= a.skew) x0a -= a.skew;
         const int64_t cntA = c1 * a.lda - e0a;
-        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
         const int64_t cntx = x1 - x0a;
         T *sA = sbase + (int64_t)s * stage_elems;
         T *sx = sA + a.sA_elems;
@@ -121,8 +124,10 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         const int64_t t = first + k * step;
         int64_t o0, o1, c0, c1, x0, x1;
         ranges(t, o0, o1, c0, c1, x0, x1);
-        const int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
-        const int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
+        int64_t x0a = x0 & ~(int64_t)(EPV - 1);
+        if (e0a >= a.skew) e0a -= a.skew;
+        if (x0a >= a.skew) x0a -= a.skew;
         const T *sA = sbase + (int64_t)s * stage_elems;
         const T *sx = sA + a.sA_elems;
 
@@ -869,9 +874,10 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         a.alpha = alpha; a.beta = beta; a.A = A; a.x = x; a.y = y;
         // Tuned on B200 (profiles/sweep_r01.jsonl): ~33-39 KB stages, 2-deep ring, and as many
         // CTAs per SM as keep ~200 KB of bulk copies in flight per SM.
+        a.skew = h->tune.gbmv_skew > 0 ? round_up(h->tune.gbmv_skew, EPV) : 0;
         auto stage_elems = [&](int64_t tl, int64_t &sa, int64_t &sx) {
-            sa = round_up((tl + kl + ku) * lda + EPV, EPV);
-            sx = round_up(tl + kl + ku + EPV, EPV);
+            sa = round_up((tl + kl + ku) * lda + EPV + a.skew, EPV);
+            sx = round_up(tl + kl + ku + EPV + a.skew, EPV);
         };
         int64_t sa, sx;
         int64_t tile = h->tune.gbmv_tile;

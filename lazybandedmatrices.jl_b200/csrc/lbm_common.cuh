@@ -22,6 +22,7 @@ struct lbm_tuning {
     int64_t gbmv_tile;        // outputs per tile (0 = auto)
     int64_t gbmv_stages;      // smem ring depth (0 = auto)
     int64_t gbmv_ctas_per_sm; // persistent grid = SMs * this (0 = auto)
+    int64_t gbmv_skew;        // experiment knob (elements): see GbmvArgs::skew
     int64_t gbmv_force;       // 0 auto, 1 direct, 2 narrow-stream, 3 wide-stream, 4 wide-T warp kernel (no ring)
     // gbmv wide (column-streaming) kernel
     int64_t gbmvw_chunk;      // columns per chunk (0 = auto)

@@ -54,13 +54,15 @@ def test_gbmm_dmma_tensor_path(L, oracle):
         (64, 64, 64, 1, 1, 1, 1, 2), (129, 67, 200, 16, 0, 0, 16, 2), (500, 500, 500, 64, 10, 10, 64, 2), (5, 5, 5, 4, 4, 4, 4, 2),
         # raw-staged interior tiles with asymmetric bands (odd lda, even ku: aligned) and an unaligned variant (odd ku)
         (900, 850, 920, 40, 36, 34, 50, 0), (900, 900, 900, 41, 35, 35, 49, 0), (1500, 1500, 1500, 200, 56, 16, 100, 0),
+        # sizes with an interior range for the warp-autonomous kernel (m, n multiples of 32, even ku): symmetric wide, asymmetric
+        (4096, 4096, 4096, 128, 128, 128, 128, 0), (2048, 2048, 2048, 40, 36, 34, 50, 0), (3072, 3072, 3072, 200, 56, 16, 100, 0),
     ]
     for s, (m, n, k, kla, kua, klb, kub, force) in enumerate(cases):
         A_np, A = _band(L, oracle, m, k, kla, kua, 31 + s, torch.float64)
         B_np, B = _band(L, oracle, k, n, klb, kub, 32 + s, torch.float64)
         want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
         tol = tol_rows(np.float64, min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
-        for f, variant in ((force, 0), (force, 1), (force, 2), (force, 3), (force, 4), (force, 5), (force, 3), (force, 6), (force, 7), (force, 10), (force, 11), (force, 21), (force, 22), (force, 24), (force, 25), (force, 26), (1, 0)):
+        for f, variant in ((force, 0), (force, 1), (force, 2), (force, 3), (force, 4), (force, 5), (force, 3), (force, 6), (force, 7), (force, 10), (force, 11), (force, 21), (force, 22), (force, 24), (force, 25), (force, 26), (force, 30), (force, 31), (force, 32), (1, 0)):
             h.set_tuning(gbmm_force=f, gbmm_variant=variant)
             try:
                 before = h.launch_count()
