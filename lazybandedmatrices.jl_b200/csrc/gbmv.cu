@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         ranges(t, o0, o1, c0, c1, x0, x1);
         int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
         int64_t x0a = x0 & ~(int64_t)(EPV - 1);
-        if (e0a >= a.skew) e0a -= a.skew;
-        if (x0a >= a.skew) x0a -= a.skew;
+        if (a.skew > 0 && e0a >= a.skew) e0a -= a.skew;
+        if (a.skew > 0 && x0a >= a.skew) x0a -= a.skew;
         const int64_t cntA = c1 * a.lda - e0a;
         const int64_t cntx = x1 - x0a;
         T *sA = sbase + (int64_t)s * stage_elems;
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + stage_bytes_bulk<T>(cntx));
         stage_issue<T>(sA, a.A + e0a, cntA, &bars[s]);
         stage_issue<T>(sx, a.x + x0a, cntx, &bars[s]);
+        if (a.skew < 0) __nanosleep((unsigned)(-a.skew));   // experiment: pace the issuing thread (gbmv_skew < 0 = ns)
         mbar_arrive(&bars[s]);
     };
 
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         ranges(t, o0, o1, c0, c1, x0, x1);
         int64_t e0a = (c0 * a.lda) & ~(int64_t)(EPV - 1);
         int64_t x0a = x0 & ~(int64_t)(EPV - 1);
-        if (e0a >= a.skew) e0a -= a.skew;
-        if (x0a >= a.skew) x0a -= a.skew;
+        if (a.skew > 0 && e0a >= a.skew) e0a -= a.skew;
+        if (a.skew > 0 && x0a >= a.skew) x0a -= a.skew;
         const T *sA = sbase + (int64_t)s * stage_elems;
         const T *sx = sA + a.sA_elems;
 
@@ -874,13 +875,20 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         a.alpha = alpha; a.beta = beta; a.A = A; a.x = x; a.y = y;
         // Tuned on B200 (profiles/sweep_r01.jsonl): ~33-39 KB stages, 2-deep ring, and as many
         // CTAs per SM as keep ~200 KB of bulk copies in flight per SM.
-        a.skew = h->tune.gbmv_skew > 0 ? round_up(h->tune.gbmv_skew, EPV) : 0;
+        a.skew = h->tune.gbmv_skew > 0 ? round_up(h->tune.gbmv_skew, EPV) : h->tune.gbmv_skew;
+        const int64_t slack = a.skew > 0 ? a.skew : 0;
         auto stage_elems = [&](int64_t tl, int64_t &sa, int64_t &sx) {
-            sa = round_up((tl + kl + ku) * lda + EPV + a.skew, EPV);
-            sx = round_up(tl + kl + ku + EPV + a.skew, EPV);
+            sa = round_up((tl + kl + ku) * lda + EPV + slack, EPV);
+            sx = round_up(tl + kl + ku + EPV + slack, EPV);
         };
         int64_t sa, sx;
         int64_t tile = h->tune.gbmv_tile;
+        // Three stored diagonals, Float64 (the metric's l = u = 1 point and every rank's (0,2) / (2,0) slab of its row shards):
+        // FOUR single-stage CTAs per SM with 1280-row tiles instead of three 2-stage ones.  Measured on one B200 at n = 2^24..2^27
+        // (benchmarks/rect_probe.py, profiles/rect_probe_r02.md): the default was 3-8 % slower on the (0,2) / (2,0) slabs -- whose
+        // bulk copies start on exact 8 KB multiples -- than on (1,1); this setting is within 1 % of the best for all three shapes.
+        const bool three_diag = sizeof(T) == 8 && nb <= 3 && h->tune.gbmv_tile <= 0 && h->tune.gbmv_stages <= 0 && h->tune.gbmv_ctas_per_sm <= 0;
+        if (three_diag) tile = 1280;
         if (tile <= 0) {
             tile = GBMV_NT;
             for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {
@@ -899,10 +907,10 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         a.sA_elems = sa;
         a.sx_elems = sx;
         const int64_t stage_bytes = (sa + sx) * (int64_t)sizeof(T);
-        int64_t stages = h->tune.gbmv_stages > 0 ? h->tune.gbmv_stages : 2;
+        int64_t stages = h->tune.gbmv_stages > 0 ? h->tune.gbmv_stages : (three_diag ? 1 : 2);
         if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
         int64_t ctas = h->tune.gbmv_ctas_per_sm > 0 ? h->tune.gbmv_ctas_per_sm
-                                                    : (200 * 1024) / (stages * stage_bytes + 256);
+                                                    : (three_diag ? 4 : (200 * 1024) / (stages * stage_bytes + 256));
         if (ctas < 1) ctas = 1;
         if (ctas > 8) ctas = 8;
         // fit ctas * (128 + stages*stage_bytes) into the SM's shared memory
