@@ -96,6 +96,36 @@ def main():
                 h.set_tuning(gbmv_skew=0)
             del data, A, x, y
             torch.cuda.empty_cache()
+    if "P" in only:
+        # programmatic dependent launch off (0, default) / on (1) at the sizes one rank of an 8-GPU job runs
+        g = 8192
+        D = L.banded_from_diagonals(g, {0: -2.0, 1: 1.0, -1: 1.0})
+        A1 = L.banded_from_diagonals(1024, {0: -2.0, 1: 1.0, -1: 1.0})
+        Lap = L.KronSum(A1, D)
+        xk = torch.rand(1024 * g, dtype=torch.float64, device="cuda")
+        yk = torch.empty_like(xk)
+        n = 1 << 24
+        G1, G8 = L.brand(n, n, 1, 1), L.brand(n, n, 8, 8)
+        xg = torch.rand(n, dtype=torch.float64, device="cuda")
+        yg = torch.empty_like(xg)
+        nt = 1 << 25
+        S = L.SymTridiagonal(torch.rand(nt, dtype=torch.float64, device="cuda"), torch.rand(nt - 1, dtype=torch.float64, device="cuda"))
+        xt = torch.rand(nt, dtype=torch.float64, device="cuda")
+        yt = torch.empty_like(xt)
+        for rep in range(2):
+            for pdl in (0, 1):
+                h.set_tuning(pdl=pdl)
+                tag = "pdl on" if pdl == 1 else "pdl off"
+                emit(f"kronsum 1024x8192 {tag}", timeit(lambda: Lap.mul_(yk, xk)), 16 * 1024 * g)
+                emit(f"gbmv n=2^24 l=u=1 {tag}", timeit(lambda: L.mul_(yg, G1, xg)), 8 * n * 5)
+                emit(f"gbmv n=2^24 l=u=8 {tag}", timeit(lambda: L.mul_(yg, G8, xg)), 8 * n * 19)
+                emit(f"symtridiag n=2^25 {tag}", timeit(lambda: L.mul_(yt, S, xt)), 32 * nt)
+                # ping-pong: each apply reads what the previous one wrote (the dependency PDL must respect)
+                def pp():
+                    L.mul_(yg, G1, xg)
+                    L.mul_(xg, G1, yg)
+                emit(f"gbmv n=2^24 l=u=1 ping-pong pair {tag}", timeit(pp, 100, 10) / 2, 8 * n * 5)
+        h.set_tuning(pdl=0)
     if "T" in only:
         for log2n in (25, 28):
             n = 1 << log2n

@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(GBMV_NT) gbmv_tile_kernel(const GbmvArgs<T> a,
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    pdl_launch_dependents();   // the next launch in the stream may start placing its CTAs as ours retire ...
     __syncthreads();
+    pdl_wait();                // ... and we touch no global memory before our own predecessor has completed
 
     // tiles of this CTA: t = blockIdx.x + k*gridDim.x
     const int64_t first = blockIdx.x;
@@ -797,7 +799,7 @@ int launch_tile(lbm_handle_t h, const GbmvArgs<T> &a, int grid, size_t smem, con
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         configured_dev_mask.fetch_or(1 << h->device, std::memory_order_release);
     }
-    kern<<<grid, GBMV_NT, smem, h->stream>>>(a, hf);
+    LBM_CUDA(h, lbm_launch_pdl(h, kern, dim3(grid), dim3(GBMV_NT), smem, a, hf));
     LBM_LAUNCH_CHECK(h, "gbmv_tile_kernel");
     return 0;
 }

@@ -162,7 +162,7 @@ int64_t lbm_launch_count(lbm_handle_t h) { return h ? h->launches : -1; }
 #define LBM_TUNE_KEYS(X)                                                                                       \
     X(gbmv_tile) X(gbmv_stages) X(gbmv_ctas_per_sm) X(gbmv_force) X(gbmv_skew) X(gbmvw_chunk) X(gbmvw_stages)               \
     X(gbmvw_ctas_per_sm) X(tri_ctas_per_sm) X(tri_force_scalar) X(tri_force_shuffle) X(tri_tile) X(tri_stages) X(kron_tr) X(kron_tc) X(kron_stages) X(kron_ctas_per_sm) X(kron_force_tile) X(gbmm_force) X(gbmm_tile) X(gbmm_variant) \
-    X(chain_tile) X(chain_force_generic) X(chain_variant) X(exchange_mode) X(exchange_fuse) X(halo_timeout_ms)
+    X(chain_tile) X(chain_force_generic) X(chain_variant) X(exchange_mode) X(exchange_fuse) X(halo_timeout_ms) X(pdl)
 
 int lbm_set_tuning(lbm_handle_t h, const char *key, int64_t value) {
     if (!h) return -1;

@@ -186,7 +186,9 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();
 
     const int64_t step = gridDim.y;
     const int64_t mine = (int64_t)blockIdx.y < a.nchunks ? (a.nchunks - blockIdx.y + step - 1) / step : 0;
@@ -403,7 +405,7 @@ int kron_ring_launch4(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         configured_dev_mask |= (1 << h->device);
     }
-    kern<<<grid, 256, smem, h->stream>>>(a, hf);
+    LBM_CUDA(h, lbm_launch_pdl(h, kern, grid, dim3(256), smem, a, hf));
     LBM_LAUNCH_CHECK(h, "kron_ring_kernel");
     return 0;
 }
@@ -426,6 +428,12 @@ int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_
 }
 
 // returns true (and the launch status in *rc) when the ring kernel took the call
+// rows per strip of the ring kernel (tuning knob kron_tr: 256 / 512 / 1024); also the unit of the fused exchange's flag words
+static inline int64_t kron_ring_tr(lbm_handle_t h) {
+    const int64_t t = h->tune.kron_tr > 0 ? h->tune.kron_tr : 512;
+    return t >= 1024 ? 1024 : t >= 512 ? 512 : 256;
+}
+
 template <typename T>
 bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t kua, const T *A, int64_t lda,
                    int64_t klb, int64_t kub, const T *B, int64_t ldb, T alpha, const T *x, T beta, T *y, int *rc,
@@ -447,25 +455,32 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     a.n1 = n1; a.n2 = n2; a.kla = (int)kla; a.kua = (int)kua; a.klb = (int)klb; a.kub = (int)kub;
     a.lda = lda; a.ldb = ldb; a.A = A; a.B = B; a.alpha = alpha; a.beta = beta; a.x = x; a.y = y;
     a.n1_in = n1_in; a.xoff = xoff; a.c_begin = c_begin; a.c_end = c_end; a.prod = prod; a.batch_stride = batch_stride;
-    int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
-    tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
-    // columns per chunk: 16 for full-size grids; a per-rank slice of <= 2048 grid columns (what one rank of an 8-GPU job
-    // holds of the 8192^2 Laplacian) runs 15 % faster with 8 -- twice the chunks per CTA to fill the ring with
-    // (benchmarks/small_kernels.py: n1 = 1024: 34.1 -> 28.8 us)
-    int64_t g = h->tune.kron_tc > 0 ? h->tune.kron_tc : ((c_end - c_begin) <= 2048 ? 8 : 16);
-    if (g > c_end - c_begin) g = c_end - c_begin;
-    if (g * nba > 256) g = 256 / nba;  // one A coefficient per thread per chunk
+    const int64_t tr = kron_ring_tr(h);
     const int64_t hmax = klb > kub ? klb : kub;
     a.hp = (int)((hmax + EPV - 1) / EPV * EPV);
     a.tr = (int)tr;
     a.seg = (int)(tr + 2 * a.hp);
-    int64_t stages = h->tune.kron_stages > 0 ? h->tune.kron_stages : 2;
+    // Defaults from benchmarks/kron_ab.py (graph replay, alternating rounds, 8192-row slabs of 512 ... 8192 grid columns,
+    // profiles/kron_ab_r02.jsonl): 512-row strips, ~25 KB stages (4 columns + halo for the f64 Laplacian), a 2-stage ring
+    // and THREE CTAs per SM are the best or within 1.5 % of it at every slab width from 1024 columns up (8192: 195 -> 174.5 us,
+    // 94 % of the copy ceiling; 1024, one rank of eight: 37.8 -> 27.1 us); 4 CTAs/SM is 25-50 % slower at every width, as
+    // are 16-column chunks.  Slabs of <= 512 columns have too few chunks per CTA for a ring: one 8-column stage, 4 CTAs/SM.
+    const int64_t ncols = c_end - c_begin;
+    int64_t g = h->tune.kron_tc;
+    if (g <= 0) {
+        g = 24960 / ((int64_t)a.seg * (int64_t)sizeof(T)) - (kla + kua);
+        g = g >= 8 ? 8 : 4;
+        if (ncols <= 512) g *= 2;
+    }
+    if (g > ncols) g = ncols;
+    if (g * nba > 256) g = 256 / nba;  // one A coefficient per thread per chunk
+    int64_t stages = h->tune.kron_stages > 0 ? h->tune.kron_stages : (ncols <= 512 ? 1 : 2);
     const int64_t sm_smem = 227 * 1024;
     auto stage_bytes = [&](int64_t gg) { return (gg + kla + kua) * (int64_t)a.seg * (int64_t)sizeof(T); };
     while (g > 2 && stages * stage_bytes(g) + 4096 > sm_smem) g /= 2;
     a.g = (int)g;
-    a.nchunks = (c_end - c_begin + g - 1) / g;
-    int64_t cps = h->tune.kron_ctas_per_sm > 0 ? h->tune.kron_ctas_per_sm : (200 * 1024) / (stages * stage_bytes(g) + 256);
+    a.nchunks = (ncols + g - 1) / g;
+    int64_t cps = h->tune.kron_ctas_per_sm > 0 ? h->tune.kron_ctas_per_sm : (ncols <= 512 ? 4 : 3);
     if (cps < 1) cps = 1;
     if (cps > 8) cps = 8;
     while (stages > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --stages;
@@ -600,8 +615,7 @@ int kronsum_sharded(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t
     int fused = 0;
     // one flag word per row strip of the ring kernel (same `tr` rule as kron_ring_try; uniform across ranks); when the
     // strips do not fit the flag block everybody uses ONE word and the unfused exchange
-    int64_t tr = h->tune.kron_tr > 0 ? h->tune.kron_tr : 256;
-    tr = tr >= 1024 ? 1024 : tr >= 512 ? 512 : 256;
+    const int64_t tr = kron_ring_tr(h);
     const int64_t nstrips = (n2 + tr - 1) / tr;
     const int nflags = nstrips <= 4096 ? (int)nstrips : 1;
     if (nflags == 1 && nstrips > 1) overlap = overlap ? 2 : 0;   // 2: overlapped but never fused

@@ -43,6 +43,7 @@ struct lbm_tuning {
     int64_t chain_tile;
     int64_t chain_force_generic;
     int64_t exchange_mode;    // multi-GPU ghost exchange: 0 auto (peer mailboxes when connected), 1 force NCCL send/recv
+    int64_t pdl;              // programmatic dependent launch of the streaming kernels: 0 auto (OFF, see lbm_launch_pdl), 1 on
     int64_t exchange_fuse;    // 0 auto (exchange fused into the compute launch when the kernel supports it), 2 never fuse
     int64_t halo_timeout_ms;  // wall-clock bound of a ghost-flag wait on the device (0 = default 30 s)
     int64_t chain_variant;    // 0 auto (= 4 when covered), 1 split-column register kernel, 2/3 transposed-smem kernel, 4 warp-autonomous TMA kernel
@@ -118,7 +119,37 @@ struct lbm_device_guard {
 static inline bool lbm_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 #ifdef __CUDACC__
+// Launch with programmatic dependent launch allowed: when the PREVIOUS kernel in the stream is one of ours and has executed
+// griddepcontrol.launch_dependents, this grid's CTAs may become resident while the previous grid drains -- launch latency, CTA
+// scheduling and the barrier / table set-up overlap its tail.  The kernel executes griddepcontrol.wait before it touches any
+// global memory a predecessor may have written (x, y, the mailboxes); a predecessor that never signals (any other kernel)
+// serialises as usual.
+// MEASURED (benchmarks/kron_small_probe.py, small_kernels.py P): no gain at per-rank sizes (37.1 vs 37.6 us) and a 25-30 % LOSS
+// at full size (8192^2 Laplacian 195 -> 253 us): the kernels are one-wave persistent grids that rely on the block scheduler
+// spreading CTAs evenly over 148 idle SMs; dependents placed as the predecessor's CTAs retire pile up on the SMs that free
+// first.  Hence OFF unless tuning knob pdl = 1.
+template <typename... KArgs, typename... Args>
+cudaError_t lbm_launch_pdl(lbm_handle_t h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = h->tune.pdl == 1 ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
+#ifdef __CUDACC__
 namespace lbm {
+
+// see lbm_launch_pdl
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ bool lbm_aligned16_dev(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

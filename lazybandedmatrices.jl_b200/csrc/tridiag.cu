@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(TRI_NT) tridiag_ring_kernel(const TriRingArgs<
         for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();
     const int64_t first = blockIdx.x, step = gridDim.x;
     const int64_t mine = first < a.ntiles ? (a.ntiles - first + step - 1) / step : 0;
     const int64_t noff = a.n - 1;  // length of the off-diagonals actually read
@@ -265,7 +267,7 @@ int launch_tri_ring2(lbm_handle_t h, const TriRingArgs<T> &a, int grid, size_t s
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         configured_dev_mask |= (1 << h->device);
     }
-    kern<<<grid, TRI_NT, smem, h->stream>>>(a, hf);
+    LBM_CUDA(h, lbm_launch_pdl(h, kern, dim3(grid), dim3(TRI_NT), smem, a, hf));
     LBM_LAUNCH_CHECK(h, "tridiag_ring_kernel");
     return 0;
 }
