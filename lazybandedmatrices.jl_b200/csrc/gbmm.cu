@@ -123,7 +123,7 @@ int gbmm_impl(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64_t 
 
     // gbmm_force: 0 auto, 1 generic diagonal-wise kernel, 2 DMMA, 3 register kernel; the register kernel wants enough
     // columns to fill the machine (C1's n = 10^4 stays on the latency-optimised diagonal-wise kernel)
-    if (h->tune.gbmm_force == 3 || (h->tune.gbmm_force == 0 && n >= 256 * (int64_t)h->sm_count)) {
+    if (h->tune.gbmm_force == 3 || h->tune.gbmm_force == 4 || (h->tune.gbmm_force == 0 && n >= 256 * (int64_t)h->sm_count)) {
         bool handled = false;
         int rc = lbm_gbmm_reg<T>(h, m, n, k, alpha, kla, kua, A, lda, klb, kub, B, ldb, beta, klc, kuc, C, ldc, &handled);
         if (handled) return rc;

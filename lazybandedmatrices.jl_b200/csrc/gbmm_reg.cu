@@ -84,6 +84,26 @@ __device__ __forceinline__ void load_run(T *dst, const T *p) {
     if ((N - PAR) & 1) dst[N - 1] = p[N - 1];
 }
 
+// the same with a RUN-TIME count n <= N: pair positions stay compile-time (register indices static), each pair is a vector
+// load when it lies wholly inside the run, a scalar at the ragged end, zeros beyond
+template <typename T, int N, int PAR>
+__device__ __forceinline__ void load_run_rt(T *dst, const T *p, int n) {
+    using V = typename vec2<T>::type;
+    if (PAR) dst[0] = 0 < n ? p[0] : (T)0;
+#pragma unroll
+    for (int r = PAR; r + 1 < N; r += 2) {
+        if (r + 1 < n) {
+            const V v = *reinterpret_cast<const V *>(p + r);
+            dst[r] = v.x;
+            dst[r + 1] = v.y;
+        } else {
+            dst[r] = r < n ? p[r] : (T)0;
+            dst[r + 1] = (T)0;
+        }
+    }
+    if ((N - PAR) & 1) dst[N - 1] = N - 1 < n ? p[N - 1] : (T)0;
+}
+
 template <typename T, int NAT, int NBT>
 struct GrGeom {
     static constexpr int NCT = NAT + NBT - 1;
@@ -105,7 +125,12 @@ struct GrGeom {
     static constexpr size_t SMEM_BYTES = (size_t)SM_ELEMS * sizeof(T) + 16;   // + the mbarrier
 };
 
-template <typename T, int NAT, int NBT, int PADODD>
+// RT (run-time row counts): NA <= NAT, NB <= NBT are NOT the template's.  Shared memory then keeps the operands in THEIR
+// OWN HBM layout (column pitch NA, NB, NA+NB-1 instead of NAT, NBT, NCT), so tight operands still arrive and leave as 1-D
+// bulk TMA copies; the register loop is the template's, with the rows r >= NA (s >= NB) read as zero by predicated scalar
+// loads.  This is what every (NA, NB) without an exact instantiation runs: unequal counts, 8 and 16 rows.  Round 1 padded
+// those to the template pitch with element-wise cp.async (45-54 % of the copy ceiling).
+template <typename T, int NAT, int NBT, int PADODD, int RT>
 __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kernel(const GrArgs<T> a) {
     using G = GrGeom<T, NAT, NBT>;
     using V = typename vec2<T>::type;
@@ -118,11 +143,14 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
 
     const int tid = threadIdx.x;
     const int NA = a.kla + a.kua + 1, NB = a.klb + a.kub + 1;
+    // shared-memory column pitches.  A C pitch that is a multiple of 8 elements would put every lane's accumulator store on
+    // the same banks (16-way): one element of skew, and that tile leaves through the element-wise store instead of the bulk one
+    const int PA = RT ? NA : NAT, PB = RT ? NB : NBT, PC = RT ? (NA + NB - 1) + (((NA + NB - 1) & 7) == 0 ? 1 : 0) : NCT;
     const int64_t ntiles = (a.n + GR_TC - 1) / GR_TC;
-    const bool tight_in = a.lda == NAT && a.ldb == NBT && lbm_aligned16_dev(a.A) && lbm_aligned16_dev(a.B);
+    const bool tight_in = a.lda == PA && a.ldb == PB && lbm_aligned16_dev(a.A) && lbm_aligned16_dev(a.B);
     const int nbc = a.klc + a.kuc + 1;
     const int off = a.kuc - a.kua - a.kub;                         // C band row of accumulator 0
-    const bool tight_out = nbc == NCT && a.ldc == NCT && off == 0 && a.beta == (T)0 && lbm_aligned16_dev(a.C);
+    const bool tight_out = nbc == PC && a.ldc == PC && off == 0 && a.beta == (T)0 && lbm_aligned16_dev(a.C);
     uint32_t parity = 0;
 
     if (tid == 0) {
@@ -139,13 +167,14 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
         // interior tile: every staged slot is inside the matrix, no index tests needed
         interior = cols == GR_TC && p0 - a.kua >= 0 && p0 + SA_COLS - 1 + a.kla < a.m && p0 + SA_COLS - 1 < a.k &&
                    j0 + GR_TC - 1 + a.klb < a.k;
-        tma_in = interior && tight_in && ((p0 * NAT * (int64_t)sizeof(T)) & 15) == 0;
+        tma_in = interior && tight_in && ((p0 * PA * (int64_t)sizeof(T)) & 15) == 0;
     };
     auto request = [&](int64_t j0) {                               // thread 0 only
         gr_fence_proxy_async();                                    // earlier generic-proxy accesses of this smem are ordered first
-        mbar_expect_tx(bar, (uint32_t)((G::SA_ELEMS + G::SB_ELEMS) * sizeof(T)));
-        bulk_g2s(sA, a.A + (j0 - a.kub - a.pad) * a.lda, (uint32_t)(G::SA_ELEMS * sizeof(T)), bar);
-        bulk_g2s(sB, a.B + j0 * a.ldb, (uint32_t)(G::SB_ELEMS * sizeof(T)), bar);
+        const uint32_t ba = (uint32_t)(SA_COLS * PA * (int)sizeof(T)), bb = (uint32_t)(GR_TC * PB * (int)sizeof(T));
+        mbar_expect_tx(bar, ba + bb);
+        bulk_g2s(sA, a.A + (j0 - a.kub - a.pad) * a.lda, ba, bar);
+        bulk_g2s(sB, a.B + j0 * a.ldb, bb, bar);
     };
 
     bool requested = false;                                        // PIPE: this tile's operands were requested a tile ago
@@ -183,7 +212,7 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
                         const int64_t p = p0 + c, i = p + r - a.kua;
                         ok = p >= 0 && p < a.k && i >= 0 && i < a.m;
                     }
-                    cp_async_elem<T>(sA_u + (uint32_t)((c * NAT + r) * (int)sizeof(T)), ok ? Ag + (r + lda32 * c) : a.A, ok);
+                    cp_async_elem<T>(sA_u + (uint32_t)((c * PA + r) * (int)sizeof(T)), ok ? Ag + (r + lda32 * c) : a.A, ok);
                     r += dr;
                     c += dc;
                     if (r >= NA) { r -= NA; ++c; }
@@ -198,14 +227,14 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
                         const int64_t p = j0 + c + r - a.kub;
                         ok = p >= 0 && p < a.k;
                     }
-                    cp_async_elem<T>(sB_u + (uint32_t)((c * NBT + r) * (int)sizeof(T)), ok ? Bg + (r + ldb32 * c) : a.B, ok);
+                    cp_async_elem<T>(sB_u + (uint32_t)((c * PB + r) * (int)sizeof(T)), ok ? Bg + (r + ldb32 * c) : a.B, ok);
                     r += dr;
                     c += dc;
                     if (r >= NB) { r -= NB; ++c; }
                 }
             }
             // ... and zeros in the NAT-NA (NBT-NB) padding rows of the template
-            if (NA < NAT) {
+            if (!RT && NA < NAT) {
                 const int np = NAT - NA, dc = GR_NT / np, dr = GR_NT - dc * np;
                 int c = tid / np, r = tid - c * np;
                 for (int e = tid; e < SA_COLS * np; e += GR_NT) {
@@ -215,7 +244,7 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
                     if (r >= np) { r -= np; ++c; }
                 }
             }
-            if (NB < NBT) {
+            if (!RT && NB < NBT) {
                 const int np = NBT - NB, dc = GR_NT / np, dr = GR_NT - dc * np;
                 int c = tid / np, r = tid - c * np;
                 for (int e = tid; e < GR_TC * np; e += GR_NT) {
@@ -242,7 +271,35 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
             T acc0[NCT], acc1[NCT];
 #pragma unroll
             for (int t = 0; t < NCT; ++t) acc0[t] = acc1[t] = (T)0;
-            {
+            if (RT) {
+                // run-time pitches: scalar loads, rows beyond the real counts read as zero (compile-time register indices)
+                const int cp = 2 * (tid + sub * GR_NT);
+                const T *pa = sA + (cp + a.pad) * PA;
+                const T *pb = sB + cp * PB;
+#pragma unroll
+                for (int q = 0; q <= NBT; ++q) {
+                    if (q > NB) break;                             // warp-uniform
+                    T av[NAT];
+                    // element index (cp+pad+q)*NA + r is even <=> odd NA: pad + q + r even; even NA: r even
+                    if (RT == 2) {
+                        if ((NA & 1) && ((q + PADODD) & 1)) load_run_rt<T, NAT, 1>(av, pa + q * PA, NA);
+                        else load_run_rt<T, NAT, 0>(av, pa + q * PA, NA);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NAT; ++r) av[r] = r < NA ? pa[q * PA + r] : (T)0;
+                    }
+                    const T b0 = q < NB ? pb[q] : (T)0;
+                    const T b1 = q >= 1 ? pb[PB + q - 1] : (T)0;
+                    if (q < NBT) {
+#pragma unroll
+                        for (int r = 0; r < NAT; ++r) acc0[r + q] = fma(av[r], b0, acc0[r + q]);
+                    }
+                    if (q >= 1) {
+#pragma unroll
+                        for (int r = 0; r < NAT; ++r) acc1[r + q - 1] = fma(av[r], b1, acc1[r + q - 1]);
+                    }
+                }
+            } else {
                 const int cp = 2 * (tid + sub * GR_NT);            // first column of this thread's pair
                 const T *pa = sA + (cp + a.pad) * NAT;             // slab column of (cp, s = 0); column cp + q starts q*NAT further on
                 const T *pb = sB + cp * NBT;                       // [B column cp (NBT values) | B column cp+1]
@@ -291,7 +348,17 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
             if (!G::PIPE) __syncthreads();                         // all reads of sA / sB done: sC (aliased) may overwrite them
 
             // ---- the C tile, HBM layout: [column cp (NCT values) | column cp+1], written as 2-element vectors ----
-            {
+            if (RT) {
+                const T sc = tma_out ? a.alpha : (T)1;
+                T *pc = sC + 2 * (tid + sub * GR_NT) * PC;
+#pragma unroll
+                for (int t = 0; t < NCT; ++t) {
+                    if (t < PC) {
+                        pc[t] = sc * acc0[t];
+                        pc[PC + t] = sc * acc1[t];
+                    }
+                }
+            } else {
                 const T sc = tma_out ? a.alpha : (T)1;             // the bulk store cannot scale: do it here
                 T *pc = sC + 2 * (tid + sub * GR_NT) * NCT;
 #pragma unroll
@@ -325,7 +392,7 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
         T *Cg = a.C + j0 * a.ldc;
         if (tma_out) {
             if (tid == 0) {
-                gr_bulk_s2g(Cg, sC, (uint32_t)(G::SC_ELEMS * sizeof(T)));
+                gr_bulk_s2g(Cg, sC, (uint32_t)(GR_TC * PC * (int)sizeof(T)));
                 gr_bulk_commit();
             }
         } else {
@@ -344,7 +411,7 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
                     in = i >= 0 && i < a.m;
                 }
                 T v = (T)0;
-                if ((unsigned)t < (unsigned)NC && in) v = sC[c * NCT + t];
+                if ((unsigned)t < (unsigned)NC && in) v = sC[c * PC + t];
                 T *dst = Cg + (row + ldc32 * c);
                 if (a.beta == (T)0) *dst = a.alpha * v;
                 else if (in) *dst = fma(a.beta, *dst, a.alpha * v);
@@ -357,13 +424,13 @@ __global__ void __launch_bounds__(GR_NT, gr_min_blocks(NAT, NBT)) gbmm_reg_kerne
     if (tid == 0) gr_bulk_wait0();                                 // smem must outlive the last bulk store
 }
 
-template <typename T, int NAT, int NBT>
+template <typename T, int NAT, int NBT, int RT = 0>
 int gr_launch(lbm_handle_t h, const GrArgs<T> &a) {
     using G = GrGeom<T, NAT, NBT>;
     static_assert((G::SA_ELEMS * sizeof(T)) % 16 == 0 && (G::SB_ELEMS * sizeof(T)) % 16 == 0 && (G::SC_ELEMS * sizeof(T)) % 16 == 0,
                   "bulk copy sizes must be multiples of 16 bytes");
     constexpr size_t smem = G::SMEM_BYTES;
-    auto kern = (a.pad & 1) ? gbmm_reg_kernel<T, NAT, NBT, 1> : gbmm_reg_kernel<T, NAT, NBT, 0>;
+    auto kern = (RT != 1 && (a.pad & 1)) ? gbmm_reg_kernel<T, NAT, NBT, RT == 1 ? 0 : 1, RT> : gbmm_reg_kernel<T, NAT, NBT, 0, RT>;
     static std::atomic<int> configured[2] = {};
     if (!(configured[a.pad & 1] & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -380,12 +447,26 @@ int gr_launch(lbm_handle_t h, const GrArgs<T> &a) {
     return 0;
 }
 
+// run-time-count variant: vector loads (RT = 2) for f64 except the widest NA < NB pairs, scalar loads (RT = 1) for f32 and
+// those (benchmarks/sweep_gbmm.py, profiles/sweep_gbmm_r02.jsonl: scalar wins every f32 shape by 1-18 points; f64 vector
+// wins by up to 8 except (11..15, 13..17) with NA < NB, where scalar wins by 1-8)
+template <typename T, int NAT, int NBT>
+int gr_launch_rt(lbm_handle_t h, const GrArgs<T> &a, int NA, int NB) {
+    if (sizeof(T) == 8 && !(NAT == 17 && NBT == 17 && NA >= 11 && NB > NA)) return gr_launch<T, NAT, NBT, 2>(h, a);
+    return gr_launch<T, NAT, NBT, 1>(h, a);
+}
+
 template <typename T, int NAT>
-int gr_dispatch_b(lbm_handle_t h, const GrArgs<T> &a, int NB) {
-    if (NB <= 3) return gr_launch<T, NAT, 3>(h, a);
-    if (NB <= 5) return gr_launch<T, NAT, 5>(h, a);
-    if (NB <= 9) return gr_launch<T, NAT, 9>(h, a);
-    return gr_launch<T, NAT, 17>(h, a);
+int gr_dispatch_b(lbm_handle_t h, const GrArgs<T> &a, int NA, int NB) {
+    // exact template counts: vector loads, compile-time pitches; anything else: the run-time-count variant (tuning knob
+    // gbmm_force = 4 keeps round 1's zero-padded staging for comparison) ...
+    // ... except 8 / 16 rows in either factor: with a 64- / 128-byte column pitch every lane of a warp reads the same banks
+    // whatever the thread-to-column map (measured 0.22 / 0.14 of the ceiling run-time vs 0.54 / 0.58 padded to 9 / 17)
+    const bool pad = h->tune.gbmm_force == 4 || NA % 8 == 0 || NB % 8 == 0;
+    if (NB <= 3) return (NA == NAT && NB == 3) || pad ? gr_launch<T, NAT, 3>(h, a) : gr_launch_rt<T, NAT, 3>(h, a, NA, NB);
+    if (NB <= 5) return (NA == NAT && NB == 5) || pad ? gr_launch<T, NAT, 5>(h, a) : gr_launch_rt<T, NAT, 5>(h, a, NA, NB);
+    if (NB <= 9) return (NA == NAT && NB == 9) || pad ? gr_launch<T, NAT, 9>(h, a) : gr_launch_rt<T, NAT, 9>(h, a, NA, NB);
+    return (NA == NAT && NB == 17) || pad ? gr_launch<T, NAT, 17>(h, a) : gr_launch_rt<T, NAT, 17>(h, a, NA, NB);
 }
 
 }  // namespace
@@ -423,10 +504,10 @@ int lbm_gbmm_reg(lbm_handle_t h, int64_t m, int64_t n, int64_t k, T alpha, int64
     if (NA == NB && NA == 10) return gr_launch<T, 10, 10>(h, a);
     if (NA == NB && NA == 12) return gr_launch<T, 12, 12>(h, a);
     if (NA == NB && NA == 14) return gr_launch<T, 14, 14>(h, a);
-    if (NA <= 3) return gr_dispatch_b<T, 3>(h, a, (int)NB);
-    if (NA <= 5) return gr_dispatch_b<T, 5>(h, a, (int)NB);
-    if (NA <= 9) return gr_dispatch_b<T, 9>(h, a, (int)NB);
-    return gr_dispatch_b<T, 17>(h, a, (int)NB);
+    if (NA <= 3) return gr_dispatch_b<T, 3>(h, a, (int)NA, (int)NB);
+    if (NA <= 5) return gr_dispatch_b<T, 5>(h, a, (int)NA, (int)NB);
+    if (NA <= 9) return gr_dispatch_b<T, 9>(h, a, (int)NA, (int)NB);
+    return gr_dispatch_b<T, 17>(h, a, (int)NA, (int)NB);
 }
 
 template int lbm_gbmm_reg<double>(lbm_handle_t, int64_t, int64_t, int64_t, double, int64_t, int64_t, const double *, int64_t,

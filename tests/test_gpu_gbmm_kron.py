@@ -121,7 +121,10 @@ def test_gbmm_register_kernel(L, oracle, dt):
              (3000, 3000, 3000, 2, 4, 5, 1), (3000, 3000, 3000, 10, 0, 3, 7),
              # exact instantiations for equal EVEN row counts 2, 4, 6, 10, 12, 14 (A*A', triangular bands, bidiagonal-like)
              (3000, 3000, 3000, 0, 1, 1, 0), (3000, 3100, 2900, 1, 0, 0, 1), (3000, 3000, 3000, 1, 2, 2, 1), (3000, 3000, 3000, 3, 2, 1, 4),
-             (3000, 3000, 3000, 5, 4, 4, 5), (2900, 3000, 3100, 6, 5, 5, 6), (3000, 3000, 3000, 0, 13, 13, 0), (3000, 3000, 3000, 4, 3, 3, 4)]
+             (3000, 3000, 3000, 5, 4, 4, 5), (2900, 3000, 3100, 6, 5, 5, 6), (3000, 3000, 3000, 0, 13, 13, 0), (3000, 3000, 3000, 4, 3, 3, 4),
+             # no exact instantiation (8 / 16 rows, unequal counts): the run-time-count variant, operands in HBM layout, bulk TMA
+             (3000, 3000, 3000, 3, 4, 4, 3), (3100, 2900, 3000, 8, 7, 7, 8), (3000, 3000, 3000, 3, 3, 1, 1), (3000, 3000, 3000, 1, 2, 2, 3),
+             (5000, 5000, 5000, 2, 3, 6, 3), (3000, 3000, 3000, 0, 0, 8, 8), (3000, 3000, 3000, 8, 8, 0, 1), (2600, 2700, 2800, 7, 8, 0, 0)]
     for s, (m, n, k, kla, kua, klb, kub) in enumerate(cases):
         A_np, A = _band(L, oracle, m, k, kla, kua, 61 + s, dt)
         B_np, B = _band(L, oracle, k, n, klb, kub, 62 + s, dt)
@@ -148,6 +151,43 @@ def test_gbmm_register_kernel(L, oracle, dt):
     inside = (i >= 0) & (i < n)
     assert np.max(np.abs(np.where(inside, got - want, 0.0))) <= tol_rows(NP[dt], 9, 1.0, 1.0)
     assert np.all(got[~inside] == 0.0)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_gbmm_register_kernel_runtime_counts_nan_poisoned(L, oracle, dt):
+    """Shapes without an exact instantiation, tight leading dimensions, NaN in every out-of-matrix slot: the run-time-count
+    variant (bulk TMA on interior tiles, index-masked cp.async on the edge tiles) and round 1's zero-padded staging
+    (gbmm_force = 4) both match the oracle."""
+    h = L.handle_for(0)
+    for s_, (n, kla, kua, klb, kub) in enumerate([(6000, 4, 3, 3, 4), (6000, 2, 1, 5, 5), (4100, 8, 7, 8, 7), (5000, 0, 5, 9, 0)]):
+        A_np = oracle.brand(n, n, kla, kua, seed=90 + s_, dtype=NP[dt])
+        B_np = oracle.brand(n, n, klb, kub, seed=95 + s_, dtype=NP[dt])
+        want = oracle.gbmm(n, n, n, A_np, kla, kua, B_np, klb, kub)
+
+        def poison(M, l, u):
+            P = M.copy()
+            r = np.arange(l + u + 1)[:, None]
+            i = np.arange(n)[None, :] + r - u
+            P[(i < 0) | (i >= n)] = np.nan
+            return L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(P.T)).cuda(), n, l, u)
+
+        A, B = poison(A_np, kla, kua), poison(B_np, klb, kub)
+        for force in (3, 4):
+            h.set_tuning(gbmm_force=force)
+            try:
+                C = A @ B
+                torch.cuda.synchronize()
+            finally:
+                h.set_tuning(gbmm_force=0)
+            got = np.asfortranarray(C.data.cpu().numpy().T)
+            l, u = kla + klb, kua + kub
+            r = np.arange(l + u + 1)[:, None]
+            i = np.arange(n)[None, :] + r - u
+            inside = (i >= 0) & (i < n)
+            assert not np.isnan(got).any(), (force, kla, kua, klb, kub)
+            tol = tol_rows(NP[dt], min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
+            assert np.max(np.abs(np.where(inside, got - want, 0.0))) <= tol, (force, kla, kua, klb, kub)
+            assert np.all(got[~inside] == 0.0)
 
 
 def test_gbmm_register_kernel_alpha_beta_padded_nan(L, oracle):
