@@ -170,7 +170,7 @@ __device__ __noinline__ void kron_halo_patch(const HaloFuse &hf, T *st, int64_t 
 // holds ghost columns) come last, and those chunks overwrite the ghost columns of their stage -- rows [rs,re) of this
 // CTA's strip only -- in shared memory from the local mailbox.
 template <typename T, int NBA, int NBB, int RPT, bool HALO>
-__global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a, const __grid_constant__ HaloFuse hf) {
+__global__ void __launch_bounds__(256, HALO ? 2 : 0) kron_ring_kernel(const KronRingArgs<T> a, const __grid_constant__ HaloFuse hf) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     T *sbase = reinterpret_cast<T *>(smem_raw + 128);
@@ -194,10 +194,35 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
     const int64_t mine = (int64_t)blockIdx.y < a.nchunks ? (a.nchunks - blockIdx.y + step - 1) / step : 0;
     // logical chunk L = blockIdx.y + kk*step; physical chunk = L+1 (mod nchunks) when HALO.  All code below works on
     // physical chunk numbers: chunk_of(kk).
+    // HALO: the rotation is chosen so that the two ghost-touching chunks (physical 0 and nchunks-1) are the LAST chunks of
+    // the two CTAs with the highest blockIdx.y -- the ones that own one chunk fewer than the others whenever the chunks do
+    // not divide evenly -- and the push / flag duty goes to a third such CTA: the exchange work then sits on CTAs that
+    // would otherwise idle at the end instead of on the ones that finish last.
+    int64_t rot = 1;      // physical = (logical + rot) mod nchunks
+    int ypush = 0;
+    if (HALO && !(hf.on & 2) && step >= 2 && a.nchunks >= step) {
+        const int64_t m1 = (a.nchunks - (step - 1) + step - 1) / step, m2 = (a.nchunks - (step - 2) + step - 1) / step;
+        if (m1 == m2) {
+            const int64_t L1 = (step - 1) + (m1 - 1) * step;   // last logical chunk of CTA step-1; CTA step-2 ends at L1 - 1
+            rot = a.nchunks - L1;
+            if (step >= 3) ypush = (int)step - 3;
+        }
+    }
     auto chunk_of = [&](int64_t kk) -> int64_t {
         const int64_t L = blockIdx.y + kk * step;
-        return (HALO && !(hf.on & 2)) ? (L + 1 < a.nchunks ? L + 1 : 0) : L;
+        if (!(HALO && !(hf.on & 2))) return L;
+        const int64_t q = L + rot;
+        return q >= a.nchunks ? q - a.nchunks : q;
     };
+    // trailing chunks of this CTA whose stage holds ghost columns (see the two loops at the end)
+    int64_t ntail = 0;
+    if (HALO && !(hf.on & 4)) {
+        while (ntail < mine && ntail < 2) {
+            const int64_t q = chunk_of(mine - 1 - ntail);
+            if (q == 0 || q + 1 == a.nchunks) ++ntail;
+            else break;
+        }
+    }
     // rows staged per grid column: [rs, re) (both 16-byte aligned: n2 % EPV == 0)
     const int64_t rs = r0 - a.hp > 0 ? r0 - a.hp : 0;
     const int64_t re = r0 + a.tr + a.hp < a.n2 ? r0 + a.tr + a.hp : a.n2;
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
     // STRIP-WISE push (rides on the latency of the prologue copies): the CTA (strip, 0) sends rows [r0, r0+tr) of this
     // rank's boundary grid columns -- all the neighbour's CTAs of the same strip need -- and publishes the epoch in the
     // strip's own flag word, so no CTA ever moves more than a few KB and nobody waits for rows it does not use.
-    if (HALO && blockIdx.y == 0) {
+    if (HALO && (int)blockIdx.y == ypush) {
         const int64_t rows = (r0 + a.tr < a.n2 ? r0 + a.tr : a.n2) - r0;
 #pragma unroll
         for (int sd = 0; sd < 2; ++sd) {
@@ -243,10 +268,17 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
                 halo_copy(hf.push_src[sd] + c * colbytes + r0 * (int64_t)sizeof(T), hf.push_dst[sd] + c * colbytes + r0 * (int64_t)sizeof(T),
                           rows * (int64_t)sizeof(T), tid, 256);
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0 && hf.push_flag[0]) st_release_sys(hf.push_flag[0] + blockIdx.x, hf.epoch);
-        if (tid == 1 && hf.push_flag[1]) st_release_sys(hf.push_flag[1] + blockIdx.x, hf.epoch);
+        // The flags are published AFTER this CTA's first chunk (below): by then the peer stores above have long been
+        // acknowledged, so the system-scope fence costs nothing; fencing here held all 256 threads for a NVLink round trip
+        // (~3 us of a 28 us kernel, on exactly the CTAs that then finish last).  The neighbour needs the ghosts only for
+        // ITS last chunks.  Exception: a CTA whose FIRST chunk already waits for the neighbour (slabs of one or two chunks)
+        // must publish before it waits, or the pair would wait for each other.
+        if (mine <= ntail) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0 && hf.push_flag[0]) st_release_sys(hf.push_flag[0] + blockIdx.x, hf.epoch);
+            if (tid == 1 && hf.push_flag[1]) st_release_sys(hf.push_flag[1] + blockIdx.x, hf.epoch);
+        }
     }
 
     // A coefficients of a chunk's columns, ca[cc][t] = A[c, c-kla+t] (zero outside the matrix):
@@ -290,7 +322,10 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
     const bool row_edge = r0 + a.tr > a.n2;  // partial strip: some threads own no row
     __syncthreads();  // sCA[0] and the zeroed halo rows visible
 
-    for (int64_t kk = 0; kk < mine; ++kk) {
+    // With the exchange fused in, the chunks whose stage holds ghost columns are the LAST one or two of the CTAs that own
+    // them (rotation above).  They run in a second copy of the chunk body, so the streaming loop proper carries no exchange
+    // code at all: with the patch call inside the one loop the allocator spilled 64 bytes in it (19 % slower at every size).
+    auto do_chunk = [&](const int64_t kk, const bool patch) {
         const int s = (int)(kk % S);
         const uint32_t parity = (uint32_t)((kk / S) & 1);
         const int64_t q = chunk_of(kk);
@@ -304,7 +339,7 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         mbar_wait(&bars[s], parity);
         // only the first / last chunk of the rank's column range can hold ghost columns: one cheap uniform test here, the
         // wait + patch itself out of line so that it does not touch the register allocation of the streaming loop
-        if (HALO && !(hf.on & 4) && (q == 0 || q + 1 == a.nchunks))
+        if (HALO && patch)
             kron_halo_patch<T>(hf, const_cast<T *>(st), c0 + a.xoff - a.kla, a.g + a.kla + a.kua, a.n1_in, a.seg, roff + (int)(r0 - rs), r0,
                                (int)((r0 + a.tr < a.n2 ? r0 + a.tr : a.n2) - r0), a.n2, (int)blockIdx.x);
         const int seg = a.seg;
@@ -393,37 +428,97 @@ __global__ void __launch_bounds__(256) kron_ring_kernel(const KronRingArgs<T> a,
         if (kk + 1 < mine && tid < ncoef) sCA[((kk + 1) & 1) * ncoef + tid] = cnext;
         __syncthreads();
         if (tid < 32 && kk + S < mine) issue(chunk_of(kk + S), s);
-    }
-    if (HALO && blockIdx.y == 0) halo_final_wait(hf, tid, blockIdx.x);
+        if (HALO && kk == 0 && (int)blockIdx.y == ypush && mine > ntail) {
+            // every thread's payload stores precede the barrier above; one thread per side fences at system scope and
+            // releases the strip's flag word (warp 2: not the warp that issues the bulk copies)
+            if (tid == 64 && hf.push_flag[0]) {
+                __threadfence_system();
+                st_release_sys(hf.push_flag[0] + blockIdx.x, hf.epoch);
+            }
+            if (tid == 65 && hf.push_flag[1]) {
+                __threadfence_system();
+                st_release_sys(hf.push_flag[1] + blockIdx.x, hf.epoch);
+            }
+        }
+    };
+    for (int64_t kk = 0; kk < mine - ntail; ++kk) do_chunk(kk, false);
+    if (HALO)
+        for (int64_t kk = mine - ntail; kk < mine; ++kk) do_chunk(kk, true);
+    if (HALO && (int)blockIdx.y == ypush) halo_final_wait(hf, tid, blockIdx.x);
 }
 
+// Chunk width, ring depth and CTAs per SM are chosen HERE, per instantiation, because they depend on how many CTAs the
+// register file admits (wider bands and the fused-exchange variant need > 85 registers: two resident CTAs, not three; a grid
+// sized for three would run a second partial wave).
+// Defaults from benchmarks/kron_ab.py (graph replay, alternating rounds, 8192-row slabs of 512 ... 8192 grid columns,
+// profiles/kron_ab_r02.jsonl): 512-row strips; with three resident CTAs ~25 KB stages (4 columns + halo for the f64
+// Laplacian) in a 2-stage ring are the best or within 1.5 % of it at every slab width from 1024 columns up (8192: 195 ->
+// 174.5 us, 94 % of the copy ceiling; 1024, one rank of eight: 37.8 -> 27.1 us); with two, twice the stage.  4 CTAs/SM is
+// 25-50 % slower at every width, as are 16-column chunks.  Slabs of <= 512 columns have too few chunks per CTA for a ring:
+// one 8-column stage, 4 CTAs/SM.
 template <typename T, int NBA, int NBB, int RPT, bool HALO>
-int kron_ring_launch4(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem, const HaloFuse &hf) {
+int kron_ring_launch4(lbm_handle_t h, KronRingArgs<T> a, int64_t batch, const HaloFuse &hf) {
     static std::atomic<int> configured_dev_mask{0};
+    static std::atomic<int> reg_ctas{0};
     auto kern = kron_ring_kernel<T, NBA, NBB, RPT, HALO>;
     if (!(configured_dev_mask & (1 << h->device))) {
         LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+        cudaFuncAttributes fa;
+        LBM_CUDA(h, cudaFuncGetAttributes(&fa, kern));
+        const int per_cta = ((fa.numRegs + 7) / 8 * 8) * 256;
+        reg_ctas = per_cta > 0 ? 65536 / per_cta : 1;
         configured_dev_mask |= (1 << h->device);
     }
+    const int64_t occ = reg_ctas < 1 ? 1 : (int64_t)reg_ctas;
+    const int64_t ncols = a.c_end - a.c_begin, nh = a.kla + a.kua;
+    int64_t cps = h->tune.kron_ctas_per_sm > 0 ? h->tune.kron_ctas_per_sm : (ncols <= 512 ? 4 : 3);
+    if (cps > occ) cps = occ;
+    if (cps < 1) cps = 1;
+    if (cps > 8) cps = 8;
+    int64_t g = h->tune.kron_tc;
+    if (g <= 0) {
+        const int64_t target = cps >= 3 ? 24960 : cps == 2 ? 41600 : 100000;   // bytes per stage
+        g = target / ((int64_t)a.seg * (int64_t)sizeof(T)) - nh;
+        g = g >= 16 ? 16 : g >= 8 ? 8 : 4;
+        if (ncols <= 512 && g < 16) g *= 2;
+    }
+    if (g > ncols) g = ncols;
+    if (g * NBA > 256) g = 256 / NBA;  // one A coefficient per thread per chunk
+    int64_t stages = h->tune.kron_stages > 0 ? h->tune.kron_stages : (ncols <= 512 ? 1 : 2);
+    const int64_t sm_smem = 227 * 1024;
+    auto stage_bytes = [&](int64_t gg) { return (gg + nh) * (int64_t)a.seg * (int64_t)sizeof(T); };
+    while (g > 2 && stages * stage_bytes(g) + 4096 > sm_smem) g /= 2;
+    while (stages > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --stages;
+    while (cps > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --cps;
+    a.g = (int)g;
+    a.nchunks = (ncols + g - 1) / g;
+    a.stages = (int)stages;
+    const int64_t nstrips = (a.n2 + a.tr - 1) / a.tr;
+    int64_t phases = ((int64_t)h->sm_count * cps) / (nstrips * batch);  // floor: every CTA resident, one wave
+    if (phases > a.nchunks) phases = a.nchunks;
+    if (phases > 65535) phases = 65535;
+    if (phases < 1) phases = 1;   // batched slices: one CTA per (strip, slice) walks all its chunks, several waves
+    dim3 grid((unsigned)nstrips, (unsigned)phases, (unsigned)batch);
+    const size_t smem = (size_t)(128 + stages * stage_bytes(g) + 2 * g * NBA * (int64_t)sizeof(T));
     LBM_CUDA(h, lbm_launch_pdl(h, kern, grid, dim3(256), smem, a, hf));
     LBM_LAUNCH_CHECK(h, "kron_ring_kernel");
     return 0;
 }
 
 template <typename T, int NBA, int NBB, int RPT>
-int kron_ring_launch3(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem, const HaloFuse *hf) {
-    if (hf) return kron_ring_launch4<T, NBA, NBB, RPT, true>(h, a, grid, smem, *hf);
+int kron_ring_launch3(lbm_handle_t h, const KronRingArgs<T> &a, int64_t batch, const HaloFuse *hf) {
+    if (hf) return kron_ring_launch4<T, NBA, NBB, RPT, true>(h, a, batch, *hf);
     HaloFuse none;
     none.on = 0;
-    return kron_ring_launch4<T, NBA, NBB, RPT, false>(h, a, grid, smem, none);
+    return kron_ring_launch4<T, NBA, NBB, RPT, false>(h, a, batch, none);
 }
 
 template <typename T, int NBA, int NBB>
-int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, dim3 grid, size_t smem, const HaloFuse *hf) {
+int kron_ring_launch2(lbm_handle_t h, const KronRingArgs<T> &a, int64_t batch, const HaloFuse *hf) {
     switch (a.tr / 256) {
-        case 1: return kron_ring_launch3<T, NBA, NBB, 1>(h, a, grid, smem, hf);
-        case 2: return kron_ring_launch3<T, NBA, NBB, 2>(h, a, grid, smem, hf);
-        default: return kron_ring_launch3<T, NBA, NBB, 4>(h, a, grid, smem, hf);
+        case 1: return kron_ring_launch3<T, NBA, NBB, 1>(h, a, batch, hf);
+        case 2: return kron_ring_launch3<T, NBA, NBB, 2>(h, a, batch, hf);
+        default: return kron_ring_launch3<T, NBA, NBB, 4>(h, a, batch, hf);
     }
 }
 
@@ -460,50 +555,17 @@ bool kron_ring_try(lbm_handle_t h, int64_t n1, int64_t n2, int64_t kla, int64_t 
     a.hp = (int)((hmax + EPV - 1) / EPV * EPV);
     a.tr = (int)tr;
     a.seg = (int)(tr + 2 * a.hp);
-    // Defaults from benchmarks/kron_ab.py (graph replay, alternating rounds, 8192-row slabs of 512 ... 8192 grid columns,
-    // profiles/kron_ab_r02.jsonl): 512-row strips, ~25 KB stages (4 columns + halo for the f64 Laplacian), a 2-stage ring
-    // and THREE CTAs per SM are the best or within 1.5 % of it at every slab width from 1024 columns up (8192: 195 -> 174.5 us,
-    // 94 % of the copy ceiling; 1024, one rank of eight: 37.8 -> 27.1 us); 4 CTAs/SM is 25-50 % slower at every width, as
-    // are 16-column chunks.  Slabs of <= 512 columns have too few chunks per CTA for a ring: one 8-column stage, 4 CTAs/SM.
-    const int64_t ncols = c_end - c_begin;
-    int64_t g = h->tune.kron_tc;
-    if (g <= 0) {
-        g = 24960 / ((int64_t)a.seg * (int64_t)sizeof(T)) - (kla + kua);
-        g = g >= 8 ? 8 : 4;
-        if (ncols <= 512) g *= 2;
-    }
-    if (g > ncols) g = ncols;
-    if (g * nba > 256) g = 256 / nba;  // one A coefficient per thread per chunk
-    int64_t stages = h->tune.kron_stages > 0 ? h->tune.kron_stages : (ncols <= 512 ? 1 : 2);
-    const int64_t sm_smem = 227 * 1024;
-    auto stage_bytes = [&](int64_t gg) { return (gg + kla + kua) * (int64_t)a.seg * (int64_t)sizeof(T); };
-    while (g > 2 && stages * stage_bytes(g) + 4096 > sm_smem) g /= 2;
-    a.g = (int)g;
-    a.nchunks = (ncols + g - 1) / g;
-    int64_t cps = h->tune.kron_ctas_per_sm > 0 ? h->tune.kron_ctas_per_sm : (ncols <= 512 ? 4 : 3);
-    if (cps < 1) cps = 1;
-    if (cps > 8) cps = 8;
-    while (stages > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --stages;
-    while (cps > 1 && cps * (stages * stage_bytes(g) + 4096) > sm_smem) --cps;
-    a.stages = (int)stages;
-    const int64_t nstrips = (n2 + tr - 1) / tr;
-    int64_t phases = ((int64_t)h->sm_count * cps) / (nstrips * batch);  // floor: every CTA resident, one wave
-    if (phases > a.nchunks) phases = a.nchunks;
-    if (phases > 65535) phases = 65535;
-    if (phases < 1) phases = 1;   // batched slices: one CTA per (strip, slice) walks all its chunks, several waves
-    dim3 grid((unsigned)nstrips, (unsigned)phases, (unsigned)batch);
-    const size_t smem = (size_t)(128 + stages * stage_bytes(g) + 2 * g * nba * (int64_t)sizeof(T));
-    if (nba == 3 && nbb == 3) *rc = kron_ring_launch2<T, 3, 3>(h, a, grid, smem, hf);
-    else if (nba == 1 && nbb == 3) *rc = kron_ring_launch2<T, 1, 3>(h, a, grid, smem, hf);
-    else if (nba == 3 && nbb == 1) *rc = kron_ring_launch2<T, 3, 1>(h, a, grid, smem, hf);
-    else if (nba == 5 && nbb == 5) *rc = kron_ring_launch2<T, 5, 5>(h, a, grid, smem, hf);
-    else if (nba == 3 && nbb == 5) *rc = kron_ring_launch2<T, 3, 5>(h, a, grid, smem, hf);
-    else if (nba == 5 && nbb == 3) *rc = kron_ring_launch2<T, 5, 3>(h, a, grid, smem, hf);
-    else if (nba == 5 && nbb == 1) *rc = kron_ring_launch2<T, 5, 1>(h, a, grid, smem, hf);
-    else if (nba == 1 && nbb == 5) *rc = kron_ring_launch2<T, 1, 5>(h, a, grid, smem, hf);
-    else if (nba == 9 && nbb == 9) *rc = kron_ring_launch2<T, 9, 9>(h, a, grid, smem, hf);
-    else if (nba == 9 && nbb == 1) *rc = kron_ring_launch2<T, 9, 1>(h, a, grid, smem, hf);
-    else *rc = kron_ring_launch2<T, 1, 9>(h, a, grid, smem, hf);
+    if (nba == 3 && nbb == 3) *rc = kron_ring_launch2<T, 3, 3>(h, a, batch, hf);
+    else if (nba == 1 && nbb == 3) *rc = kron_ring_launch2<T, 1, 3>(h, a, batch, hf);
+    else if (nba == 3 && nbb == 1) *rc = kron_ring_launch2<T, 3, 1>(h, a, batch, hf);
+    else if (nba == 5 && nbb == 5) *rc = kron_ring_launch2<T, 5, 5>(h, a, batch, hf);
+    else if (nba == 3 && nbb == 5) *rc = kron_ring_launch2<T, 3, 5>(h, a, batch, hf);
+    else if (nba == 5 && nbb == 3) *rc = kron_ring_launch2<T, 5, 3>(h, a, batch, hf);
+    else if (nba == 5 && nbb == 1) *rc = kron_ring_launch2<T, 5, 1>(h, a, batch, hf);
+    else if (nba == 1 && nbb == 5) *rc = kron_ring_launch2<T, 1, 5>(h, a, batch, hf);
+    else if (nba == 9 && nbb == 9) *rc = kron_ring_launch2<T, 9, 9>(h, a, batch, hf);
+    else if (nba == 9 && nbb == 1) *rc = kron_ring_launch2<T, 9, 1>(h, a, batch, hf);
+    else *rc = kron_ring_launch2<T, 1, 9>(h, a, batch, hf);
     return true;
 }
 
