@@ -149,3 +149,24 @@ def test_julia_shim_calls_have_the_declared_argument_counts():
                     checked.add(name)
     missing = sorted(set(sigs) - checked)
     assert not missing, f"entry points bound in the @sig table but never used by a method of the shim: {missing}"
+
+
+def test_integration_md_index_is_the_shim():
+    """INTEGRATION.md's dispatch table is generated from the shim (julia/gen_index.py): it must be up to date, and every entry
+    point of the header must be reachable from some method of the shim it lists."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_index", os.path.join(root, "lazybandedmatrices.jl_b200", "julia", "gen_index.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = mod.rows()
+    doc = open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()
+    block = doc[doc.index("<!-- BEGIN INDEX -->"):doc.index("<!-- END INDEX -->")]
+    have = [ln for ln in block.splitlines() if ln.startswith("| `LBMB200.jl:")]
+    assert have == want, "INTEGRATION.md index is stale: python lazybandedmatrices.jl_b200/julia/gen_index.py --write"
+    names = set(re.findall(r"`(lbm_[?a-z0-9_]+)`", "\n".join(want)))
+    gen = _gen_sigs()
+    missing = [h for h in gen.header_signatures() if h not in names and re.sub(r"^lbm_[ds]", "lbm_?", h) not in names]
+    assert not missing, missing
