@@ -437,7 +437,7 @@ def run_b200(args):
         try:
             with open(tpath) as fh:
                 traffic = json.load(fh).get(f"gbmv_l{l}_n2^{args.log2n or LOG2N}_gpus{world}")
-                traffic_src = "constant from the committed ncu --set full capture (profiles/gbmv_r01_ncu_summary.md), not measured in this run"
+                traffic_src = "constant from the committed ncu --set full capture (profiles/ncu_M_r02.md), not measured in this run"
         except Exception:
             traffic = None
     configs = []

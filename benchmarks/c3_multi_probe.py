@@ -63,7 +63,8 @@ for reps in (20, 200):
     run("sharded, two-kernel exchange", lambda: sh.mul_(y, xb), reps)
     h.set_tuning(exchange_mode=0, exchange_fuse=0)
     run("local operator of the same slab, no neighbours (KronSum.mul_)", lambda: loc.mul_(yl, xl), reps)
-for tc, st, cps in ((4, 2, 3), (8, 1, 3), (8, 2, 2), (8, 1, 4), (16, 1, 2)):
+cfgs = [tuple(int(v) for v in c.split(":")) for c in os.environ.get("C3_CFGS", "4:2:3,8:1:3,8:2:2,8:1:4,16:1:2").split(",")]
+for tc, st, cps in cfgs:
     h.set_tuning(kron_tc=tc, kron_stages=st, kron_ctas_per_sm=cps)
     run(f"sharded, fused exchange, tc={tc} stages={st} cps={cps}", lambda: sh.mul_(y, xb), 200)
 h.set_tuning(kron_tc=0, kron_stages=0, kron_ctas_per_sm=0)

@@ -102,5 +102,41 @@ elif which == "MM":
     for _ in range(2):
         L.mul_(Y.t(), A, X.t())
         M.mul_(Y[0], X[0])
+elif which == "RT":
+    # banded x banded without an exact instantiation: the run-time-count variant of the register kernel
+    n = 1 << 24
+    for (la, ua, lb, ub) in ((3, 3, 1, 1), (5, 5, 8, 8)):
+        A = L.brand(n, n, la, ua, seed=1)
+        B = L.brand(n, n, lb, ub, seed=2)
+        Cm = L.BandedMatrix(torch.empty((n, la + ua + lb + ub + 1), dtype=torch.float64, device="cuda"), n, la + lb, ua + ub)
+        for _ in range(2):
+            L.gbmm(A, B, out=Cm)
+        del A, B, Cm
+elif which == "SV":
+    n = 1 << 26
+    d = torch.rand(n, dtype=torch.float64, device="cuda") + 4
+    e = torch.rand(n - 1, dtype=torch.float64, device="cuda")
+    b = torch.rand(n, dtype=torch.float64, device="cuda")
+    x = torch.empty_like(b)
+    S = L.SymTridiagonal(d, e)
+    for _ in range(2):
+        S.solve(b, out=x, check=False)
+elif which == "C3S":
+    # the 1024-column slab one rank of eight holds, plain and with the fused-exchange instantiation (no neighbours)
+    g, n1 = 8192, 1024
+    from lbm_b200.shard import RowShard, ShardedKronSum
+    D = L.banded_from_diagonals(g, {0: -2.0, 1: 1.0, -1: 1.0})
+    A = L.banded_from_diagonals(n1, {0: -2.0, 1: 1.0, -1: 1.0})
+    p = RowShard.plan(n1, 1, 1, 0, 1)
+    sh = ShardedKronSum(n1, g, 1, 1, A.data[p.c0:p.c1].contiguous(), D, 0, 1)
+    xb = sh.new_buffer(torch.float64, torch.device("cuda", 0))
+    xb.uniform_()
+    y = torch.empty((p.m_loc, g), dtype=torch.float64, device="cuda")
+    h = L.handle_for(0)
+    for fuse in (0, 3):
+        h.set_tuning(exchange_fuse=fuse)
+        for _ in range(2):
+            sh.mul_(y, xb)
+    h.set_tuning(exchange_fuse=0)
 torch.cuda.synchronize()
 print("ok")
