@@ -38,3 +38,11 @@ for name, fn in (("lbm_dgbmv_multi (one pass over A)", lambda: L.mul_(Y.t(), A, 
     ms = timeit(fn)
     print(json.dumps({"config": f"MM banded*dense f64 n=2^22 l=u=128 nrhs=8, {name}", "ms": round(ms, 3), "GBs": round(byts / ms / 1e6, 1),
                       "frac_hbm_measured": round(byts / ms / 1e6 / PEAK, 3)}), flush=True)
+# op T (A' * X): gbmv_wide_t_multi_kernel (round 2) vs column by column
+for chunk, stages, cps in ((0, 0, 0), (32, 2, 0), (32, 3, 1), (64, 2, 0), (64, 3, 0), (32, 4, 0)):
+    h.set_tuning(gbmvw_chunk=chunk, gbmvw_stages=stages, gbmvw_ctas_per_sm=cps)
+    ms = timeit(lambda: L.mul_(Y.t(), A.T, X.t()))
+    print(json.dumps({"config": f"MM wide multi op T chunk={chunk} stages={stages} ctas={cps}", "ms": round(ms, 3), "frac_hbm_measured": round(byts / ms / 1e6 / PEAK, 3)}), flush=True)
+h.set_tuning(gbmvw_chunk=0, gbmvw_stages=0, gbmvw_ctas_per_sm=0)
+ms = timeit(lambda: [L.mul_(Y[c], A.T, X[c]) for c in range(nrhs)])
+print(json.dumps({"config": "MM op T column by column (8 gbmv launches)", "ms": round(ms, 3), "frac_hbm_measured": round(byts / ms / 1e6 / PEAK, 3)}), flush=True)

@@ -501,6 +501,103 @@ __global__ void __launch_bounds__(256) gbmv_wide_t_ring_kernel(const GbmvWideArg
     }
 }
 
+// The same for R right-hand sides (mul!(C, A', B::Matrix) with wide bands; round 1 ran it column by column: R passes over A).
+// One slab of A and R x-windows per stage; a lane keeps R accumulators for its column, so every value of A read from shared
+// memory feeds R FMAs ((R+1)/R shared-memory reads per FMA instead of 2) and A crosses HBM once per R columns.
+template <typename T, int R>
+__global__ void __launch_bounds__(256) gbmv_wide_t_multi_kernel(const GbmvWideMultiArgs<T> am) {
+    const GbmvWideArgs<T> &a = am.w;
+    constexpr int EPV = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sbase = reinterpret_cast<T *>(smem_raw + 128);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.stages;
+    const int sxe = (int)a.sx_elems;
+    const int64_t stage_elems = a.sA_elems + R * a.sx_elems;
+    const int C = a.chunk;
+    const int nb = (int)(a.kl + a.ku + 1);
+
+    const int64_t J0 = (int64_t)blockIdx.x * a.run;            // run is a multiple of EPV
+    const int64_t J1 = J0 + a.run < a.n ? J0 + a.run : a.n;
+    if (J0 >= J1) return;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int64_t nchunks = (J1 - J0 + C - 1) / C;
+
+    auto issue = [&](int64_t q, int s) {  // thread 0 only
+        const int64_t cb = J0 + q * C;
+        const int64_t cq = cb + C < J1 ? C : J1 - cb;
+        int64_t x0 = cb - a.ku > 0 ? cb - a.ku : 0;
+        x0 &= ~(int64_t)(EPV - 1);
+        int64_t x1 = cb + cq + a.kl < a.m ? cb + cq + a.kl : a.m;
+        if (x1 < x0) x1 = x0;
+        T *sA = sbase + (int64_t)s * stage_elems;
+        T *sx = sA + a.sA_elems;
+        const int64_t cntA = stage_round<T>(cq * a.lda, (a.n - cb) * a.lda);
+        const int64_t cntx = stage_round<T>(x1 - x0, a.m - x0);
+        mbar_add_tx(&bars[s], stage_bytes_bulk<T>(cntA) + R * stage_bytes_bulk<T>(cntx));
+        stage_issue<T>(sA, a.A + cb * a.lda, cntA, &bars[s]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) stage_issue<T>(sx + r * a.sx_elems, a.x + r * am.ldx + x0, cntx, &bars[s]);
+        mbar_arrive(&bars[s]);
+    };
+    if (tid == 0) {
+        const int64_t pro = nchunks < S ? nchunks : S;
+        for (int64_t q = 0; q < pro; ++q) issue(q, (int)q);
+    }
+    const int lda = (int)a.lda;
+    const int rw = (nb + 7) / 8;                             // band rows per warp
+    T *spart = sbase + (int64_t)S * stage_elems;             // [8][R][C] partial sums
+    for (int64_t q = 0; q < nchunks; ++q) {
+        const int s = (int)(q % S);
+        const uint32_t parity = (uint32_t)((q / S) & 1);
+        const int64_t cb = J0 + q * C;
+        const int cq = (int)(cb + C < J1 ? C : J1 - cb);
+        int64_t x0 = cb - a.ku > 0 ? cb - a.ku : 0;
+        x0 &= ~(int64_t)(EPV - 1);
+        const T *sA = sbase + (int64_t)s * stage_elems;
+        const T *sx = sA + a.sA_elems;
+        mbar_wait(&bars[s], parity);
+        for (int jj = lane; jj < cq; jj += 32) {
+            const int64_t j = cb + jj;
+            const T *col = sA + jj * lda;
+            const int xoff = (int)(j - a.ku - x0);            // sx index of row i = j - ku (r = 0)
+            int rlo = (int)(a.ku - j > 0 ? a.ku - j : 0);     // valid band rows: 0 <= j + r - ku < m
+            int rhi = (int)(a.m - 1 - j + a.ku < nb - 1 ? a.m - 1 - j + a.ku : nb - 1);
+            const int w0 = warp * rw, w1 = w0 + rw - 1;
+            if (rlo < w0) rlo = w0;
+            if (rhi > w1) rhi = w1;
+            T acc[R];
+#pragma unroll
+            for (int c = 0; c < R; ++c) acc[c] = (T)0;
+#pragma unroll 2
+            for (int r = rlo; r <= rhi; ++r) {
+                const T av = col[r];
+                const T *xr = sx + xoff + r;
+#pragma unroll
+                for (int c = 0; c < R; ++c) acc[c] = fma(av, xr[c * sxe], acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < R; ++c) spart[(warp * R + c) * C + jj] = acc[c];
+        }
+        __syncthreads();
+        for (int e = tid; e < R * cq; e += 256) {
+            const int c = e / cq, jj = e - c * cq;
+            T acc = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += spart[(w * R + c) * C + jj];
+            T *yp = a.y + c * am.ldy + cb + jj;
+            *yp = (a.beta == (T)0) ? a.alpha * acc : fma(a.beta, *yp, a.alpha * acc);
+        }
+        __syncthreads();
+        if (tid == 0 && q + S < nchunks) issue(q + S, s);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gbmv_wide_t_kernel(int64_t m, int64_t n, int64_t kl, int64_t ku, T alpha,
                                                          const T *__restrict__ A, int64_t lda,
@@ -1181,6 +1278,64 @@ int gbmv_multi_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl
                 else LBM_WIDE_MULTI(2);
 #undef LBM_WIDE_MULTI
                 LBM_LAUNCH_CHECK(h, "gbmv_wide_n_multi_kernel");
+                c += R;
+            }
+        }
+    }
+    // wide bands, op = T: groups of 8 / 4 / 2 columns share one pass over A (gbmv_wide_t_multi_kernel)
+    {
+        const bool wide_t_multi_ok = tr && nb > 33 && nin > 0 && n > 0 && alpha != (T)0 && A && X && Y && lbm_aligned16(A) && lbm_aligned16(X) &&
+                                     ldx % EPV == 0 && h->tune.gbmv_force != 1 && h->tune.gbmv_force != 4;
+        if (wide_t_multi_ok) {
+            lbm_device_guard g(h->device);
+            while (nrhs - c >= 2) {
+                const int R = nrhs - c >= 8 ? 8 : (nrhs - c >= 4 ? 4 : 2);
+                GbmvWideMultiArgs<T> am;
+                GbmvWideArgs<T> &a = am.w;
+                a.m = m; a.n = n; a.kl = kl; a.ku = ku; a.lda = lda;
+                a.alpha = alpha; a.beta = beta; a.A = A; a.x = X + c * ldx; a.y = Y + c * ldy;
+                am.ldx = ldx; am.ldy = ldy;
+                int64_t chunk = h->tune.gbmvw_chunk > 0 ? round_up(h->tune.gbmvw_chunk, 32) : 32;
+                if (chunk > 256) chunk = 256;
+                auto sA_el = [&](int64_t ch) { return round_up(ch * lda + 2 * EPV, EPV); };
+                auto sx_el = [&](int64_t ch) { return round_up(ch + nb + 3 * EPV, EPV); };
+                auto sbytes = [&](int64_t ch) { return (sA_el(ch) + R * sx_el(ch)) * (int64_t)sizeof(T); };
+                while (chunk > 32 && sbytes(chunk) + 128 + 8 * R * chunk * (int64_t)sizeof(T) > smem_cap) chunk -= 32;
+                a.chunk = (int)chunk;
+                a.sA_elems = sA_el(chunk);
+                a.sx_elems = sx_el(chunk);
+                const int64_t stage_bytes = sbytes(chunk);
+                const int64_t part_bytes = 8 * R * chunk * (int64_t)sizeof(T);
+                int64_t stages = h->tune.gbmvw_stages > 0 ? h->tune.gbmvw_stages : 3;
+                if (stages > GBMV_MAX_STAGES) stages = GBMV_MAX_STAGES;
+                while (stages > 1 && stages * stage_bytes + 128 + part_bytes > smem_cap) --stages;
+                a.stages = (int)stages;
+                const int64_t smem_cta = stages * stage_bytes + 128 + part_bytes;
+                if (smem_cta > smem_cap) break;   // band too wide for R windows + a 32-column slab: column by column below
+                int64_t ctas = h->tune.gbmvw_ctas_per_sm > 0 ? h->tune.gbmvw_ctas_per_sm : (227 * 1024) / (smem_cta + 1024);
+                if (ctas < 1) ctas = 1;
+                if (ctas > 8) ctas = 8;
+                int64_t grid = (int64_t)h->sm_count * ctas;
+                int64_t run = (n + grid - 1) / grid;
+                if (run < chunk) run = chunk;
+                run = round_up(run, 32);
+                grid = (n + run - 1) / run;
+                a.run = run;
+#define LBM_WIDE_T_MULTI(RR)                                                                                            \
+    do {                                                                                                                \
+        static std::atomic<int> cfg{0};                                                                                 \
+        auto kern = gbmv_wide_t_multi_kernel<T, RR>;                                                                    \
+        if (!(cfg & (1 << h->device))) {                                                                                \
+            LBM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));    \
+            cfg |= (1 << h->device);                                                                                    \
+        }                                                                                                               \
+        kern<<<(unsigned)grid, 256, (size_t)smem_cta, h->stream>>>(am);                                                 \
+    } while (0)
+                if (R == 8) LBM_WIDE_T_MULTI(8);
+                else if (R == 4) LBM_WIDE_T_MULTI(4);
+                else LBM_WIDE_T_MULTI(2);
+#undef LBM_WIDE_T_MULTI
+                LBM_LAUNCH_CHECK(h, "gbmv_wide_t_multi_kernel");
                 c += R;
             }
         }

@@ -205,14 +205,14 @@ def test_gbmv_large_linearity_and_sampled_rows(L, oracle):
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 def test_gbmv_multi_banded_times_dense(L, oracle, dt):
     """`mul!(C, A::BandedMatrix, B::Matrix, alpha, beta)` -> lbm_?gbmv_multi: groups of 8/4/2 columns share one
-    pass over A (narrow bands, and wide bands for op N; wide op T goes column by column); both ops, ragged nrhs, padded ldx/ldy, and NaNs
+    pass over A (narrow and wide bands, both ops: wide op T through gbmv_wide_t_multi_kernel since round 2); both ops, ragged nrhs, padded ldx/ldy, and NaNs
     parked in A's out-of-matrix slots."""
     npdt = NP[dt]
     cases = [  # (m, n, kl, ku, nrhs, pad)
         (1000, 1000, 1, 1, 8, 0), (3001, 2999, 4, 2, 11, 4), (777, 777, 8, 8, 3, 0), (5000, 5003, 16, 16, 5, 8),
         (40, 33, 5, 2, 2, 0), (9, 9, 3, 0, 7, 0), (2000, 2000, 128, 128, 3, 0), (70001, 70001, 2, 2, 13, 0), (5, 5, 1, 1, 1, 0),
         (300, 300, 0, 0, 4, 0),
-        # wide bands, op N: gbmv_wide_n_multi_kernel (one pass over A per 8 / 4 / 2 columns); op T stays column by column
+        # wide bands: gbmv_wide_n_multi_kernel / gbmv_wide_t_multi_kernel (one pass over A per 8 / 4 / 2 columns)
         (3000, 2900, 40, 30, 11, 4), (4097, 4097, 128, 128, 8, 0), (1500, 1700, 100, 3, 2, 0), (2500, 2500, 17, 17, 6, 2),
     ]
     for s, (m, n, kl, ku, nrhs, pad) in enumerate(cases):
