@@ -560,9 +560,11 @@ def run_b200(args):
         L.fill_uniform(sh.owned(xb).view(-1), 5, offset=p.r0 * g)
         y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
         l0 = h.launch_count()
-        ms = timeit(lambda: sh.mul_(y, xb), 20, 5)
+        # 200 applies per timed window (8 ms at N=8): at 40 us per apply a 20-apply window still sits on the ramp of the first
+        # launches (benchmarks/c3_multi_probe.py: 34.7 us per apply over 20, 30.9 us over 200, same build, N=2)
+        ms = timeit(lambda: sh.mul_(y, xb), 200, 20)
         cfg("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192, grid-column-sharded", ms, 16 * g * g, kernel="kron_ring_kernel<double,3,3>",
-            launches_per_apply=(h.launch_count() - l0) / 25)
+            launches_per_apply=(h.launch_count() - l0) / 220, applies_timed=200)
         if not args.no_parity:
             L.fill_uniform(sh.owned(xb).view(-1), 0x55, offset=p.r0 * g)
             y.fill_(float("nan"))

@@ -128,7 +128,7 @@ def main():
         xb = sh.new_buffer(torch.float64, dev)
         L.fill_uniform(sh.owned(xb).view(-1), 5, offset=p.r0 * g)
         y = torch.empty((p.m_loc, g), dtype=torch.float64, device=dev)
-        both("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192", lambda: sh.mul_(y, xb), 16 * g * g, 20, 5)
+        both("C3 2-D Laplacian kron(D,I)+kron(I,D) 8192x8192", lambda: sh.mul_(y, xb), 16 * g * g, 200, 20)
         del sh, xb, y
         torch.cuda.empty_cache()
 
