@@ -987,7 +987,18 @@ int gbmv_impl(lbm_handle_t h, char trans, int64_t m, int64_t n, int64_t kl, int6
         // (benchmarks/rect_probe.py, profiles/rect_probe_r02.md): the default was 3-8 % slower on the (0,2) / (2,0) slabs -- whose
         // bulk copies start on exact 8 KB multiples -- than on (1,1); this setting is within 1 % of the best for all three shapes.
         const bool three_diag = sizeof(T) == 8 && nb <= 3 && h->tune.gbmv_tile <= 0 && h->tune.gbmv_stages <= 0 && h->tune.gbmv_ctas_per_sm <= 0;
-        if (three_diag) tile = 1280;
+        if (three_diag) {
+            tile = 1280;
+            // one rank of an 8-GPU job holds 2^24 rows: 13108 tiles of 1280 over 592 CTAs is 22.1 per CTA, i.e. 23 for some
+            // (4 % of imbalance); 1024-row tiles give 27.7 -> 28 (1 %).  Measured on the (0,2) / (2,0) slabs at that size:
+            // 103.5 -> 100.7 us; the (1,1) slab of rank 0 prefers 1280 at every size (rect_probe_r02.md), so only rectangular
+            // slabs switch, and only when the tile count favours it by more than 1.5 %.
+            if (kl != ku) {
+                const int64_t ctas4 = (int64_t)h->sm_count * 4;
+                auto cost = [&](int64_t tl) { const int64_t nt = (nout + tl - 1) / tl; return ((nt + ctas4 - 1) / ctas4) * tl; };
+                if (cost(1024) * 1000 < cost(1280) * 985) tile = 1024;
+            }
+        }
         if (tile <= 0) {
             tile = GBMV_NT;
             for (int64_t tl = 2 * GBMV_NT; tl <= 2048; tl += GBMV_NT) {
