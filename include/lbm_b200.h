@@ -49,6 +49,15 @@ int lbm_sync(lbm_handle_t h);
 const char *lbm_last_error_string(lbm_handle_t h);       /* h may be NULL: last create error */
 int64_t lbm_launch_count(lbm_handle_t h);                /* kernels launched through h so far */
 int lbm_set_tuning(lbm_handle_t h, const char *key, int64_t value); /* kernel selection knobs */
+/* Keys (0 = automatic everywhere; unknown key: -2).  They select among kernels / configurations that all compute the same result:
+ *   gbmv_tile, gbmv_stages, gbmv_ctas_per_sm, gbmv_force (1 direct, 2 tile ring, 3 wide-N, 4 warp-per-output T), gbmvw_chunk, gbmvw_stages,
+ *   gbmvw_ctas_per_sm; tri_tile, tri_stages, tri_ctas_per_sm, tri_force_scalar, tri_force_shuffle;
+ *   kron_tr (256/512/1024 rows per strip), kron_tc (grid columns per chunk), kron_stages, kron_ctas_per_sm, kron_force_tile;
+ *   gbmm_force (1 diagonal-wise, 2 FP64 DMMA, 3 register kernel, 4 register kernel with round-1 zero-padded staging),
+ *   gbmm_tile, gbmm_variant (DMMA kernel variants; 30-32 = warp-autonomous); chain_tile, chain_force_generic, chain_variant;
+ *   exchange_mode (1 = ncclSend/Recv instead of peer mailboxes), exchange_fuse (2 = two-kernel exchange instead of the
+ *   exchange fused into the compute launch), halo_timeout_ms (wall-clock bound of a ghost wait, default 30000),
+ *   pdl (1 = programmatic dependent launch of the ring kernels; measured slower, off). */
 int64_t lbm_get_tuning(lbm_handle_t h, const char *key);
 
 /* ---- memory helpers (for hosts without their own CUDA allocator, e.g. the Julia shim) - */
