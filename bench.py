@@ -635,7 +635,10 @@ def run_b200(args):
                     4 * e32 * 9 * 9 + 4 * e32 * 9 * 9)
 
     if not args.no_wide:
-        for nm, fn in (("M-128", c_wide), ("GM", c_gm), ("C2", c2), ("C3", c3), ("C4", c4), ("C5", c5)):
+        # M-128 goes LAST: it holds up to 0.8 of the device memory (138 GB per GPU at N=2), and whatever is timed right after
+        # that much memory is released read 76 % instead of 91 % in some processes (GM at N=2, rounds 1 and 2; the same
+        # per-rank problem alone on a GPU is a steady 91 %, benchmarks/gm_n2_probe.py)
+        for nm, fn in (("GM", c_gm), ("C2", c2), ("C3", c3), ("C4", c4), ("C5", c5), ("M-128", c_wide)):
             guarded(nm, fn)
     clocks2 = sampler2.stop() if (rank == 0 and not args.no_wide) else None
 
