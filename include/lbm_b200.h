@@ -144,7 +144,9 @@ int lbm_stridiag_sum(lbm_handle_t h, int64_t n, const float *dl, const float *d,
 /* Materialises ApplyMatrix(*, A, B) (reference README.md:8-26; [up] BandedMatrices gbmm!).
  * A m x k (kla,kua), B k x n (klb,kub), C m x n stored with band (klc,kuc) which must
  * cover the product band clipped to the matrix: klc >= min(kla+klb, m-1),
- * kuc >= min(kua+kub, n-1).  Out-of-matrix slots of C are written 0 when beta == 0. */
+ * kuc >= min(kua+kub, n-1).  Out-of-matrix slots of C are written 0 when beta == 0.
+ * lbm_sgbmm with both factors >= 33 stored diagonals and a tight ldc computes in Float64 on the tensor path (operands widened
+ * into handle-owned scratch, 8 bytes per stored element of A, B and C; the diagonal-wise Float32 kernel when that is not free). */
 int lbm_dgbmm(lbm_handle_t h, int64_t m, int64_t n, int64_t k, double alpha,
               int64_t kla, int64_t kua, const double *A, int64_t lda,
               int64_t klb, int64_t kub, const double *B, int64_t ldb, double beta,

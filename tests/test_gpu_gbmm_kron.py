@@ -86,6 +86,50 @@ def test_gbmm_dmma_tensor_path(L, oracle):
     assert np.max(np.abs(dg - dw)) <= tol_rows(np.float64, 70, 1.0, 1.0, 1.5, 0.25, 1.0)
 
 
+def test_gbmm_f32_wide_bands_through_the_f64_tensor_path(L, oracle):
+    """lbm_sgbmm with both bands >= 33 diagonals: A, B (and C when beta != 0) are widened into scratch, the FP64 DMMA kernel
+    runs, the band is rounded back.  Against the f32 oracle within the f32 bound; NaNs parked in the out-of-matrix slots;
+    alpha / beta with an output band wider than the product band; the diagonal-wise kernel (gbmm_force = 1) agrees."""
+    h = L.handle_for(0)
+    dt, npdt = torch.float32, np.float32
+    for s_, (m, n, k, kla, kua, klb, kub) in enumerate([(1000, 1000, 1000, 128, 128, 128, 128), (700, 650, 720, 40, 35, 33, 50),
+                                                         (2048, 2048, 2048, 40, 36, 34, 50), (300, 400, 350, 64, 10, 10, 64)]):
+        A_np = oracle.brand(m, k, kla, kua, seed=70 + s_, dtype=npdt)
+        B_np = oracle.brand(k, n, klb, kub, seed=75 + s_, dtype=npdt)
+        want = oracle.gbmm(m, n, k, A_np, kla, kua, B_np, klb, kub)
+
+        def poison(M, rows, l, u):
+            P = M.copy()
+            r = np.arange(l + u + 1)[:, None]
+            i = np.arange(P.shape[1])[None, :] + r - u
+            P[(i < 0) | (i >= rows)] = np.nan
+            return L.BandedMatrix(torch.from_numpy(np.ascontiguousarray(P.T)).cuda(), rows, l, u)
+
+        A, B = poison(A_np, m, kla, kua), poison(B_np, k, klb, kub)
+        tol = tol_rows(npdt, min(kla + kua + 1, klb + kub + 1), 1.0, 1.0)
+        for force in (0, 1):
+            h.set_tuning(gbmm_force=force)
+            try:
+                before = h.launch_count()
+                C = A @ B
+                torch.cuda.synchronize()
+                nl = h.launch_count() - before
+            finally:
+                h.set_tuning(gbmm_force=0)
+            assert (nl >= 5) if force == 0 else (nl == 1), (force, nl)      # widen x2, zero corners, DMMA interior + corners, round
+            assert C.data.dtype == torch.float32
+            _cmp_band(oracle, C, want, m, kla + klb, kua + kub, tol)
+    m = n = k = 400
+    A_np, A = _band(L, oracle, m, k, 40, 33, 1, dt)
+    B_np, B = _band(L, oracle, k, n, 35, 36, 2, dt)
+    C0_np, C0 = _band(L, oracle, m, n, 80, 75, 3, dt)
+    want = oracle.gbmm(m, n, k, A_np, 40, 33, B_np, 35, 36, klc=80, kuc=75, alpha=-1.5, beta=0.25, Cin=C0_np)
+    L.gbmm(A, B, alpha=-1.5, out=C0, beta=0.25)
+    got = np.asfortranarray(C0.data.cpu().numpy().T)
+    dg, dw = oracle.band_to_dense(got, m, 80, 75), oracle.band_to_dense(want, m, 80, 75)
+    assert np.max(np.abs(dg - dw)) <= tol_rows(npdt, 70, 1.0, 1.0, 1.5, 0.25, 1.0)
+
+
 def test_gbmm_dmma_nan_poisoned_out_of_matrix_slots(L, oracle):
     """Interior tiles of the DMMA kernel stage RAW dense windows (out-of-band positions alias neighbouring
     columns' slots, including out-of-matrix ones) and mask in registers: NaNs parked in every out-of-matrix
